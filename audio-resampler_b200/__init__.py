@@ -1,0 +1,136 @@
+"""audio-resampler_b200 -- Python view of libresampler_b200.so.
+
+The product is the C-ABI shared library built from ``csrc/`` (C host code + sm_100a CUDA
+kernels; see ../include/*.h).  This module only locates/builds it and hands out a ctypes
+handle with the prototypes attached; tests and bench.py go through that handle, i.e.
+through the same boundary a C caller of the reference would use.
+
+The directory name contains a hyphen (it mirrors the upstream project name), so import it
+with ``importlib`` -- ``__graft_entry__.load_package()`` does that.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+LIB_PATH = HERE / "lib" / "libresampler_b200.so"
+
+# flag values, reference resampler.h:28-38
+SUBSAMPLE_INTERPOLATE = 0x1
+BLACKMAN_HARRIS = 0x2
+INCLUDE_LOWPASS = 0x4
+RESAMPLE_MULTITHREADED = 0x8
+NO_FILTER_REDUCTION = 0x10
+EXTRAPOLATE_ENDPOINTS = 0x40
+EXTEND_CONVOLUTION_MATH = 0x100
+
+# (filters, taps) of the reference's quality presets -1..-4, artest.c:154-169
+PRESETS = {1: (48, 48), 2: (320, 156), 3: (380, 380), 4: (988, 988)}
+
+
+class ResampleResult(C.Structure):
+    _fields_ = [("input_used", C.c_uint), ("output_generated", C.c_uint)]
+
+
+class Resample(C.Structure):
+    """include/resampler.h -- leading public fields (reference resampler.h:44-48)."""
+    _fields_ = [("numChannels", C.c_int), ("numSamples", C.c_int), ("numFilters", C.c_int),
+                ("numTaps", C.c_int), ("inputIndex", C.c_int), ("flags", C.c_int),
+                ("tempFilter", C.c_void_p), ("outputOffset", C.c_double), ("fixedRatio", C.c_double),
+                ("lowpassRatio", C.c_double), ("subsample", C.c_void_p),
+                ("buffers", C.c_void_p), ("filters", C.POINTER(C.POINTER(C.c_float))),
+                ("device", C.c_void_p)]
+
+
+class BiquadCoefficients(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("a0", "a1", "a2", "a3", "a4", "b1", "b2", "b3", "b4")]
+
+
+class Biquad(C.Structure):
+    _fields_ = [("a", C.c_float * 5), ("b", C.c_float * 5), ("x", C.c_float * 4), ("y", C.c_float * 4),
+                ("order", C.c_int), ("index", C.c_int)]
+
+
+def build(verbose: bool = False) -> Path:
+    """Compile csrc/ for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", str(HERE), "-j", str(os.cpu_count() or 4)], capture_output=True, text=True)
+    if verbose or r.returncode:
+        print(r.stdout[-4000:], r.stderr[-4000:])
+    if r.returncode:
+        raise RuntimeError("building libresampler_b200.so failed")
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the library and attach the prototypes of include/*.h.  Raises when the
+    library is missing: there is no Python or CPU fallback for any of it."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} not built; run __graft_entry__.build()")
+    lib = C.CDLL(str(LIB_PATH), mode=os.RTLD_LOCAL)
+    ctx, f32p = C.POINTER(Resample), C.POINTER(C.c_float)
+    f32pp, vp, dbl, i32 = C.POINTER(f32p), C.c_void_p, C.c_double, C.c_int
+    proto = {
+        # include/resampler.h
+        "resampleInit": (ctx, [i32, i32, i32, dbl, i32]),
+        "resampleFixedRatioInit": (ctx, [i32, i32, i32, dbl, dbl, i32, i32]),
+        "resampleProcess": (ResampleResult, [ctx, f32pp, i32, f32pp, i32, dbl]),
+        "resampleProcessInterleaved": (ResampleResult, [ctx, f32p, i32, f32p, i32, dbl]),
+        "resampleProcessAndFlush": (ResampleResult, [ctx, f32pp, i32, f32pp, i32, dbl]),
+        "resampleProcessAndFlushInterleaved": (ResampleResult, [ctx, f32p, i32, f32p, i32, dbl]),
+        "resampleGetRequiredSamples": (C.c_uint, [ctx, i32, dbl]),
+        "resampleGetExpectedOutput": (C.c_uint, [ctx, i32, dbl]),
+        "resampleAdvancePosition": (None, [ctx, dbl]),
+        "resampleGetLowpassRatio": (dbl, [ctx]),
+        "resampleGetPosition": (dbl, [ctx]),
+        "resampleGetNumFilters": (i32, [ctx]),
+        "resampleInterpolationUsed": (i32, [ctx]),
+        "resampleReset": (None, [ctx]),
+        "resampleFree": (None, [ctx]),
+        # include/biquad.h
+        "biquad_init": (None, [C.POINTER(Biquad), C.POINTER(BiquadCoefficients), dbl]),
+        "biquad_lowpass": (None, [C.POINTER(BiquadCoefficients), dbl]),
+        "biquad_highpass": (None, [C.POINTER(BiquadCoefficients), dbl]),
+        "biquad_apply_buffer": (None, [C.POINTER(Biquad), f32p, i32, i32]),
+        "biquad_apply_sample": (C.c_float, [C.POINTER(Biquad), C.c_float]),
+        # include/resampler_b200.h (device pointers travel as integers)
+        "resampleB200SetDevice": (i32, [i32]),
+        "resampleB200GetDeviceCount": (i32, []),
+        "resampleB200Synchronize": (None, [ctx]),
+        "resampleB200KernelLaunches": (C.c_ulonglong, []),
+        "resampleProcessInterleavedDevice": (ResampleResult, [ctx, vp, i32, vp, i32, dbl, vp]),
+        "resampleProcessDevice": (ResampleResult, [ctx, C.POINTER(vp), i32, C.POINTER(vp), i32, dbl, vp]),
+        "resampleBatchProcessInterleavedDevice": (None, [C.POINTER(ctx), i32, C.POINTER(vp), C.POINTER(i32),
+                                                         C.POINTER(vp), C.POINTER(i32), C.POINTER(dbl),
+                                                         C.POINTER(ResampleResult), vp]),
+        "resampleProcessBlocksInterleavedDevice": (i32, [ctx, vp, C.POINTER(i32), C.POINTER(dbl), i32, vp, i32,
+                                                          C.POINTER(ResampleResult), C.POINTER(dbl), vp]),
+        "biquad_apply_cascade_interleaved": (None, [C.POINTER(C.POINTER(Biquad)), i32, i32, f32p, i32]),
+        "biquad_apply_cascade_interleaved_device": (None, [C.POINTER(C.POINTER(Biquad)), i32, i32, vp, i32, vp]),
+    }
+    for name, (res, args) in proto.items():
+        fn = getattr(lib, name)          # AttributeError here = the library does not export what include/*.h declares
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "resampleInit", "resampleFixedRatioInit", "resampleProcess", "resampleProcessInterleaved",
+    "resampleProcessAndFlush", "resampleProcessAndFlushInterleaved", "resampleGetRequiredSamples",
+    "resampleGetExpectedOutput", "resampleAdvancePosition", "resampleGetLowpassRatio", "resampleGetPosition",
+    "resampleGetNumFilters", "resampleInterpolationUsed", "resampleReset", "resampleFree",
+    "biquad_init", "biquad_lowpass", "biquad_highpass", "biquad_apply_buffer", "biquad_apply_sample",
+    "resampleB200SetDevice", "resampleB200GetDeviceCount", "resampleB200Synchronize", "resampleB200KernelLaunches",
+    "resampleProcessInterleavedDevice", "resampleProcessDevice", "resampleBatchProcessInterleavedDevice",
+    "resampleProcessBlocksInterleavedDevice", "biquad_apply_cascade_interleaved",
+    "biquad_apply_cascade_interleaved_device",
+]

@@ -1,0 +1,448 @@
+/*
+ * art_device.cu -- device-side context of a resampler: history, filter bank, staging,
+ * job construction and kernel launches.  Implements art_device.h.
+ *
+ * What it replaces in the reference: the per-channel ring buffers (resampler.c:171-174),
+ * their compaction (:497-503, :614-620), the zero post-fill of a flush (:663-685) and the
+ * per-channel worker threads of workers.c (channels are simply a grid dimension here).
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include "art_kernels.cuh"
+#include "art_device.h"
+
+unsigned long long g_artLaunches = 0;
+
+extern "C" unsigned long long artDevLaunchCount (void) { return g_artLaunches; }
+
+/* ---- filter banks are immutable and identical for equal (T, F, coefficients): share them ---- */
+struct ArtBank {
+    int device, T, Tp, F, refs;
+    unsigned long long hash;
+    float *d_rows;
+    std::vector<float> packed;
+};
+
+static std::mutex g_bankMutex;
+static std::vector<ArtBank *> g_banks;
+
+static ArtBank *bank_acquire (int device, int T, int F, const float *const *rows)
+{
+    const int Tp = (T + 31) & ~31;
+    std::vector<float> packed ((size_t) (F + 2) * Tp, 0.0f);
+    unsigned long long h = 1469598103934665603ULL;
+    for (int r = 0; r <= F; ++r) {
+        memcpy (&packed[(size_t) r * Tp], rows[r], sizeof (float) * T);
+        const unsigned char *b = reinterpret_cast<const unsigned char *> (rows[r]);
+        for (size_t i = 0; i < sizeof (float) * T; ++i) { h ^= b[i]; h *= 1099511628211ULL; }
+    }
+    std::lock_guard<std::mutex> lock (g_bankMutex);
+    for (ArtBank *b : g_banks)
+        if (b->device == device && b->T == T && b->F == F && b->hash == h && b->packed == packed) {
+            b->refs++;
+            return b;
+        }
+    ArtBank *b = new ArtBank;
+    b->device = device; b->T = T; b->Tp = Tp; b->F = F; b->refs = 1; b->hash = h;
+    b->packed.swap (packed);
+    if (cudaMalloc (&b->d_rows, b->packed.size () * sizeof (float)) != cudaSuccess ||
+        cudaMemcpy (b->d_rows, b->packed.data (), b->packed.size () * sizeof (float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        fprintf (stderr, "libresampler_b200: cannot place the filter bank on the GPU: %s\n",
+                 cudaGetErrorString (cudaGetLastError ()));
+        delete b;
+        return nullptr;
+    }
+    g_banks.push_back (b);
+    return b;
+}
+
+static void bank_release (ArtBank *bank)
+{
+    std::lock_guard<std::mutex> lock (g_bankMutex);
+    if (--bank->refs > 0)
+        return;
+    for (size_t i = 0; i < g_banks.size (); ++i)
+        if (g_banks[i] == bank) { g_banks.erase (g_banks.begin () + i); break; }
+    cudaFree (bank->d_rows);
+    delete bank;
+}
+
+/* ---- context ---------------------------------------------------------------------------------- */
+struct ArtDev {
+    int device, smCount;
+    int C, T, F, mode;
+    ArtBank *bank;
+    cudaStream_t stream;
+    float *hist[2];
+    int cur;
+    float *d_in, *d_out;
+    size_t inCap, outCap;           // floats
+    ArtClass klass;
+};
+
+static void use_device (const ArtDev *dev)
+{
+    int now = -1;
+    if (cudaGetDevice (&now) != cudaSuccess || now != dev->device)
+        ART_CUDA_CHECK (cudaSetDevice (dev->device));
+}
+
+extern "C" ArtDev *artDevCreate (int channels, int taps, int filters, int mode, const float *const *rows)
+{
+    int device = 0, count = 0;
+    cudaError_t e = cudaGetDeviceCount (&count);
+    if (e != cudaSuccess || count == 0) {
+        fprintf (stderr, "libresampler_b200: no usable CUDA device (%s); this library has no CPU path\n",
+                 e != cudaSuccess ? cudaGetErrorString (e) : "device count is 0");
+        return nullptr;
+    }
+    if (cudaGetDevice (&device) != cudaSuccess) {
+        fprintf (stderr, "libresampler_b200: cudaGetDevice failed: %s\n", cudaGetErrorString (cudaGetLastError ()));
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties (&prop, device) != cudaSuccess || prop.major < 10) {
+        fprintf (stderr, "libresampler_b200: device %d is not a Blackwell (sm_100a) GPU; kernels are built for sm_100a only\n", device);
+        return nullptr;
+    }
+
+    ArtDev *dev = new ArtDev ();
+    dev->device = device;
+    dev->smCount = prop.multiProcessorCount;
+    dev->C = channels; dev->T = taps; dev->F = filters; dev->mode = mode;
+    dev->bank = bank_acquire (device, taps, filters, rows);
+    if (!dev->bank) { delete dev; return nullptr; }
+    ART_CUDA_CHECK (cudaStreamCreateWithFlags (&dev->stream, cudaStreamNonBlocking));
+    const size_t histBytes = sizeof (float) * (size_t) (channels > 0 ? channels : 1) * taps;
+    for (int i = 0; i < 2; ++i) {
+        ART_CUDA_CHECK (cudaMalloc (&dev->hist[i], histBytes));
+        ART_CUDA_CHECK (cudaMemset (dev->hist[i], 0, histBytes));
+    }
+    dev->cur = 0;
+    dev->d_in = dev->d_out = nullptr;
+    dev->inCap = dev->outCap = 0;
+
+    ArtClass &k = dev->klass;
+    memset (&k, 0, sizeof k);
+    k.bank = dev->bank->d_rows;
+    k.T = taps; k.Tp = dev->bank->Tp; k.F = filters; k.C = channels; k.mode = mode;
+    k.sort = getenv ("ART_B200_NOSORT") ? 0 : 1;
+    return dev;
+}
+
+extern "C" void artDevDestroy (ArtDev *dev)
+{
+    if (!dev) return;
+    use_device (dev);
+    cudaStreamSynchronize (dev->stream);
+    cudaFree (dev->hist[0]);
+    cudaFree (dev->hist[1]);
+    cudaFree (dev->d_in);
+    cudaFree (dev->d_out);
+    cudaStreamDestroy (dev->stream);
+    bank_release (dev->bank);
+    delete dev;
+}
+
+extern "C" void artDevReset (ArtDev *dev)
+{
+    use_device (dev);
+    ART_CUDA_CHECK (cudaMemsetAsync (dev->hist[dev->cur], 0, sizeof (float) * (size_t) dev->C * dev->T, dev->stream));
+    ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+}
+
+extern "C" int artDevDeviceIndex (const ArtDev *dev) { return dev->device; }
+
+extern "C" int artDevSelect (int device)
+{
+    cudaError_t e = cudaSetDevice (device);
+    if (e != cudaSuccess)
+        fprintf (stderr, "libresampler_b200: cudaSetDevice(%d): %s\n", device, cudaGetErrorString (e));
+    return e == cudaSuccess ? 0 : (int) e;
+}
+
+extern "C" int artDevCount (void)
+{
+    int n = 0;
+    return cudaGetDeviceCount (&n) == cudaSuccess ? n : 0;
+}
+
+extern "C" void artDevSynchronize (ArtDev *dev)
+{
+    use_device (dev);
+    ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+}
+
+extern "C" void artDevGetHistory (ArtDev *dev, float *hostPlanar)
+{
+    use_device (dev);
+    ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+    ART_CUDA_CHECK (cudaMemcpy (hostPlanar, dev->hist[dev->cur], sizeof (float) * (size_t) dev->C * dev->T, cudaMemcpyDeviceToHost));
+}
+
+extern "C" void artDevSetHistory (ArtDev *dev, const float *hostPlanar)
+{
+    use_device (dev);
+    ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+    ART_CUDA_CHECK (cudaMemcpy (dev->hist[dev->cur], hostPlanar, sizeof (float) * (size_t) dev->C * dev->T, cudaMemcpyHostToDevice));
+}
+
+/* ---- job construction ----------------------------------------------------------------------------- */
+
+static void fill_job (ArtDev *dev, const ArtCallPlan &p, ArtJob &j)
+{
+    memset (&j, 0, sizeof j);
+    j.P = p.st.P;
+    j.ratio = p.st.ratio;
+    j.I = p.st.I;
+    j.origin = p.st.I - p.pre;
+    j.outputs = p.outputs;
+    j.inValid = p.inValid;
+    j.prevAvail = 0;
+    j.consumed = p.consumed;
+    j.hist = dev->hist[dev->cur];
+    j.histOut = p.consumed ? dev->hist[dev->cur ^ 1] : nullptr;
+}
+
+static void finish_job (ArtDev *dev, const ArtCallPlan &p)
+{
+    if (p.consumed)
+        dev->cur ^= 1;
+}
+
+static void run_single (ArtDev *dev, const ArtCallPlan &p, ArtJob &job, cudaStream_t stream)
+{
+    ArtClass k = dev->klass;
+    k.numJobs = 1;
+    if (p.outputs) {
+        ArtLaunchGeom g;
+        artPlanGenericGeometry (k, p.st.ratio, p.outputs, dev->smCount, g);
+        job.tile0 = 0;
+        g.totalTiles = (int) ((p.outputs + k.NB - 1) / k.NB);
+        artLaunchGeneric (k, g, job, nullptr, stream);
+    }
+    if (job.histOut)
+        artLaunchHistory (k, job, nullptr, 1, stream);
+    finish_job (dev, p);
+}
+
+static void reserve (ArtDev *dev, size_t inFloats, size_t outFloats)
+{
+    if (inFloats > dev->inCap) {
+        ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+        cudaFree (dev->d_in);
+        dev->inCap = inFloats + inFloats / 4 + 1024;
+        ART_CUDA_CHECK (cudaMalloc (&dev->d_in, dev->inCap * sizeof (float)));
+    }
+    if (outFloats > dev->outCap) {
+        ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+        cudaFree (dev->d_out);
+        dev->outCap = outFloats + outFloats / 4 + 1024;
+        ART_CUDA_CHECK (cudaMalloc (&dev->d_out, dev->outCap * sizeof (float)));
+    }
+}
+
+/* ---- host-memory entry points ------------------------------------------------------------------------ */
+
+extern "C" void artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, const float *in, float *out)
+{
+    use_device (dev);
+    const size_t C = dev->C;
+    const size_t inFloats = (size_t) plan->inValid * C, outFloats = (size_t) plan->outputs * C;
+    reserve (dev, inFloats, outFloats);
+    if (inFloats)
+        ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_in, in, inFloats * sizeof (float), cudaMemcpyHostToDevice, dev->stream));
+    ArtJob job;
+    fill_job (dev, *plan, job);
+    job.in = dev->d_in;  job.inFS = C;  job.inCS = 1;
+    job.out = dev->d_out; job.outFS = C; job.outCS = 1;
+    run_single (dev, *plan, job, dev->stream);
+    if (outFloats)
+        ART_CUDA_CHECK (cudaMemcpyAsync (out, dev->d_out, outFloats * sizeof (float), cudaMemcpyDeviceToHost, dev->stream));
+    ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+}
+
+extern "C" void artDevRunHostPlanar (ArtDev *dev, const ArtCallPlan *plan, const float *const *in, float *const *out)
+{
+    use_device (dev);
+    const size_t C = dev->C;
+    const size_t nin = plan->inValid, nout = plan->outputs;
+    reserve (dev, nin * C, nout * C);
+    for (size_t c = 0; c < C && nin; ++c)
+        ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_in + c * nin, in[c], nin * sizeof (float), cudaMemcpyHostToDevice, dev->stream));
+    ArtJob job;
+    fill_job (dev, *plan, job);
+    job.in = dev->d_in;  job.inFS = 1;  job.inCS = (long long) nin;
+    job.out = dev->d_out; job.outFS = 1; job.outCS = (long long) nout;
+    run_single (dev, *plan, job, dev->stream);
+    for (size_t c = 0; c < C && nout; ++c)
+        ART_CUDA_CHECK (cudaMemcpyAsync (out[c], dev->d_out + c * nout, nout * sizeof (float), cudaMemcpyDeviceToHost, dev->stream));
+    ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+}
+
+/* ---- device-memory entry points ------------------------------------------------------------------------ */
+
+extern "C" void artDevRunDeviceInterleaved (ArtDev *dev, const ArtCallPlan *plan, const float *d_in, float *d_out, void *stream)
+{
+    use_device (dev);
+    cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
+    ArtJob job;
+    fill_job (dev, *plan, job);
+    job.in = d_in;   job.inFS = dev->C;  job.inCS = 1;
+    job.out = d_out; job.outFS = dev->C; job.outCS = 1;
+    run_single (dev, *plan, job, st);
+}
+
+extern "C" void artDevRunDevicePlanar (ArtDev *dev, const ArtCallPlan *plan, const float *const *d_in, float *const *d_out, void *stream)
+{
+    use_device (dev);
+    cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
+    const int C = dev->C;
+    ArtJob job;
+    fill_job (dev, *plan, job);
+    job.inFS = 1; job.outFS = 1;
+
+    // equally spaced planes need no pointer table
+    bool uniformIn = d_in != nullptr, uniformOut = true;
+    const long long pin = (C > 1 && d_in) ? (long long) (d_in[1] - d_in[0]) : 0;
+    const long long pout = C > 1 ? (long long) (d_out[1] - d_out[0]) : 0;
+    for (int c = 1; c < C; ++c) {
+        if (d_in && d_in[c] - d_in[c - 1] != pin) uniformIn = false;
+        if (d_out[c] - d_out[c - 1] != pout) uniformOut = false;
+    }
+    void *table = nullptr;
+    if (uniformIn || !d_in) { job.in = d_in ? d_in[0] : nullptr; job.inCS = pin; }
+    if (uniformOut) { job.out = d_out[0]; job.outCS = pout; }
+    if ((d_in && !uniformIn) || !uniformOut) {
+        std::vector<const void *> h (2 * (size_t) C, nullptr);
+        for (int c = 0; c < C; ++c) { h[c] = d_in ? d_in[c] : nullptr; h[C + c] = d_out[c]; }
+        ART_CUDA_CHECK (cudaMallocAsync (&table, sizeof (void *) * 2 * C, st));
+        // pageable source: staged by the runtime before the call returns
+        ART_CUDA_CHECK (cudaMemcpyAsync (table, h.data (), sizeof (void *) * 2 * C, cudaMemcpyHostToDevice, st));
+        if (d_in && !uniformIn) job.inPlanes = reinterpret_cast<const float *const *> (table);
+        if (!uniformOut) job.outPlanes = reinterpret_cast<float *const *> (table) + C;
+    }
+    run_single (dev, *plan, job, st);
+    if (table)
+        ART_CUDA_CHECK (cudaFreeAsync (table, st));
+}
+
+/* ---- many contexts, one launch ----------------------------------------------------------------------------- */
+
+extern "C" void artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
+                                           const float *const *d_in, float *const *d_out, void *stream)
+{
+    if (count <= 0) return;
+    ArtDev *lead = devs[0];
+    use_device (lead);
+    cudaStream_t st = stream ? (cudaStream_t) stream : lead->stream;
+
+    double minRatio = plans[0].st.ratio;
+    unsigned int maxOut = 0;
+    unsigned long long totalOut = 0;
+    for (int i = 0; i < count; ++i) {
+        if (devs[i]->bank != lead->bank || devs[i]->C != lead->C || devs[i]->mode != lead->mode || devs[i]->device != lead->device) {
+            fprintf (stderr, "libresampler_b200: a batch must hold contexts of one configuration on one GPU\n");
+            abort ();
+        }
+        if (plans[i].st.ratio < minRatio) minRatio = plans[i].st.ratio;
+        if (plans[i].outputs > maxOut) maxOut = plans[i].outputs;
+        totalOut += plans[i].outputs;
+    }
+
+    ArtClass k = lead->klass;
+    k.numJobs = count;
+    ArtLaunchGeom g;
+    g.totalTiles = 0;
+    if (maxOut)
+        artPlanGenericGeometry (k, minRatio, (unsigned int) (totalOut > 0xffffffffULL ? 0xffffffffULL : totalOut), lead->smCount, g);
+
+    std::vector<ArtJob> jobs (count);
+    int tiles = 0;
+    bool anyHist = false;
+    for (int i = 0; i < count; ++i) {
+        fill_job (devs[i], plans[i], jobs[i]);
+        jobs[i].in = d_in ? d_in[i] : nullptr;  jobs[i].inFS = lead->C;  jobs[i].inCS = 1;
+        jobs[i].out = d_out[i];                 jobs[i].outFS = lead->C; jobs[i].outCS = 1;
+        jobs[i].tile0 = tiles;
+        if (maxOut) tiles += (int) ((plans[i].outputs + k.NB - 1) / k.NB);
+        anyHist |= jobs[i].histOut != nullptr;
+    }
+    g.totalTiles = tiles;
+
+    ArtJob *d_jobs = nullptr;
+    ART_CUDA_CHECK (cudaMallocAsync (&d_jobs, sizeof (ArtJob) * count, st));
+    ART_CUDA_CHECK (cudaMemcpyAsync (d_jobs, jobs.data (), sizeof (ArtJob) * count, cudaMemcpyHostToDevice, st));
+    if (tiles)
+        artLaunchGeneric (k, g, jobs[0], d_jobs, st);
+    if (anyHist)
+        artLaunchHistory (k, jobs[0], d_jobs, count, st);
+    ART_CUDA_CHECK (cudaFreeAsync (d_jobs, st));
+    for (int i = 0; i < count; ++i)
+        finish_job (devs[i], plans[i]);
+}
+
+/* ---- consecutive blocks of one stream, one launch (ASRC) ------------------------------------------------------ */
+
+extern "C" void artDevRunBlocksInterleaved (ArtDev *dev, const ArtCallPlan *plans, int count,
+                                            const long long *inOffset, const long long *outOffset,
+                                            const float *d_in, float *d_out, void *stream)
+{
+    if (count <= 0) return;
+    use_device (dev);
+    cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
+    const int C = dev->C;
+
+    double minRatio = plans[0].st.ratio;
+    unsigned int maxOut = 0;
+    unsigned long long totalOut = 0;
+    long long totalIn = 0;
+    for (int i = 0; i < count; ++i) {
+        if (plans[i].st.ratio < minRatio) minRatio = plans[i].st.ratio;
+        if (plans[i].outputs > maxOut) maxOut = plans[i].outputs;
+        totalOut += plans[i].outputs;
+        totalIn += plans[i].consumed;
+    }
+    ArtClass k = dev->klass;
+    k.numJobs = count;
+    ArtLaunchGeom g;
+    g.totalTiles = 0;
+    if (maxOut)
+        artPlanGenericGeometry (k, minRatio, (unsigned int) (totalOut > 0xffffffffULL ? 0xffffffffULL : totalOut), dev->smCount, g);
+
+    std::vector<ArtJob> jobs (count + 1);
+    int tiles = 0;
+    for (int i = 0; i < count; ++i) {
+        ArtJob &j = jobs[i];
+        fill_job (dev, plans[i], j);
+        j.histOut = nullptr;
+        j.prevAvail = inOffset[i];
+        j.in = d_in + inOffset[i] * C;    j.inFS = C;  j.inCS = 1;
+        j.out = d_out + outOffset[i] * C; j.outFS = C; j.outCS = 1;
+        j.tile0 = tiles;
+        if (maxOut) tiles += (int) ((plans[i].outputs + k.NB - 1) / k.NB);
+    }
+    g.totalTiles = tiles;
+    // the history after the sequence: newest T frames of (history ++ all consumed input)
+    ArtJob &hj = jobs[count];
+    memset (&hj, 0, sizeof hj);
+    hj.hist = dev->hist[dev->cur];
+    hj.histOut = totalIn ? dev->hist[dev->cur ^ 1] : nullptr;
+    hj.in = d_in; hj.inFS = C; hj.inCS = 1;
+    hj.inValid = (int) totalIn;
+    hj.consumed = totalIn;
+
+    ArtJob *d_jobs = nullptr;
+    ART_CUDA_CHECK (cudaMallocAsync (&d_jobs, sizeof (ArtJob) * count, st));
+    ART_CUDA_CHECK (cudaMemcpyAsync (d_jobs, jobs.data (), sizeof (ArtJob) * count, cudaMemcpyHostToDevice, st));
+    if (tiles)
+        artLaunchGeneric (k, g, jobs[0], d_jobs, st);
+    if (hj.histOut) {
+        artLaunchHistory (k, hj, nullptr, 1, st);
+        dev->cur ^= 1;
+    }
+    ART_CUDA_CHECK (cudaFreeAsync (d_jobs, st));
+}

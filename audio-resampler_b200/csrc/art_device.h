@@ -1,0 +1,93 @@
+/*
+ * art_device.h -- the thin C ABI between the C host code (art_context.c, art_biquad.c)
+ * and the CUDA translation units (art_device.cu, art_sinc_kernels.cu, ...).
+ * Internal: nothing here is exported from libresampler_b200.so.
+ *
+ * Division of labour
+ *   host (C)   : the reference's API surface and scalar state -- filter-bank design in
+ *                double, outputOffset/inputIndex bookkeeping through art_plan.h, flags.
+ *   device     : everything that touches samples -- the per-channel history (replaces the
+ *                16*T ring of resampler.c:139,171-174), the filter bank, the convolution.
+ *
+ * There is no CPU implementation of any of these: when no usable CUDA device exists
+ * artDevCreate() reports the CUDA error and returns NULL, and every later entry point
+ * aborts on a CUDA error rather than returning silence.
+ */
+#ifndef ART_DEVICE_H
+#define ART_DEVICE_H
+
+#include "art_plan.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ArtDev ArtDev;
+
+/* What one resampleProcess* call has to do, as decided on the host by art_plan.h. */
+typedef struct {
+    ArtLoopState st;            /* loop-entry state (after the flush adjustment, if any)             */
+    int          pre;           /* input-region frames swallowed before the loop: T/2 on flush, else 0 */
+    int          inValid;       /* frames of caller data in the input region; the rest reads as zero  */
+    unsigned int outputs;       /* output_generated                                                   */
+    unsigned int consumed;      /* pre + input_used = frames of the input region entering the history */
+} ArtCallPlan;
+
+/* Kernel selection hints, fixed per context. */
+enum {
+    ART_MODE_INTERP  = 1,       /* SUBSAMPLE_INTERPOLATE                                   */
+    ART_MODE_LOWPASS = 2,       /* INCLUDE_LOWPASS (disables the pass-through shortcut)     */
+    ART_MODE_PRECISE = 4        /* EXTEND_CONVOLUTION_MATH: double accumulation             */
+};
+
+ArtDev *artDevCreate (int channels, int taps, int filters, int mode, const float *const *rows);
+void    artDevDestroy (ArtDev *dev);
+void    artDevReset (ArtDev *dev);                   /* zero the history (resampler.c:387-388) */
+int     artDevDeviceIndex (const ArtDev *dev);
+int     artDevSelect (int device);                   /* cudaSetDevice; 0 on success            */
+int     artDevCount (void);                          /* usable CUDA devices, 0 when none       */
+
+/* Host-memory entry points: stage in, run, stage out, synchronise. */
+void artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, const float *in, float *out);
+void artDevRunHostPlanar (ArtDev *dev, const ArtCallPlan *plan, const float *const *in, float *const *out);
+
+/* Device-memory entry points: enqueue on `stream` (a cudaStream_t, NULL = the context's
+ * own stream) and return without synchronising. */
+void artDevRunDeviceInterleaved (ArtDev *dev, const ArtCallPlan *plan, const float *d_in, float *d_out, void *stream);
+void artDevRunDevicePlanar (ArtDev *dev, const ArtCallPlan *plan, const float *const *d_in, float *const *d_out, void *stream);
+
+/* Many contexts of one configuration in a single launch (device memory, interleaved). */
+void artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
+                                const float *const *d_in, float *const *d_out, void *stream);
+
+/* Consecutive blocks of ONE stream, each with its own ratio (ASRC), in a single launch.
+ * Block b reads d_in + inOffset[b]*channels; the frames before it in the same buffer are
+ * its history.  Only valid when every block consumed all of its input. */
+void artDevRunBlocksInterleaved (ArtDev *dev, const ArtCallPlan *plans, int count,
+                                 const long long *inOffset, const long long *outOffset,
+                                 const float *d_in, float *d_out, void *stream);
+
+void artDevSynchronize (ArtDev *dev);
+void artDevGetHistory (ArtDev *dev, float *hostPlanar);        /* [channels][taps], for tests/extrapolation */
+void artDevSetHistory (ArtDev *dev, const float *hostPlanar);
+
+/* statistics for bench.py's gpu_launches claim */
+unsigned long long artDevLaunchCount (void);
+
+/* ---- biquad cascade (biquad.c:106-163, order <= 4), float32 direct form I ---------- */
+typedef struct {
+    float a[5], b[5];           /* as stored in the reference's Biquad (biquad.h:31-35)      */
+    float x[4], y[4];           /* oldest..newest delayed input/output: x[0] = x[n-1] ...    */
+    int   order;
+} ArtBiquadStage;
+
+/* buffer: host or device memory holding frames*stride floats; channel c of stage-set s uses
+ * stages[s*channels + c] and samples buffer[c + f*stride].  States are read from and written
+ * back to `stages` (host memory).  onDevice selects the address space of `buffer`. */
+void artBiquadRun (ArtBiquadStage *stages, int numStages, int channels, float *buffer,
+                   long long frames, int stride, int onDevice, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,92 @@
+/*
+ * art_kernels.cuh -- structures shared by the CUDA translation units (sm_100a only).
+ *
+ * HBM layout
+ *   bank      : (F+2) rows x Tp floats, Tp = T rounded up to 32, zero padded.  Row r, tap t is
+ *               filters[r][t] of the reference (resampler.c:146-168); row F+1 is all zero so a
+ *               clamped row index can never read out of bounds.  128-byte aligned rows.
+ *   history   : C x T floats, planar -- the newest T samples each channel has consumed.  This
+ *               replaces the reference's 16*T ring + memmove compaction (resampler.c:139,
+ *               :497-503): an output window never reaches further back than T samples before
+ *               the first sample of the current call (art_plan.h), so "history ++ input block"
+ *               is all a call can touch.
+ *   input     : caller's block, interleaved [frame][C] or planar (frame stride / channel stride,
+ *               or a table of per-channel pointers).
+ *   output    : likewise.
+ *
+ * Sample coordinates: "region index" i counts frames from the first frame of the call's input
+ * region (i >= 0: this call's input, zero beyond inValid; i < 0: history, or -- in block mode --
+ * the frames that precede this block in the same buffer).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include "art_plan.h"
+
+struct ArtJob {
+    double        P, ratio;          // loop-entry outputOffset, effective ratio
+    int           I;                 // loop-entry inputIndex
+    int           origin;            // ring index that region index 0 maps to (I - pre)
+    unsigned int  outputs;           // frames to produce
+    int           inValid;           // frames of caller data in the input region
+    long long     prevAvail;         // consumed frames preceding the region in the same buffer
+    long long     consumed;          // region frames that enter the history (history kernel)
+    int           tile0;             // first tile of this job inside the launch
+    int           pad_;
+    const float  *hist;              // [C][T] history at call entry
+    float        *histOut;           // [C][T] history after the call (may be null)
+    const float  *in;                // base of region frame 0, channel 0
+    float        *out;
+    long long     inFS, inCS, outFS, outCS;      // frame / channel strides in floats
+    const float *const *inPlanes;    // optional per-channel pointer tables (device memory)
+    float *const       *outPlanes;
+};
+
+struct ArtClass {
+    const float *bank;
+    int T, Tp, F, C, mode;
+    int NB;          // output frames per tile
+    int Cg;          // channels per CTA (smem planes; a multiple of the CV the kernel was built for)
+    int Wp;          // floats per smem plane
+    int numJobs;
+    int sort;        // 1: group a tile's outputs by filter row before convolving
+};
+
+__device__ __forceinline__ float art_fetch (const ArtJob &j, int T, int c, long long idx)
+{
+    if (idx >= j.inValid)
+        return 0.0f;
+    if (idx >= -j.prevAvail) {
+        const float *p = j.inPlanes ? j.inPlanes[c] + idx * j.inFS : j.in + idx * j.inFS + c * j.inCS;
+        return __ldg (p);
+    }
+    const long long h = T + idx + j.prevAvail;
+    return h >= 0 ? j.hist[(long long) c * T + h] : 0.0f;
+}
+
+__device__ __forceinline__ float *art_out_ptr (const ArtJob &j, int c, long long frame)
+{
+    return j.outPlanes ? j.outPlanes[c] + frame * j.outFS : j.out + frame * j.outFS + c * j.outCS;
+}
+
+/* launchers (host side, C++ linkage, defined next to their kernels) */
+struct ArtLaunchGeom { int totalTiles; size_t smemBytes; int CV; };
+
+void artPlanGenericGeometry (ArtClass &k, double minRatio, unsigned int maxOutputs, int smCount, ArtLaunchGeom &g);
+/* `single` is used when d_jobs is null (one job, passed by value); otherwise d_jobs[numJobs] */
+void artLaunchGeneric (const ArtClass &k, const ArtLaunchGeom &g, const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream);
+void artLaunchHistory (const ArtClass &k, const ArtJob &single, const ArtJob *d_jobs, int numJobs, cudaStream_t stream);
+
+extern unsigned long long g_artLaunches;
+
+#define ART_CUDA_CHECK(expr)                                                                  \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            fprintf (stderr, "libresampler_b200: CUDA error %s at %s:%d (%s)\n",             \
+                     cudaGetErrorString (e_), __FILE__, __LINE__, #expr);                     \
+            abort ();                                                                         \
+        }                                                                                     \
+    } while (0)

@@ -1,0 +1,446 @@
+/*
+ * art_sinc_generic.cu -- the any-ratio windowed-sinc kernel (sm_100a).
+ *
+ * Replaces the inner loop of resampleProcess / resampleProcessInterleaved
+ * (resampler.c:523-526, :640-643), subsample_interpolate / subsample_no_interpolate
+ * (:1135-1157), their _precise twins (:1159-1181) and apply_filter (:1033-1057).
+ *
+ * One CTA owns a tile of NB consecutive output frames of one job for a group of Cg
+ * channels:
+ *   1. every thread derives the position of its outputs from the closed form in
+ *      art_plan.h (binary64, same operation order as the reference) and records
+ *      (window start, filter row, interpolation weight);
+ *   2. the tile's outputs are grouped by filter row (shared-memory counting sort) --
+ *      a row pair is 2*T floats that no neighbouring output shares when the phase
+ *      step is large, so grouping is what turns 3 KB of filter traffic per output
+ *      into 3 KB per row per tile;
+ *   3. the input window of the tile (history ++ input block) is staged planar in
+ *      shared memory with coalesced loads;
+ *   4. a warp takes a run of up to 8 outputs that share a row pair: lanes split the
+ *      taps, each lane keeps 8 x CV x 2 accumulators in registers, the row pair is
+ *      read once per run through L1, the samples come from shared memory
+ *      (conflict free: 32 consecutive floats per load);
+ *   5. the 8 x CV partial sums are combined with a transposing shuffle reduction
+ *      (one shuffle per value instead of five) and written to global memory.
+ *
+ * Arithmetic: float FMA accumulation, float lerp of the two row sums (the reference
+ * lerps in double after two float sums; the difference is below 1 ulp of the sums).
+ * ART_MODE_PRECISE accumulates in double like apply_filter_precise.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <type_traits>
+#include "art_kernels.cuh"
+#include "art_device.h"
+
+#define ART_G_THREADS 256
+#define ART_G_WARPS   (ART_G_THREADS / 32)
+#define ART_RUN       8
+
+#define KEY_PASS0(F) ((F) + 1)      /* pass-through of the centre sample (resampler.c:1141-1142) */
+#define KEY_PASS1(F) ((F) + 2)      /* ... of the one after it (row index == F)                  */
+#define NUM_KEYS(F)  ((F) + 3)
+
+/* Sum NV register values per lane across the warp so that lane L ends up with the total of
+ * value (L * NV / 32).  log2(NV) exchange stages halve the value count while consuming one
+ * lane bit each; the remaining lane bits are folded with a plain butterfly. */
+template <int NV, typename AccT>
+__device__ __forceinline__ AccT art_transpose_reduce (AccT (&v)[NV], int lane)
+{
+    int off = 16;
+#pragma unroll
+    for (int n = NV; n > 1; n >>= 1, off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            AccT send = upper ? v[i] : v[i + n / 2];
+            AccT keep = upper ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync (0xffffffffu, send, off);
+        }
+    }
+#pragma unroll
+    for (; off >= 1; off >>= 1)
+        v[0] += __shfl_xor_sync (0xffffffffu, v[0], off);
+    return v[0];
+}
+
+__device__ __forceinline__ int art_find_job (const ArtJob *jobs, int numJobs, int tile)
+{
+    int lo = 0, hi = numJobs - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].tile0 <= tile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+template <bool INTERP, bool PRECISE, int CV>
+__global__ void __launch_bounds__ (ART_G_THREADS, 2)
+art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single, const ArtJob *__restrict__ jobs)
+{
+    typedef typename std::conditional<PRECISE, double, float>::type AccT;
+
+    extern __shared__ __align__ (16) unsigned char smem_raw[];
+    const int nkeys = NUM_KEYS (k.F);
+    const int nkeysPad = (nkeys + 2 + 3) & ~3;
+
+    float *xs = reinterpret_cast<float *> (smem_raw);                   // [Cg][Wp]
+    int *srel = reinterpret_cast<int *> (xs + (size_t) k.Cg * k.Wp);    // [NB] window start - tile origin
+    float *wgt = reinterpret_cast<float *> (srel + k.NB);               // [NB] interpolation weight
+    int *binEnd = reinterpret_cast<int *> (wgt + k.NB);                 // [nkeysPad] counts -> starts -> ends
+    int *chunk0 = binEnd + nkeysPad;                                    // [nkeysPad] first run index per key
+    unsigned short *key = reinterpret_cast<unsigned short *> (chunk0 + nkeysPad);   // [NB]
+    unsigned short *order = key + k.NB;                                 // [NB] tile-local output index, grouped by key
+
+    __shared__ long long sh_first, sh_last;
+    __shared__ double sh_base0;
+    __shared__ int sh_w0;
+    __shared__ int sh_scan[ART_G_WARPS];
+    __shared__ int sh_scan2[ART_G_WARPS];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // one job travels by value in the parameter space (no descriptor upload on the latency path);
+    // batches and block sequences come as an array in global memory
+    const ArtJob &job = jobs ? jobs[k.numJobs > 1 ? art_find_job (jobs, k.numJobs, blockIdx.x) : 0] : single;
+    const unsigned int n0 = (unsigned int) (blockIdx.x - job.tile0) * (unsigned int) k.NB;
+    if (n0 >= job.outputs)
+        return;
+    const int cnt = (int) min ((unsigned int) k.NB, job.outputs - n0);
+    const int c0 = blockIdx.y * k.Cg;
+    const int nc = min (k.Cg, k.C - c0);
+    const int T = k.T, half = T / 2, F = k.F;
+
+    ArtLoopState st;
+    st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = T;
+    const long long D = 15LL * T;
+
+    for (int i = tid; i < nkeysPad; i += ART_G_THREADS) {
+        binEnd[i] = 0;
+        chunk0[i] = 0;
+    }
+    if (tid == 0) {                         // the rounding chain up to the tile's first output, once
+        int w;
+        const double pos = art_output_pos (&st, n0, &w);
+        sh_w0 = w;
+        (void) pos;
+        sh_base0 = art_ring_base (st.P, T, w);
+    }
+    __syncthreads ();
+    const int w0 = sh_w0;
+    const double base0 = sh_base0;
+
+    /* ---- 1. positions ------------------------------------------------------------------ */
+    for (int i = tid; i < cnt; i += ART_G_THREADS) {
+        int w;
+        const double pos = art_output_pos_from (&st, n0 + i, w0, base0, &w);
+        const double whole = floor (pos);
+        const double fr = pos - whole;
+        // region index of the first tap: ring index (whole - half + 1), un-compacted, minus origin
+        const long long s = (long long) whole - half + 1 + (long long) w * D - job.origin;
+        int kk;
+        float f = 0.0f;
+        if (INTERP) {
+            double ph = fr * F;                                   // resampler.c:1149-1152
+            int row = (int) floor (ph);
+            ph -= row;
+            if (row >= F) { row = F - 1; ph = 1.0; }             // fr*F rounded up to F: same point on the bank
+            kk = row;
+            f = (float) ph;
+        }
+        else {
+            int row = (int) floor (fr * F + 0.5);                 // resampler.c:1137
+            if (!(k.mode & ART_MODE_LOWPASS) && row % F == 0)     // resampler.c:1141-1142
+                kk = row ? KEY_PASS1 (F) : KEY_PASS0 (F);
+            else
+                kk = row;
+        }
+        if (i == 0) sh_first = s;
+        if (i == cnt - 1) sh_last = s;
+        srel[i] = (int) s;                 // region index of the first tap (frame counts are ints)
+        wgt[i] = f;
+        key[i] = (unsigned short) kk;
+        if (k.sort)
+            atomicAdd (&binEnd[kk], 1);
+    }
+    __syncthreads ();
+
+    const long long sFirst = sh_first;
+    const int span = (int) (sh_last - sFirst) + k.Tp;            // floats of window the tile touches
+    if (span > k.Wp) {
+        if (tid == 0)
+            printf ("libresampler_b200: tile window %d exceeds plane %d (ratio %g)\n", span, k.Wp, job.ratio);
+        __trap ();
+    }
+
+    /* ---- 3. stage the window (issued before the scan so the loads overlap it) ------------ */
+    {
+        const bool interleavedSrc = (job.inPlanes == nullptr) && (job.inCS == 1);
+        if (interleavedSrc) {
+            const int total = span * k.Cg;
+            for (int e = tid; e < total; e += ART_G_THREADS) {
+                const int j = e / k.Cg, cc = e - j * k.Cg;
+                xs[cc * k.Wp + j] = cc < nc ? art_fetch (job, T, c0 + cc, sFirst + j) : 0.0f;
+            }
+        }
+        else {
+            for (int cc = 0; cc < k.Cg; ++cc)
+                for (int j = tid; j < span; j += ART_G_THREADS)
+                    xs[cc * k.Wp + j] = cc < nc ? art_fetch (job, T, c0 + cc, sFirst + j) : 0.0f;
+        }
+    }
+
+    /* ---- 2. group by filter row ---------------------------------------------------------- */
+    int totalRuns;
+    if (k.sort) {
+        // exclusive scans of counts (-> starts) and of ceil(count / RUN) (-> first run), in one pass
+        const int per = (nkeys + ART_G_THREADS - 1) / ART_G_THREADS;
+        const int b0 = tid * per, b1 = min (b0 + per, nkeys);
+        int sumC = 0, sumR = 0;
+        for (int b = b0; b < b1; ++b) {
+            sumC += binEnd[b];
+            sumR += (binEnd[b] + ART_RUN - 1) / ART_RUN;
+        }
+        int incC = sumC, incR = sumR;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int a = __shfl_up_sync (0xffffffffu, incC, o);
+            int r = __shfl_up_sync (0xffffffffu, incR, o);
+            if (lane >= o) { incC += a; incR += r; }
+        }
+        if (lane == 31) { sh_scan[warp] = incC; sh_scan2[warp] = incR; }
+        __syncthreads ();
+        int baseC = 0, baseR = 0;
+        for (int w = 0; w < warp; ++w) { baseC += sh_scan[w]; baseR += sh_scan2[w]; }
+        int runC = baseC + incC - sumC, runR = baseR + incR - sumR;
+        for (int b = b0; b < b1; ++b) {
+            const int c = binEnd[b];
+            binEnd[b] = runC;          // start of the bin; the scatter below advances it to the end
+            chunk0[b] = runR;
+            runC += c;
+            runR += (c + ART_RUN - 1) / ART_RUN;
+        }
+        int tr = 0;
+        for (int w = 0; w < ART_G_WARPS; ++w) tr += sh_scan2[w];
+        totalRuns = tr;
+        if (tid == 0) chunk0[nkeys] = tr;
+        __syncthreads ();
+        for (int i = tid; i < cnt; i += ART_G_THREADS) {
+            const int slot = atomicAdd (&binEnd[key[i]], 1);
+            order[slot] = (unsigned short) i;
+        }
+    }
+    else
+        totalRuns = (cnt + ART_RUN - 1) / ART_RUN;
+    __syncthreads ();
+
+    /* ---- 4. convolve: one warp per run ---------------------------------------------------- */
+    const int NI = k.Tp >> 5;
+    for (int run = warp; run < totalRuns; run += ART_G_WARPS) {
+        int kk, e0, len;
+        if (k.sort) {
+            int lo = 0, hi = nkeys - 1;                       // largest key with chunk0[key] <= run
+            while (lo < hi) {
+                int mid = (lo + hi + 1) >> 1;
+                if (chunk0[mid] <= run) lo = mid; else hi = mid - 1;
+            }
+            kk = lo;
+            const int begin = kk ? binEnd[kk - 1] : 0;
+            e0 = begin + (run - chunk0[kk]) * ART_RUN;
+            len = min (ART_RUN, binEnd[kk] - e0);
+        }
+        else {
+            // ungrouped: consecutive outputs; a run must still share one key, so cut at the first change
+            e0 = run * ART_RUN;
+            len = min (ART_RUN, cnt - e0);
+            kk = -1;
+        }
+
+        int done = 0;
+        while (done < len) {
+            int sub = len;                                    // grouped: the whole run shares kk
+            if (!k.sort) {                                    // raw order: cut where the row changes
+                kk = key[e0 + done];
+                sub = 1;
+                while (done + sub < len && key[e0 + done + sub] == kk) ++sub;
+            }
+            const int eBase = e0 + done;
+#define ART_ENTRY(j) (k.sort ? (int) order[eBase + (j)] : eBase + (j))     /* tile-local output index */
+
+            if (kk > F) {
+                /* pass-through: the stored sample itself */
+                const int shift = (kk == KEY_PASS1 (F)) ? 1 : 0;
+                for (int q = lane; q < sub * nc; q += 32) {
+                    const int j = q / nc, cc = q - j * nc;
+                    const int i = ART_ENTRY (j);
+                    const int at = (int) ((long long) srel[i] - sFirst) + half - 1 + shift;
+                    *art_out_ptr (job, c0 + cc, (long long) n0 + i) = xs[cc * k.Wp + at];
+                }
+            }
+            else {
+                const float *__restrict__ rowA = k.bank + (size_t) kk * k.Tp + lane;
+                const float *__restrict__ rowB = rowA + k.Tp;
+                int base[ART_RUN];
+                float f[ART_RUN];
+#pragma unroll
+                for (int j = 0; j < ART_RUN; ++j) {
+                    const int i = ART_ENTRY (min (j, sub - 1));   // idle slots shadow the last real entry
+                    base[j] = (int) ((long long) srel[i] - sFirst) + lane;
+                    f[j] = wgt[i];
+                }
+
+                for (int cg = 0; cg < nc; cg += CV) {
+                    AccT a0[ART_RUN][CV], a1[ART_RUN][CV];
+#pragma unroll
+                    for (int j = 0; j < ART_RUN; ++j)
+#pragma unroll
+                        for (int v = 0; v < CV; ++v) { a0[j][v] = 0; a1[j][v] = 0; }
+
+                    const float *xg = xs + cg * k.Wp;
+#pragma unroll 2
+                    for (int i = 0; i < NI; ++i) {
+                        const AccT ca = __ldg (rowA + 32 * i);
+                        const AccT cb = INTERP ? (AccT) __ldg (rowB + 32 * i) : (AccT) 0;
+#pragma unroll
+                        for (int j = 0; j < ART_RUN; ++j)
+#pragma unroll
+                            for (int v = 0; v < CV; ++v) {
+                                const AccT x = xg[v * k.Wp + base[j] + 32 * i];
+                                a0[j][v] = fma (ca, x, a0[j][v]);
+                                if (INTERP) a1[j][v] = fma (cb, x, a1[j][v]);
+                            }
+                    }
+
+                    AccT vals[ART_RUN * CV];
+#pragma unroll
+                    for (int j = 0; j < ART_RUN; ++j)
+#pragma unroll
+                        for (int v = 0; v < CV; ++v)
+                            vals[j * CV + v] = INTERP ? fma ((AccT) f[j], a1[j][v] - a0[j][v], a0[j][v]) : a0[j][v];
+
+                    const AccT total = art_transpose_reduce<ART_RUN * CV, AccT> (vals, lane);
+                    constexpr int LPV = 32 / (ART_RUN * CV);         // lanes holding the same value
+                    const int q = lane / LPV, j = q / CV, v = q - j * CV;
+                    if ((lane % LPV) == 0 && j < sub && cg + v < nc)
+                        *art_out_ptr (job, c0 + cg + v, (long long) n0 + ART_ENTRY (j)) = (float) total;
+                }
+            }
+#undef ART_ENTRY
+            done += sub;
+        }
+    }
+}
+
+/* ---- history: the newest T consumed samples of every channel ------------------------------- */
+__global__ void art_history_kernel (const ArtClass k, const __grid_constant__ ArtJob single, const ArtJob *__restrict__ jobs)
+{
+    const ArtJob &job = jobs ? jobs[blockIdx.y] : single;
+    if (!job.histOut)
+        return;
+    const int total = k.C * k.T;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+        const int c = e / k.T, i = e - c * k.T;
+        job.histOut[e] = art_fetch (job, k.T, c, job.consumed - k.T + i);
+    }
+}
+
+/* ---- host side ----------------------------------------------------------------------------- */
+
+static size_t generic_smem (const ArtClass &k)
+{
+    const int nkeys = NUM_KEYS (k.F);
+    const int nkeysPad = (nkeys + 2 + 3) & ~3;
+    return (size_t) k.Cg * k.Wp * 4 + (size_t) k.NB * (4 + 4 + 2 + 2) + (size_t) nkeysPad * 8 + 16;
+}
+
+static int plane_floats (int NB, double ratio, int Tp)
+{
+    // NB consecutive outputs span at most (NB-1)/ratio + 2 input frames; + the padded tap count
+    double span = (double) (NB - 1) / ratio + 2.0 + Tp;
+    if (span > 1.0e9) span = 1.0e9;
+    return (((int) span) + 31) & ~31;
+}
+
+void artPlanGenericGeometry (ArtClass &k, double minRatio, unsigned int maxOutputs, int smCount, ArtLaunchGeom &g)
+{
+    const size_t budget = 110 * 1024;        // two CTAs per SM inside the 227 KB carve-out
+    const int C = k.C;
+    int cv = C >= 4 ? 4 : (C >= 2 ? 2 : 1);
+    if (k.mode & ART_MODE_PRECISE) cv = C >= 2 ? 2 : 1;
+    const int maxCg = ((C < 8 ? C : 8) + cv - 1) / cv * cv;
+
+    // small calls: shorter tiles so that the grid still covers the GPU
+    int nbCap = 4096;
+    while (nbCap > 256 &&
+           (unsigned long long) nbCap * smCount * 2 > (unsigned long long) maxOutputs * ((C + maxCg - 1) / maxCg))
+        nbCap >>= 1;
+
+    // A row pair is fetched once per run: what amortises it is (outputs per row in a tile) x
+    // (channels per CTA).  Maximise that, then the tile length.
+    double bestScore = -1.0;
+    int bestNB = 0, bestCg = 0;
+    for (int NB = nbCap; NB >= 1; NB >>= 1)
+        for (int Cg = maxCg; Cg >= cv; Cg -= cv) {
+            ArtClass t = k;
+            t.NB = NB; t.Cg = Cg; t.Wp = plane_floats (NB, minRatio, k.Tp);
+            if (t.Wp >= (1 << 26) || generic_smem (t) > budget)
+                continue;
+            double perRow = (double) NB / (k.F + 1);
+            if (perRow < 1.0) perRow = 1.0;
+            if (perRow > ART_RUN) perRow = ART_RUN + (perRow - ART_RUN) * 0.05;   // beyond a full run only L1 traffic improves
+            const double score = perRow * Cg + 1e-6 * NB;
+            if (score > bestScore) { bestScore = score; bestNB = NB; bestCg = Cg; }
+        }
+    if (!bestNB) {
+        fprintf (stderr, "libresampler_b200: ratio %g needs a %d-float window per output; unsupported\n",
+                 minRatio, plane_floats (1, minRatio, k.Tp));
+        abort ();
+    }
+    k.NB = bestNB;
+    k.Cg = bestCg;
+    k.Wp = plane_floats (bestNB, minRatio, k.Tp);
+    g.CV = cv;
+    g.smemBytes = generic_smem (k);
+}
+
+template <bool INTERP, bool PRECISE, int CV>
+static void launch_one (const ArtClass &k, const ArtLaunchGeom &g, const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream)
+{
+    auto kern = art_sinc_generic_kernel<INTERP, PRECISE, CV>;
+    static size_t configured = 0;
+    if (g.smemBytes > configured) {
+        ART_CUDA_CHECK (cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = 227 * 1024;
+    }
+    dim3 grid (g.totalTiles, (k.C + k.Cg - 1) / k.Cg);
+    kern<<<grid, ART_G_THREADS, g.smemBytes, stream>>> (k, single, d_jobs);
+    ART_CUDA_CHECK (cudaGetLastError ());
+    ++g_artLaunches;
+}
+
+void artLaunchGeneric (const ArtClass &k, const ArtLaunchGeom &g, const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream)
+{
+    if (g.totalTiles <= 0)
+        return;
+    const bool interp = k.mode & ART_MODE_INTERP, precise = k.mode & ART_MODE_PRECISE;
+#define ART_DISPATCH(CVV)                                                                 \
+    do {                                                                                  \
+        if (interp && !precise)       launch_one<true, false, CVV> (k, g, single, d_jobs, stream); \
+        else if (!interp && !precise) launch_one<false, false, CVV> (k, g, single, d_jobs, stream); \
+        else if (interp)              launch_one<true, true, CVV> (k, g, single, d_jobs, stream);  \
+        else                          launch_one<false, true, CVV> (k, g, single, d_jobs, stream); \
+    } while (0)
+    if (g.CV == 4) ART_DISPATCH (4);
+    else if (g.CV == 2) ART_DISPATCH (2);
+    else ART_DISPATCH (1);
+#undef ART_DISPATCH
+}
+
+void artLaunchHistory (const ArtClass &k, const ArtJob &single, const ArtJob *d_jobs, int numJobs, cudaStream_t stream)
+{
+    const int total = k.C * k.T;
+    dim3 grid ((total + 255) / 256 > 64 ? 64 : (total + 255) / 256, numJobs);
+    art_history_kernel<<<grid, 256, 0, stream>>> (k, single, d_jobs);
+    ART_CUDA_CHECK (cudaGetLastError ());
+    ++g_artLaunches;
+}

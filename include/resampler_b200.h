@@ -1,0 +1,65 @@
+/*
+ * resampler_b200.h -- extension entry points of libresampler_b200.so (not in the reference).
+ *
+ * The reference API takes host pointers and returns synchronously, which on a GPU measures
+ * PCIe.  These entry points keep the reference's semantics (same ResampleResult, same
+ * position bookkeeping -- they share the planner with resampleProcess*, resampler.c:433-658)
+ * but take DEVICE pointers, enqueue on a CUDA stream and return without synchronising.
+ * `stream` is a cudaStream_t passed as void* (NULL = the context's private stream); no CUDA
+ * or torch type appears in any signature.
+ */
+#ifndef ART_B200_EXT_H
+#define ART_B200_EXT_H
+
+#include "resampler.h"
+#include "biquad.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* which GPU a context lives on is the CUDA current device at init time; these helpers let a
+ * non-CUDA host program pick it */
+int  resampleB200SetDevice (int device);                 /* 0 on success */
+int  resampleB200GetDeviceCount (void);
+void resampleB200Synchronize (Resample *cxt);            /* wait for the context's private stream */
+unsigned long long resampleB200KernelLaunches (void);    /* kernels launched by this library so far */
+
+/* device-pointer twins of resampleProcessInterleaved (resampler.c:550) / resampleProcess (:433).
+ * A flush is numInputFrames == -1, as in the reference. */
+ResampleResult resampleProcessInterleavedDevice (Resample *cxt, const float *d_input, int numInputFrames,
+                                                 float *d_output, int numOutputFrames, double ratio, void *stream);
+ResampleResult resampleProcessDevice (Resample *cxt, const float *const *d_input, int numInputFrames,
+                                      float *const *d_output, int numOutputFrames, double ratio, void *stream);
+
+/* Many independent contexts of identical configuration (same channels/taps/filters/lowpass/flags,
+ * same GPU) in ONE launch -- what workers.c's per-channel threads and a caller's per-stream loop
+ * become on a GPU.  Element i of every array belongs to cxts[i].  results may be NULL. */
+void resampleBatchProcessInterleavedDevice (Resample *const *cxts, int numContexts,
+                                            const float *const *d_inputs, const int *numInputFrames,
+                                            float *const *d_outputs, const int *numOutputFrames,
+                                            const double *ratios, ResampleResult *results, void *stream);
+
+/* ASRC: numBlocks consecutive blocks of ONE stream, block b holding blockFrames[b] input frames
+ * and resampled at ratios[b], exactly as numBlocks successive resampleProcessInterleaved calls
+ * would be (positions[b], if non-NULL, receives resampleGetPosition after block b).  Input blocks
+ * are contiguous in d_input; outputs are packed contiguously into d_output.  Stops early -- and
+ * returns the number of blocks completed -- when a block cannot consume all of its input within
+ * outputCapacityFrames. */
+int resampleProcessBlocksInterleavedDevice (Resample *cxt, const float *d_input, const int *blockFrames,
+                                            const double *ratios, int numBlocks,
+                                            float *d_output, int outputCapacityFrames,
+                                            ResampleResult *results, double *positions, void *stream);
+
+/* The cascade art.c applies around the resampler (art.c:1011-1017, :1052-1058): numStages sets of
+ * numChannels Biquads over one interleaved buffer, in ONE pass over memory.  stages[s] points at
+ * the caller's array of numChannels Biquad structs for stage s (e.g. lowpass1, lowpass2). */
+void biquad_apply_cascade_interleaved (Biquad *const *stages, int numStages, int numChannels,
+                                       float *buffer, int numFrames);
+void biquad_apply_cascade_interleaved_device (Biquad *const *stages, int numStages, int numChannels,
+                                              float *d_buffer, int numFrames, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,477 @@
+/*
+ * art_oracle.c -- TEST INFRASTRUCTURE ONLY (see art_oracle.h).
+ *
+ * Scalar CPU restatement of the audio-resampler hot path.  The arithmetic
+ * (operation order, float/double types, the ring-compaction bookkeeping that
+ * decides how positions are rounded) follows the reference exactly so that
+ * input_used / output_generated / position are bit-identical to it; the
+ * code structure is this project's own (one strided core, contiguous bank
+ * and ring storage).  Build with -O2 -ffp-contract=off: the reference's
+ * -fassociative-math only changes the float summation order, which parity
+ * tolerates.
+ */
+#include "art_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+/* ------------------------------------------------------------------ bank */
+
+/* One windowed-sinc row centred `fraction` of a sample past tap taps/2-1.
+ * Restates init_filter, resampler.c:1090-1133. */
+static void build_row (const OracleResampler *r, float *row, double *scratch, double fraction)
+{
+    static const double bh[4] = { 0.35875, 0.48829, 0.14128, 0.01168 };   /* resampler.c:1093-1096 */
+    const int taps = r->taps, half = taps / 2;
+    double total = 0.0;
+
+    for (int t = 0; t < taps; ++t) {
+        double dist = fabs ((half - 1) + fraction - t) * M_PI;             /* :1106 */
+        double wpos = dist / half;                                          /* :1107 */
+        double v = 1.0;
+
+        if (dist != 0.0) {                                                  /* :1110-1117 */
+            v = sin (dist * r->lowpass_ratio) / (dist * r->lowpass_ratio);
+            if (r->flags & ORC_BLACKMAN_HARRIS)
+                v *= bh[0] + bh[1] * cos (wpos) + bh[2] * cos (2 * wpos) + bh[3] * cos (3 * wpos);
+            else
+                v *= 0.5 * (1.0 + cos (wpos));
+        }
+
+        scratch[t] = v;
+        total += v;                                                         /* :1121 */
+    }
+
+    /* unity DC gain, then round to float from the centre outwards while
+     * carrying the rounding error to the next tap visited (:1126-1132).
+     * Visiting order: half, half-1, half+1, half-2, ..., taps-1, 0. */
+    const double gain = 1.0 / total;
+    double carried = 0.0;
+
+    for (int k = 0; k < half; ++k) {
+        const int order[2] = { half + k, half - 1 - k };
+        for (int j = 0; j < 2; ++j) {
+            int t = order[j];
+            scratch[t] *= gain;
+            row[t] = (float) (scratch[t] - carried);
+            carried += row[t] - scratch[t];
+        }
+    }
+}
+
+/* resampleInit, resampler.c:115-199 */
+OracleResampler *oracle_init (int channels, int taps, int phases, double lowpass_ratio, int flags)
+{
+    if (lowpass_ratio > 0.0 && lowpass_ratio < 1.0)                         /* :120-125 */
+        flags |= ORC_LOWPASS;
+    else {
+        flags &= ~ORC_LOWPASS;
+        lowpass_ratio = 1.0;
+    }
+
+    if ((taps & 3) || taps <= 0 || taps > 1024)                             /* :127-130 */
+        return NULL;
+    if (phases < 1 || phases > 1024)                                        /* :132-135 */
+        return NULL;
+    if (flags & ORC_EXTRAPOLATE) {
+        fprintf (stderr, "oracle: EXTRAPOLATE_ENDPOINTS is not restated (SURVEY 8f rank 1)\n");
+        return NULL;
+    }
+
+    OracleResampler *r = calloc (1, sizeof *r);
+    r->channels = channels;
+    r->taps = taps;
+    r->phases = phases;
+    r->flags = flags;
+    r->lowpass_ratio = lowpass_ratio;
+    r->ring_len = 16 * taps;                                                /* :139 */
+    r->bank = calloc ((size_t) (phases + 1) * taps, sizeof (float));
+    r->ring = calloc ((size_t) (channels > 0 ? channels : 1) * r->ring_len, sizeof (float));
+
+    double *scratch = malloc (sizeof (double) * taps);
+    for (int p = 0; p < phases; ++p)                                        /* :149-155 */
+        build_row (r, r->bank + (size_t) p * taps, scratch, (double) p / phases);
+    free (scratch);
+
+    /* the extra row is row 0 delayed by one tap (:156-159) ... */
+    float *last = r->bank + (size_t) phases * taps;
+    for (int t = 0; t < taps; ++t)
+        last[(t + 1) % taps] = r->bank[t];
+    /* ... and the two window outliers are cleared (:167-168) */
+    r->bank[taps - 1] = 0.0f;
+    last[0] = 0.0f;
+
+    r->read_pos = taps / 2;                                                 /* :176-177 */
+    r->write_index = taps;
+    return r;
+}
+
+static unsigned long common_divisor (unsigned long a, unsigned long b)     /* resampler.c:999-1008 */
+{
+    while (b) { unsigned long t = a % b; a = b; b = t; }
+    return a;
+}
+
+/* resampleFixedRatioInit, resampler.c:310-356 */
+OracleResampler *oracle_fixed_ratio_init (int channels, int taps, int max_phases, double src_rate,
+                                          double dst_rate, int lowpass_hz, int flags)
+{
+    double lowpass = lowpass_hz / (dst_rate / 2.0);                         /* :312 */
+    double ratio = dst_rate / src_rate;                                     /* :313 */
+
+    if (lowpass_hz > dst_rate / 2.0)                                        /* :316-319 */
+        return NULL;
+
+    if (src_rate == floor (src_rate) && dst_rate == floor (dst_rate) && !(flags & ORC_NO_REDUCTION)) {
+        unsigned long need = (unsigned long) dst_rate /                     /* :324 */
+                             common_divisor ((unsigned long) src_rate, (unsigned long) dst_rate);
+        if (need <= (unsigned long) max_phases) {                           /* :326-334 */
+            flags &= ~ORC_INTERPOLATE;
+            max_phases = (int) need;
+            if (max_phases & (max_phases - 1))
+                flags |= ORC_SNAP;
+        }
+    }
+
+    if (!lowpass_hz && (flags & ORC_LOWPASS) && dst_rate < src_rate) {      /* :340-348 */
+        lowpass = 1.0 - (7.5 / taps / ratio);
+        if (lowpass < 0.8) lowpass = 0.8;
+        if (lowpass < ratio) lowpass = ratio;
+    }
+
+    OracleResampler *r = oracle_init (channels, taps, max_phases, lowpass * ratio, flags | ORC_FIXED_RATIO);
+    if (r)
+        r->fixed_ratio = dst_rate / src_rate;                               /* :353 */
+    return r;
+}
+
+void oracle_free (OracleResampler *r)
+{
+    if (!r) return;
+    free (r->bank);
+    free (r->ring);
+    free (r);
+}
+
+/* resampleReset, resampler.c:383-397 */
+void oracle_reset (OracleResampler *r)
+{
+    memset (r->ring, 0, sizeof (float) * (size_t) r->channels * r->ring_len);
+    r->read_pos = r->taps / 2;
+    r->write_index = r->taps;
+    r->flags &= ~ORC_FLUSHED;
+}
+
+/* resampleAdvancePosition, resampler.c:927-935 */
+void oracle_advance (OracleResampler *r, double delta)
+{
+    if (delta < 0.0)
+        return;
+    if (!(r->flags & ORC_INTERPOLATE) && floor (delta) != delta)
+        return;
+    r->read_pos += delta;
+}
+
+/* resampleGetPosition, resampler.c:965-968 */
+double oracle_position (const OracleResampler *r)
+{
+    return r->read_pos + (r->taps / 2.0) - r->write_index;
+}
+
+const float *oracle_bank_row (const OracleResampler *r, int row)
+{
+    return r->bank + (size_t) row * r->taps;
+}
+
+/* ------------------------------------------------------------ convolution */
+
+/* apply_filter "version 2", resampler.c:1033-1044: float accumulator, pairs
+ * taken from both ends towards the middle. */
+static double dot_outside_in (const float *coef, const float *x, int taps)
+{
+    float acc = 0.0f;
+    for (int lo = 0, hi = taps - 1; lo < hi; ++lo, --hi)
+        acc += (coef[lo] * x[lo]) + (coef[hi] * x[hi]);
+    return acc;
+}
+
+/* apply_filter_precise, resampler.c:1049-1057 */
+static double dot_double (const float *coef, const float *x, int taps)
+{
+    double acc = 0.0;
+    for (int t = 0; t < taps; ++t)
+        acc += (double) coef[t] * x[t];
+    return acc;
+}
+
+/* subsample_interpolate / subsample_no_interpolate and their _precise twins,
+ * resampler.c:1135-1181.  `line` is one channel's ring, `where` the read
+ * position in ring coordinates. */
+static double sample_at (const OracleResampler *r, const float *line, double where)
+{
+    double (*dot) (const float *, const float *, int) =
+        (r->flags & ORC_EXTENDED_MATH) ? dot_double : dot_outside_in;      /* :191-196 */
+    const int taps = r->taps;
+    const double whole = floor (where);
+
+    if (r->flags & ORC_INTERPOLATE) {
+        double frac = (where - whole) * r->phases;                          /* :1149-1150 */
+        int row = (int) floor (frac);
+        frac -= row;                                                        /* :1152 */
+        const float *x = line + (int) whole - taps / 2 + 1;                 /* :1153 */
+        return dot (r->bank + (size_t) row * taps, x, taps) * (1.0 - frac) +
+               dot (r->bank + (size_t) (row + 1) * taps, x, taps) * frac;   /* :1155-1156 */
+    }
+
+    int row = (int) floor ((where - whole) * r->phases + 0.5);              /* :1137 */
+    const float *centre = line + (int) whole;
+    if (!(r->flags & ORC_LOWPASS) && row % r->phases == 0)                  /* :1141-1142 */
+        return centre[row / r->phases];
+    return dot (r->bank + (size_t) row * taps, centre - taps / 2 + 1, taps);   /* :1144 */
+}
+
+/* ------------------------------------------------------------- streaming */
+
+/* Ring compaction: keep the newest `taps` samples, shift both cursors
+ * (resampler.c:497-503 / :614-620 / :667-673). */
+static void compact_ring (OracleResampler *r)
+{
+    const int drop = r->ring_len - r->taps;
+    for (int c = 0; c < r->channels; ++c) {
+        float *line = r->ring + (size_t) c * r->ring_len;
+        memmove (line, line + drop, sizeof (float) * r->taps);
+    }
+    r->read_pos -= drop;
+    r->write_index -= drop;
+}
+
+/* postfillAllChannels, resampler.c:663-685 (zero fill only) */
+static void append_silence (OracleResampler *r)
+{
+    const int half = r->taps / 2;
+    if (r->ring_len - r->write_index < half)
+        compact_ring (r);
+    for (int c = 0; c < r->channels; ++c) {
+        float *line = r->ring + (size_t) c * r->ring_len;
+        memset (line + r->write_index, 0, sizeof (float) * (r->ring_len - r->write_index));
+    }
+    r->flags |= ORC_FLUSHED;
+    r->write_index += half;
+}
+
+/* The control loop shared by resampleProcess (resampler.c:433-541) and
+ * resampleProcessInterleaved (:550-658).  in_base[c]/out_base[c] point at
+ * frame 0 of channel c; consecutive frames are *_stride floats apart. */
+static OracleResult run (OracleResampler *r, const float *const *in_base, int in_stride, int n_in,
+                         float *const *out_base, int out_stride, int n_out, double ratio)
+{
+    OracleResult res = { 0, 0 };
+    const int half = r->taps / 2;
+    double step = 0.0;                                   /* "offset2" */
+
+    if (r->flags & ORC_FIXED_RATIO) ratio = r->fixed_ratio;                 /* :435-436 */
+    if (r->flags & ORC_FLUSHED) n_in = 0;                                   /* :438-439 */
+    if (n_in < 0) append_silence (r);                                       /* :491-492 */
+
+    while (n_out > 0) {
+        if (r->read_pos + step >= r->write_index - half) {                  /* :495 */
+            if (n_in <= 0)
+                break;
+            if (r->write_index == r->ring_len)                              /* :497 */
+                compact_ring (r);
+            for (int c = 0; c < r->channels; ++c)
+                r->ring[(size_t) c * r->ring_len + r->write_index] =
+                    in_base[c][(size_t) res.input_used * in_stride];
+            r->write_index++;
+            res.input_used++;
+            n_in--;
+        }
+        else {
+            for (int c = 0; c < r->channels; ++c)
+                out_base[c][(size_t) res.output_generated * out_stride] =
+                    (float) sample_at (r, r->ring + (size_t) c * r->ring_len, r->read_pos + step);
+            step = ++res.output_generated / ratio;                          /* :526 */
+            n_out--;
+        }
+    }
+
+    r->read_pos += step;                                                    /* :531 */
+    if (r->flags & ORC_SNAP) {                                              /* :533-535 */
+        double whole = floor (r->read_pos);
+        r->read_pos = whole + floor ((r->read_pos - whole) * r->phases + 0.5) / r->phases;
+    }
+    return res;
+}
+
+OracleResult oracle_process_interleaved (OracleResampler *r, const float *in, int n_in,
+                                         float *out, int n_out, double ratio)
+{
+    const int C = r->channels;
+    const float **ib = malloc (sizeof *ib * (C > 0 ? C : 1));
+    float **ob = malloc (sizeof *ob * (C > 0 ? C : 1));
+    for (int c = 0; c < C; ++c) { ib[c] = in ? in + c : NULL; ob[c] = out + c; }
+    OracleResult res = run (r, ib, C, n_in, ob, C, n_out, ratio);
+    free (ib); free (ob);
+    return res;
+}
+
+OracleResult oracle_process_planar (OracleResampler *r, const float *const *in, int n_in,
+                                    float *const *out, int n_out, double ratio)
+{
+    const int C = r->channels;
+    const float **ib = malloc (sizeof *ib * (C > 0 ? C : 1));
+    for (int c = 0; c < C; ++c) ib[c] = in ? in[c] : NULL;
+    OracleResult res = run (r, ib, 1, n_in, out, 1, n_out, ratio);
+    free (ib);
+    return res;
+}
+
+/* resampleProcessAndFlushInterleaved, resampler.c:741-758 */
+OracleResult oracle_process_flush_interleaved (OracleResampler *r, const float *in, int n_in,
+                                               float *out, int n_out, double ratio)
+{
+    OracleResult res = oracle_process_interleaved (r, in, n_in, out, n_out, ratio);
+    if ((n_in -= res.input_used) != 0 || (n_out -= res.output_generated) == 0)
+        return res;
+    OracleResult tail = oracle_process_interleaved (r, NULL, -1,
+        out + (size_t) res.output_generated * r->channels, n_out, ratio);
+    res.output_generated += tail.output_generated;
+    return res;
+}
+
+/* resampleProcessAndFlush, resampler.c:712-739 */
+OracleResult oracle_process_flush_planar (OracleResampler *r, const float *const *in, int n_in,
+                                          float *const *out, int n_out, double ratio)
+{
+    OracleResult res = oracle_process_planar (r, in, n_in, out, n_out, ratio);
+    if ((n_in -= res.input_used) != 0 || (n_out -= res.output_generated) == 0)
+        return res;
+    float **shifted = malloc (sizeof *shifted * r->channels);
+    for (int c = 0; c < r->channels; ++c) shifted[c] = out[c] + res.output_generated;
+    OracleResult tail = oracle_process_planar (r, NULL, -1, shifted, n_out, ratio);
+    free (shifted);
+    res.output_generated += tail.output_generated;
+    return res;
+}
+
+/* resampleGetRequiredSamples, resampler.c:853-880 (accumulates 1/ratio) */
+unsigned int oracle_required_input (const OracleResampler *r, int n_out, double ratio)
+{
+    const int half = r->taps / 2, drop = r->ring_len - r->taps;
+    int wi = r->write_index;
+    double pos = r->read_pos;
+    unsigned int used = 0;
+
+    if (r->flags & ORC_FIXED_RATIO) ratio = r->fixed_ratio;
+    while (n_out > 0) {
+        if (pos >= wi - half) {
+            if (wi == r->ring_len) { pos -= drop; wi -= drop; }
+            wi++; used++;
+        }
+        else { pos += 1.0 / ratio; n_out--; }
+    }
+    return used;
+}
+
+/* resampleGetExpectedOutput, resampler.c:882-918 */
+unsigned int oracle_expected_output (const OracleResampler *r, int n_in, double ratio)
+{
+    const int half = r->taps / 2, drop = r->ring_len - r->taps;
+    int wi = r->write_index;
+    double pos = r->read_pos;
+    unsigned int made = 0;
+
+    if (r->flags & ORC_FIXED_RATIO) ratio = r->fixed_ratio;
+    if (r->flags & ORC_FLUSHED) n_in = 0;
+    else if (n_in < 0) wi += half;
+
+    for (;;) {
+        if (pos >= wi - half) {
+            if (n_in <= 0) break;
+            if (wi == r->ring_len) { pos -= drop; wi -= drop; }
+            wi++; n_in--;
+        }
+        else { pos += 1.0 / ratio; made++; }
+    }
+    return made;
+}
+
+/* ----------------------------------------------------------------- biquad */
+
+static void biquad_common (OracleBiquadCoeffs *c, double frequency, int highpass)
+{
+    /* biquad.c:18-30 and :34-46 */
+    double q = sqrt (0.5), k = tan (M_PI * frequency);
+    double norm = 1.0 / (1.0 + k / q + k * k);
+    memset (c, 0, sizeof *c);
+    if (highpass) {
+        c->a0 = norm;
+        c->a1 = -2.0 * norm;
+    }
+    else {
+        c->a0 = k * k * norm;
+        c->a1 = 2 * c->a0;            /* note: doubles the already-rounded float a0 */
+    }
+    c->a2 = c->a0;
+    c->b1 = 2.0 * (k * k - 1.0) * norm;
+    c->b2 = (1.0 - k / q + k * k) * norm;
+}
+
+void oracle_biquad_lowpass (OracleBiquadCoeffs *c, double f)  { biquad_common (c, f, 0); }
+void oracle_biquad_highpass (OracleBiquadCoeffs *c, double f) { biquad_common (c, f, 1); }
+
+/* biquad_init, biquad.c:51-74 */
+void oracle_biquad_init (OracleBiquad *q, const OracleBiquadCoeffs *c, double gain)
+{
+    const float fwd[5] = { c->a0, c->a1, c->a2, c->a3, c->a4 };
+    const float bwd[5] = { 0.0f, c->b1, c->b2, c->b3, c->b4 };
+    memset (q, 0, sizeof *q);
+    for (int i = 0; i < 5; ++i) {
+        q->a[i] = fwd[i] * gain;
+        q->b[i] = bwd[i];
+    }
+    q->order = 1;
+    for (int i = 2; i <= 4; ++i)
+        if (fwd[i] != 0.0f || bwd[i] != 0.0f)
+            q->order = i;
+}
+
+/* biquad_apply_buffer, biquad.c:106-163: direct form I in float, the newest
+ * history entry sits at cursor & 3.  The sum is formed left to right exactly
+ * as the reference's expression is written. */
+void oracle_biquad_run (OracleBiquad *q, float *buf, int count, int stride)
+{
+    int cur = q->cursor;
+    while (count--) {
+        float acc = *buf * q->a[0];
+        for (int d = 1; d <= q->order; ++d) {
+            int slot = (cur - (d - 1)) & 3;
+            acc = acc + (q->xh[slot] * q->a[d]) - (q->b[d] * q->yh[slot]);
+        }
+        ++cur;
+        q->xh[cur & 3] = *buf;
+        *buf = q->yh[cur & 3] = acc;
+        buf += stride;
+    }
+    q->cursor = cur;
+}
+
+/* ------------------------------------------------------------------ noise */
+
+/* fill_buffer_with_noise, artest.c:744-754 */
+void oracle_noise (unsigned long long *state, float *dst, int count)
+{
+    unsigned long long s = *state;
+    while (count--) {
+        for (int k = 0; k < 3; ++k)
+            s = ((s << 4) - s) ^ 1;
+        *dst++ = (float) ((int) (s >> 32) / 4294967296.0);
+    }
+    *state = s;
+}

@@ -1,0 +1,354 @@
+"""ctypes views of the three libraries the tests juggle.
+
+* ``Oracle``   -- oracle/liboracle.so, this project's CPU restatement (the checker).
+* ``Reference``-- oracle/_ref/libartref.so, the unmodified reference compiled by
+                  oracle/Makefile (present here and, prebuilt, on the GPU box).
+* ``Product``  -- audio-resampler_b200/lib/libresampler_b200.so through its C ABI
+                  (include/resampler.h, include/biquad.h, include/resampler_b200.h).
+
+All three expose the same small Python surface (``Stream`` objects with
+``process`` / ``flush`` / ``position`` ...) so parity tests read like the reference's
+own artest loop (artest.c:446-491).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+ORACLE_DIR = ROOT / "oracle"
+PKG_DIR = ROOT / "audio-resampler_b200"
+
+# flag values, resampler.h:28-38
+SUBSAMPLE_INTERPOLATE = 0x1
+BLACKMAN_HARRIS = 0x2
+INCLUDE_LOWPASS = 0x4
+RESAMPLE_MULTITHREADED = 0x8
+NO_FILTER_REDUCTION = 0x10
+EXTRAPOLATE_ENDPOINTS = 0x40
+EXTEND_CONVOLUTION_MATH = 0x100
+
+PRESETS = {1: (48, 48), 2: (320, 156), 3: (380, 380), 4: (988, 988)}  # (filters, taps), artest.c:154-169
+
+
+class Result(C.Structure):
+    _fields_ = [("input_used", C.c_uint), ("output_generated", C.c_uint)]
+
+
+f32p = C.POINTER(C.c_float)
+f32pp = C.POINTER(f32p)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(f32p)
+
+
+def _build_oracle():
+    subprocess.run(["make", "-s", "-C", str(ORACLE_DIR)], check=True, capture_output=True)
+
+
+def load_oracle() -> C.CDLL:
+    so = ORACLE_DIR / "liboracle.so"
+    if not so.exists() or so.stat().st_mtime < (ORACLE_DIR / "art_oracle.c").stat().st_mtime:
+        _build_oracle()
+    lib = C.CDLL(str(so))
+    vp = C.c_void_p
+    lib.oracle_init.restype = vp
+    lib.oracle_init.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
+    lib.oracle_fixed_ratio_init.restype = vp
+    lib.oracle_fixed_ratio_init.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+    lib.oracle_free.argtypes = [vp]
+    lib.oracle_reset.argtypes = [vp]
+    lib.oracle_advance.argtypes = [vp, C.c_double]
+    lib.oracle_position.restype = C.c_double
+    lib.oracle_position.argtypes = [vp]
+    lib.oracle_bank_row.restype = f32p
+    lib.oracle_bank_row.argtypes = [vp, C.c_int]
+    for name in ("oracle_process_interleaved", "oracle_process_flush_interleaved"):
+        fn = getattr(lib, name)
+        fn.restype = Result
+        fn.argtypes = [vp, f32p, C.c_int, f32p, C.c_int, C.c_double]
+    for name in ("oracle_process_planar", "oracle_process_flush_planar"):
+        fn = getattr(lib, name)
+        fn.restype = Result
+        fn.argtypes = [vp, f32pp, C.c_int, f32pp, C.c_int, C.c_double]
+    lib.oracle_required_input.restype = C.c_uint
+    lib.oracle_required_input.argtypes = [vp, C.c_int, C.c_double]
+    lib.oracle_expected_output.restype = C.c_uint
+    lib.oracle_expected_output.argtypes = [vp, C.c_int, C.c_double]
+    lib.oracle_noise.argtypes = [C.POINTER(C.c_ulonglong), f32p, C.c_int]
+    return lib
+
+
+class RefResample(C.Structure):
+    """Leading public fields of the reference context (resampler.h:44-48)."""
+    _fields_ = [("numChannels", C.c_int), ("numSamples", C.c_int), ("numFilters", C.c_int),
+                ("numTaps", C.c_int), ("inputIndex", C.c_int), ("flags", C.c_int),
+                ("tempFilter", C.c_void_p), ("outputOffset", C.c_double), ("fixedRatio", C.c_double),
+                ("lowpassRatio", C.c_double), ("subsample", C.c_void_p),
+                ("buffers", f32pp), ("filters", f32pp)]
+
+
+class BiquadCoefficients(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("a0", "a1", "a2", "a3", "a4", "b1", "b2", "b3", "b4")]
+
+
+class Biquad(C.Structure):
+    _fields_ = [("a", C.c_float * 5), ("b", C.c_float * 5), ("x", C.c_float * 4), ("y", C.c_float * 4),
+                ("order", C.c_int), ("index", C.c_int)]
+
+
+def bind_reference_api(lib: C.CDLL) -> C.CDLL:
+    """Attach the prototypes of resampler.h:64-78 and biquad.h:41-47 (shared by the
+    reference build and by the product, which exports the same symbols)."""
+    ctx = C.POINTER(RefResample)
+    lib.resampleInit.restype = ctx
+    lib.resampleInit.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
+    lib.resampleFixedRatioInit.restype = ctx
+    lib.resampleFixedRatioInit.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+    for name in ("resampleProcess", "resampleProcessAndFlush"):
+        fn = getattr(lib, name)
+        fn.restype = Result
+        fn.argtypes = [ctx, f32pp, C.c_int, f32pp, C.c_int, C.c_double]
+    for name in ("resampleProcessInterleaved", "resampleProcessAndFlushInterleaved"):
+        fn = getattr(lib, name)
+        fn.restype = Result
+        fn.argtypes = [ctx, f32p, C.c_int, f32p, C.c_int, C.c_double]
+    lib.resampleGetRequiredSamples.restype = C.c_uint
+    lib.resampleGetRequiredSamples.argtypes = [ctx, C.c_int, C.c_double]
+    lib.resampleGetExpectedOutput.restype = C.c_uint
+    lib.resampleGetExpectedOutput.argtypes = [ctx, C.c_int, C.c_double]
+    lib.resampleAdvancePosition.argtypes = [ctx, C.c_double]
+    lib.resampleAdvancePosition.restype = None
+    lib.resampleGetLowpassRatio.restype = C.c_double
+    lib.resampleGetLowpassRatio.argtypes = [ctx]
+    lib.resampleGetPosition.restype = C.c_double
+    lib.resampleGetPosition.argtypes = [ctx]
+    lib.resampleGetNumFilters.restype = C.c_int
+    lib.resampleGetNumFilters.argtypes = [ctx]
+    lib.resampleInterpolationUsed.restype = C.c_int
+    lib.resampleInterpolationUsed.argtypes = [ctx]
+    lib.resampleReset.argtypes = [ctx]
+    lib.resampleReset.restype = None
+    lib.resampleFree.argtypes = [ctx]
+    lib.resampleFree.restype = None
+    lib.biquad_init.argtypes = [C.POINTER(Biquad), C.POINTER(BiquadCoefficients), C.c_double]
+    lib.biquad_init.restype = None
+    lib.biquad_lowpass.argtypes = [C.POINTER(BiquadCoefficients), C.c_double]
+    lib.biquad_lowpass.restype = None
+    lib.biquad_highpass.argtypes = [C.POINTER(BiquadCoefficients), C.c_double]
+    lib.biquad_highpass.restype = None
+    lib.biquad_apply_buffer.argtypes = [C.POINTER(Biquad), f32p, C.c_int, C.c_int]
+    lib.biquad_apply_buffer.restype = None
+    lib.biquad_apply_sample.argtypes = [C.POINTER(Biquad), C.c_float]
+    lib.biquad_apply_sample.restype = C.c_float
+    return lib
+
+
+def reference_path() -> Path:
+    return ORACLE_DIR / "_ref" / "libartref.so"
+
+
+def load_reference() -> C.CDLL | None:
+    so = reference_path()
+    if not so.exists():
+        try:
+            _build_oracle()
+        except Exception:
+            return None
+    if not so.exists():
+        return None
+    # RTLD_LOCAL: the product exports the same symbol names
+    return bind_reference_api(C.CDLL(str(so), mode=os.RTLD_LOCAL))
+
+
+def product_path() -> Path:
+    return PKG_DIR / "lib" / "libresampler_b200.so"
+
+
+def load_product() -> C.CDLL:
+    so = product_path()
+    if not so.exists():
+        raise RuntimeError(f"{so} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    return bind_reference_api(C.CDLL(str(so), mode=os.RTLD_LOCAL))
+
+
+# ---------------------------------------------------------------------------
+# uniform Stream facade
+
+
+class _ApiStream:
+    """A context of a library that speaks the reference C API (reference build or product)."""
+
+    def __init__(self, lib, channels, taps, filters, lowpass_ratio=0.0, flags=SUBSAMPLE_INTERPOLATE | BLACKMAN_HARRIS,
+                 fixed=None):
+        self.lib, self.channels = lib, channels
+        if fixed is None:
+            self.ctx = lib.resampleInit(channels, taps, filters, lowpass_ratio, flags)
+        else:
+            src, dst, lowpass_hz = fixed
+            self.ctx = lib.resampleFixedRatioInit(channels, taps, filters, float(src), float(dst), int(lowpass_hz), flags)
+        if not self.ctx:
+            raise ValueError("init returned NULL")
+
+    # -- state -----------------------------------------------------------
+    def advance(self, delta): self.lib.resampleAdvancePosition(self.ctx, delta)
+    def position(self): return self.lib.resampleGetPosition(self.ctx)
+    def reset(self): self.lib.resampleReset(self.ctx)
+    def num_filters(self): return self.lib.resampleGetNumFilters(self.ctx)
+    def lowpass_ratio(self): return self.lib.resampleGetLowpassRatio(self.ctx)
+    def interpolation_used(self): return self.lib.resampleInterpolationUsed(self.ctx)
+    def required_input(self, n_out, ratio): return self.lib.resampleGetRequiredSamples(self.ctx, n_out, ratio)
+    def expected_output(self, n_in, ratio): return self.lib.resampleGetExpectedOutput(self.ctx, n_in, ratio)
+    def taps(self): return self.ctx.contents.numTaps
+
+    def bank(self):
+        c = self.ctx.contents
+        return np.stack([np.ctypeslib.as_array(c.filters[i], shape=(c.numTaps,)).copy()
+                         for i in range(c.numFilters + 1)])
+
+    def close(self):
+        if self.ctx:
+            self.lib.resampleFree(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- processing --------------------------------------------------------
+    def process(self, x: np.ndarray | None, n_out: int, ratio: float, *, flush_after=False, planar=False):
+        """x: (frames, channels) float32, or None for an explicit flush call (numInputFrames = -1)."""
+        ch = self.channels
+        if x is None:
+            n_in = -1
+        else:
+            x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, ch)
+            n_in = x.shape[0]
+        if not planar:
+            out = np.zeros((max(n_out, 1), ch), np.float32)
+            fn = self.lib.resampleProcessAndFlushInterleaved if flush_after else self.lib.resampleProcessInterleaved
+            res = fn(self.ctx, _ptr(x) if x is not None else None, n_in, _ptr(out), n_out, ratio)
+            return out[:res.output_generated].copy(), res.input_used, res.output_generated
+        planes_in = np.ascontiguousarray(x.T) if x is not None else None
+        planes_out = np.zeros((ch, max(n_out, 1)), np.float32)
+        in_arr = (f32p * ch)(*[_ptr(planes_in[c]) for c in range(ch)]) if x is not None else None
+        out_arr = (f32p * ch)(*[_ptr(planes_out[c]) for c in range(ch)])
+        fn = self.lib.resampleProcessAndFlush if flush_after else self.lib.resampleProcess
+        res = fn(self.ctx, in_arr, n_in, out_arr, n_out, ratio)
+        return planes_out[:, :res.output_generated].T.copy(), res.input_used, res.output_generated
+
+
+class _OracleStream:
+    def __init__(self, lib, channels, taps, filters, lowpass_ratio=0.0, flags=SUBSAMPLE_INTERPOLATE | BLACKMAN_HARRIS,
+                 fixed=None):
+        self.lib, self.channels, self._taps = lib, channels, taps
+        if fixed is None:
+            self.ctx = lib.oracle_init(channels, taps, filters, lowpass_ratio, flags)
+        else:
+            src, dst, lowpass_hz = fixed
+            self.ctx = lib.oracle_fixed_ratio_init(channels, taps, filters, float(src), float(dst), int(lowpass_hz), flags)
+        if not self.ctx:
+            raise ValueError("init returned NULL")
+
+    class _Hdr(C.Structure):
+        _fields_ = [("channels", C.c_int), ("taps", C.c_int), ("phases", C.c_int), ("flags", C.c_int),
+                    ("ring_len", C.c_int), ("write_index", C.c_int), ("read_pos", C.c_double),
+                    ("fixed_ratio", C.c_double), ("lowpass_ratio", C.c_double)]
+
+    def _hdr(self): return C.cast(self.ctx, C.POINTER(self._Hdr)).contents
+    def advance(self, delta): self.lib.oracle_advance(self.ctx, delta)
+    def position(self): return self.lib.oracle_position(self.ctx)
+    def reset(self): self.lib.oracle_reset(self.ctx)
+    def num_filters(self): return self._hdr().phases
+    def lowpass_ratio(self): return self._hdr().lowpass_ratio
+    def interpolation_used(self): return self._hdr().flags & SUBSAMPLE_INTERPOLATE
+    def required_input(self, n_out, ratio): return self.lib.oracle_required_input(self.ctx, n_out, ratio)
+    def expected_output(self, n_in, ratio): return self.lib.oracle_expected_output(self.ctx, n_in, ratio)
+    def taps(self): return self._taps
+
+    def bank(self):
+        h = self._hdr()
+        return np.stack([np.ctypeslib.as_array(self.lib.oracle_bank_row(self.ctx, i), shape=(h.taps,)).copy()
+                         for i in range(h.phases + 1)])
+
+    def close(self):
+        if self.ctx:
+            self.lib.oracle_free(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def process(self, x, n_out, ratio, *, flush_after=False, planar=False):
+        ch = self.channels
+        if x is None:
+            n_in = -1
+        else:
+            x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, ch)
+            n_in = x.shape[0]
+        if not planar:
+            out = np.zeros((max(n_out, 1), ch), np.float32)
+            fn = self.lib.oracle_process_flush_interleaved if flush_after else self.lib.oracle_process_interleaved
+            res = fn(self.ctx, _ptr(x) if x is not None else None, n_in, _ptr(out), n_out, ratio)
+            return out[:res.output_generated].copy(), res.input_used, res.output_generated
+        planes_in = np.ascontiguousarray(x.T) if x is not None else None
+        planes_out = np.zeros((ch, max(n_out, 1)), np.float32)
+        in_arr = (f32p * ch)(*[_ptr(planes_in[c]) for c in range(ch)]) if x is not None else None
+        out_arr = (f32p * ch)(*[_ptr(planes_out[c]) for c in range(ch)])
+        fn = self.lib.oracle_process_flush_planar if flush_after else self.lib.oracle_process_planar
+        res = fn(self.ctx, in_arr, n_in, out_arr, n_out, ratio)
+        return planes_out[:, :res.output_generated].T.copy(), res.input_used, res.output_generated
+
+
+_cache: dict = {}
+
+
+def oracle():
+    if "oracle" not in _cache:
+        _cache["oracle"] = load_oracle()
+    return _cache["oracle"]
+
+
+def reference():
+    if "reference" not in _cache:
+        _cache["reference"] = load_reference()
+    return _cache["reference"]
+
+
+def product():
+    if "product" not in _cache:
+        _cache["product"] = load_product()
+    return _cache["product"]
+
+
+def oracle_stream(*a, **k): return _OracleStream(oracle(), *a, **k)
+def reference_stream(*a, **k): return _ApiStream(reference(), *a, **k)
+def product_stream(*a, **k): return _ApiStream(product(), *a, **k)
+
+
+def artest_noise(count: int, state: int = 0x3141592653589793):
+    """artest.c:744-754 via the oracle's restatement; returns (samples, new_state)."""
+    st = C.c_ulonglong(state)
+    out = np.empty(count, np.float32)
+    oracle().oracle_noise(C.byref(st), _ptr(out), count)
+    return out, st.value
+
+
+def peak_error(a: np.ndarray, b: np.ndarray) -> float:
+    """max|a-b| / peak(b) -- the parity measure of BASELINE.md section 2."""
+    if a.shape != b.shape:
+        return float("inf")
+    if a.size == 0:
+        return 0.0
+    peak = float(np.max(np.abs(b)))
+    return float(np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)))) / (peak if peak > 0 else 1.0)

@@ -1,0 +1,135 @@
+"""CPU tests: pin the oracle (oracle/art_oracle.c) to the reference.
+
+* against the committed golden vectors (generated from the unmodified reference by
+  tests/golden/make_golden.py) -- these run everywhere;
+* against oracle/_ref/libartref.so directly when it is present.
+Counts and positions must be bit-identical; samples within 1e-6 of peak (the reference's own
+build-to-build noise floor is 1.2e-7).
+"""
+import ctypes as C
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import artlibs as A
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+sys.path.insert(0, str(GOLDEN))
+import make_golden  # noqa: E402
+
+TOL = 1e-6
+
+
+@pytest.mark.parametrize("case", make_golden.CASES, ids=[c["name"] for c in make_golden.CASES])
+def test_oracle_matches_golden(case):
+    g = np.load(GOLDEN / f"{case['name']}.npz")
+    out, meta = make_golden.run_case(case, A.oracle_stream)
+    assert np.array_equal(meta, g["meta"]), "input_used / output_generated / position differ from the reference"
+    assert out.shape == g["out"].shape
+    assert A.peak_error(out, g["out"]) <= TOL
+
+
+def test_passthrough_golden_is_exact():
+    """2x upsampling without lowpass returns every input sample verbatim (resampler.c:1141-1142)."""
+    case = next(c for c in make_golden.CASES if c["name"] == "fixed_mono_p1_x2_passthrough")
+    out, _ = make_golden.run_case(case, A.oracle_stream)
+    rng = np.random.default_rng(case["seed"])
+    x = rng.uniform(-0.5, 0.5, (case["calls"][0], 1)).astype(np.float32)
+    assert np.array_equal(out[0:2 * len(x):2], x)
+
+
+def test_bank_known_answers():
+    """SURVEY.md 8c known-answer structure of the 48x48 Blackman-Harris bank."""
+    g = np.load(GOLDEN / "bank_48x48_bh.npz")["bank"]
+    s = A.oracle_stream(1, 48, 48, 0.0)
+    bank = s.bank()
+    assert bank.shape == (49, 48)
+    assert np.max(np.abs(bank - g)) < 1e-12            # summation order of the -fassociative-math build
+    assert bank[0, 23] == 1.0 and np.max(np.abs(np.delete(bank[0], 23))) < 1e-15
+    assert np.allclose(bank[24, 20:28], [-0.08048406, 0.11964639, -0.20751575, 0.6350419,
+                                         0.6350419, -0.20751576, 0.11964639, -0.08048406], atol=1e-7)
+    assert np.array_equal(bank[48, 2:], bank[0, 1:-1]) and bank[48, 0] == 0.0 and bank[0, 47] == 0.0
+    assert np.max(np.abs(bank[:48].sum(axis=1, dtype=np.float64) - 1.0)) < 1e-12
+
+
+def test_biquad_design_known_answer():
+    g = np.load(GOLDEN / "biquad_lowpass_0p2067.npz")["coeffs"]
+    lib = A.oracle()
+
+    class Co(C.Structure):
+        _fields_ = [(n, C.c_float) for n in ("a0", "a1", "a2", "a3", "a4", "b1", "b2", "b3", "b4")]
+    co = Co()
+    lib.oracle_biquad_lowpass(C.byref(co), C.c_double(0.45 * 44100 / 96000))
+    got = np.array([co.a0, co.a1, co.a2, co.b1, co.b2], np.float32)
+    assert np.array_equal(got, g)
+    assert np.allclose(got, [0.21753205, 0.43506411, 0.21753205, -0.31955418, 0.18968238], atol=1e-7)
+
+
+def test_oracle_biquad_cascade_matches_golden():
+    g = np.load(GOLDEN / "biquad_cascade_3ch.npz")["out"]
+    lib = A.oracle()
+
+    class Co(C.Structure):
+        _fields_ = [(n, C.c_float) for n in ("a0", "a1", "a2", "a3", "a4", "b1", "b2", "b3", "b4")]
+
+    class Bq(C.Structure):
+        _fields_ = [("a", C.c_float * 5), ("b", C.c_float * 5), ("xh", C.c_float * 4), ("yh", C.c_float * 4),
+                    ("order", C.c_int), ("cursor", C.c_int)]
+    co = Co()
+    lib.oracle_biquad_lowpass(C.byref(co), C.c_double(0.45 * 44100 / 96000))
+    rng = np.random.default_rng(21)
+    y = rng.uniform(-0.5, 0.5, (5000, 3)).astype(np.float32)
+    stages = [[Bq() for _ in range(3)] for _ in range(2)]
+    for st in stages:
+        for q in st:
+            lib.oracle_biquad_init(C.byref(q), C.byref(co), C.c_double(1.0))
+    for lo, hi in [(0, 1234), (1234, 5000)]:
+        for c in range(3):
+            for st in stages:
+                lib.oracle_biquad_run(C.byref(st[c]), y[lo:, c:].ctypes.data_as(A.f32p), hi - lo, 3)
+    assert A.peak_error(y, g) <= TOL
+
+
+@pytest.mark.skipif(A.reference() is None, reason="oracle/_ref/libartref.so not built")
+def test_oracle_vs_live_reference_random_sessions():
+    rng = np.random.default_rng(5)
+    for trial in range(12):
+        ch = int(rng.integers(1, 4))
+        filters, taps = A.PRESETS[int(rng.integers(1, 4))]
+        fixed = rng.random() < 0.3
+        if fixed:
+            src, dst = [(44100, 48000), (48000, 44100), (22050, 44100), (48000, 32000)][int(rng.integers(0, 4))]
+            kw = dict(flags=7, fixed=(src, dst, 0))
+            ratio = 0.0
+        else:
+            ratio = float(np.exp(rng.uniform(np.log(0.3), np.log(3.0))))
+            kw = dict(lowpass_ratio=float(rng.choice([0.0, 0.8])), flags=int(rng.choice([1, 3, 2, 0x103])))
+        o = A.oracle_stream(ch, taps, filters, **kw)
+        r = A.reference_stream(ch, taps, filters, **kw)
+        if kw.get("flags", 3) & 1 or fixed:
+            o.advance(taps / 2)
+            r.advance(taps / 2)
+        for call in range(5):
+            n = int(rng.integers(0, 3000))
+            x = rng.uniform(-0.5, 0.5, (n, ch)).astype(np.float32)
+            cap = int(rng.integers(0, 4000))
+            planar = bool(rng.integers(0, 2))
+            yo, uo, go = o.process(x, cap, ratio, planar=planar)
+            yr, ur, gr = r.process(x, cap, ratio)
+            assert (uo, go) == (ur, gr)
+            assert o.position() == r.position()
+            assert A.peak_error(yo, yr) <= TOL
+        yo, uo, go = o.process(None, 5000, ratio)
+        yr, ur, gr = r.process(None, 5000, ratio)
+        assert (uo, go) == (ur, gr) and A.peak_error(yo, yr) <= TOL
+        assert o.required_input(1000, ratio or 1.0) == r.required_input(1000, ratio or 1.0)
+        o.reset(); r.reset()
+        assert o.expected_output(1000, ratio or 1.0) == r.expected_output(1000, ratio or 1.0)
+
+
+def test_artest_noise_generator_known_prefix():
+    """artest.c:744-754 with the reference's seed; first values recorded from the reference build."""
+    x, _ = A.artest_noise(4)
+    assert np.allclose(x, [0.36142448, -0.19244033, -0.4861091, 0.38178906], atol=1e-8)

@@ -18,6 +18,50 @@ unsigned long long g_artLaunches = 0;
 
 extern "C" unsigned long long artDevLaunchCount (void) { return g_artLaunches; }
 
+/* ---- optional per-kernel timing (bench.py's roofline leg): CUDA events recorded on the launching
+ * stream right around the convolution kernels, collected after the timed region ------------------ */
+static bool g_profile = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_profEvents;
+static std::mutex g_profMutex;
+
+void artProfileBegin (cudaStream_t stream, void **token)
+{
+    *token = nullptr;
+    if (!g_profile) return;
+    cudaEvent_t a, b;
+    ART_CUDA_CHECK (cudaEventCreate (&a));
+    ART_CUDA_CHECK (cudaEventCreate (&b));
+    ART_CUDA_CHECK (cudaEventRecord (a, stream));
+    std::lock_guard<std::mutex> lock (g_profMutex);
+    g_profEvents.emplace_back (a, b);
+    *token = b;
+}
+
+void artProfileEnd (cudaStream_t stream, void *token)
+{
+    if (token) ART_CUDA_CHECK (cudaEventRecord ((cudaEvent_t) token, stream));
+}
+
+extern "C" void artDevProfileEnable (int on) { g_profile = on != 0; }
+
+extern "C" unsigned long long artDevProfileCollect (double *totalMs)
+{
+    std::lock_guard<std::mutex> lock (g_profMutex);
+    double sum = 0.0;
+    for (auto &p : g_profEvents) {
+        float ms = 0.0f;
+        ART_CUDA_CHECK (cudaEventSynchronize (p.second));
+        ART_CUDA_CHECK (cudaEventElapsedTime (&ms, p.first, p.second));
+        sum += ms;
+        cudaEventDestroy (p.first);
+        cudaEventDestroy (p.second);
+    }
+    const unsigned long long n = g_profEvents.size ();
+    g_profEvents.clear ();
+    if (totalMs) *totalMs = sum;
+    return n;
+}
+
 /* ---- filter banks are immutable and identical for equal (T, F, coefficients): share them ---- */
 struct ArtBank {
     int device, T, Tp, F, refs;

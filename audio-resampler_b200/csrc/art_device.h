@@ -71,8 +71,10 @@ void artDevSynchronize (ArtDev *dev);
 void artDevGetHistory (ArtDev *dev, float *hostPlanar);        /* [channels][taps], for tests/extrapolation */
 void artDevSetHistory (ArtDev *dev, const float *hostPlanar);
 
-/* statistics for bench.py's gpu_launches claim */
+/* statistics for bench.py's gpu_launches claim and roofline leg */
 unsigned long long artDevLaunchCount (void);
+void artDevProfileEnable (int on);
+unsigned long long artDevProfileCollect (double *totalMs);   /* returns timed launches, clears */
 
 /* ---- biquad cascade (biquad.c:106-163, order <= 4), float32 direct form I ---------- */
 typedef struct {

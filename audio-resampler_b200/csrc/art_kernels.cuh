@@ -81,6 +81,10 @@ void artLaunchHistory (const ArtClass &k, const ArtJob &single, const ArtJob *d_
 
 extern unsigned long long g_artLaunches;
 
+/* per-kernel event timing, active only after artDevProfileEnable(1) */
+void artProfileBegin (cudaStream_t stream, void **token);
+void artProfileEnd (cudaStream_t stream, void *token);
+
 #define ART_CUDA_CHECK(expr)                                                                  \
     do {                                                                                      \
         cudaError_t e_ = (expr);                                                              \

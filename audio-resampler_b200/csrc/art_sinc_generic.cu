@@ -407,13 +407,19 @@ template <bool INTERP, bool PRECISE, int CV>
 static void launch_one (const ArtClass &k, const ArtLaunchGeom &g, const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream)
 {
     auto kern = art_sinc_generic_kernel<INTERP, PRECISE, CV>;
-    static size_t configured = 0;
-    if (g.smemBytes > configured) {
-        ART_CUDA_CHECK (cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = 227 * 1024;
+    static size_t configured[16] = { 0 };      // per device: the opt-in is per (function, context)
+    int device = 0;
+    ART_CUDA_CHECK (cudaGetDevice (&device));
+    if (g.smemBytes > configured[device & 15]) {
+        // the planner keeps tiles below 110 KB (two CTAs per SM); opt in to exactly that much
+        ART_CUDA_CHECK (cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        configured[device & 15] = 112 * 1024;
     }
     dim3 grid (g.totalTiles, (k.C + k.Cg - 1) / k.Cg);
+    void *prof;
+    artProfileBegin (stream, &prof);
     kern<<<grid, ART_G_THREADS, g.smemBytes, stream>>> (k, single, d_jobs);
+    artProfileEnd (stream, prof);
     ART_CUDA_CHECK (cudaGetLastError ());
     ++g_artLaunches;
 }

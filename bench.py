@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- output Msamples/s of the windowed-sinc resampling hot path at BASELINE.json's
+metric config (stereo float32, 44.1 kHz -> 48 kHz, preset -3 = 380 filters x 380 taps, interpolated).
+
+A *step* is one pass of the hot path over one batch of synthetic input: STREAMS independent stereo
+streams, FRAMES input frames each, resampled by one call of resampleBatchProcessInterleavedDevice
+(include/resampler_b200.h) -- i.e. through the C ABI of libresampler_b200.so.  Stream state carries
+over from step to step exactly as in a real conversion.
+
+  value        whole-job output samples/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e          the same metric through the reference-facing host-pointer API
+               (resampleProcessInterleaved, include/resampler.h) with pinned HOST buffers: the H2D copy of
+               every step's input and the D2H copy of its output are inside the timed region
+  roofline     the convolution kernel alone: algorithmic bytes 4*(1+1/ratio) per output sample
+                x samples per launch / the kernel's own launch duration, measured live
+               with CUDA events recorded by the library around each launch on its stream
+  cpu_baseline the UNMODIFIED reference (oracle/_ref/libartref.so, kind "reference") or, when that
+               did not travel, the oracle port -- on this host's cores, bounded sample
+
+`--impl reference` times the reference's own CPU implementation instead (rank 0 only).
+Multi-GPU: independent streams are sharded across ranks with no data-path collective (weak scaling);
+torch.distributed (NCCL) only provides the barrier and the max-over-ranks of the device time.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+TAPS, FILTERS, CHANNELS = 380, 380, 2            # preset -3 (artest.c:161-163), stereo
+SRC, DST = 44100, 48000
+RATIO = DST / SRC
+FLAGS = 0x1 | 0x2                                 # SUBSAMPLE_INTERPOLATE | BLACKMAN_HARRIS (artest.c:126)
+BYTES_PER_OUTPUT_SAMPLE = 4.0 * (1.0 + 1.0 / RATIO)      # one write + 1/ratio reads
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.device)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([f.strip() for f in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------- reference arm
+
+def cpu_reference_run(frames_per_stream: int, threads: int, block: int = 16384):
+    """The reference's CPU path on `threads` host threads, one stereo context per thread
+    (BASELINE.md section 3 mode iii), art.c-sized calls.  Returns (output samples, seconds, kind)."""
+    import artlibs as A
+    ref = A.reference()
+    kind = "reference" if ref is not None else "port"
+    make = A.reference_stream if ref is not None else A.oracle_stream
+    rng = np.random.default_rng(1234)
+    x = rng.uniform(-0.5, 0.5, (block, CHANNELS)).astype(np.float32)
+    streams = [make(CHANNELS, TAPS, FILTERS, 0.0, flags=FLAGS) for _ in range(threads)]
+    for s in streams:
+        s.advance(TAPS / 2)
+    calls = max(1, frames_per_stream // block)
+    cap = int(block * RATIO) + TAPS
+
+    def work(s):
+        made = 0
+        out = np.empty((cap, CHANNELS), np.float32)
+        fn = s.lib.resampleProcessInterleaved if kind == "reference" else s.lib.oracle_process_interleaved
+        xp, op = x.ctypes.data_as(A.f32p), out.ctypes.data_as(A.f32p)
+        for _ in range(calls):
+            made += fn(s.ctx, xp, block, op, cap, RATIO).output_generated
+        return made
+
+    with ThreadPoolExecutor(threads) as pool:
+        list(pool.map(work, streams[:1]))                       # touch code/pages once
+        t0 = time.perf_counter()
+        made = sum(pool.map(work, streams))
+        dt = time.perf_counter() - t0
+    return made * CHANNELS, dt, kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames = 1 << 19                                            # per thread per step: ~0.15 s of one core
+    for _ in range(max(0, args.warmup)):
+        cpu_reference_run(frames // 8, cores)
+    samples, secs = 0, 0.0
+    kind = "reference"
+    for _ in range(args.steps):
+        s, dt, kind = cpu_reference_run(frames, cores)
+        samples += s; secs += dt
+    value = samples / secs / 1e6
+    line = {
+        "impl": "reference", "metric": "output Msamples/sec at preset -3 (380-tap), 44.1k->48k", "value": value,
+        "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "stereo float32 44.1k->48k preset -3 (380x380, interpolated); CPU reference, "
+                               f"{cores} independent stereo streams (one per host thread), 16384-frame calls"},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": kind,
+                         "sample": f"{cores} streams x {frames} input frames per step"},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as entry
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libresampler_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    pkg = entry.load_package()
+    if not pkg.LIB_PATH.exists():
+        entry.build()
+    lib = pkg.load()
+    assert lib.resampleB200SetDevice(local) == 0
+
+    streams, frames = args.streams, args.frames
+    dev = torch.device("cuda", local)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(20261017 + rank)
+    # inputs: [streams][frames][2] float32 uniform in [-0.5, 0.5) (artest.c:744-754 style), resident in HBM
+    x = (torch.rand((streams, frames, CHANNELS), device=dev, dtype=torch.float32, generator=gen) - 0.5)
+    cap = int(frames * RATIO) + TAPS + 16
+    y = torch.empty((streams, cap, CHANNELS), device=dev, dtype=torch.float32)
+
+    ctxs = [lib.resampleInit(CHANNELS, TAPS, FILTERS, 0.0, FLAGS) for _ in range(streams)]
+    assert all(ctxs), "resampleInit failed"
+    for c in ctxs:
+        lib.resampleAdvancePosition(c, TAPS / 2)
+
+    ctx_t = C.POINTER(pkg.Resample)
+    ctx_arr = (ctx_t * streams)(*ctxs)
+    in_arr = (C.c_void_p * streams)(*[x[i].data_ptr() for i in range(streams)])
+    out_arr = (C.c_void_p * streams)(*[y[i].data_ptr() for i in range(streams)])
+    nin_arr = (C.c_int * streams)(*([frames] * streams))
+    nout_arr = (C.c_int * streams)(*([cap] * streams))
+    ratio_arr = (C.c_double * streams)(*([RATIO] * streams))
+    res_arr = (pkg.ResampleResult * streams)()
+    stream_ptr = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def step():
+        lib.resampleBatchProcessInterleavedDevice(ctx_arr, streams, in_arr, nin_arr, out_arr, nout_arr,
+                                                  ratio_arr, res_arr, stream_ptr)
+        return sum(r.output_generated for r in res_arr)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+
+    # ---- timed region: device-resident ------------------------------------------------------------
+    launches0 = lib.resampleB200KernelLaunches()
+    lib.resampleB200ProfileEnable(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out_frames = 0
+    with ClockSampler(local) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            out_frames += step()
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    lib.resampleB200ProfileEnable(0)
+    kern_ms = C.c_double(0.0)
+    kern_launches = lib.resampleB200ProfileCollect(C.byref(kern_ms))
+    launches = lib.resampleB200KernelLaunches() - launches0
+
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    tot = torch.tensor([float(out_frames)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_max, total_frames = float(t.item()), float(tot.item())
+    value = total_frames * CHANNELS / (ms_max * 1e-3) / 1e6
+
+    # ---- end to end through the host-pointer API -----------------------------------------------------
+    e2e = measure_e2e(lib, pkg, torch, dist, world, dev, streams, frames, cap, args)
+
+    # ---- roofline of the convolution kernel ------------------------------------------------------------
+    peak, peak_src = load_peaks()
+    per_launch_samples = out_frames * CHANNELS / max(1, kern_launches)
+    kern_avg_ms = kern_ms.value / max(1, kern_launches)
+    achieved = per_launch_samples * BYTES_PER_OUTPUT_SAMPLE / (kern_avg_ms * 1e-3) / 1e9
+    flops = per_launch_samples * (4 * TAPS + 3) / (kern_avg_ms * 1e-3) / 1e12
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "art_sinc_generic_kernel<interp,float,CV=2>",
+                "kernel_ms_per_launch": kern_avg_ms, "kernel_share_of_step": kern_ms.value / ms,
+                "algorithmic_bytes_per_output_sample": BYTES_PER_OUTPUT_SAMPLE,
+                "fp32_tflops": flops, "fp32_fma_peak_tflops_at_max_clock": 74.4,
+                "note": "arithmetic intensity 198 flop/B puts this path above the FP32 ridge: FP32 FMA issue binds, not HBM"}
+    prof = ROOT / "profiles" / "r01_ncu_summary.json"
+    if prof.exists():
+        try:
+            roofline["traffic"] = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    line = {
+        "metric": "output Msamples/sec at preset -3 (380-tap), 44.1k->48k", "value": value, "unit": "Msamples/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"stereo float32 44.1k->48k preset -3 (380x380, interpolated, resampleInit): "
+                               f"{streams} independent stereo streams x {frames} input frames per step per GPU, "
+                               "one batched launch", "streams_per_gpu": streams, "frames_per_stream": frames,
+                   "l2": f"inputs {streams * frames * CHANNELS * 4 / 2**20:.0f} MiB + outputs per step exceed the 126 MB L2",
+                   "parallelism": f"streams sharded over {world} GPU(s), no data-path collective"},
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            s, dt, kind = cpu_reference_run(1 << 20, cores)
+            line["cpu_baseline"] = {"value": s / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": kind,
+                                    "sample": f"{cores} stereo streams (one per host thread) x {1 << 20} input frames, "
+                                              "16384-frame calls, same config"}
+        print(json.dumps(line), flush=True)
+    for c in ctxs:
+        lib.resampleFree(c)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_e2e(lib, pkg, torch, dist, world, dev, streams, frames, cap, args):
+    """Same workload through resampleProcessInterleaved with pinned host buffers; a few host threads
+    keep several contexts in flight so that H2D, kernels and D2H of different streams overlap."""
+    n = min(streams, args.e2e_streams)
+    hx = torch.empty((n, frames, CHANNELS), dtype=torch.float32).uniform_(-0.5, 0.5).pin_memory()
+    hy = torch.empty((n, cap, CHANNELS), dtype=torch.float32).pin_memory()
+    ctxs = [lib.resampleInit(CHANNELS, TAPS, FILTERS, 0.0, FLAGS) for _ in range(n)]
+    for c in ctxs:
+        lib.resampleAdvancePosition(c, TAPS / 2)
+    f32p = C.POINTER(C.c_float)
+    xp = [C.cast(hx[i].data_ptr(), f32p) for i in range(n)]
+    yp = [C.cast(hy[i].data_ptr(), f32p) for i in range(n)]
+    local = dev.index
+
+    def one(i):
+        lib.resampleB200SetDevice(local)
+        return lib.resampleProcessInterleaved(ctxs[i], xp[i], frames, yp[i], cap, RATIO).output_generated
+
+    steps = max(1, min(args.steps, 5))
+    with ThreadPoolExecutor(args.e2e_threads) as pool:
+        for _ in range(2):
+            list(pool.map(one, range(n)))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        made = 0
+        for _ in range(steps):
+            made += sum(pool.map(one, range(n)))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    tot = torch.tensor([float(made)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    for c in ctxs:
+        lib.resampleFree(c)
+    per_step_out = made / steps
+    return {"value": float(tot.item()) * CHANNELS / float(t.item()) / 1e6, "unit": "Msamples/s",
+            "h2d_bytes_per_step": int(n * frames * CHANNELS * 4), "d2h_bytes_per_step": int(per_step_out * CHANNELS * 4),
+            "api": "resampleProcessInterleaved (host pointers, pinned), "
+                   f"{n} streams x {frames} frames per step, {args.e2e_threads} host threads"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=64, help="independent stereo streams per GPU per step")
+    ap.add_argument("--frames", type=int, default=1 << 18, help="input frames per stream per step")
+    ap.add_argument("--e2e-streams", type=int, default=16)
+    ap.add_argument("--e2e-threads", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

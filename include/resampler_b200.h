@@ -24,6 +24,11 @@ int  resampleB200SetDevice (int device);                 /* 0 on success */
 int  resampleB200GetDeviceCount (void);
 void resampleB200Synchronize (Resample *cxt);            /* wait for the context's private stream */
 unsigned long long resampleB200KernelLaunches (void);    /* kernels launched by this library so far */
+/* measurement aid: when enabled, every convolution kernel launch is bracketed by CUDA events on its
+ * own stream; Collect waits for them, returns how many launches were timed and their summed
+ * duration in milliseconds, and clears the list */
+void resampleB200ProfileEnable (int on);
+unsigned long long resampleB200ProfileCollect (double *totalMs);
 
 /* device-pointer twins of resampleProcessInterleaved (resampler.c:550) / resampleProcess (:433).
  * A flush is numInputFrames == -1, as in the reference. */

@@ -212,7 +212,11 @@ def run_gpu_arm(args):
     nout_arr = (C.c_int * streams)(*([cap] * streams))
     ratio_arr = (C.c_double * streams)(*([RATIO] * streams))
     res_arr = (pkg.ResampleResult * streams)()
-    stream_ptr = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # a dedicated non-default stream: handle 0 (torch's default stream) would read as NULL = "the
+    # context's private stream" in the C API, and events on the default stream would then time nothing
+    work_stream = torch.cuda.Stream(device=dev)
+    assert work_stream.cuda_stream != 0
+    stream_ptr = C.c_void_p(work_stream.cuda_stream)
 
     def step():
         lib.resampleBatchProcessInterleavedDevice(ctx_arr, streams, in_arr, nin_arr, out_arr, nout_arr,
@@ -235,12 +239,17 @@ def run_gpu_arm(args):
     out_frames = 0
     with ClockSampler(local) as clocks:
         barrier()
-        ev0.record()
+        wall0 = time.perf_counter()
+        ev0.record(work_stream)
         for _ in range(args.steps):
             out_frames += step()
-        ev1.record()
+        ev1.record(work_stream)
         barrier()
+        wall_ms = (time.perf_counter() - wall0) * 1e3
     ms = ev0.elapsed_time(ev1)
+    # the device time can be shorter than the host-observed time (launch latency) but never by much
+    # for multi-ms steps; a large gap means the events did not bracket the work
+    assert ms > 0.5 * wall_ms or wall_ms < 5.0, f"event time {ms:.3f} ms vs wall {wall_ms:.3f} ms: events miss the work"
     lib.resampleB200ProfileEnable(0)
     kern_ms = C.c_double(0.0)
     kern_launches = lib.resampleB200ProfileCollect(C.byref(kern_ms))
@@ -285,7 +294,7 @@ def run_gpu_arm(args):
                                "one batched launch", "streams_per_gpu": streams, "frames_per_stream": frames,
                    "l2": f"inputs {streams * frames * CHANNELS * 4 / 2**20:.0f} MiB + outputs per step exceed the 126 MB L2",
                    "parallelism": f"streams sharded over {world} GPU(s), no data-path collective"},
-        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "wall_ms_per_step": wall_ms / args.steps, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
     if rank == 0:
         if world == 1 and not args.no_cpu:

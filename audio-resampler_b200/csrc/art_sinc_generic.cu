@@ -14,14 +14,17 @@
  *      a row pair is 2*T floats that no neighbouring output shares when the phase
  *      step is large, so grouping is what turns 3 KB of filter traffic per output
  *      into 3 KB per row per tile;
- *   3. the input window of the tile (history ++ input block) is staged planar in
- *      shared memory with coalesced loads;
- *   4. a warp takes a run of up to 8 outputs that share a row pair: lanes split the
- *      taps, each lane keeps 8 x CV x 2 accumulators in registers, the row pair is
- *      read once per run through L1, the samples come from shared memory
- *      (conflict free: 32 consecutive floats per load);
- *   5. the 8 x CV partial sums are combined with a transposing shuffle reduction
- *      (one shuffle per value instead of five) and written to global memory.
+ *   3. the input window of the tile (history ++ input block) is staged in shared
+ *      memory with coalesced loads, channel-interleaved in groups of CV so that one
+ *      LDS.64 / LDS.128 brings a sample of every channel of the group;
+ *   4. a warp takes a run of up to 8 outputs that share a row pair (run table built
+ *      with the sort): lanes split the taps, each lane keeps 8 x CV x 2 accumulators
+ *      in registers, the row pair is read once per run through L1, the samples come
+ *      from shared memory (conflict free: 32 consecutive vectors per load, immediate
+ *      offsets from one pointer per output); runs of <= 4, 2, 1 outputs use
+ *      narrower register tiles instead of idle slots;
+ *   5. the partial sums are combined with a transposing shuffle reduction (one
+ *      shuffle per value instead of five) and written to global memory.
  *
  * Arithmetic: float FMA accumulation, float lerp of the two row sums (the reference
  * lerps in double after two float sums; the difference is below 1 ulp of the sums).
@@ -74,6 +77,85 @@ __device__ __forceinline__ int art_find_job (const ArtJob *jobs, int numJobs, in
     return lo;
 }
 
+template <int CV> struct ArtVec;
+template <> struct ArtVec<1> { typedef float  type; __device__ static float get (const float  &x, int)   { return x; } };
+template <> struct ArtVec<2> { typedef float2 type; __device__ static float get (const float2 &x, int v) { return v ? x.y : x.x; } };
+template <> struct ArtVec<4> { typedef float4 type; __device__ static float get (const float4 &x, int v) { return v == 0 ? x.x : v == 1 ? x.y : v == 2 ? x.z : x.w; } };
+
+struct ArtTileCtx {
+    const float *xs;                 // staged window, [group][Wp][CV]
+    const int *srel;                 // region index of the first tap, per tile-local output
+    const float *wgt;                // interpolation weight, per tile-local output
+    const unsigned short *order;     // tile-local output indices grouped by filter row
+    long long sFirst;                // region index staged at xs[.][0]
+    unsigned int n0;                 // first output frame of the tile
+    int c0, nc;                      // first channel of the CTA, channels it owns
+    int Wp, Tp, half;
+};
+
+/* SLOTS outputs that share the row pair `kk`, all channel groups of the CTA. */
+template <bool INTERP, typename AccT, int CV, int SLOTS>
+__device__ __forceinline__ void art_run_tile (const ArtTileCtx &t, const ArtJob &job, const float *__restrict__ bank,
+                                              int kk, int e0, int len, int lane)
+{
+    typedef typename ArtVec<CV>::type VecT;
+    const float *__restrict__ rowA = bank + (size_t) kk * t.Tp + lane;
+    const float *__restrict__ rowB = rowA + t.Tp;
+    const int NI = t.Tp >> 5;
+
+    int off[SLOTS];
+    float f[SLOTS];
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) {
+        const int i = t.order[e0 + min (j, len - 1)];            // idle slots shadow the last real entry
+        off[j] = (int) ((long long) t.srel[i] - t.sFirst) + lane;
+        f[j] = t.wgt[i];
+    }
+
+    for (int cg = 0; cg < t.nc; cg += CV) {
+        AccT a0[SLOTS][CV], a1[SLOTS][CV];
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j)
+#pragma unroll
+            for (int v = 0; v < CV; ++v) { a0[j][v] = 0; a1[j][v] = 0; }
+
+        const VecT *xp[SLOTS];
+        const VecT *plane = reinterpret_cast<const VecT *> (t.xs) + (size_t) (cg / CV) * t.Wp;
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j)
+            xp[j] = plane + off[j];
+
+#pragma unroll 4
+        for (int i = 0; i < NI; ++i) {
+            const AccT ca = __ldg (rowA + 32 * i);
+            const AccT cb = INTERP ? (AccT) __ldg (rowB + 32 * i) : (AccT) 0;
+#pragma unroll
+            for (int j = 0; j < SLOTS; ++j) {
+                const VecT xv = xp[j][32 * i];
+#pragma unroll
+                for (int v = 0; v < CV; ++v) {
+                    const AccT x = ArtVec<CV>::get (xv, v);
+                    a0[j][v] = fma (ca, x, a0[j][v]);
+                    if (INTERP) a1[j][v] = fma (cb, x, a1[j][v]);
+                }
+            }
+        }
+
+        AccT vals[SLOTS * CV];
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j)
+#pragma unroll
+            for (int v = 0; v < CV; ++v)
+                vals[j * CV + v] = INTERP ? fma ((AccT) f[j], a1[j][v] - a0[j][v], a0[j][v]) : a0[j][v];
+
+        const AccT total = art_transpose_reduce<SLOTS * CV, AccT> (vals, lane);
+        constexpr int LPV = 32 / (SLOTS * CV);                   // lanes holding the same value
+        const int q = lane / LPV, j = q / CV, v = q - j * CV;
+        if ((lane % LPV) == 0 && j < len && cg + v < t.nc)
+            *art_out_ptr (job, t.c0 + cg + v, (long long) t.n0 + t.order[e0 + j]) = (float) total;
+    }
+}
+
 template <bool INTERP, bool PRECISE, int CV>
 __global__ void __launch_bounds__ (ART_G_THREADS, 2)
 art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single, const ArtJob *__restrict__ jobs)
@@ -83,13 +165,15 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
     extern __shared__ __align__ (16) unsigned char smem_raw[];
     const int nkeys = NUM_KEYS (k.F);
     const int nkeysPad = (nkeys + 2 + 3) & ~3;
+    const int maxRuns = k.NB / ART_RUN + nkeys + 8;
 
-    float *xs = reinterpret_cast<float *> (smem_raw);                   // [Cg][Wp]
-    int *srel = reinterpret_cast<int *> (xs + (size_t) k.Cg * k.Wp);    // [NB] window start - tile origin
+    float *xs = reinterpret_cast<float *> (smem_raw);                   // [Cg/CV][Wp][CV]
+    int *srel = reinterpret_cast<int *> (xs + (size_t) k.Cg * k.Wp);    // [NB] region index of the first tap
     float *wgt = reinterpret_cast<float *> (srel + k.NB);               // [NB] interpolation weight
     int *binEnd = reinterpret_cast<int *> (wgt + k.NB);                 // [nkeysPad] counts -> starts -> ends
     int *chunk0 = binEnd + nkeysPad;                                    // [nkeysPad] first run index per key
-    unsigned short *key = reinterpret_cast<unsigned short *> (chunk0 + nkeysPad);   // [NB]
+    unsigned int *runTab = reinterpret_cast<unsigned int *> (chunk0 + nkeysPad);      // [maxRuns] key<<20 | start<<4 | len-1
+    unsigned short *key = reinterpret_cast<unsigned short *> (runTab + maxRuns);      // [NB]
     unsigned short *order = key + k.NB;                                 // [NB] tile-local output index, grouped by key
 
     __shared__ long long sh_first, sh_last;
@@ -121,9 +205,8 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
     }
     if (tid == 0) {                         // the rounding chain up to the tile's first output, once
         int w;
-        const double pos = art_output_pos (&st, n0, &w);
+        (void) art_output_pos (&st, n0, &w);
         sh_w0 = w;
-        (void) pos;
         sh_base0 = art_ring_base (st.P, T, w);
     }
     __syncthreads ();
@@ -160,13 +243,12 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
         srel[i] = (int) s;                 // region index of the first tap (frame counts are ints)
         wgt[i] = f;
         key[i] = (unsigned short) kk;
-        if (k.sort)
-            atomicAdd (&binEnd[kk], 1);
+        atomicAdd (&binEnd[kk], 1);
     }
     __syncthreads ();
 
     const long long sFirst = sh_first;
-    const int span = (int) (sh_last - sFirst) + k.Tp;            // floats of window the tile touches
+    const int span = (int) (sh_last - sFirst) + k.Tp;            // samples of window the tile touches
     if (span > k.Wp) {
         if (tid == 0)
             printf ("libresampler_b200: tile window %d exceeds plane %d (ratio %g)\n", span, k.Wp, job.ratio);
@@ -175,24 +257,25 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
 
     /* ---- 3. stage the window (issued before the scan so the loads overlap it) ------------ */
     {
+        // xs[(group * Wp + j) * CV + v] = sample j of channel group*CV + v
         const bool interleavedSrc = (job.inPlanes == nullptr) && (job.inCS == 1);
         if (interleavedSrc) {
             const int total = span * k.Cg;
             for (int e = tid; e < total; e += ART_G_THREADS) {
                 const int j = e / k.Cg, cc = e - j * k.Cg;
-                xs[cc * k.Wp + j] = cc < nc ? art_fetch (job, T, c0 + cc, sFirst + j) : 0.0f;
+                xs[((cc / CV) * k.Wp + j) * CV + (cc % CV)] = cc < nc ? art_fetch (job, T, c0 + cc, sFirst + j) : 0.0f;
             }
         }
         else {
             for (int cc = 0; cc < k.Cg; ++cc)
                 for (int j = tid; j < span; j += ART_G_THREADS)
-                    xs[cc * k.Wp + j] = cc < nc ? art_fetch (job, T, c0 + cc, sFirst + j) : 0.0f;
+                    xs[((cc / CV) * k.Wp + j) * CV + (cc % CV)] = cc < nc ? art_fetch (job, T, c0 + cc, sFirst + j) : 0.0f;
         }
     }
 
     /* ---- 2. group by filter row ---------------------------------------------------------- */
     int totalRuns;
-    if (k.sort) {
+    {
         // exclusive scans of counts (-> starts) and of ceil(count / RUN) (-> first run), in one pass
         const int per = (nkeys + ART_G_THREADS - 1) / ART_G_THREADS;
         const int b0 = tid * per, b1 = min (b0 + per, nkeys);
@@ -217,117 +300,47 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
             const int c = binEnd[b];
             binEnd[b] = runC;          // start of the bin; the scatter below advances it to the end
             chunk0[b] = runR;
+            // the run table: every run knows its row, where its outputs sit in `order`, and how many
+            for (int r = 0, left = c; left > 0; ++r, left -= ART_RUN)
+                runTab[runR + r] = ((unsigned int) b << 20) | ((unsigned int) (runC + r * ART_RUN) << 4) |
+                                   (unsigned int) (min (left, ART_RUN) - 1);
             runC += c;
             runR += (c + ART_RUN - 1) / ART_RUN;
         }
         int tr = 0;
         for (int w = 0; w < ART_G_WARPS; ++w) tr += sh_scan2[w];
         totalRuns = tr;
-        if (tid == 0) chunk0[nkeys] = tr;
         __syncthreads ();
         for (int i = tid; i < cnt; i += ART_G_THREADS) {
             const int slot = atomicAdd (&binEnd[key[i]], 1);
             order[slot] = (unsigned short) i;
         }
     }
-    else
-        totalRuns = (cnt + ART_RUN - 1) / ART_RUN;
     __syncthreads ();
 
     /* ---- 4. convolve: one warp per run ---------------------------------------------------- */
-    const int NI = k.Tp >> 5;
+    ArtTileCtx t;
+    t.xs = xs; t.srel = srel; t.wgt = wgt; t.order = order;
+    t.sFirst = sFirst; t.n0 = n0; t.c0 = c0; t.nc = nc; t.Wp = k.Wp; t.Tp = k.Tp; t.half = half;
+
     for (int run = warp; run < totalRuns; run += ART_G_WARPS) {
-        int kk, e0, len;
-        if (k.sort) {
-            int lo = 0, hi = nkeys - 1;                       // largest key with chunk0[key] <= run
-            while (lo < hi) {
-                int mid = (lo + hi + 1) >> 1;
-                if (chunk0[mid] <= run) lo = mid; else hi = mid - 1;
+        const unsigned int packed = runTab[run];
+        const int kk = (int) (packed >> 20), e0 = (int) ((packed >> 4) & 0xffff), len = (int) (packed & 15) + 1;
+
+        if (kk > F) {
+            /* pass-through: the stored sample itself */
+            const int shift = (kk == KEY_PASS1 (F)) ? 1 : 0;
+            for (int q = lane; q < len * nc; q += 32) {
+                const int j = q / nc, cc = q - j * nc;
+                const int i = order[e0 + j];
+                const int at = (int) ((long long) srel[i] - sFirst) + half - 1 + shift;
+                *art_out_ptr (job, c0 + cc, (long long) n0 + i) = xs[((cc / CV) * k.Wp + at) * CV + (cc % CV)];
             }
-            kk = lo;
-            const int begin = kk ? binEnd[kk - 1] : 0;
-            e0 = begin + (run - chunk0[kk]) * ART_RUN;
-            len = min (ART_RUN, binEnd[kk] - e0);
         }
-        else {
-            // ungrouped: consecutive outputs; a run must still share one key, so cut at the first change
-            e0 = run * ART_RUN;
-            len = min (ART_RUN, cnt - e0);
-            kk = -1;
-        }
-
-        int done = 0;
-        while (done < len) {
-            int sub = len;                                    // grouped: the whole run shares kk
-            if (!k.sort) {                                    // raw order: cut where the row changes
-                kk = key[e0 + done];
-                sub = 1;
-                while (done + sub < len && key[e0 + done + sub] == kk) ++sub;
-            }
-            const int eBase = e0 + done;
-#define ART_ENTRY(j) (k.sort ? (int) order[eBase + (j)] : eBase + (j))     /* tile-local output index */
-
-            if (kk > F) {
-                /* pass-through: the stored sample itself */
-                const int shift = (kk == KEY_PASS1 (F)) ? 1 : 0;
-                for (int q = lane; q < sub * nc; q += 32) {
-                    const int j = q / nc, cc = q - j * nc;
-                    const int i = ART_ENTRY (j);
-                    const int at = (int) ((long long) srel[i] - sFirst) + half - 1 + shift;
-                    *art_out_ptr (job, c0 + cc, (long long) n0 + i) = xs[cc * k.Wp + at];
-                }
-            }
-            else {
-                const float *__restrict__ rowA = k.bank + (size_t) kk * k.Tp + lane;
-                const float *__restrict__ rowB = rowA + k.Tp;
-                int base[ART_RUN];
-                float f[ART_RUN];
-#pragma unroll
-                for (int j = 0; j < ART_RUN; ++j) {
-                    const int i = ART_ENTRY (min (j, sub - 1));   // idle slots shadow the last real entry
-                    base[j] = (int) ((long long) srel[i] - sFirst) + lane;
-                    f[j] = wgt[i];
-                }
-
-                for (int cg = 0; cg < nc; cg += CV) {
-                    AccT a0[ART_RUN][CV], a1[ART_RUN][CV];
-#pragma unroll
-                    for (int j = 0; j < ART_RUN; ++j)
-#pragma unroll
-                        for (int v = 0; v < CV; ++v) { a0[j][v] = 0; a1[j][v] = 0; }
-
-                    const float *xg = xs + cg * k.Wp;
-#pragma unroll 2
-                    for (int i = 0; i < NI; ++i) {
-                        const AccT ca = __ldg (rowA + 32 * i);
-                        const AccT cb = INTERP ? (AccT) __ldg (rowB + 32 * i) : (AccT) 0;
-#pragma unroll
-                        for (int j = 0; j < ART_RUN; ++j)
-#pragma unroll
-                            for (int v = 0; v < CV; ++v) {
-                                const AccT x = xg[v * k.Wp + base[j] + 32 * i];
-                                a0[j][v] = fma (ca, x, a0[j][v]);
-                                if (INTERP) a1[j][v] = fma (cb, x, a1[j][v]);
-                            }
-                    }
-
-                    AccT vals[ART_RUN * CV];
-#pragma unroll
-                    for (int j = 0; j < ART_RUN; ++j)
-#pragma unroll
-                        for (int v = 0; v < CV; ++v)
-                            vals[j * CV + v] = INTERP ? fma ((AccT) f[j], a1[j][v] - a0[j][v], a0[j][v]) : a0[j][v];
-
-                    const AccT total = art_transpose_reduce<ART_RUN * CV, AccT> (vals, lane);
-                    constexpr int LPV = 32 / (ART_RUN * CV);         // lanes holding the same value
-                    const int q = lane / LPV, j = q / CV, v = q - j * CV;
-                    if ((lane % LPV) == 0 && j < sub && cg + v < nc)
-                        *art_out_ptr (job, c0 + cg + v, (long long) n0 + ART_ENTRY (j)) = (float) total;
-                }
-            }
-#undef ART_ENTRY
-            done += sub;
-        }
+        else if (len > 4) art_run_tile<INTERP, AccT, CV, 8> (t, job, k.bank, kk, e0, len, lane);
+        else if (len > 2) art_run_tile<INTERP, AccT, CV, 4> (t, job, k.bank, kk, e0, len, lane);
+        else if (len > 1) art_run_tile<INTERP, AccT, CV, 2> (t, job, k.bank, kk, e0, len, lane);
+        else              art_run_tile<INTERP, AccT, CV, 1> (t, job, k.bank, kk, e0, len, lane);
     }
 }
 
@@ -350,7 +363,8 @@ static size_t generic_smem (const ArtClass &k)
 {
     const int nkeys = NUM_KEYS (k.F);
     const int nkeysPad = (nkeys + 2 + 3) & ~3;
-    return (size_t) k.Cg * k.Wp * 4 + (size_t) k.NB * (4 + 4 + 2 + 2) + (size_t) nkeysPad * 8 + 16;
+    const int maxRuns = k.NB / ART_RUN + nkeys + 8;
+    return (size_t) k.Cg * k.Wp * 4 + (size_t) k.NB * (4 + 4 + 2 + 2) + (size_t) nkeysPad * 8 + (size_t) maxRuns * 4 + 16;
 }
 
 static int plane_floats (int NB, double ratio, int Tp)

@@ -460,5 +460,6 @@ int resampleB200GetDeviceCount (void) { return artDevCount (); }
 
 void resampleB200Synchronize (Resample *cxt) { artDevSynchronize (cxt->device); }
 unsigned long long resampleB200KernelLaunches (void) { return artDevLaunchCount (); }
+void resampleB200PathCounts (unsigned long long *generic, unsigned long long *periodic) { artDevPathCounts (generic, periodic); }
 void resampleB200ProfileEnable (int on) { artDevProfileEnable (on); }
 unsigned long long resampleB200ProfileCollect (double *totalMs) { return artDevProfileCollect (totalMs); }

@@ -15,6 +15,13 @@
 #include "art_device.h"
 
 unsigned long long g_artLaunches = 0;
+static unsigned long long g_pathLaunches[2] = { 0, 0 };        // [0] generic kernel, [1] periodic kernel
+
+extern "C" void artDevPathCounts (unsigned long long *generic, unsigned long long *periodic)
+{
+    if (generic) *generic = g_pathLaunches[0];
+    if (periodic) *periodic = g_pathLaunches[1];
+}
 
 extern "C" unsigned long long artDevLaunchCount (void) { return g_artLaunches; }
 
@@ -257,19 +264,119 @@ static void finish_job (ArtDev *dev, const ArtCallPlan &p)
         dev->cur ^= 1;
 }
 
+/* ---- kernel choice and launch ------------------------------------------------------------------------
+ * One "launch" covers a list of jobs of one configuration: a single call, the contexts of a batch, or
+ * the blocks of an ASRC sequence.  Rational ratios with a small numerator go to the periodic kernel
+ * (every job of the launch must share the ratio); everything else to the generic kernel.  Long calls
+ * are cut into segments for the periodic kernel (see artPeriodicSegmentOutputs). */
+struct ArtLaunchPlan {
+    ArtClass k;
+    bool periodic;
+    ArtPeriodic per;
+    int CV;
+    ArtLaunchGeom g;
+    unsigned int segLen;
+};
+
+static bool g_forceGeneric = false, g_envRead = false;
+
+static void plan_launch (ArtDev *lead, double minRatio, bool oneRatio, unsigned int maxOut, unsigned long long totalOut,
+                         bool allowPeriodic, ArtLaunchPlan &lp)
+{
+    if (!g_envRead) {
+        g_forceGeneric = getenv ("ART_B200_GENERIC") != nullptr;     // debugging / A-B measurements
+        g_envRead = true;
+    }
+    lp.k = lead->klass;
+    lp.periodic = false;
+    lp.segLen = 0;
+    if (!maxOut)
+        return;
+    const unsigned int total32 = (unsigned int) (totalOut > 0xffffffffULL ? 0xffffffffULL : totalOut);
+    if (allowPeriodic && oneRatio && !g_forceGeneric &&
+        artPlanPeriodic (lp.k, minRatio, maxOut, lead->smCount, lp.per, lp.CV)) {
+        lp.periodic = true;
+        lp.segLen = artPeriodicSegmentOutputs (lp.per, minRatio);
+        return;
+    }
+    artPlanGenericGeometry (lp.k, minRatio, total32, lead->smCount, lp.g);
+}
+
+/* append the job (cut into segments when the periodic kernel needs that); returns CTAs/tiles added */
+static int append_job (const ArtLaunchPlan &lp, const ArtJob &base, std::vector<ArtJob> &jobs, int firstCta)
+{
+    int ctas = 0;
+    if (!base.outputs) {
+        if (base.histOut) {                 // nothing to produce, but the history still has to move on
+            ArtJob j = base;
+            j.tile0 = firstCta;
+            jobs.push_back (j);
+        }
+        return 0;
+    }
+    if (!lp.periodic) {
+        ArtJob j = base;
+        j.tile0 = firstCta;
+        jobs.push_back (j);
+        return (int) ((base.outputs + lp.k.NB - 1) / lp.k.NB);
+    }
+    for (unsigned int at = 0; at < base.outputs; at += lp.segLen) {
+        ArtJob j = base;
+        j.nStart = base.nStart + at;
+        j.outputs = base.outputs - at < lp.segLen ? base.outputs - at : lp.segLen;
+        j.tile0 = firstCta + ctas;
+        if (at) j.histOut = nullptr;        // one history update per call
+        jobs.push_back (j);
+        ctas += artPeriodicCtas (lp.per, j.outputs);
+    }
+    return ctas;
+}
+
+static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cudaStream_t stream)
+{
+    if (jobs.empty ())
+        return;
+    const int n = (int) jobs.size ();
+    lp.k.numJobs = n;
+    bool anyHist = false;
+    for (const ArtJob &j : jobs) anyHist |= j.histOut != nullptr;
+
+    ArtJob *d_jobs = nullptr;
+    if (n > 1) {
+        ART_CUDA_CHECK (cudaMallocAsync (&d_jobs, sizeof (ArtJob) * n, stream));
+        // pageable source: staged by the runtime before the call returns
+        ART_CUDA_CHECK (cudaMemcpyAsync (d_jobs, jobs.data (), sizeof (ArtJob) * n, cudaMemcpyHostToDevice, stream));
+    }
+    if (ctas > 0) {
+        if (lp.periodic) {
+            const size_t tableFloats = (size_t) n * lp.per.L * lp.k.Tp, tableInts = (size_t) n * lp.per.L;
+            void *tables = nullptr;
+            ART_CUDA_CHECK (cudaMallocAsync (&tables, tableFloats * sizeof (float) + tableInts * sizeof (int), stream));
+            lp.per.Hc = reinterpret_cast<float *> (tables);
+            lp.per.S = reinterpret_cast<int *> (lp.per.Hc + tableFloats);
+            artLaunchPeriodic (lp.k, lp.per, lp.CV, ctas, n, jobs[0], d_jobs, stream);
+            ++g_pathLaunches[1];
+            ART_CUDA_CHECK (cudaFreeAsync (tables, stream));
+        }
+        else {
+            lp.g.totalTiles = ctas;
+            artLaunchGeneric (lp.k, lp.g, jobs[0], d_jobs, stream);
+            ++g_pathLaunches[0];
+        }
+    }
+    if (anyHist)
+        artLaunchHistory (lp.k, jobs[0], d_jobs, n, stream);
+    if (d_jobs)
+        ART_CUDA_CHECK (cudaFreeAsync (d_jobs, stream));
+}
+
 static void run_single (ArtDev *dev, const ArtCallPlan &p, ArtJob &job, cudaStream_t stream)
 {
-    ArtClass k = dev->klass;
-    k.numJobs = 1;
-    if (p.outputs) {
-        ArtLaunchGeom g;
-        artPlanGenericGeometry (k, p.st.ratio, p.outputs, dev->smCount, g);
-        job.tile0 = 0;
-        g.totalTiles = (int) ((p.outputs + k.NB - 1) / k.NB);
-        artLaunchGeneric (k, g, job, nullptr, stream);
-    }
-    if (job.histOut)
-        artLaunchHistory (k, job, nullptr, 1, stream);
+    ArtLaunchPlan lp;
+    plan_launch (dev, p.st.ratio, true, p.outputs, p.outputs, true, lp);
+    std::vector<ArtJob> jobs;
+    const int ctas = append_job (lp, job, jobs, 0);
+    dispatch (lp, jobs, ctas, stream);
     finish_job (dev, p);
 }
 
@@ -385,6 +492,7 @@ extern "C" void artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPla
     cudaStream_t st = stream ? (cudaStream_t) stream : lead->stream;
 
     double minRatio = plans[0].st.ratio;
+    bool oneRatio = true;
     unsigned int maxOut = 0;
     unsigned long long totalOut = 0;
     for (int i = 0; i < count; ++i) {
@@ -392,39 +500,25 @@ extern "C" void artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPla
             fprintf (stderr, "libresampler_b200: a batch must hold contexts of one configuration on one GPU\n");
             abort ();
         }
+        if (plans[i].st.ratio != plans[0].st.ratio) oneRatio = false;
         if (plans[i].st.ratio < minRatio) minRatio = plans[i].st.ratio;
         if (plans[i].outputs > maxOut) maxOut = plans[i].outputs;
         totalOut += plans[i].outputs;
     }
 
-    ArtClass k = lead->klass;
-    k.numJobs = count;
-    ArtLaunchGeom g;
-    g.totalTiles = 0;
-    if (maxOut)
-        artPlanGenericGeometry (k, minRatio, (unsigned int) (totalOut > 0xffffffffULL ? 0xffffffffULL : totalOut), lead->smCount, g);
-
-    std::vector<ArtJob> jobs (count);
-    int tiles = 0;
-    bool anyHist = false;
+    ArtLaunchPlan lp;
+    plan_launch (lead, minRatio, oneRatio, maxOut, totalOut, true, lp);
+    std::vector<ArtJob> jobs;
+    jobs.reserve (count);
+    int ctas = 0;
     for (int i = 0; i < count; ++i) {
-        fill_job (devs[i], plans[i], jobs[i]);
-        jobs[i].in = d_in ? d_in[i] : nullptr;  jobs[i].inFS = lead->C;  jobs[i].inCS = 1;
-        jobs[i].out = d_out[i];                 jobs[i].outFS = lead->C; jobs[i].outCS = 1;
-        jobs[i].tile0 = tiles;
-        if (maxOut) tiles += (int) ((plans[i].outputs + k.NB - 1) / k.NB);
-        anyHist |= jobs[i].histOut != nullptr;
+        ArtJob j;
+        fill_job (devs[i], plans[i], j);
+        j.in = d_in ? d_in[i] : nullptr;  j.inFS = lead->C;  j.inCS = 1;
+        j.out = d_out[i];                 j.outFS = lead->C; j.outCS = 1;
+        ctas += append_job (lp, j, jobs, ctas);
     }
-    g.totalTiles = tiles;
-
-    ArtJob *d_jobs = nullptr;
-    ART_CUDA_CHECK (cudaMallocAsync (&d_jobs, sizeof (ArtJob) * count, st));
-    ART_CUDA_CHECK (cudaMemcpyAsync (d_jobs, jobs.data (), sizeof (ArtJob) * count, cudaMemcpyHostToDevice, st));
-    if (tiles)
-        artLaunchGeneric (k, g, jobs[0], d_jobs, st);
-    if (anyHist)
-        artLaunchHistory (k, jobs[0], d_jobs, count, st);
-    ART_CUDA_CHECK (cudaFreeAsync (d_jobs, st));
+    dispatch (lp, jobs, ctas, st);
     for (int i = 0; i < count; ++i)
         finish_job (devs[i], plans[i]);
 }
@@ -450,43 +544,34 @@ extern "C" void artDevRunBlocksInterleaved (ArtDev *dev, const ArtCallPlan *plan
         totalOut += plans[i].outputs;
         totalIn += plans[i].consumed;
     }
-    ArtClass k = dev->klass;
-    k.numJobs = count;
-    ArtLaunchGeom g;
-    g.totalTiles = 0;
-    if (maxOut)
-        artPlanGenericGeometry (k, minRatio, (unsigned int) (totalOut > 0xffffffffULL ? 0xffffffffULL : totalOut), dev->smCount, g);
+    ArtLaunchPlan lp;
+    plan_launch (dev, minRatio, false, maxOut, totalOut, false, lp);
 
-    std::vector<ArtJob> jobs (count + 1);
-    int tiles = 0;
+    std::vector<ArtJob> jobs;
+    jobs.reserve (count + 1);
+    int ctas = 0;
     for (int i = 0; i < count; ++i) {
-        ArtJob &j = jobs[i];
+        ArtJob j;
         fill_job (dev, plans[i], j);
         j.histOut = nullptr;
         j.prevAvail = inOffset[i];
         j.in = d_in + inOffset[i] * C;    j.inFS = C;  j.inCS = 1;
         j.out = d_out + outOffset[i] * C; j.outFS = C; j.outCS = 1;
-        j.tile0 = tiles;
-        if (maxOut) tiles += (int) ((plans[i].outputs + k.NB - 1) / k.NB);
+        ctas += append_job (lp, j, jobs, ctas);
     }
-    g.totalTiles = tiles;
     // the history after the sequence: newest T frames of (history ++ all consumed input)
-    ArtJob &hj = jobs[count];
-    memset (&hj, 0, sizeof hj);
-    hj.hist = dev->hist[dev->cur];
-    hj.histOut = totalIn ? dev->hist[dev->cur ^ 1] : nullptr;
-    hj.in = d_in; hj.inFS = C; hj.inCS = 1;
-    hj.inValid = (int) totalIn;
-    hj.consumed = totalIn;
-
-    ArtJob *d_jobs = nullptr;
-    ART_CUDA_CHECK (cudaMallocAsync (&d_jobs, sizeof (ArtJob) * count, st));
-    ART_CUDA_CHECK (cudaMemcpyAsync (d_jobs, jobs.data (), sizeof (ArtJob) * count, cudaMemcpyHostToDevice, st));
-    if (tiles)
-        artLaunchGeneric (k, g, jobs[0], d_jobs, st);
-    if (hj.histOut) {
-        artLaunchHistory (k, hj, nullptr, 1, st);
-        dev->cur ^= 1;
+    if (totalIn) {
+        ArtJob hj;
+        memset (&hj, 0, sizeof hj);
+        hj.hist = dev->hist[dev->cur];
+        hj.histOut = dev->hist[dev->cur ^ 1];
+        hj.in = d_in; hj.inFS = C; hj.inCS = 1;
+        hj.inValid = (int) totalIn;
+        hj.consumed = totalIn;
+        hj.tile0 = ctas;                    // owns no tiles: outputs == 0
+        jobs.push_back (hj);
     }
-    ART_CUDA_CHECK (cudaFreeAsync (d_jobs, st));
+    dispatch (lp, jobs, ctas, st);
+    if (totalIn)
+        dev->cur ^= 1;
 }

@@ -73,6 +73,7 @@ void artDevSetHistory (ArtDev *dev, const float *hostPlanar);
 
 /* statistics for bench.py's gpu_launches claim and roofline leg */
 unsigned long long artDevLaunchCount (void);
+void artDevPathCounts (unsigned long long *generic, unsigned long long *periodic);
 void artDevProfileEnable (int on);
 unsigned long long artDevProfileCollect (double *totalMs);   /* returns timed launches, clears */
 

@@ -33,8 +33,8 @@ struct ArtJob {
     int           inValid;           // frames of caller data in the input region
     long long     prevAvail;         // consumed frames preceding the region in the same buffer
     long long     consumed;          // region frames that enter the history (history kernel)
-    int           tile0;             // first tile of this job inside the launch
-    int           pad_;
+    int           tile0;             // first tile / CTA of this job inside the launch
+    unsigned int  nStart;            // call-relative index of this job's first output (segments of one call)
     const float  *hist;              // [C][T] history at call entry
     float        *histOut;           // [C][T] history after the call (may be null)
     const float  *in;                // base of region frame 0, channel 0
@@ -53,6 +53,41 @@ struct ArtClass {
     int numJobs;
     int sort;        // 1: group a tile's outputs by filter row before convolving
 };
+
+/* rational-ratio kernel: per-launch geometry and the phase tables it reads (art_sinc_periodic.cu) */
+struct ArtPeriodic {
+    int L, M;            // outputs / inputs per period (ratio = L / M in lowest terms)
+    int rowsPerCta;      // rows of 8 phases per CTA
+    int Kp;              // union-window taps per phase block, multiple of 32
+    int Qc;              // periods per staged chunk
+    int Qblk;            // periods per CTA
+    int Wc;              // staged samples per chunk = (Qc - 1) * M + Kp
+    float *Hc;           // [segments][L][Tp]  interpolated filter of every phase
+    int   *S;            // [segments][L]      region index of the first tap, period 0
+};
+
+/* Sum NV register values per lane across the warp so that lane L ends up with the total of
+ * value (L * NV / 32).  log2(NV) exchange stages halve the value count while consuming one
+ * lane bit each; the remaining lane bits are folded with a plain butterfly. */
+template <int NV, typename AccT>
+__device__ __forceinline__ AccT art_transpose_reduce (AccT (&v)[NV], int lane)
+{
+    int off = 16;
+#pragma unroll
+    for (int n = NV; n > 1; n >>= 1, off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            AccT send = upper ? v[i] : v[i + n / 2];
+            AccT keep = upper ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync (0xffffffffu, send, off);
+        }
+    }
+#pragma unroll
+    for (; off >= 1; off >>= 1)
+        v[0] += __shfl_xor_sync (0xffffffffu, v[0], off);
+    return v[0];
+}
 
 __device__ __forceinline__ float art_fetch (const ArtJob &j, int T, int c, long long idx)
 {
@@ -78,6 +113,13 @@ void artPlanGenericGeometry (ArtClass &k, double minRatio, unsigned int maxOutpu
 /* `single` is used when d_jobs is null (one job, passed by value); otherwise d_jobs[numJobs] */
 void artLaunchGeneric (const ArtClass &k, const ArtLaunchGeom &g, const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream);
 void artLaunchHistory (const ArtClass &k, const ArtJob &single, const ArtJob *d_jobs, int numJobs, cudaStream_t stream);
+
+bool artRational (double ratio, int maxL, int *L, int *M);
+bool artPlanPeriodic (const ArtClass &k, double ratio, unsigned int maxOutputs, int smCount, ArtPeriodic &p, int &CV);
+unsigned int artPeriodicSegmentOutputs (const ArtPeriodic &p, double ratio);
+int  artPeriodicCtas (const ArtPeriodic &p, unsigned int outputs);
+void artLaunchPeriodic (const ArtClass &k, const ArtPeriodic &p, int CV, int totalCtas, int numSegs,
+                        const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream);
 
 extern unsigned long long g_artLaunches;
 

@@ -44,29 +44,6 @@
 #define KEY_PASS1(F) ((F) + 2)      /* ... of the one after it (row index == F)                  */
 #define NUM_KEYS(F)  ((F) + 3)
 
-/* Sum NV register values per lane across the warp so that lane L ends up with the total of
- * value (L * NV / 32).  log2(NV) exchange stages halve the value count while consuming one
- * lane bit each; the remaining lane bits are folded with a plain butterfly. */
-template <int NV, typename AccT>
-__device__ __forceinline__ AccT art_transpose_reduce (AccT (&v)[NV], int lane)
-{
-    int off = 16;
-#pragma unroll
-    for (int n = NV; n > 1; n >>= 1, off >>= 1) {
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < n / 2; ++i) {
-            AccT send = upper ? v[i] : v[i + n / 2];
-            AccT keep = upper ? v[i + n / 2] : v[i];
-            v[i] = keep + __shfl_xor_sync (0xffffffffu, send, off);
-        }
-    }
-#pragma unroll
-    for (; off >= 1; off >>= 1)
-        v[0] += __shfl_xor_sync (0xffffffffu, v[0], off);
-    return v[0];
-}
-
 __device__ __forceinline__ int art_find_job (const ArtJob *jobs, int numJobs, int tile)
 {
     int lo = 0, hi = numJobs - 1;
@@ -187,10 +164,11 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
     // one job travels by value in the parameter space (no descriptor upload on the latency path);
     // batches and block sequences come as an array in global memory
     const ArtJob &job = jobs ? jobs[k.numJobs > 1 ? art_find_job (jobs, k.numJobs, blockIdx.x) : 0] : single;
-    const unsigned int n0 = (unsigned int) (blockIdx.x - job.tile0) * (unsigned int) k.NB;
-    if (n0 >= job.outputs)
+    const unsigned int t0 = (unsigned int) (blockIdx.x - job.tile0) * (unsigned int) k.NB;
+    if (t0 >= job.outputs)
         return;
-    const int cnt = (int) min ((unsigned int) k.NB, job.outputs - n0);
+    const int cnt = (int) min ((unsigned int) k.NB, job.outputs - t0);
+    const unsigned int n0 = job.nStart + t0;                      // call-relative index of the tile's first output
     const int c0 = blockIdx.y * k.Cg;
     const int nc = min (k.Cg, k.C - c0);
     const int T = k.T, half = T / 2, F = k.F;

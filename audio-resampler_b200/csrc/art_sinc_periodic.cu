@@ -1,0 +1,372 @@
+/*
+ * art_sinc_periodic.cu -- the rational-ratio windowed-sinc kernel (sm_100a).
+ *
+ * Same reference functions as art_sinc_generic.cu (resampler.c:523-526, :640-643, :1135-1157,
+ * :1033-1044), restructured for ratios L/M with a small numerator (44.1k->48k = 160/147,
+ * 48k->44.1k = 147/160, 96k->44.1k = 147/320, ... -- every BASELINE config but the ASRC one).
+ *
+ * With ratio = L/M the read position advances by exactly M input samples every L outputs, so
+ * output n = L*q + j ("phase j of period q") applies the SAME two filter rows with the SAME
+ * interpolation weight for every q:
+ *
+ *      y[j, q] = sum_k h_j[k] * x[s_j + M*q + k],   h_j = (1 - f_j) * row(fi_j) + f_j * row(fi_j + 1)
+ *
+ * i.e. a (phases x taps) by (taps x periods) product whose left operand is a banded matrix of L
+ * pre-interpolated filters and whose right operand is the input read at stride M.  Both operands
+ * are now reused (each h_j by every period and channel, each input sample by every phase), which
+ * the per-output dot product of the generic kernel cannot offer, and the interpolation costs T
+ * multiply-adds per phase per call instead of T per output sample: T FMAs per sample, not 2T.
+ *
+ *   1. art_phase_table_kernel: for the L phases of a segment, evaluate the reference's position
+ *      arithmetic exactly (art_plan.h) at the segment's first period, then h_j in double -> float.
+ *      Later periods reuse (fi_j, f_j, s_j + M*q): the exact positions drift from that by
+ *      < 1e-9 sample over a segment (the host caps segment length accordingly), far below the
+ *      1e-6 * peak tolerance; the planner still owns input_used/output_generated/position exactly.
+ *   2. art_sinc_periodic_kernel: a CTA owns up to 32 phases (4 rows of 8) and a run of periods.
+ *      The phases' filters sit in shared memory, shifted to a common origin ("union window" of
+ *      Kp taps); the input is staged chunk by chunk.  A warp computes an 8-phase x 8-column tile
+ *      (columns = periods x channels): lanes split the taps, 64 accumulators per lane, 16 shared
+ *      loads per 64 FMAs, then two transposing shuffle reductions and coalesced-by-phase stores.
+ *
+ * Non-interpolated contexts (resampleFixedRatioInit's reduced bank, resampler.c:323-335) use the
+ * same kernel: h_j is the bank row itself, or a unit impulse where the reference returns the
+ * stored sample verbatim (resampler.c:1141-1142) -- 1.0 * x + 0 * rest is exact.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include "art_kernels.cuh"
+#include "art_device.h"
+
+#define ART_P_THREADS 256
+#define ART_P_WARPS   (ART_P_THREADS / 32)
+#define ART_P_ROWS_MAX 4
+
+template <int CV> struct ArtPVec;
+template <> struct ArtPVec<1> { typedef float  type; __device__ static float get (const float  &x, int)   { return x; } };
+template <> struct ArtPVec<2> { typedef float2 type; __device__ static float get (const float2 &x, int v) { return v ? x.y : x.x; } };
+template <> struct ArtPVec<4> { typedef float4 type; __device__ static float get (const float4 &x, int v) { return v == 0 ? x.x : v == 1 ? x.y : v == 2 ? x.z : x.w; } };
+
+__device__ __forceinline__ int art_find_job_p (const ArtJob *jobs, int numJobs, int cta)
+{
+    int lo = 0, hi = numJobs - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].tile0 <= cta) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+/* ---- 1. the phase table ----------------------------------------------------------------------- */
+__global__ void __launch_bounds__ (128)
+art_phase_table_kernel (const ArtClass k, const ArtPeriodic p, const __grid_constant__ ArtJob single,
+                        const ArtJob *__restrict__ jobs)
+{
+    const int j = blockIdx.x, seg = blockIdx.y;
+    const ArtJob &job = jobs ? jobs[seg] : single;
+    const int T = k.T, half = T / 2, F = k.F;
+    __shared__ int sh_row, sh_pass;
+    __shared__ double sh_f;
+
+    if (threadIdx.x == 0) {
+        ArtLoopState st;
+        st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = T;
+        int w;
+        const double pos = art_output_pos (&st, job.nStart + j, &w);
+        const double whole = floor (pos), fr = pos - whole;
+        const long long s = (long long) whole - half + 1 + (long long) w * 15LL * T - job.origin;
+        int row, pass = -1;
+        double f = 0.0;
+        if (k.mode & ART_MODE_INTERP) {
+            double ph = fr * F;                                  // resampler.c:1149-1152
+            row = (int) floor (ph);
+            f = ph - row;
+            if (row >= F) { row = F - 1; f = 1.0; }
+        }
+        else {
+            row = (int) floor (fr * F + 0.5);                    // resampler.c:1137
+            if (!(k.mode & ART_MODE_LOWPASS) && row % F == 0)    // resampler.c:1141-1142
+                pass = half - 1 + (row ? 1 : 0);
+        }
+        sh_row = row; sh_f = f; sh_pass = pass;
+        p.S[(size_t) seg * p.L + j] = (int) s;
+    }
+    __syncthreads ();
+    const int row = sh_row, pass = sh_pass;
+    const double f = sh_f;
+    float *dst = p.Hc + ((size_t) seg * p.L + j) * k.Tp;
+    const float *ra = k.bank + (size_t) row * k.Tp, *rb = ra + k.Tp;
+    for (int t = threadIdx.x; t < k.Tp; t += blockDim.x) {
+        float h;
+        if (pass >= 0)
+            h = t == pass ? 1.0f : 0.0f;
+        else if (k.mode & ART_MODE_INTERP) {
+            const double a = ra[t], b = rb[t];
+            h = (float) (a + f * (b - a));
+        }
+        else
+            h = ra[t];
+        dst[t] = h;
+    }
+}
+
+/* ---- 2. the banded product --------------------------------------------------------------------- */
+template <int CV>
+__global__ void __launch_bounds__ (ART_P_THREADS, 2)
+art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_constant__ ArtJob single,
+                          const ArtJob *__restrict__ jobs)
+{
+    typedef typename ArtPVec<CV>::type VecT;
+    constexpr int QT = 8 / CV;                                  // periods per warp tile
+
+    extern __shared__ __align__ (16) unsigned char smem_raw[];
+    float *Hs = reinterpret_cast<float *> (smem_raw);            // [rows][NIg][8][32]
+    float *xs = Hs + (size_t) p.rowsPerCta * 8 * p.Kp;           // [Wc][CV]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int seg = jobs ? (k.numJobs > 1 ? art_find_job_p (jobs, k.numJobs, blockIdx.x) : 0) : 0;
+    const ArtJob &job = jobs ? jobs[seg] : single;
+    const int L = p.L, M = p.M, T = k.T;
+    const int Q = (int) ((job.outputs + L - 1) / L);             // periods in this segment
+    const int R = (L + 7) >> 3;                                   // phase rows
+    const int PB = (R + p.rowsPerCta - 1) / p.rowsPerCta;         // phase blocks
+    const int local = blockIdx.x - job.tile0;
+    const int pb = local % PB, qb = local / PB;                   // phase block fastest: neighbours share input in L2
+    const int row0 = pb * p.rowsPerCta;
+    const int nrows = min (p.rowsPerCta, R - row0);
+    const int j0 = row0 * 8;
+    const int qStart = qb * p.Qblk, qEnd = min (Q, qStart + p.Qblk);
+    if (qStart >= qEnd)
+        return;
+    const int c0 = blockIdx.y * CV;
+    const int NIg = p.Kp >> 5;
+
+    const int *S = p.S + (size_t) seg * L;
+    const float *Hc = p.Hc + (size_t) seg * L * k.Tp;
+    const long long S0 = S[j0];
+
+    /* the CTA's filters, shifted to the common origin S0, laid out [row][step][phase][lane] */
+    for (int e = tid; e < nrows * 8 * p.Kp; e += ART_P_THREADS) {
+        const int jj = e / p.Kp, m = e - jj * p.Kp;
+        const int j = j0 + jj;
+        float v = 0.0f;
+        if (j < L) {
+            const int t = m - (int) (S[j] - S0);
+            if (t >= 0 && t < T)
+                v = Hc[(size_t) j * k.Tp + t];
+        }
+        Hs[(((jj >> 3) * NIg + (m >> 5)) * 8 + (jj & 7)) * 32 + (m & 31)] = v;
+    }
+
+    for (int q0 = qStart; q0 < qEnd; q0 += p.Qc) {
+        const int nq = min (p.Qc, qEnd - q0);
+        __syncthreads ();                                         // previous chunk fully consumed (and Hs visible)
+        /* stage the chunk's window: region [S0 + M*q0, ... + (nq-1)*M + Kp), channel-interleaved */
+        {
+            const long long a = S0 + (long long) M * q0;
+            const int len = (nq - 1) * M + p.Kp;
+            const int total = len * CV;
+            for (int e = tid; e < total; e += ART_P_THREADS) {
+                const int i = e / CV, v = e - i * CV;
+                xs[e] = (c0 + v < k.C) ? art_fetch (job, T, c0 + v, a + i) : 0.0f;
+            }
+        }
+        __syncthreads ();
+
+        const int qTiles = (nq + QT - 1) / QT;
+        for (int tile = warp; tile < nrows * qTiles; tile += ART_P_WARPS) {
+            const int row = tile % nrows, qloc = (tile / nrows) * QT;
+
+            float acc[8][8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) acc[a][b] = 0.0f;
+
+            const float *hp = Hs + (size_t) row * NIg * 256 + lane;
+            const VecT *xp[QT];
+#pragma unroll
+            for (int qq = 0; qq < QT; ++qq)
+                xp[qq] = reinterpret_cast<const VecT *> (xs) + (size_t) min (qloc + qq, p.Qc - 1) * M + lane;
+
+#pragma unroll 2
+            for (int i = 0; i < NIg; ++i) {
+                float h[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj)
+                    h[jj] = hp[(i * 8 + jj) * 32];
+#pragma unroll
+                for (int qq = 0; qq < QT; ++qq) {
+                    const VecT xv = xp[qq][32 * i];
+#pragma unroll
+                    for (int v = 0; v < CV; ++v) {
+                        const float x = ArtPVec<CV>::get (xv, v);
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj)
+                            acc[jj][qq * CV + v] = fmaf (h[jj], x, acc[jj][qq * CV + v]);
+                    }
+                }
+            }
+
+            /* reduce across lanes: value index = col * 8 + jj, so that consecutive lanes hold consecutive
+             * phases = consecutive output frames */
+#pragma unroll
+            for (int halfSel = 0; halfSel < 2; ++halfSel) {
+                float vals[32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj)
+                        vals[c * 8 + jj] = acc[jj][halfSel * 4 + c];
+                const float total = art_transpose_reduce<32, float> (vals, lane);
+                const int col = halfSel * 4 + (lane >> 3), jj = lane & 7;
+                const int qq = col / CV, v = col - qq * CV;
+                const int j = j0 + row * 8 + jj;
+                const long long nl = (long long) (q0 + qloc + qq) * L + j;        // output index inside the segment
+                if (j < L && qloc + qq < nq && nl < (long long) job.outputs && c0 + v < k.C)
+                    *art_out_ptr (job, c0 + v, (long long) job.nStart + nl) = total;
+            }
+        }
+    }
+}
+
+/* ---- host side ----------------------------------------------------------------------------------- */
+
+/* Smallest-denominator fraction L/M equal to `ratio` within double rounding, L <= maxL. */
+bool artRational (double ratio, int maxL, int *Lout, int *Mout)
+{
+    if (!(ratio > 1e-6) || !(ratio < 1e6))
+        return false;
+    double x = ratio;
+    long long p0 = 0, q0 = 1, p1 = 1, q1 = 0;                    // convergents p/q of ratio
+    for (int it = 0; it < 64; ++it) {
+        const double a = floor (x);
+        if (a > 1e9) break;
+        const long long p2 = (long long) a * p1 + p0, q2 = (long long) a * q1 + q0;
+        if (p2 > maxL || q2 > (1LL << 30)) break;
+        p0 = p1; q0 = q1; p1 = p2; q1 = q2;
+        if (q1 > 0) {
+            const double err = fabs ((double) p1 / (double) q1 - ratio);
+            if (err <= 4.0e-16 * ratio) {
+                // the period must close on the input axis too: L / ratio == M to rounding
+                if (fabs ((double) p1 / ratio - (double) q1) <= 1e-12 * (double) q1) {
+                    *Lout = (int) p1; *Mout = (int) q1;
+                    return true;
+                }
+                return false;
+            }
+        }
+        const double fr = x - a;
+        if (fr < 1e-15) break;
+        x = 1.0 / fr;
+    }
+    return false;
+}
+
+static size_t periodic_smem (const ArtPeriodic &p, int CV)
+{
+    return ((size_t) p.rowsPerCta * 8 * p.Kp + (size_t) p.Wc * CV) * sizeof (float) + 16;
+}
+
+/* Tile geometry for one launch; returns false when the periodic form does not pay or fit. */
+bool artPlanPeriodic (const ArtClass &k, double ratio, unsigned int maxOutputs, int smCount, ArtPeriodic &p, int &CV)
+{
+    int L, M;
+    if (k.mode & ART_MODE_PRECISE) return false;                 // double accumulation: generic kernel
+    if (!artRational (ratio, 1024, &L, &M)) return false;
+    if (L < 5) return false;                                      // an 8-phase tile would idle: generic kernel
+    if (maxOutputs < (unsigned) (4 * L)) return false;
+    CV = k.C >= 4 ? 4 : (k.C >= 2 ? 2 : 1);
+    const int QT = 8 / CV;
+    const size_t budget = 110 * 1024;
+
+    p.L = L; p.M = M;
+    const int R = (L + 7) / 8;
+    int bestRows = 0, bestQc = 0;
+    double bestScore = 0.0;
+    for (int rows = ART_P_ROWS_MAX; rows >= 1; --rows) {
+        // shifts inside a phase block: consecutive phases advance by M/L samples
+        const int spread = (int) (((long long) (rows * 8 - 1) * M + L - 1) / L) + 2;
+        const int Kp = (k.T + spread + 31) & ~31;
+        for (int Qc = 64; Qc >= QT; Qc -= QT) {
+            ArtPeriodic t = p;
+            t.rowsPerCta = rows; t.Kp = Kp; t.Qc = Qc; t.Wc = (Qc - 1) * M + Kp;
+            if (periodic_smem (t, CV) > budget) continue;
+            // staged input is reused by rows*8 phases, the filters by Qc periods: weigh both, prefer
+            // enough tiles per chunk to keep 8 warps busy
+            const int tiles = rows * (Qc / QT);
+            double score = (double) rows * 8 * Qc / (rows * 8 + Qc) * (tiles >= 8 ? 1.0 : tiles / 8.0);
+            score *= (double) k.T / Kp;                           // union-window padding is wasted FMAs
+            const int usedRows = (R + rows - 1) / rows * rows;
+            score *= (double) R / usedRows;                       // idle rows in the last phase block
+            if (score > bestScore) { bestScore = score; bestRows = rows; bestQc = Qc; }
+            break;                                                // largest Qc that fits for this row count
+        }
+    }
+    if (!bestRows) return false;
+    p.rowsPerCta = bestRows;
+    {
+        const int spread = (int) (((long long) (bestRows * 8 - 1) * M + L - 1) / L) + 2;
+        p.Kp = (k.T + spread + 31) & ~31;
+    }
+    p.Qc = bestQc;
+    p.Wc = (p.Qc - 1) * M + p.Kp;
+    // periods per CTA: a few chunks, but keep the grid a few waves deep
+    const int PB = (R + p.rowsPerCta - 1) / p.rowsPerCta;
+    const long long periods = (maxOutputs + L - 1) / L;
+    int chunks = 8;
+    while (chunks > 1 && periods / ((long long) p.Qc * chunks) * PB < (long long) smCount * 2)
+        chunks >>= 1;
+    p.Qblk = p.Qc * chunks;
+    return true;
+}
+
+/* longest segment whose drift from exact periodicity stays below ~1e-9 sample */
+unsigned int artPeriodicSegmentOutputs (const ArtPeriodic &p, double ratio)
+{
+    const double perPeriod = fabs ((double) p.L / ratio - (double) p.M) + 4.0e-16 * p.M;
+    double periods = 1.0e-9 / perPeriod;
+    if (periods > 1.0e6) periods = 1.0e6;
+    if (periods < 64.0) periods = 64.0;
+    return (unsigned int) periods * (unsigned int) p.L;
+}
+
+int artPeriodicCtas (const ArtPeriodic &p, unsigned int outputs)
+{
+    const int R = (p.L + 7) / 8, PB = (R + p.rowsPerCta - 1) / p.rowsPerCta;
+    const long long Q = ((long long) outputs + p.L - 1) / p.L;
+    return (int) (PB * ((Q + p.Qblk - 1) / p.Qblk));
+}
+
+template <int CV>
+static void launch_periodic (const ArtClass &k, const ArtPeriodic &p, int totalCtas, int numSegs,
+                             const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream)
+{
+    auto kern = art_sinc_periodic_kernel<CV>;
+    static size_t configured[16] = { 0 };
+    int device = 0;
+    ART_CUDA_CHECK (cudaGetDevice (&device));
+    const size_t smem = periodic_smem (p, CV);
+    if (smem > configured[device & 15]) {
+        ART_CUDA_CHECK (cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        configured[device & 15] = 112 * 1024;
+    }
+    dim3 tgrid (p.L, numSegs);
+    art_phase_table_kernel<<<tgrid, 128, 0, stream>>> (k, p, single, d_jobs);
+    ART_CUDA_CHECK (cudaGetLastError ());
+    dim3 grid (totalCtas, (k.C + CV - 1) / CV);
+    void *prof;
+    artProfileBegin (stream, &prof);
+    kern<<<grid, ART_P_THREADS, smem, stream>>> (k, p, single, d_jobs);
+    artProfileEnd (stream, prof);
+    ART_CUDA_CHECK (cudaGetLastError ());
+    g_artLaunches += 2;
+}
+
+void artLaunchPeriodic (const ArtClass &k, const ArtPeriodic &p, int CV, int totalCtas, int numSegs,
+                        const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream)
+{
+    if (totalCtas <= 0) return;
+    if (CV == 4) launch_periodic<4> (k, p, totalCtas, numSegs, single, d_jobs, stream);
+    else if (CV == 2) launch_periodic<2> (k, p, totalCtas, numSegs, single, d_jobs, stream);
+    else launch_periodic<1> (k, p, totalCtas, numSegs, single, d_jobs, stream);
+}

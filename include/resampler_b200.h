@@ -24,6 +24,8 @@ int  resampleB200SetDevice (int device);                 /* 0 on success */
 int  resampleB200GetDeviceCount (void);
 void resampleB200Synchronize (Resample *cxt);            /* wait for the context's private stream */
 unsigned long long resampleB200KernelLaunches (void);    /* kernels launched by this library so far */
+/* how many convolution launches went to the any-ratio kernel and to the rational-ratio kernel */
+void resampleB200PathCounts (unsigned long long *generic, unsigned long long *periodic);
 /* measurement aid: when enabled, every convolution kernel launch is bracketed by CUDA events on its
  * own stream; Collect waits for them, returns how many launches were timed and their summed
  * duration in milliseconds, and clears the list */

@@ -228,3 +228,34 @@ def test_size_independent_properties_full_size():
     o.advance(190)
     yo, _, _ = o.process(a[:20000], cap, ratio)
     assert A.peak_error(ya[:yo.shape[0] - 400], yo[:-400]) <= TOL
+
+
+def test_kernel_selection():
+    """Rational ratios with a small numerator must run on the periodic kernel, everything else on the
+    generic one -- and both must agree with each other on a ratio both can take."""
+    import ctypes as C
+    import os
+    lib = A.product()
+    lib.resampleB200PathCounts.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+
+    def counts():
+        g, p = C.c_ulonglong(), C.c_ulonglong()
+        lib.resampleB200PathCounts(C.byref(g), C.byref(p))
+        return g.value, p.value
+
+    rng = np.random.default_rng(20)
+    x = rng.uniform(-0.5, 0.5, (20000, 2)).astype(np.float32)
+    s = A.product_stream(2, 380, 380, 0.0); s.advance(190)
+    g0, p0 = counts()
+    y_per, _, _ = s.process(x, 30000, 48000 / 44100)
+    g1, p1 = counts()
+    assert (g1 - g0, p1 - p0) == (0, 1)
+    s2 = A.product_stream(2, 380, 380, 0.0); s2.advance(190)
+    y_gen, _, _ = s2.process(x, 30000, 0.91234567)                 # no small-numerator fraction
+    g2, p2 = counts()
+    assert (g2 - g1, p2 - p1) == (1, 0)
+    s3 = A.product_stream(2, 380, 380, 0.0, flags=BH_INTERP | A.EXTEND_CONVOLUTION_MATH); s3.advance(190)
+    y_prec, _, _ = s3.process(x, 30000, 48000 / 44100)             # double accumulation: generic kernel
+    g3, p3 = counts()
+    assert (g3 - g2, p3 - p2) == (1, 0)
+    assert A.peak_error(y_per, y_prec) <= 3e-7                     # the two kernels, same stream

@@ -294,7 +294,7 @@ static void plan_launch (ArtDev *lead, double minRatio, bool oneRatio, unsigned 
         return;
     const unsigned int total32 = (unsigned int) (totalOut > 0xffffffffULL ? 0xffffffffULL : totalOut);
     if (allowPeriodic && oneRatio && !g_forceGeneric &&
-        artPlanPeriodic (lp.k, minRatio, maxOut, lead->smCount, lp.per, lp.CV)) {
+        artPlanPeriodic (lp.k, minRatio, maxOut, totalOut, lead->smCount, lp.per, lp.CV)) {
         lp.periodic = true;
         lp.segLen = artPeriodicSegmentOutputs (lp.per, minRatio);
         return;
@@ -349,11 +349,12 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
     }
     if (ctas > 0) {
         if (lp.periodic) {
-            const size_t tableFloats = (size_t) n * lp.per.L * lp.k.Tp, tableInts = (size_t) n * lp.per.L;
+            const size_t tableFloats = (size_t) n * lp.per.PB * lp.per.rowsPerCta * 8 * lp.per.Kp;
+            const size_t tableInts = (size_t) n * lp.per.PB;
             void *tables = nullptr;
             ART_CUDA_CHECK (cudaMallocAsync (&tables, tableFloats * sizeof (float) + tableInts * sizeof (int), stream));
-            lp.per.Hc = reinterpret_cast<float *> (tables);
-            lp.per.S = reinterpret_cast<int *> (lp.per.Hc + tableFloats);
+            lp.per.Hblk = reinterpret_cast<float *> (tables);
+            lp.per.S0 = reinterpret_cast<int *> (lp.per.Hblk + tableFloats);
             artLaunchPeriodic (lp.k, lp.per, lp.CV, ctas, n, jobs[0], d_jobs, stream);
             ++g_pathLaunches[1];
             ART_CUDA_CHECK (cudaFreeAsync (tables, stream));

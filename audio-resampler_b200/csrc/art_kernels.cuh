@@ -62,8 +62,10 @@ struct ArtPeriodic {
     int Qc;              // periods per staged chunk
     int Qblk;            // periods per CTA
     int Wc;              // staged samples per chunk = (Qc - 1) * M + Kp
-    float *Hc;           // [segments][L][Tp]  interpolated filter of every phase
-    int   *S;            // [segments][L]      region index of the first tap, period 0
+    int PB;              // phase blocks = ceil(ceil(L / 8) / rowsPerCta)
+    float *Hblk;         // [segments][PB][rowsPerCta*8*Kp]  interpolated filters of a phase block, already
+                         //   shifted to the block's origin and in the kernel's shared-memory layout
+    int   *S0;           // [segments][PB]  region index of the block's first tap, period 0
 };
 
 /* Sum NV register values per lane across the warp so that lane L ends up with the total of
@@ -115,7 +117,8 @@ void artLaunchGeneric (const ArtClass &k, const ArtLaunchGeom &g, const ArtJob &
 void artLaunchHistory (const ArtClass &k, const ArtJob &single, const ArtJob *d_jobs, int numJobs, cudaStream_t stream);
 
 bool artRational (double ratio, int maxL, int *L, int *M);
-bool artPlanPeriodic (const ArtClass &k, double ratio, unsigned int maxOutputs, int smCount, ArtPeriodic &p, int &CV);
+bool artPlanPeriodic (const ArtClass &k, double ratio, unsigned int maxOutputs, unsigned long long totalOutputs,
+                      int smCount, ArtPeriodic &p, int &CV);
 unsigned int artPeriodicSegmentOutputs (const ArtPeriodic &p, double ratio);
 int  artPeriodicCtas (const ArtPeriodic &p, unsigned int outputs);
 void artLaunchPeriodic (const ArtClass &k, const ArtPeriodic &p, int CV, int totalCtas, int numSegs,

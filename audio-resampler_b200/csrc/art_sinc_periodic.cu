@@ -56,7 +56,47 @@ __device__ __forceinline__ int art_find_job_p (const ArtJob *jobs, int numJobs, 
     return lo;
 }
 
+/* ---- TMA bulk copy + mbarrier (sm_90+/sm_100: cp.async.bulk -> SASS UBLKCP) ---------------------- */
+__device__ __forceinline__ unsigned int art_smem_u32 (const void *p)
+{
+    return (unsigned int) __cvta_generic_to_shared (p);
+}
+__device__ __forceinline__ void art_mbar_init (unsigned long long *bar, unsigned int count)
+{
+    asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(art_smem_u32 (bar)), "r"(count));
+    asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void art_mbar_expect_tx (unsigned long long *bar, unsigned int bytes)
+{
+    asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(art_smem_u32 (bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void art_mbar_wait (unsigned long long *bar, unsigned int parity)
+{
+    // try_wait suspends the thread for a bounded time itself; the spin limit only turns a lost copy
+    // (a bug) into a trap instead of a hung GPU
+    for (unsigned int spins = 0; spins < (1u << 26); ++spins) {
+        unsigned int done;
+        asm volatile (
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(art_smem_u32 (bar)), "r"(parity) : "memory");
+        if (done) return;
+    }
+    printf ("libresampler_b200: bulk copy never completed (block %d)\n", blockIdx.x);
+    __trap ();
+}
+/* bytes must be a multiple of 16, both addresses 16-byte aligned */
+__device__ __forceinline__ void art_bulk_g2s (void *dstSmem, const void *srcGlobal, unsigned int bytes, unsigned long long *bar)
+{
+    asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                  :: "r"(art_smem_u32 (dstSmem)), "l"(srcGlobal), "r"(bytes), "r"(art_smem_u32 (bar)) : "memory");
+}
+
 /* ---- 1. the phase table ----------------------------------------------------------------------- */
+/* One block per (padded) phase.  Writes the phase's interpolated filter straight into the layout the
+ * product kernel keeps in shared memory: [row][step][phase-in-row][lane], shifted so that tap 0 of the
+ * phase block's first phase sits at m = 0. */
 __global__ void __launch_bounds__ (128)
 art_phase_table_kernel (const ArtClass k, const ArtPeriodic p, const __grid_constant__ ArtJob single,
                         const ArtJob *__restrict__ jobs)
@@ -64,48 +104,62 @@ art_phase_table_kernel (const ArtClass k, const ArtPeriodic p, const __grid_cons
     const int j = blockIdx.x, seg = blockIdx.y;
     const ArtJob &job = jobs ? jobs[seg] : single;
     const int T = k.T, half = T / 2, F = k.F;
-    __shared__ int sh_row, sh_pass;
+    const int perBlock = p.rowsPerCta * 8;
+    const int pb = j / perBlock, jj = j - pb * perBlock, jb = pb * perBlock;
+    __shared__ int sh_row, sh_pass, sh_shift;
     __shared__ double sh_f;
 
     if (threadIdx.x == 0) {
         ArtLoopState st;
         st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = T;
-        int w;
-        const double pos = art_output_pos (&st, job.nStart + j, &w);
-        const double whole = floor (pos), fr = pos - whole;
-        const long long s = (long long) whole - half + 1 + (long long) w * 15LL * T - job.origin;
-        int row, pass = -1;
+        long long sj = 0, sb = 0;
+        int row = 0, pass = -1;
         double f = 0.0;
-        if (k.mode & ART_MODE_INTERP) {
-            double ph = fr * F;                                  // resampler.c:1149-1152
-            row = (int) floor (ph);
-            f = ph - row;
-            if (row >= F) { row = F - 1; f = 1.0; }
+        for (int which = 0; which < 2; ++which) {               // 0: the block's first phase, 1: this phase
+            const int ph = which ? j : jb;
+            if (ph >= p.L) break;
+            int w;
+            const double pos = art_output_pos (&st, job.nStart + ph, &w);
+            const double whole = floor (pos), fr = pos - whole;
+            const long long s = (long long) whole - half + 1 + (long long) w * 15LL * T - job.origin;
+            if (!which) { sb = s; continue; }
+            sj = s;
+            if (k.mode & ART_MODE_INTERP) {
+                double phs = fr * F;                             // resampler.c:1149-1152
+                row = (int) floor (phs);
+                f = phs - row;
+                if (row >= F) { row = F - 1; f = 1.0; }
+            }
+            else {
+                row = (int) floor (fr * F + 0.5);                // resampler.c:1137
+                if (!(k.mode & ART_MODE_LOWPASS) && row % F == 0)    // resampler.c:1141-1142
+                    pass = half - 1 + (row ? 1 : 0);
+            }
         }
-        else {
-            row = (int) floor (fr * F + 0.5);                    // resampler.c:1137
-            if (!(k.mode & ART_MODE_LOWPASS) && row % F == 0)    // resampler.c:1141-1142
-                pass = half - 1 + (row ? 1 : 0);
-        }
-        sh_row = row; sh_f = f; sh_pass = pass;
-        p.S[(size_t) seg * p.L + j] = (int) s;
+        sh_row = row; sh_f = f; sh_pass = pass; sh_shift = (int) (sj - sb);
+        if (j == jb)
+            p.S0[(size_t) seg * p.PB + pb] = (int) sb;
     }
     __syncthreads ();
-    const int row = sh_row, pass = sh_pass;
+    const int row = sh_row, pass = sh_pass, shift = sh_shift;
     const double f = sh_f;
-    float *dst = p.Hc + ((size_t) seg * p.L + j) * k.Tp;
+    const int NIg = p.Kp >> 5;
+    float *dst = p.Hblk + ((size_t) seg * p.PB + pb) * perBlock * p.Kp;
     const float *ra = k.bank + (size_t) row * k.Tp, *rb = ra + k.Tp;
-    for (int t = threadIdx.x; t < k.Tp; t += blockDim.x) {
-        float h;
-        if (pass >= 0)
-            h = t == pass ? 1.0f : 0.0f;
-        else if (k.mode & ART_MODE_INTERP) {
-            const double a = ra[t], b = rb[t];
-            h = (float) (a + f * (b - a));
+    for (int m = threadIdx.x; m < p.Kp; m += blockDim.x) {
+        const int t = m - shift;
+        float h = 0.0f;
+        if (j < p.L && t >= 0 && t < T) {
+            if (pass >= 0)
+                h = t == pass ? 1.0f : 0.0f;
+            else if (k.mode & ART_MODE_INTERP) {
+                const double a = ra[t], b = rb[t];
+                h = (float) (a + f * (b - a));
+            }
+            else
+                h = ra[t];
         }
-        else
-            h = ra[t];
-        dst[t] = h;
+        dst[(((jj >> 3) * NIg + (m >> 5)) * 8 + (jj & 7)) * 32 + (m & 31)] = h;
     }
 }
 
@@ -118,9 +172,10 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
     typedef typename ArtPVec<CV>::type VecT;
     constexpr int QT = 8 / CV;                                  // periods per warp tile
 
-    extern __shared__ __align__ (16) unsigned char smem_raw[];
+    extern __shared__ __align__ (128) unsigned char smem_raw[];
     float *Hs = reinterpret_cast<float *> (smem_raw);            // [rows][NIg][8][32]
-    float *xs = Hs + (size_t) p.rowsPerCta * 8 * p.Kp;           // [Wc][CV]
+    float *xsRaw = Hs + (size_t) p.rowsPerCta * 8 * p.Kp;        // [Wc + 4][CV] (+4: alignment slack of the bulk copy)
+    __shared__ __align__ (8) unsigned long long bars[2];         // [0] filters, [1] input chunk
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int seg = jobs ? (k.numJobs > 1 ? art_find_job_p (jobs, k.numJobs, blockIdx.x) : 0) : 0;
@@ -128,9 +183,8 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
     const int L = p.L, M = p.M, T = k.T;
     const int Q = (int) ((job.outputs + L - 1) / L);             // periods in this segment
     const int R = (L + 7) >> 3;                                   // phase rows
-    const int PB = (R + p.rowsPerCta - 1) / p.rowsPerCta;         // phase blocks
     const int local = blockIdx.x - job.tile0;
-    const int pb = local % PB, qb = local / PB;                   // phase block fastest: neighbours share input in L2
+    const int pb = local % p.PB, qb = local / p.PB;               // phase block fastest: neighbours share input in L2
     const int row0 = pb * p.rowsPerCta;
     const int nrows = min (p.rowsPerCta, R - row0);
     const int j0 = row0 * 8;
@@ -139,38 +193,61 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
         return;
     const int c0 = blockIdx.y * CV;
     const int NIg = p.Kp >> 5;
+    const long long S0 = p.S0[(size_t) seg * p.PB + pb];
 
-    const int *S = p.S + (size_t) seg * L;
-    const float *Hc = p.Hc + (size_t) seg * L * k.Tp;
-    const long long S0 = S[j0];
-
-    /* the CTA's filters, shifted to the common origin S0, laid out [row][step][phase][lane] */
-    for (int e = tid; e < nrows * 8 * p.Kp; e += ART_P_THREADS) {
-        const int jj = e / p.Kp, m = e - jj * p.Kp;
-        const int j = j0 + jj;
-        float v = 0.0f;
-        if (j < L) {
-            const int t = m - (int) (S[j] - S0);
-            if (t >= 0 && t < T)
-                v = Hc[(size_t) j * k.Tp + t];
-        }
-        Hs[(((jj >> 3) * NIg + (m >> 5)) * 8 + (jj & 7)) * 32 + (m & 31)] = v;
+    if (tid == 0) {
+        art_mbar_init (&bars[0], 1);
+        art_mbar_init (&bars[1], 1);
     }
+    __syncthreads ();
+    /* the CTA's filters: one bulk copy of the block the table kernel laid out */
+    if (tid == 0) {
+        const unsigned int bytes = (unsigned int) (p.rowsPerCta * 8 * p.Kp * sizeof (float));
+        art_mbar_expect_tx (&bars[0], bytes);
+        art_bulk_g2s (Hs, p.Hblk + ((size_t) seg * p.PB + pb) * p.rowsPerCta * 8 * p.Kp, bytes, &bars[0]);
+    }
+
+    // the bulk path needs the chunk to be one contiguous, fully valid span of the caller's interleaved block
+    const bool bulkOk = (job.inPlanes == nullptr) && job.inCS == 1 && job.inFS == CV && k.C == CV;
+    unsigned int xPhase = 0;
+    bool filtersReady = false;
 
     for (int q0 = qStart; q0 < qEnd; q0 += p.Qc) {
         const int nq = min (p.Qc, qEnd - q0);
-        __syncthreads ();                                         // previous chunk fully consumed (and Hs visible)
-        /* stage the chunk's window: region [S0 + M*q0, ... + (nq-1)*M + Kp), channel-interleaved */
-        {
-            const long long a = S0 + (long long) M * q0;
-            const int len = (nq - 1) * M + p.Kp;
+        const long long a = S0 + (long long) M * q0;             // region index of the chunk's first sample
+        const int len = (nq - 1) * M + p.Kp;                      // samples per channel
+        __syncthreads ();                                         // previous chunk fully consumed
+
+        int xoff = 0;                                             // float offset of sample 0 inside xsRaw
+        const float *g = job.in + a * CV;
+        const bool fast = bulkOk && a >= -job.prevAvail && a + len + 4 <= (long long) job.inValid;
+        if (fast) {
+            // align the source down to 16 bytes; the same slack appears in front of the data in shared memory
+            xoff = (int) ((reinterpret_cast<unsigned long long> (g) >> 2) & 3);
+            if (tid == 0) {
+                const unsigned int bytes = (unsigned int) (((size_t) len * CV + xoff + 3) & ~(size_t) 3) * sizeof (float);
+                art_mbar_expect_tx (&bars[1], bytes);
+                art_bulk_g2s (xsRaw, g - xoff, bytes, &bars[1]);
+            }
+        }
+        else {
             const int total = len * CV;
             for (int e = tid; e < total; e += ART_P_THREADS) {
                 const int i = e / CV, v = e - i * CV;
-                xs[e] = (c0 + v < k.C) ? art_fetch (job, T, c0 + v, a + i) : 0.0f;
+                xsRaw[e] = (c0 + v < k.C) ? art_fetch (job, T, c0 + v, a + i) : 0.0f;
             }
         }
-        __syncthreads ();
+        if (!filtersReady) {
+            art_mbar_wait (&bars[0], 0);
+            filtersReady = true;
+        }
+        if (fast) {
+            art_mbar_wait (&bars[1], xPhase);
+            xPhase ^= 1;
+        }
+        else
+            __syncthreads ();
+        const float *xs = xsRaw + xoff;
 
         const int qTiles = (nq + QT - 1) / QT;
         for (int tile = warp; tile < nrows * qTiles; tile += ART_P_WARPS) {
@@ -178,9 +255,9 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
 
             float acc[8][8];
 #pragma unroll
-            for (int a = 0; a < 8; ++a)
+            for (int a2 = 0; a2 < 8; ++a2)
 #pragma unroll
-                for (int b = 0; b < 8; ++b) acc[a][b] = 0.0f;
+                for (int b2 = 0; b2 < 8; ++b2) acc[a2][b2] = 0.0f;
 
             const float *hp = Hs + (size_t) row * NIg * 256 + lane;
             const VecT *xp[QT];
@@ -264,11 +341,12 @@ bool artRational (double ratio, int maxL, int *Lout, int *Mout)
 
 static size_t periodic_smem (const ArtPeriodic &p, int CV)
 {
-    return ((size_t) p.rowsPerCta * 8 * p.Kp + (size_t) p.Wc * CV) * sizeof (float) + 16;
+    return ((size_t) p.rowsPerCta * 8 * p.Kp + (size_t) (p.Wc + 4) * CV) * sizeof (float) + 128;
 }
 
 /* Tile geometry for one launch; returns false when the periodic form does not pay or fit. */
-bool artPlanPeriodic (const ArtClass &k, double ratio, unsigned int maxOutputs, int smCount, ArtPeriodic &p, int &CV)
+bool artPlanPeriodic (const ArtClass &k, double ratio, unsigned int maxOutputs, unsigned long long totalOutputs,
+                      int smCount, ArtPeriodic &p, int &CV)
 {
     int L, M;
     if (k.mode & ART_MODE_PRECISE) return false;                 // double accumulation: generic kernel
@@ -310,11 +388,13 @@ bool artPlanPeriodic (const ArtClass &k, double ratio, unsigned int maxOutputs, 
     }
     p.Qc = bestQc;
     p.Wc = (p.Qc - 1) * M + p.Kp;
-    // periods per CTA: a few chunks, but keep the grid a few waves deep
-    const int PB = (R + p.rowsPerCta - 1) / p.rowsPerCta;
-    const long long periods = (maxOutputs + L - 1) / L;
-    int chunks = 8;
-    while (chunks > 1 && periods / ((long long) p.Qc * chunks) * PB < (long long) smCount * 2)
+    // periods per CTA: several chunks (the filter block is fetched once per CTA), but keep the whole
+    // launch a few waves deep
+    p.PB = (R + p.rowsPerCta - 1) / p.rowsPerCta;
+    const long long periods = (long long) ((totalOutputs + L - 1) / L);
+    const int groups = (k.C + CV - 1) / CV;
+    int chunks = 16;
+    while (chunks > 1 && periods / ((long long) p.Qc * chunks) * p.PB * groups < (long long) smCount * 4)
         chunks >>= 1;
     p.Qblk = p.Qc * chunks;
     return true;
@@ -332,9 +412,8 @@ unsigned int artPeriodicSegmentOutputs (const ArtPeriodic &p, double ratio)
 
 int artPeriodicCtas (const ArtPeriodic &p, unsigned int outputs)
 {
-    const int R = (p.L + 7) / 8, PB = (R + p.rowsPerCta - 1) / p.rowsPerCta;
     const long long Q = ((long long) outputs + p.L - 1) / p.L;
-    return (int) (PB * ((Q + p.Qblk - 1) / p.Qblk));
+    return (int) (p.PB * ((Q + p.Qblk - 1) / p.Qblk));
 }
 
 template <int CV>
@@ -350,7 +429,7 @@ static void launch_periodic (const ArtClass &k, const ArtPeriodic &p, int totalC
         ART_CUDA_CHECK (cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         configured[device & 15] = 112 * 1024;
     }
-    dim3 tgrid (p.L, numSegs);
+    dim3 tgrid (p.PB * p.rowsPerCta * 8, numSegs);
     art_phase_table_kernel<<<tgrid, 128, 0, stream>>> (k, p, single, d_jobs);
     ART_CUDA_CHECK (cudaGetLastError ());
     dim3 grid (totalCtas, (k.C + CV - 1) / CV);

@@ -341,6 +341,29 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
     bool anyHist = false;
     for (const ArtJob &j : jobs) anyHist |= j.histOut != nullptr;
 
+    // periodic kernel: jobs whose filters coincide share one phase table.  The table depends on the
+    // fractional read position of every phase, i.e. on (P, I, ratio, first output); contexts driven in
+    // lock step (the usual many-stream case) collapse to a single table.
+    int numTables = 0;
+    if (lp.periodic && ctas > 0) {
+        std::vector<int> reps;
+        for (int i = 0; i < n; ++i) {
+            int t = -1;
+            for (size_t r = 0; r < reps.size () && t < 0; ++r) {
+                const ArtJob &o = jobs[reps[r]];
+                if (o.P == jobs[i].P && o.I == jobs[i].I && o.ratio == jobs[i].ratio &&
+                    o.nStart == jobs[i].nStart && o.origin == jobs[i].origin)
+                    t = (int) r;
+                if (r >= 64) break;                     // keep the search linear; beyond that just add tables
+            }
+            if (t < 0) { t = (int) reps.size (); reps.push_back (i); }
+            jobs[i].table = t;
+        }
+        numTables = (int) reps.size ();
+        for (int t = 0; t < numTables; ++t)
+            jobs[t].repJob = reps[t];
+    }
+
     ArtJob *d_jobs = nullptr;
     if (n > 1) {
         ART_CUDA_CHECK (cudaMallocAsync (&d_jobs, sizeof (ArtJob) * n, stream));
@@ -349,13 +372,13 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
     }
     if (ctas > 0) {
         if (lp.periodic) {
-            const size_t tableFloats = (size_t) n * lp.per.PB * lp.per.rowsPerCta * 8 * lp.per.Kp;
+            const size_t tableFloats = (size_t) numTables * lp.per.PB * lp.per.rowsPerCta * 8 * lp.per.Kp;
             const size_t tableInts = (size_t) n * lp.per.PB;
             void *tables = nullptr;
             ART_CUDA_CHECK (cudaMallocAsync (&tables, tableFloats * sizeof (float) + tableInts * sizeof (int), stream));
             lp.per.Hblk = reinterpret_cast<float *> (tables);
             lp.per.S0 = reinterpret_cast<int *> (lp.per.Hblk + tableFloats);
-            artLaunchPeriodic (lp.k, lp.per, lp.CV, ctas, n, jobs[0], d_jobs, stream);
+            artLaunchPeriodic (lp.k, lp.per, lp.CV, ctas, n, numTables, jobs[0], d_jobs, stream);
             ++g_pathLaunches[1];
             ART_CUDA_CHECK (cudaFreeAsync (tables, stream));
         }

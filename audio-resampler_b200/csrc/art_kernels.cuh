@@ -42,6 +42,8 @@ struct ArtJob {
     long long     inFS, inCS, outFS, outCS;      // frame / channel strides in floats
     const float *const *inPlanes;    // optional per-channel pointer tables (device memory)
     float *const       *outPlanes;
+    int           table;             // periodic kernel: which phase table this job reads
+    int           repJob;            // periodic kernel: entry t holds the job whose state defines table t
 };
 
 struct ArtClass {
@@ -63,9 +65,9 @@ struct ArtPeriodic {
     int Qblk;            // periods per CTA
     int Wc;              // staged samples per chunk = (Qc - 1) * M + Kp
     int PB;              // phase blocks = ceil(ceil(L / 8) / rowsPerCta)
-    float *Hblk;         // [segments][PB][rowsPerCta*8*Kp]  interpolated filters of a phase block, already
+    float *Hblk;         // [tables][PB][rowsPerCta*8*Kp]  interpolated filters of a phase block, already
                          //   shifted to the block's origin and in the kernel's shared-memory layout
-    int   *S0;           // [segments][PB]  region index of the block's first tap, period 0
+    int   *S0;           // [jobs][PB]  region index of the block's first tap, period 0
 };
 
 /* Sum NV register values per lane across the warp so that lane L ends up with the total of
@@ -89,6 +91,23 @@ __device__ __forceinline__ AccT art_transpose_reduce (AccT (&v)[NV], int lane)
     for (; off >= 1; off >>= 1)
         v[0] += __shfl_xor_sync (0xffffffffu, v[0], off);
     return v[0];
+}
+
+/* packed FP32 pairs: fma.rn.f32x2 (SASS FFMA2) performs two IEEE fused multiply-adds per instruction;
+ * ptxas turns a {x, x} operand into a scalar broadcast, so (pair) x (scalar) + (pair) costs one issue slot */
+__device__ __forceinline__ unsigned long long art_pack2 (float lo, float hi)
+{
+    unsigned long long r;
+    asm ("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void art_unpack2 (unsigned long long v, float &lo, float &hi)
+{
+    asm ("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void art_ffma2 (unsigned long long &acc, unsigned long long a, unsigned long long b)
+{
+    asm ("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
 }
 
 __device__ __forceinline__ float art_fetch (const ArtJob &j, int T, int c, long long idx)
@@ -121,7 +140,7 @@ bool artPlanPeriodic (const ArtClass &k, double ratio, unsigned int maxOutputs, 
                       int smCount, ArtPeriodic &p, int &CV);
 unsigned int artPeriodicSegmentOutputs (const ArtPeriodic &p, double ratio);
 int  artPeriodicCtas (const ArtPeriodic &p, unsigned int outputs);
-void artLaunchPeriodic (const ArtClass &k, const ArtPeriodic &p, int CV, int totalCtas, int numSegs,
+void artLaunchPeriodic (const ArtClass &k, const ArtPeriodic &p, int CV, int totalCtas, int numJobs, int numTables,
                         const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream);
 
 extern unsigned long long g_artLaunches;

@@ -133,12 +133,110 @@ __device__ __forceinline__ void art_run_tile (const ArtTileCtx &t, const ArtJob 
     }
 }
 
+/* float32 version of art_run_tile built on packed FFMA2.  Interpolated: one accumulator pair per
+ * (output, channel) holds (row A sum, row B sum), the coefficient pair (A[k], B[k]) is packed once per
+ * tap and the sample is a scalar operand -- half the FMA issue slots of the scalar form.  Not
+ * interpolated: pairs run over adjacent channels instead. */
+template <bool INTERP, int CV, int SLOTS>
+__device__ __forceinline__ void art_run_tile_f32 (const ArtTileCtx &t, const ArtJob &job, const float *__restrict__ bank,
+                                                  int kk, int e0, int len, int lane)
+{
+    typedef typename ArtVec<CV>::type VecT;
+    constexpr int NP = INTERP ? CV : (CV >= 2 ? CV / 2 : 1);    // accumulator pairs per output
+    const float *__restrict__ rowA = bank + (size_t) kk * t.Tp + lane;
+    const float *__restrict__ rowB = rowA + t.Tp;
+    const int NI = t.Tp >> 5;
+
+    int off[SLOTS];
+    float f[SLOTS];
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) {
+        const int i = t.order[e0 + min (j, len - 1)];            // idle slots shadow the last real entry
+        off[j] = (int) ((long long) t.srel[i] - t.sFirst) + lane;
+        f[j] = t.wgt[i];
+    }
+
+    for (int cg = 0; cg < t.nc; cg += CV) {
+        unsigned long long acc2[SLOTS][NP];
+        float acc1[SLOTS];                                        // only for !INTERP && CV == 1
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j) {
+            acc1[j] = 0.0f;
+#pragma unroll
+            for (int v = 0; v < NP; ++v) acc2[j][v] = 0ull;
+        }
+
+        const VecT *xp[SLOTS];
+        const VecT *plane = reinterpret_cast<const VecT *> (t.xs) + (size_t) (cg / CV) * t.Wp;
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j)
+            xp[j] = plane + off[j];
+
+#pragma unroll 4
+        for (int i = 0; i < NI; ++i) {
+            const float ca = __ldg (rowA + 32 * i);
+            const float cb = INTERP ? __ldg (rowB + 32 * i) : ca;
+            const unsigned long long c2 = art_pack2 (ca, cb);     // (A, B) when interpolating, (A, A) otherwise
+#pragma unroll
+            for (int j = 0; j < SLOTS; ++j) {
+                const VecT xv = xp[j][32 * i];
+                if (INTERP) {
+#pragma unroll
+                    for (int v = 0; v < CV; ++v) {
+                        const float x = ArtVec<CV>::get (xv, v);
+                        art_ffma2 (acc2[j][v], c2, art_pack2 (x, x));
+                    }
+                }
+                else if (CV >= 2) {
+#pragma unroll
+                    for (int v = 0; v < CV; v += 2)
+                        art_ffma2 (acc2[j][v / 2], art_pack2 (ArtVec<CV>::get (xv, v), ArtVec<CV>::get (xv, v + 1)), c2);
+                }
+                else
+                    acc1[j] = fmaf (ca, ArtVec<CV>::get (xv, 0), acc1[j]);
+            }
+        }
+
+        float vals[SLOTS * CV];
+#pragma unroll
+        for (int j = 0; j < SLOTS; ++j) {
+            if (INTERP) {
+#pragma unroll
+                for (int v = 0; v < CV; ++v) {
+                    float a0, a1;
+                    art_unpack2 (acc2[j][v], a0, a1);
+                    vals[j * CV + v] = fmaf (f[j], a1 - a0, a0);
+                }
+            }
+            else if (CV >= 2) {
+#pragma unroll
+                for (int v = 0; v < CV; v += 2)
+                    art_unpack2 (acc2[j][v / 2], vals[j * CV + v], vals[j * CV + v + 1]);
+            }
+            else
+                vals[j * CV] = acc1[j];
+        }
+
+        const float total = art_transpose_reduce<SLOTS * CV, float> (vals, lane);
+        constexpr int LPV = 32 / (SLOTS * CV);                   // lanes holding the same value
+        const int q = lane / LPV, j = q / CV, v = q - j * CV;
+        if ((lane % LPV) == 0 && j < len && cg + v < t.nc)
+            *art_out_ptr (job, t.c0 + cg + v, (long long) t.n0 + t.order[e0 + j]) = total;
+    }
+}
+
+template <bool INTERP, bool PRECISE, int CV, int SLOTS>
+__device__ __forceinline__ void art_run_any (const ArtTileCtx &t, const ArtJob &job, const float *__restrict__ bank,
+                                             int kk, int e0, int len, int lane)
+{
+    if (PRECISE) art_run_tile<INTERP, double, CV, SLOTS> (t, job, bank, kk, e0, len, lane);
+    else         art_run_tile_f32<INTERP, CV, SLOTS> (t, job, bank, kk, e0, len, lane);
+}
+
 template <bool INTERP, bool PRECISE, int CV>
 __global__ void __launch_bounds__ (ART_G_THREADS, 2)
 art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single, const ArtJob *__restrict__ jobs)
 {
-    typedef typename std::conditional<PRECISE, double, float>::type AccT;
-
     extern __shared__ __align__ (16) unsigned char smem_raw[];
     const int nkeys = NUM_KEYS (k.F);
     const int nkeysPad = (nkeys + 2 + 3) & ~3;
@@ -315,10 +413,10 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
                 *art_out_ptr (job, c0 + cc, (long long) n0 + i) = xs[((cc / CV) * k.Wp + at) * CV + (cc % CV)];
             }
         }
-        else if (len > 4) art_run_tile<INTERP, AccT, CV, 8> (t, job, k.bank, kk, e0, len, lane);
-        else if (len > 2) art_run_tile<INTERP, AccT, CV, 4> (t, job, k.bank, kk, e0, len, lane);
-        else if (len > 1) art_run_tile<INTERP, AccT, CV, 2> (t, job, k.bank, kk, e0, len, lane);
-        else              art_run_tile<INTERP, AccT, CV, 1> (t, job, k.bank, kk, e0, len, lane);
+        else if (len > 4) art_run_any<INTERP, PRECISE, CV, 8> (t, job, k.bank, kk, e0, len, lane);
+        else if (len > 2) art_run_any<INTERP, PRECISE, CV, 4> (t, job, k.bank, kk, e0, len, lane);
+        else if (len > 1) art_run_any<INTERP, PRECISE, CV, 2> (t, job, k.bank, kk, e0, len, lane);
+        else              art_run_any<INTERP, PRECISE, CV, 1> (t, job, k.bank, kk, e0, len, lane);
     }
 }
 

@@ -95,14 +95,14 @@ __device__ __forceinline__ void art_bulk_g2s (void *dstSmem, const void *srcGlob
 
 /* ---- 1. the phase table ----------------------------------------------------------------------- */
 /* One block per (padded) phase.  Writes the phase's interpolated filter straight into the layout the
- * product kernel keeps in shared memory: [row][step][phase-in-row][lane], shifted so that tap 0 of the
- * phase block's first phase sits at m = 0. */
+ * product kernel keeps in shared memory: [row][step][half-row][lane][4 phases], shifted so that tap 0 of
+ * the phase block's first phase sits at m = 0. */
 __global__ void __launch_bounds__ (128)
 art_phase_table_kernel (const ArtClass k, const ArtPeriodic p, const __grid_constant__ ArtJob single,
                         const ArtJob *__restrict__ jobs)
 {
-    const int j = blockIdx.x, seg = blockIdx.y;
-    const ArtJob &job = jobs ? jobs[seg] : single;
+    const int j = blockIdx.x, tbl = blockIdx.y;
+    const ArtJob &job = jobs ? jobs[jobs[tbl].repJob] : single;
     const int T = k.T, half = T / 2, F = k.F;
     const int perBlock = p.rowsPerCta * 8;
     const int pb = j / perBlock, jj = j - pb * perBlock, jb = pb * perBlock;
@@ -137,14 +137,12 @@ art_phase_table_kernel (const ArtClass k, const ArtPeriodic p, const __grid_cons
             }
         }
         sh_row = row; sh_f = f; sh_pass = pass; sh_shift = (int) (sj - sb);
-        if (j == jb)
-            p.S0[(size_t) seg * p.PB + pb] = (int) sb;
     }
     __syncthreads ();
     const int row = sh_row, pass = sh_pass, shift = sh_shift;
     const double f = sh_f;
     const int NIg = p.Kp >> 5;
-    float *dst = p.Hblk + ((size_t) seg * p.PB + pb) * perBlock * p.Kp;
+    float *dst = p.Hblk + ((size_t) tbl * p.PB + pb) * perBlock * p.Kp;
     const float *ra = k.bank + (size_t) row * k.Tp, *rb = ra + k.Tp;
     for (int m = threadIdx.x; m < p.Kp; m += blockDim.x) {
         const int t = m - shift;
@@ -159,8 +157,24 @@ art_phase_table_kernel (const ArtClass k, const ArtPeriodic p, const __grid_cons
             else
                 h = ra[t];
         }
-        dst[(((jj >> 3) * NIg + (m >> 5)) * 8 + (jj & 7)) * 32 + (m & 31)] = h;
+        // [row][step][phases 0-3 | 4-7][lane][4]: a lane fetches the 8 phases of its tap with two LDS.128
+        dst[((((jj >> 3) * NIg + (m >> 5)) * 2 + ((jj >> 2) & 1)) * 32 + (m & 31)) * 4 + (jj & 3)] = h;
     }
+}
+
+/* Where every job's phase blocks start (jobs that share a table still have their own integer offsets). */
+__global__ void art_phase_origin_kernel (const ArtClass k, const ArtPeriodic p, const __grid_constant__ ArtJob single,
+                                         const ArtJob *__restrict__ jobs, int numJobs)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= numJobs * p.PB) return;
+    const int seg = e / p.PB, pb = e - seg * p.PB;
+    const ArtJob &job = jobs ? jobs[seg] : single;
+    ArtLoopState st;
+    st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = k.T;
+    int w;
+    const double pos = art_output_pos (&st, job.nStart + pb * p.rowsPerCta * 8, &w);
+    p.S0[e] = (int) ((long long) floor (pos) - k.T / 2 + 1 + (long long) w * 15LL * k.T - job.origin);
 }
 
 /* ---- 2. the banded product --------------------------------------------------------------------- */
@@ -173,7 +187,7 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
     constexpr int QT = 8 / CV;                                  // periods per warp tile
 
     extern __shared__ __align__ (128) unsigned char smem_raw[];
-    float *Hs = reinterpret_cast<float *> (smem_raw);            // [rows][NIg][8][32]
+    float *Hs = reinterpret_cast<float *> (smem_raw);            // [rows][NIg][2][32][4]
     float *xsRaw = Hs + (size_t) p.rowsPerCta * 8 * p.Kp;        // [Wc + 4][CV] (+4: alignment slack of the bulk copy)
     __shared__ __align__ (8) unsigned long long bars[2];         // [0] filters, [1] input chunk
 
@@ -204,7 +218,7 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
     if (tid == 0) {
         const unsigned int bytes = (unsigned int) (p.rowsPerCta * 8 * p.Kp * sizeof (float));
         art_mbar_expect_tx (&bars[0], bytes);
-        art_bulk_g2s (Hs, p.Hblk + ((size_t) seg * p.PB + pb) * p.rowsPerCta * 8 * p.Kp, bytes, &bars[0]);
+        art_bulk_g2s (Hs, p.Hblk + ((size_t) job.table * p.PB + pb) * p.rowsPerCta * 8 * p.Kp, bytes, &bars[0]);
     }
 
     // the bulk path needs the chunk to be one contiguous, fully valid span of the caller's interleaved block
@@ -253,13 +267,14 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
         for (int tile = warp; tile < nrows * qTiles; tile += ART_P_WARPS) {
             const int row = tile % nrows, qloc = (tile / nrows) * QT;
 
-            float acc[8][8];
+            // 64 accumulators as 32 packed pairs: acc2[pp][col] = phases (2pp, 2pp+1) of the row, column col
+            unsigned long long acc2[4][8];
 #pragma unroll
-            for (int a2 = 0; a2 < 8; ++a2)
+            for (int a2 = 0; a2 < 4; ++a2)
 #pragma unroll
-                for (int b2 = 0; b2 < 8; ++b2) acc[a2][b2] = 0.0f;
+                for (int b2 = 0; b2 < 8; ++b2) acc2[a2][b2] = 0ull;
 
-            const float *hp = Hs + (size_t) row * NIg * 256 + lane;
+            const float4 *hp = reinterpret_cast<const float4 *> (Hs) + (size_t) row * NIg * 64 + lane;
             const VecT *xp[QT];
 #pragma unroll
             for (int qq = 0; qq < QT; ++qq)
@@ -267,22 +282,29 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
 
 #pragma unroll 2
             for (int i = 0; i < NIg; ++i) {
-                float h[8];
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
-                    h[jj] = hp[(i * 8 + jj) * 32];
+                const float4 ha = hp[(i * 2) * 32], hb = hp[(i * 2 + 1) * 32];
+                unsigned long long h2[4];
+                h2[0] = art_pack2 (ha.x, ha.y); h2[1] = art_pack2 (ha.z, ha.w);
+                h2[2] = art_pack2 (hb.x, hb.y); h2[3] = art_pack2 (hb.z, hb.w);
 #pragma unroll
                 for (int qq = 0; qq < QT; ++qq) {
                     const VecT xv = xp[qq][32 * i];
 #pragma unroll
                     for (int v = 0; v < CV; ++v) {
                         const float x = ArtPVec<CV>::get (xv, v);
+                        const unsigned long long x2 = art_pack2 (x, x);         // folded into a scalar operand
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj)
-                            acc[jj][qq * CV + v] = fmaf (h[jj], x, acc[jj][qq * CV + v]);
+                        for (int pp = 0; pp < 4; ++pp)
+                            art_ffma2 (acc2[pp][qq * CV + v], h2[pp], x2);
                     }
                 }
             }
+            float acc[8][8];
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+                for (int b2 = 0; b2 < 8; ++b2)
+                    art_unpack2 (acc2[pp][b2], acc[2 * pp][b2], acc[2 * pp + 1][b2]);
 
             /* reduce across lanes: value index = col * 8 + jj, so that consecutive lanes hold consecutive
              * phases = consecutive output frames */
@@ -393,10 +415,39 @@ bool artPlanPeriodic (const ArtClass &k, double ratio, unsigned int maxOutputs, 
     p.PB = (R + p.rowsPerCta - 1) / p.rowsPerCta;
     const long long periods = (long long) ((totalOutputs + L - 1) / L);
     const int groups = (k.C + CV - 1) / CV;
-    int chunks = 16;
-    while (chunks > 1 && periods / ((long long) p.Qc * chunks) * p.PB * groups < (long long) smCount * 4)
-        chunks >>= 1;
-    p.Qblk = p.Qc * chunks;
+    // candidates: 1..16 chunks per CTA; score = how full the last wave is (2 CTAs per SM) x how well
+    // the once-per-CTA filter fetch is amortised
+    const long long perJob = (maxOutputs + L - 1) / L;
+    const long long jobsApprox = perJob ? (periods + perJob - 1) / perJob : 1;
+    const long long slots = (long long) smCount * 2;
+    int bestChunks = 1;
+    double best = -1.0;
+    for (int chunks = 1; chunks <= 16; ++chunks) {
+        const long long perCta = (long long) p.Qc * chunks;
+        const long long ctas = jobsApprox * p.PB * groups * ((perJob + perCta - 1) / perCta);
+        const long long waves = (ctas + slots - 1) / slots;
+        const double fill = (double) ctas / (double) (waves * slots);
+        const double amort = (double) chunks / (chunks + 0.35);
+        const double sc = fill * amort;
+        if (sc > best) { best = sc; bestChunks = chunks; }
+    }
+    p.Qblk = p.Qc * bestChunks;
+
+    // experiment knobs (profiling only): ART_P_ROWS / ART_P_QC / ART_P_CHUNKS override the choice
+    if (const char *e = getenv ("ART_P_ROWS")) {
+        p.rowsPerCta = atoi (e);
+        const int spread = (int) (((long long) (p.rowsPerCta * 8 - 1) * M + L - 1) / L) + 2;
+        p.Kp = (k.T + spread + 31) & ~31;
+        p.PB = (R + p.rowsPerCta - 1) / p.rowsPerCta;
+    }
+    if (const char *e = getenv ("ART_P_QC")) p.Qc = atoi (e);
+    p.Wc = (p.Qc - 1) * M + p.Kp;
+    p.Qblk = p.Qc * bestChunks;
+    if (const char *e = getenv ("ART_P_CHUNKS")) p.Qblk = p.Qc * atoi (e);
+    if (periodic_smem (p, CV) > 200 * 1024) return false;
+    if (getenv ("ART_B200_TRACE"))
+        fprintf (stderr, "[art] periodic L=%d M=%d rows=%d Kp=%d Qc=%d Qblk=%d PB=%d CV=%d smem=%zu\n",
+                 p.L, p.M, p.rowsPerCta, p.Kp, p.Qc, p.Qblk, p.PB, CV, periodic_smem (p, CV));
     return true;
 }
 
@@ -417,7 +468,7 @@ int artPeriodicCtas (const ArtPeriodic &p, unsigned int outputs)
 }
 
 template <int CV>
-static void launch_periodic (const ArtClass &k, const ArtPeriodic &p, int totalCtas, int numSegs,
+static void launch_periodic (const ArtClass &k, const ArtPeriodic &p, int totalCtas, int numJobs, int numTables,
                              const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream)
 {
     auto kern = art_sinc_periodic_kernel<CV>;
@@ -426,11 +477,13 @@ static void launch_periodic (const ArtClass &k, const ArtPeriodic &p, int totalC
     ART_CUDA_CHECK (cudaGetDevice (&device));
     const size_t smem = periodic_smem (p, CV);
     if (smem > configured[device & 15]) {
-        ART_CUDA_CHECK (cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-        configured[device & 15] = 112 * 1024;
+        const size_t want = smem > 112 * 1024 ? 200 * 1024 : 112 * 1024;
+        ART_CUDA_CHECK (cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) want));
+        configured[device & 15] = want;
     }
-    dim3 tgrid (p.PB * p.rowsPerCta * 8, numSegs);
+    dim3 tgrid (p.PB * p.rowsPerCta * 8, numTables);
     art_phase_table_kernel<<<tgrid, 128, 0, stream>>> (k, p, single, d_jobs);
+    art_phase_origin_kernel<<<(numJobs * p.PB + 127) / 128, 128, 0, stream>>> (k, p, single, d_jobs, numJobs);
     ART_CUDA_CHECK (cudaGetLastError ());
     dim3 grid (totalCtas, (k.C + CV - 1) / CV);
     void *prof;
@@ -438,14 +491,14 @@ static void launch_periodic (const ArtClass &k, const ArtPeriodic &p, int totalC
     kern<<<grid, ART_P_THREADS, smem, stream>>> (k, p, single, d_jobs);
     artProfileEnd (stream, prof);
     ART_CUDA_CHECK (cudaGetLastError ());
-    g_artLaunches += 2;
+    g_artLaunches += 3;
 }
 
-void artLaunchPeriodic (const ArtClass &k, const ArtPeriodic &p, int CV, int totalCtas, int numSegs,
+void artLaunchPeriodic (const ArtClass &k, const ArtPeriodic &p, int CV, int totalCtas, int numJobs, int numTables,
                         const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream)
 {
     if (totalCtas <= 0) return;
-    if (CV == 4) launch_periodic<4> (k, p, totalCtas, numSegs, single, d_jobs, stream);
-    else if (CV == 2) launch_periodic<2> (k, p, totalCtas, numSegs, single, d_jobs, stream);
-    else launch_periodic<1> (k, p, totalCtas, numSegs, single, d_jobs, stream);
+    if (CV == 4) launch_periodic<4> (k, p, totalCtas, numJobs, numTables, single, d_jobs, stream);
+    else if (CV == 2) launch_periodic<2> (k, p, totalCtas, numJobs, numTables, single, d_jobs, stream);
+    else launch_periodic<1> (k, p, totalCtas, numJobs, numTables, single, d_jobs, stream);
 }

@@ -114,6 +114,9 @@ def load() -> C.CDLL:
         "resampleBatchProcessInterleavedDevice": (None, [C.POINTER(ctx), i32, C.POINTER(vp), C.POINTER(i32),
                                                          C.POINTER(vp), C.POINTER(i32), C.POINTER(dbl),
                                                          C.POINTER(ResampleResult), vp]),
+        "resampleBatchProcessInterleaved": (None, [C.POINTER(ctx), i32, C.POINTER(f32p), C.POINTER(i32),
+                                                   C.POINTER(f32p), C.POINTER(i32), C.POINTER(dbl),
+                                                   C.POINTER(ResampleResult)]),
         "resampleProcessBlocksInterleavedDevice": (i32, [ctx, vp, C.POINTER(i32), C.POINTER(dbl), i32, vp, i32,
                                                           C.POINTER(ResampleResult), C.POINTER(dbl), vp]),
         "biquad_apply_cascade_interleaved": (None, [C.POINTER(C.POINTER(Biquad)), i32, i32, f32p, i32]),
@@ -135,6 +138,6 @@ EXPORTED_SYMBOLS = [
     "resampleB200SetDevice", "resampleB200GetDeviceCount", "resampleB200Synchronize", "resampleB200KernelLaunches",
     "resampleB200PathCounts", "resampleB200ProfileEnable", "resampleB200ProfileCollect",
     "resampleProcessInterleavedDevice", "resampleProcessDevice", "resampleBatchProcessInterleavedDevice",
-    "resampleProcessBlocksInterleavedDevice", "biquad_apply_cascade_interleaved",
+    "resampleBatchProcessInterleaved", "resampleProcessBlocksInterleavedDevice", "biquad_apply_cascade_interleaved",
     "biquad_apply_cascade_interleaved_device",
 ]

@@ -338,6 +338,29 @@ void resampleBatchProcessInterleavedDevice (Resample *const *cxts, int numContex
     free (devs);
 }
 
+void resampleBatchProcessInterleaved (Resample *const *cxts, int numContexts,
+                                      const float *const *inputs, const int *numInputFrames,
+                                      float *const *outputs, const int *numOutputFrames,
+                                      const double *ratios, ResampleResult *results)
+{
+    ArtCallPlan *calls;
+    ArtDev **devs;
+    int i;
+
+    if (numContexts <= 0)
+        return;
+    calls = malloc (sizeof *calls * numContexts);
+    devs = malloc (sizeof *devs * numContexts);
+    for (i = 0; i < numContexts; ++i) {
+        ResampleResult r = plan_call (cxts[i], numInputFrames[i], numOutputFrames[i], ratios ? ratios[i] : 0.0, &calls[i]);
+        devs[i] = cxts[i]->device;
+        if (results) results[i] = r;
+    }
+    artDevRunHostBatchInterleaved (devs, calls, numContexts, inputs, outputs);
+    free (calls);
+    free (devs);
+}
+
 int resampleProcessBlocksInterleavedDevice (Resample *cxt, const float *d_input, const int *blockFrames,
                                             const double *ratios, int numBlocks,
                                             float *d_output, int outputCapacityFrames,

@@ -132,7 +132,28 @@ struct ArtDev {
     float *d_in, *d_out;
     size_t inCap, outCap;           // floats
     ArtClass klass;
+    // host-pointer path: copies in, kernels and copies out run on three streams so that PCIe traffic in
+    // both directions overlaps the convolution (created on first use)
+    cudaStream_t sIn, sOut;
+    std::vector<cudaEvent_t> events;
+    // phase tables of single-job periodic launches: reused from call to call (calls on one context are
+    // stream-ordered), so the latency path has no allocation in it
+    void *tableBuf;
+    size_t tableCap;
 };
+
+static void host_pipe_init (ArtDev *dev, size_t events)
+{
+    if (!dev->sIn) {
+        ART_CUDA_CHECK (cudaStreamCreateWithFlags (&dev->sIn, cudaStreamNonBlocking));
+        ART_CUDA_CHECK (cudaStreamCreateWithFlags (&dev->sOut, cudaStreamNonBlocking));
+    }
+    while (dev->events.size () < events) {
+        cudaEvent_t e;
+        ART_CUDA_CHECK (cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
+        dev->events.push_back (e);
+    }
+}
 
 static void use_device (const ArtDev *dev)
 {
@@ -160,6 +181,20 @@ extern "C" ArtDev *artDevCreate (int channels, int taps, int filters, int mode, 
         return nullptr;
     }
 
+    {
+        // the per-launch scratch (job arrays, phase tables) comes from the stream-ordered pool; keep what
+        // it has instead of returning it to the driver at every synchronisation (default threshold is 0)
+        static bool poolTuned[64] = { false };
+        if (device < 64 && !poolTuned[device]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool (&pool, device) == cudaSuccess) {
+                unsigned long long keep = ~0ULL;
+                cudaMemPoolSetAttribute (pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            poolTuned[device] = true;
+        }
+    }
+
     ArtDev *dev = new ArtDev ();
     dev->device = device;
     dev->smCount = prop.multiProcessorCount;
@@ -175,6 +210,9 @@ extern "C" ArtDev *artDevCreate (int channels, int taps, int filters, int mode, 
     dev->cur = 0;
     dev->d_in = dev->d_out = nullptr;
     dev->inCap = dev->outCap = 0;
+    dev->sIn = dev->sOut = nullptr;
+    dev->tableBuf = nullptr;
+    dev->tableCap = 0;
 
     ArtClass &k = dev->klass;
     memset (&k, 0, sizeof k);
@@ -193,7 +231,10 @@ extern "C" void artDevDestroy (ArtDev *dev)
     cudaFree (dev->hist[1]);
     cudaFree (dev->d_in);
     cudaFree (dev->d_out);
+    cudaFree (dev->tableBuf);
     cudaStreamDestroy (dev->stream);
+    if (dev->sIn) { cudaStreamDestroy (dev->sIn); cudaStreamDestroy (dev->sOut); }
+    for (cudaEvent_t e : dev->events) cudaEventDestroy (e);
     bank_release (dev->bank);
     delete dev;
 }
@@ -332,7 +373,7 @@ static int append_job (const ArtLaunchPlan &lp, const ArtJob &base, std::vector<
     return ctas;
 }
 
-static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cudaStream_t stream)
+static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cudaStream_t stream, ArtDev *owner = nullptr)
 {
     if (jobs.empty ())
         return;
@@ -374,13 +415,27 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
         if (lp.periodic) {
             const size_t tableFloats = (size_t) numTables * lp.per.PB * lp.per.rowsPerCta * 8 * lp.per.Kp;
             const size_t tableInts = (size_t) n * lp.per.PB;
+            const size_t bytes = tableFloats * sizeof (float) + tableInts * sizeof (int);
             void *tables = nullptr;
-            ART_CUDA_CHECK (cudaMallocAsync (&tables, tableFloats * sizeof (float) + tableInts * sizeof (int), stream));
+            const bool persistent = owner && n == 1;
+            if (persistent) {
+                if (bytes > owner->tableCap) {
+                    ART_CUDA_CHECK (cudaStreamSynchronize (stream));
+                    cudaFree (owner->tableBuf);
+                    ART_CUDA_CHECK (cudaMalloc (&owner->tableBuf, bytes));
+                    owner->tableCap = bytes;
+                }
+                tables = owner->tableBuf;
+            }
+            else
+                ART_CUDA_CHECK (cudaMallocAsync (&tables, bytes, stream));
             lp.per.Hblk = reinterpret_cast<float *> (tables);
             lp.per.S0 = reinterpret_cast<int *> (lp.per.Hblk + tableFloats);
             artLaunchPeriodic (lp.k, lp.per, lp.CV, ctas, n, numTables, jobs[0], d_jobs, stream);
             ++g_pathLaunches[1];
-            ART_CUDA_CHECK (cudaFreeAsync (tables, stream));
+            if (!persistent)
+                ART_CUDA_CHECK (cudaFreeAsync (tables, stream));
+            anyHist = false;                    // the periodic prep kernel moved the history already
         }
         else {
             lp.g.totalTiles = ctas;
@@ -400,7 +455,7 @@ static void run_single (ArtDev *dev, const ArtCallPlan &p, ArtJob &job, cudaStre
     plan_launch (dev, p.st.ratio, true, p.outputs, p.outputs, true, lp);
     std::vector<ArtJob> jobs;
     const int ctas = append_job (lp, job, jobs, 0);
-    dispatch (lp, jobs, ctas, stream);
+    dispatch (lp, jobs, ctas, stream, dev);
     finish_job (dev, p);
 }
 
@@ -422,22 +477,124 @@ static void reserve (ArtDev *dev, size_t inFloats, size_t outFloats)
 
 /* ---- host-memory entry points ------------------------------------------------------------------------ */
 
+/* One call, host memory, interleaved.  Large calls are cut into pieces of consecutive outputs; piece c
+ * needs the input frames up to art_inputs_before(last output of c), so its upload, its kernels and its
+ * download form a three-stage pipeline across pieces.  The samples are the same as for one big launch:
+ * every output is evaluated from (P, I, n) alone. */
 extern "C" void artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, const float *in, float *out)
 {
     use_device (dev);
     const size_t C = dev->C;
     const size_t inFloats = (size_t) plan->inValid * C, outFloats = (size_t) plan->outputs * C;
     reserve (dev, inFloats, outFloats);
-    if (inFloats)
-        ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_in, in, inFloats * sizeof (float), cudaMemcpyHostToDevice, dev->stream));
-    ArtJob job;
-    fill_job (dev, *plan, job);
-    job.in = dev->d_in;  job.inFS = C;  job.inCS = 1;
-    job.out = dev->d_out; job.outFS = C; job.outCS = 1;
-    run_single (dev, *plan, job, dev->stream);
-    if (outFloats)
-        ART_CUDA_CHECK (cudaMemcpyAsync (out, dev->d_out, outFloats * sizeof (float), cudaMemcpyDeviceToHost, dev->stream));
+
+    // a piece costs ~25 us of launch latency; only cut when its copies take several times that
+    int pieces = (int) (((unsigned long long) plan->outputs * C) >> 20);
+    if (pieces < 1 || plan->pre) pieces = 1;
+    if (pieces > 8) pieces = 8;
+    if (getenv ("ART_B200_NOPIPE")) pieces = 1;
+
+    if (pieces == 1) {
+        if (inFloats)
+            ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_in, in, inFloats * sizeof (float), cudaMemcpyHostToDevice, dev->stream));
+        ArtJob job;
+        fill_job (dev, *plan, job);
+        job.in = dev->d_in;  job.inFS = C;  job.inCS = 1;
+        job.out = dev->d_out; job.outFS = C; job.outCS = 1;
+        run_single (dev, *plan, job, dev->stream);
+        if (outFloats)
+            ART_CUDA_CHECK (cudaMemcpyAsync (out, dev->d_out, outFloats * sizeof (float), cudaMemcpyDeviceToHost, dev->stream));
+        ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+        return;
+    }
+
+    host_pipe_init (dev, 2 * (size_t) pieces);
+    ArtLaunchPlan lp;
+    plan_launch (dev, plan->st.ratio, true, plan->outputs / pieces + 1, plan->outputs, true, lp);
+    long long uploaded = 0;
+    for (int c = 0; c < pieces; ++c) {
+        const unsigned int n0 = (unsigned int) ((unsigned long long) plan->outputs * c / pieces);
+        const unsigned int n1 = (unsigned int) ((unsigned long long) plan->outputs * (c + 1) / pieces);
+        long long need = c == pieces - 1 ? (long long) plan->inValid : art_inputs_before (&plan->st, n1 - 1);
+        if (need > plan->inValid) need = plan->inValid;
+        if (need < uploaded) need = uploaded;
+        if (need > uploaded)
+            ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_in + uploaded * C, in + uploaded * C, (size_t) (need - uploaded) * C * sizeof (float),
+                                             cudaMemcpyHostToDevice, dev->sIn));
+        uploaded = need;
+        ART_CUDA_CHECK (cudaEventRecord (dev->events[2 * c], dev->sIn));
+        ART_CUDA_CHECK (cudaStreamWaitEvent (dev->stream, dev->events[2 * c], 0));
+
+        ArtJob job;
+        fill_job (dev, *plan, job);
+        job.in = dev->d_in;  job.inFS = C;  job.inCS = 1;
+        job.out = dev->d_out; job.outFS = C; job.outCS = 1;
+        job.nStart = n0;
+        job.outputs = n1 - n0;
+        job.inValid = (int) uploaded;
+        if (c != pieces - 1) job.histOut = nullptr;          // the history moves once, after the last upload
+        std::vector<ArtJob> jobs;
+        const int ctas = append_job (lp, job, jobs, 0);
+        dispatch (lp, jobs, ctas, dev->stream, dev);
+
+        ART_CUDA_CHECK (cudaEventRecord (dev->events[2 * c + 1], dev->stream));
+        ART_CUDA_CHECK (cudaStreamWaitEvent (dev->sOut, dev->events[2 * c + 1], 0));
+        if (n1 > n0)
+            ART_CUDA_CHECK (cudaMemcpyAsync (out + (size_t) n0 * C, dev->d_out + (size_t) n0 * C, (size_t) (n1 - n0) * C * sizeof (float),
+                                             cudaMemcpyDeviceToHost, dev->sOut));
+    }
+    finish_job (dev, *plan);
+    ART_CUDA_CHECK (cudaStreamSynchronize (dev->sOut));
     ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+}
+
+/* Many contexts, host memory, interleaved: the same three-stage pipeline over groups of contexts -- a
+ * group's uploads, one launch for the group, its downloads (group size 1 measured best on B200: 64 us
+ * per 2 MB stereo stream against a PCIe floor of 42 us). */
+extern "C" void artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
+                                           const float *const *d_in, float *const *d_out, void *stream);
+
+extern "C" void artDevRunHostBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
+                                               const float *const *in, float *const *out)
+{
+    if (count <= 0) return;
+    ArtDev *lead = devs[0];
+    use_device (lead);
+    const int group = 1;                   // measured: larger groups coarsen the pipeline more than they save
+    const int groups = (count + group - 1) / group;
+    host_pipe_init (lead, 2 * (size_t) groups);
+    const size_t C = lead->C;
+    std::vector<const float *> dIn (count);
+    std::vector<float *> dOut (count);
+    for (int g = 0; g < groups; ++g) {
+        const int i0 = g * group, i1 = i0 + group < count ? i0 + group : count;
+        for (int i = i0; i < i1; ++i) {
+            ArtDev *dev = devs[i];
+            const ArtCallPlan &p = plans[i];
+            if (dev->device != lead->device) {
+                fprintf (stderr, "libresampler_b200: a batch must live on one GPU\n");
+                abort ();
+            }
+            const size_t inFloats = (size_t) p.inValid * C, outFloats = (size_t) p.outputs * C;
+            reserve (dev, inFloats, outFloats);
+            dIn[i] = dev->d_in;
+            dOut[i] = dev->d_out;
+            if (inFloats)
+                ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_in, in[i], inFloats * sizeof (float), cudaMemcpyHostToDevice, lead->sIn));
+        }
+        ART_CUDA_CHECK (cudaEventRecord (lead->events[2 * g], lead->sIn));
+        ART_CUDA_CHECK (cudaStreamWaitEvent (lead->stream, lead->events[2 * g], 0));
+        artDevRunBatchInterleaved (devs + i0, plans + i0, i1 - i0, dIn.data () + i0, dOut.data () + i0, lead->stream);
+        ART_CUDA_CHECK (cudaEventRecord (lead->events[2 * g + 1], lead->stream));
+        ART_CUDA_CHECK (cudaStreamWaitEvent (lead->sOut, lead->events[2 * g + 1], 0));
+        for (int i = i0; i < i1; ++i) {
+            const size_t outFloats = (size_t) plans[i].outputs * C;
+            if (outFloats)
+                ART_CUDA_CHECK (cudaMemcpyAsync (out[i], devs[i]->d_out, outFloats * sizeof (float), cudaMemcpyDeviceToHost, lead->sOut));
+        }
+    }
+    ART_CUDA_CHECK (cudaStreamSynchronize (lead->sOut));
+    ART_CUDA_CHECK (cudaStreamSynchronize (lead->stream));
 }
 
 extern "C" void artDevRunHostPlanar (ArtDev *dev, const ArtCallPlan *plan, const float *const *in, float *const *out)
@@ -542,7 +699,7 @@ extern "C" void artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPla
         j.out = d_out[i];                 j.outFS = lead->C; j.outCS = 1;
         ctas += append_job (lp, j, jobs, ctas);
     }
-    dispatch (lp, jobs, ctas, st);
+    dispatch (lp, jobs, ctas, st, count == 1 ? lead : nullptr);
     for (int i = 0; i < count; ++i)
         finish_job (devs[i], plans[i]);
 }

@@ -50,6 +50,8 @@ int     artDevCount (void);                          /* usable CUDA devices, 0 w
 /* Host-memory entry points: stage in, run, stage out, synchronise. */
 void artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, const float *in, float *out);
 void artDevRunHostPlanar (ArtDev *dev, const ArtCallPlan *plan, const float *const *in, float *const *out);
+void artDevRunHostBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
+                                    const float *const *in, float *const *out);
 
 /* Device-memory entry points: enqueue on `stream` (a cudaStream_t, NULL = the context's
  * own stream) and return without synchronising. */

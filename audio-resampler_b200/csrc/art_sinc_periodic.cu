@@ -97,11 +97,9 @@ __device__ __forceinline__ void art_bulk_g2s (void *dstSmem, const void *srcGlob
 /* One block per (padded) phase.  Writes the phase's interpolated filter straight into the layout the
  * product kernel keeps in shared memory: [row][step][half-row][lane][4 phases], shifted so that tap 0 of
  * the phase block's first phase sits at m = 0. */
-__global__ void __launch_bounds__ (128)
-art_phase_table_kernel (const ArtClass k, const ArtPeriodic p, const __grid_constant__ ArtJob single,
-                        const ArtJob *__restrict__ jobs)
+__device__ __forceinline__ void art_phase_table_block (const ArtClass &k, const ArtPeriodic &p, const ArtJob &single,
+                                                        const ArtJob *__restrict__ jobs, int j, int tbl)
 {
-    const int j = blockIdx.x, tbl = blockIdx.y;
     const ArtJob &job = jobs ? jobs[jobs[tbl].repJob] : single;
     const int T = k.T, half = T / 2, F = k.F;
     const int perBlock = p.rowsPerCta * 8;
@@ -144,7 +142,7 @@ art_phase_table_kernel (const ArtClass k, const ArtPeriodic p, const __grid_cons
     const int NIg = p.Kp >> 5;
     float *dst = p.Hblk + ((size_t) tbl * p.PB + pb) * perBlock * p.Kp;
     const float *ra = k.bank + (size_t) row * k.Tp, *rb = ra + k.Tp;
-    for (int m = threadIdx.x; m < p.Kp; m += blockDim.x) {
+    for (int m = threadIdx.x; m < p.Kp; m += 128) {
         const int t = m - shift;
         float h = 0.0f;
         if (j < p.L && t >= 0 && t < T) {
@@ -162,19 +160,45 @@ art_phase_table_kernel (const ArtClass k, const ArtPeriodic p, const __grid_cons
     }
 }
 
-/* Where every job's phase blocks start (jobs that share a table still have their own integer offsets). */
-__global__ void art_phase_origin_kernel (const ArtClass k, const ArtPeriodic p, const __grid_constant__ ArtJob single,
-                                         const ArtJob *__restrict__ jobs, int numJobs)
+/* Everything the product kernel needs before it can start, in ONE launch (a call's GPU time is
+ * dominated by launch latency for small blocks): phase tables, per-job block origins, and -- because it
+ * only reads what the product kernel also only reads -- the history update of resampler.c's ring. */
+__global__ void __launch_bounds__ (128)
+art_periodic_prep_kernel (const ArtClass k, const ArtPeriodic p, const __grid_constant__ ArtJob single,
+                          const ArtJob *__restrict__ jobs, int numJobs, int numTables, int histBlocksPerJob)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= numJobs * p.PB) return;
-    const int seg = e / p.PB, pb = e - seg * p.PB;
-    const ArtJob &job = jobs ? jobs[seg] : single;
-    ArtLoopState st;
-    st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = k.T;
-    int w;
-    const double pos = art_output_pos (&st, job.nStart + pb * p.rowsPerCta * 8, &w);
-    p.S0[e] = (int) ((long long) floor (pos) - k.T / 2 + 1 + (long long) w * 15LL * k.T - job.origin);
+    const int padded = p.PB * p.rowsPerCta * 8;
+    const int tableBlocks = numTables * padded;
+    const int originBlocks = (numJobs * p.PB + 127) / 128;
+    int b = blockIdx.x;
+    if (b < tableBlocks) {
+        art_phase_table_block (k, p, single, jobs, b % padded, b / padded);
+        return;
+    }
+    b -= tableBlocks;
+    if (b < originBlocks) {
+        const int e = b * 128 + threadIdx.x;
+        if (e >= numJobs * p.PB) return;
+        const int seg = e / p.PB, pb = e - seg * p.PB;
+        const ArtJob &job = jobs ? jobs[seg] : single;
+        ArtLoopState st;
+        st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = k.T;
+        int w;
+        const double pos = art_output_pos (&st, job.nStart + pb * p.rowsPerCta * 8, &w);
+        p.S0[e] = (int) ((long long) floor (pos) - k.T / 2 + 1 + (long long) w * 15LL * k.T - job.origin);
+        return;
+    }
+    b -= originBlocks;
+    {
+        const int seg = b / histBlocksPerJob, hb = b - seg * histBlocksPerJob;
+        const ArtJob &job = jobs ? jobs[seg] : single;
+        if (!job.histOut) return;
+        const int total = k.C * k.T;
+        for (int e = hb * 128 + threadIdx.x; e < total; e += histBlocksPerJob * 128) {
+            const int c = e / k.T, i = e - c * k.T;
+            job.histOut[e] = art_fetch (job, k.T, c, job.consumed - k.T + i);
+        }
+    }
 }
 
 /* ---- 2. the banded product --------------------------------------------------------------------- */
@@ -481,9 +505,10 @@ static void launch_periodic (const ArtClass &k, const ArtPeriodic &p, int totalC
         ART_CUDA_CHECK (cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) want));
         configured[device & 15] = want;
     }
-    dim3 tgrid (p.PB * p.rowsPerCta * 8, numTables);
-    art_phase_table_kernel<<<tgrid, 128, 0, stream>>> (k, p, single, d_jobs);
-    art_phase_origin_kernel<<<(numJobs * p.PB + 127) / 128, 128, 0, stream>>> (k, p, single, d_jobs, numJobs);
+    int histBlocks = (k.C * k.T + 127) / 128;
+    if (histBlocks > 32) histBlocks = 32;
+    const int prepBlocks = numTables * p.PB * p.rowsPerCta * 8 + (numJobs * p.PB + 127) / 128 + numJobs * histBlocks;
+    art_periodic_prep_kernel<<<prepBlocks, 128, 0, stream>>> (k, p, single, d_jobs, numJobs, numTables, histBlocks);
     ART_CUDA_CHECK (cudaGetLastError ());
     dim3 grid (totalCtas, (k.C + CV - 1) / CV);
     void *prof;
@@ -491,7 +516,7 @@ static void launch_periodic (const ArtClass &k, const ArtPeriodic &p, int totalC
     kern<<<grid, ART_P_THREADS, smem, stream>>> (k, p, single, d_jobs);
     artProfileEnd (stream, prof);
     ART_CUDA_CHECK (cudaGetLastError ());
-    g_artLaunches += 3;
+    g_artLaunches += 2;
 }
 
 void artLaunchPeriodic (const ArtClass &k, const ArtPeriodic &p, int CV, int totalCtas, int numJobs, int numTables,

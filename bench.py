@@ -311,24 +311,42 @@ def run_gpu_arm(args):
 
 
 def measure_e2e(lib, pkg, torch, dist, world, dev, streams, frames, cap, args):
-    """Same workload through resampleProcessInterleaved with pinned host buffers; a few host threads
-    keep several contexts in flight so that H2D, kernels and D2H of different streams overlap."""
+    """Same workload with pinned HOST buffers, host->device and device->host copies inside the timed region.
+
+    value          through the reference-facing call, resampleProcessInterleaved (include/resampler.h), one
+                   context per call, a few host threads keeping several contexts in flight;
+    batched_value  through the host-pointer batch extension (resampleBatchProcessInterleaved), one call per step.
+    """
     n = min(streams, args.e2e_streams)
     hx = torch.empty((n, frames, CHANNELS), dtype=torch.float32).uniform_(-0.5, 0.5).pin_memory()
     hy = torch.empty((n, cap, CHANNELS), dtype=torch.float32).pin_memory()
-    ctxs = [lib.resampleInit(CHANNELS, TAPS, FILTERS, 0.0, FLAGS) for _ in range(n)]
-    for c in ctxs:
-        lib.resampleAdvancePosition(c, TAPS / 2)
     f32p = C.POINTER(C.c_float)
     xp = [C.cast(hx[i].data_ptr(), f32p) for i in range(n)]
     yp = [C.cast(hy[i].data_ptr(), f32p) for i in range(n)]
     local = dev.index
+    steps = max(1, min(args.steps, 8))
+
+    def fresh():
+        ctxs = [lib.resampleInit(CHANNELS, TAPS, FILTERS, 0.0, FLAGS) for _ in range(n)]
+        for c in ctxs:
+            lib.resampleAdvancePosition(c, TAPS / 2)
+        return ctxs
+
+    def reduce(made, dt):
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        tot = torch.tensor([float(made)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        return float(tot.item()) * CHANNELS / float(t.item()) / 1e6
+
+    # -- reference-facing API, several host threads -------------------------------------------------
+    ctxs = fresh()
 
     def one(i):
         lib.resampleB200SetDevice(local)
         return lib.resampleProcessInterleaved(ctxs[i], xp[i], frames, yp[i], cap, RATIO).output_generated
 
-    steps = max(1, min(args.steps, 5))
     with ThreadPoolExecutor(args.e2e_threads) as pool:
         for _ in range(2):
             list(pool.map(one, range(n)))
@@ -341,18 +359,45 @@ def measure_e2e(lib, pkg, torch, dist, world, dev, streams, frames, cap, args):
             made += sum(pool.map(one, range(n)))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-    t = torch.tensor([dt], device=dev, dtype=torch.float64)
-    tot = torch.tensor([float(made)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    value = reduce(made, dt)
+    per_step_out = made / steps
     for c in ctxs:
         lib.resampleFree(c)
-    per_step_out = made / steps
-    return {"value": float(tot.item()) * CHANNELS / float(t.item()) / 1e6, "unit": "Msamples/s",
+
+    # -- host-pointer batch extension, one call per step ---------------------------------------------
+    ctxs = fresh()
+    ctx_t = C.POINTER(pkg.Resample)
+    ctx_arr = (ctx_t * n)(*ctxs)
+    in_arr, out_arr = (f32p * n)(*xp), (f32p * n)(*yp)
+    nin_arr, nout_arr = (C.c_int * n)(*([frames] * n)), (C.c_int * n)(*([cap] * n))
+    ratio_arr = (C.c_double * n)(*([RATIO] * n))
+    res_arr = (pkg.ResampleResult * n)()
+
+    def batch():
+        lib.resampleBatchProcessInterleaved(ctx_arr, n, in_arr, nin_arr, out_arr, nout_arr, ratio_arr, res_arr)
+        return sum(r.output_generated for r in res_arr)
+
+    for _ in range(2):
+        batch()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    made = 0
+    for _ in range(steps):
+        made += batch()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    batched = reduce(made, dt)
+    for c in ctxs:
+        lib.resampleFree(c)
+
+    return {"value": value, "unit": "Msamples/s",
             "h2d_bytes_per_step": int(n * frames * CHANNELS * 4), "d2h_bytes_per_step": int(per_step_out * CHANNELS * 4),
             "api": "resampleProcessInterleaved (host pointers, pinned), "
-                   f"{n} streams x {frames} frames per step, {args.e2e_threads} host threads"}
+                   f"{n} streams x {frames} frames per step, {args.e2e_threads} host threads",
+            "batched_value": batched,
+            "batched_api": "resampleBatchProcessInterleaved (host pointers, pinned), one call per step"}
 
 
 def main():

@@ -47,6 +47,14 @@ void resampleBatchProcessInterleavedDevice (Resample *const *cxts, int numContex
                                             float *const *d_outputs, const int *numOutputFrames,
                                             const double *ratios, ResampleResult *results, void *stream);
 
+/* The same for HOST buffers: uploads, kernels and downloads of successive contexts are pipelined on
+ * three streams (PCIe in both directions overlaps the convolution); returns when all outputs are in
+ * host memory.  Pinned host buffers are needed for the copies to be asynchronous. */
+void resampleBatchProcessInterleaved (Resample *const *cxts, int numContexts,
+                                      const float *const *inputs, const int *numInputFrames,
+                                      float *const *outputs, const int *numOutputFrames,
+                                      const double *ratios, ResampleResult *results);
+
 /* ASRC: numBlocks consecutive blocks of ONE stream, block b holding blockFrames[b] input frames
  * and resampled at ratios[b], exactly as numBlocks successive resampleProcessInterleaved calls
  * would be (positions[b], if non-NULL, receives resampleGetPosition after block b).  Input blocks

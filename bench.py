@@ -67,7 +67,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)],
+                                          "-lms", "20", "-i", str(self.device)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -102,6 +102,28 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- multi-rank plumbing
+
+def shard_streams(total_streams: int, world: int, rank: int):
+    """Independent streams are the unit of sharding: contiguous, sizes differing by at most one.
+    Returns (first, count) of the streams this rank owns."""
+    base, extra = divmod(total_streams, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def reduce_over_ranks(dist, device, elapsed_ms: float, units: float):
+    """The job's time is the slowest rank's (MAX), its work the sum over ranks: no other collective exists
+    on this path.  Works on any backend (nccl on the GPU box, gloo in the CPU tests)."""
+    import torch
+    t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
+    u = torch.tensor([units], device=device, dtype=torch.float64)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    return float(t.item()), float(u.item())
 
 
 # --------------------------------------------------------------------------------------- reference arm
@@ -255,12 +277,7 @@ def run_gpu_arm(args):
     kern_launches = lib.resampleB200ProfileCollect(C.byref(kern_ms))
     launches = lib.resampleB200KernelLaunches() - launches0
 
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    tot = torch.tensor([float(out_frames)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_max, total_frames = float(t.item()), float(tot.item())
+    ms_max, total_frames = reduce_over_ranks(dist if world > 1 else None, dev, ms, float(out_frames))
     value = total_frames * CHANNELS / (ms_max * 1e-3) / 1e6
 
     # ---- end to end through the host-pointer API -----------------------------------------------------
@@ -333,12 +350,8 @@ def measure_e2e(lib, pkg, torch, dist, world, dev, streams, frames, cap, args):
         return ctxs
 
     def reduce(made, dt):
-        t = torch.tensor([dt], device=dev, dtype=torch.float64)
-        tot = torch.tensor([float(made)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        return float(tot.item()) * CHANNELS / float(t.item()) / 1e6
+        t, tot = reduce_over_ranks(dist if world > 1 else None, dev, dt, float(made))
+        return tot * CHANNELS / t / 1e6
 
     # -- reference-facing API, several host threads -------------------------------------------------
     ctxs = fresh()

@@ -261,13 +261,16 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
 
     // one job travels by value in the parameter space (no descriptor upload on the latency path);
     // batches and block sequences come as an array in global memory
-    const ArtJob &job = jobs ? jobs[k.numJobs > 1 ? art_find_job (jobs, k.numJobs, blockIdx.x) : 0] : single;
-    const unsigned int t0 = (unsigned int) (blockIdx.x - job.tile0) * (unsigned int) k.NB;
+    // channel group varies fastest across the grid, so the CTAs reading the same frames run together (L2)
+    const int groups = (k.C + k.Cg - 1) / k.Cg;
+    const int tileIdx = blockIdx.x / groups, cgroup = blockIdx.x - tileIdx * groups;
+    const ArtJob &job = jobs ? jobs[k.numJobs > 1 ? art_find_job (jobs, k.numJobs, tileIdx) : 0] : single;
+    const unsigned int t0 = (unsigned int) (tileIdx - job.tile0) * (unsigned int) k.NB;
     if (t0 >= job.outputs)
         return;
     const int cnt = (int) min ((unsigned int) k.NB, job.outputs - t0);
     const unsigned int n0 = job.nStart + t0;                      // call-relative index of the tile's first output
-    const int c0 = blockIdx.y * k.Cg;
+    const int c0 = cgroup * k.Cg;
     const int nc = min (k.Cg, k.C - c0);
     const int T = k.T, half = T / 2, F = k.F;
 
@@ -505,7 +508,7 @@ static void launch_one (const ArtClass &k, const ArtLaunchGeom &g, const ArtJob 
         ART_CUDA_CHECK (cudaFuncSetAttribute (kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         configured[device & 15] = 112 * 1024;
     }
-    dim3 grid (g.totalTiles, (k.C + k.Cg - 1) / k.Cg);
+    const unsigned int grid = (unsigned int) g.totalTiles * (unsigned int) ((k.C + k.Cg - 1) / k.Cg);
     void *prof;
     artProfileBegin (stream, &prof);
     kern<<<grid, ART_G_THREADS, g.smemBytes, stream>>> (k, single, d_jobs);

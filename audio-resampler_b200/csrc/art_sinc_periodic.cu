@@ -202,8 +202,9 @@ art_periodic_prep_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
 }
 
 /* ---- 2. the banded product --------------------------------------------------------------------- */
-template <int CV>
-__global__ void __launch_bounds__ (ART_P_THREADS, 2)
+/* THREADS = 256 with two CTAs per SM (shared memory <= 110 KB), or 512 with one large CTA per SM */
+template <int CV, int THREADS>
+__global__ void __launch_bounds__ (THREADS, THREADS == 256 ? 2 : 1)
 art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_constant__ ArtJob single,
                           const ArtJob *__restrict__ jobs)
 {
@@ -216,12 +217,16 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
     __shared__ __align__ (8) unsigned long long bars[2];         // [0] filters, [1] input chunk
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int seg = jobs ? (k.numJobs > 1 ? art_find_job_p (jobs, k.numJobs, blockIdx.x) : 0) : 0;
+    // channel group varies fastest across the grid: the CTAs that read the same frames of an interleaved
+    // block run together, so each 128-byte line comes from DRAM once and from L2 for the other groups
+    const int groups = (k.C + CV - 1) / CV;
+    const int cta = blockIdx.x / groups, cgroup = blockIdx.x - cta * groups;
+    const int seg = jobs ? (k.numJobs > 1 ? art_find_job_p (jobs, k.numJobs, cta) : 0) : 0;
     const ArtJob &job = jobs ? jobs[seg] : single;
     const int L = p.L, M = p.M, T = k.T;
     const int Q = (int) ((job.outputs + L - 1) / L);             // periods in this segment
     const int R = (L + 7) >> 3;                                   // phase rows
-    const int local = blockIdx.x - job.tile0;
+    const int local = cta - job.tile0;
     const int pb = local % p.PB, qb = local / p.PB;               // phase block fastest: neighbours share input in L2
     const int row0 = pb * p.rowsPerCta;
     const int nrows = min (p.rowsPerCta, R - row0);
@@ -229,7 +234,7 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
     const int qStart = qb * p.Qblk, qEnd = min (Q, qStart + p.Qblk);
     if (qStart >= qEnd)
         return;
-    const int c0 = blockIdx.y * CV;
+    const int c0 = cgroup * CV;
     const int NIg = p.Kp >> 5;
     const long long S0 = p.S0[(size_t) seg * p.PB + pb];
 
@@ -268,9 +273,29 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
                 art_bulk_g2s (xsRaw, g - xoff, bytes, &bars[1]);
             }
         }
+        else if (CV > 1 && job.inPlanes == nullptr && job.inCS == 1 && c0 + CV <= k.C &&
+                 a >= -job.prevAvail && a + len <= (long long) job.inValid &&
+                 ((reinterpret_cast<unsigned long long> (job.in + a * job.inFS + c0) & (sizeof (VecT) - 1)) == 0) &&
+                 ((job.inFS * sizeof (float)) & (sizeof (VecT) - 1)) == 0) {
+            // a CV-channel group of a wider interleaved block: one vector load per frame, four in flight
+            const float *g0 = job.in + a * job.inFS + c0;
+            VecT *dst = reinterpret_cast<VecT *> (xsRaw);
+            int i = tid;
+            for (; i + 3 * THREADS < len; i += 4 * THREADS) {
+                VecT v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    v[u] = __ldg (reinterpret_cast<const VecT *> (g0 + (long long) (i + u * THREADS) * job.inFS));
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    dst[i + u * THREADS] = v[u];
+            }
+            for (; i < len; i += THREADS)
+                dst[i] = __ldg (reinterpret_cast<const VecT *> (g0 + (long long) i * job.inFS));
+        }
         else {
             const int total = len * CV;
-            for (int e = tid; e < total; e += ART_P_THREADS) {
+            for (int e = tid; e < total; e += THREADS) {
                 const int i = e / CV, v = e - i * CV;
                 xsRaw[e] = (c0 + v < k.C) ? art_fetch (job, T, c0 + v, a + i) : 0.0f;
             }
@@ -288,7 +313,7 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
         const float *xs = xsRaw + xoff;
 
         const int qTiles = (nq + QT - 1) / QT;
-        for (int tile = warp; tile < nrows * qTiles; tile += ART_P_WARPS) {
+        for (int tile = warp; tile < nrows * qTiles; tile += (THREADS / 32)) {
             const int row = tile % nrows, qloc = (tile / nrows) * QT;
 
             // 64 accumulators as 32 packed pairs: acc2[pp][col] = phases (2pp, 2pp+1) of the row, column col
@@ -401,29 +426,35 @@ bool artPlanPeriodic (const ArtClass &k, double ratio, unsigned int maxOutputs, 
     if (maxOutputs < (unsigned) (4 * L)) return false;
     CV = k.C >= 4 ? 4 : (k.C >= 2 ? 2 : 1);
     const int QT = 8 / CV;
-    const size_t budget = 110 * 1024;
 
     p.L = L; p.M = M;
     const int R = (L + 7) / 8;
     int bestRows = 0, bestQc = 0;
     double bestScore = 0.0;
-    for (int rows = ART_P_ROWS_MAX; rows >= 1; --rows) {
-        // shifts inside a phase block: consecutive phases advance by M/L samples
-        const int spread = (int) (((long long) (rows * 8 - 1) * M + L - 1) / L) + 2;
-        const int Kp = (k.T + spread + 31) & ~31;
-        for (int Qc = 64; Qc >= QT; Qc -= QT) {
-            ArtPeriodic t = p;
-            t.rowsPerCta = rows; t.Kp = Kp; t.Qc = Qc; t.Wc = (Qc - 1) * M + Kp;
-            if (periodic_smem (t, CV) > budget) continue;
-            // staged input is reused by rows*8 phases, the filters by Qc periods: weigh both, prefer
-            // enough tiles per chunk to keep 8 warps busy
-            const int tiles = rows * (Qc / QT);
-            double score = (double) rows * 8 * Qc / (rows * 8 + Qc) * (tiles >= 8 ? 1.0 : tiles / 8.0);
-            score *= (double) k.T / Kp;                           // union-window padding is wasted FMAs
-            const int usedRows = (R + rows - 1) / rows * rows;
-            score *= (double) R / usedRows;                       // idle rows in the last phase block
-            if (score > bestScore) { bestScore = score; bestRows = rows; bestQc = Qc; }
-            break;                                                // largest Qc that fits for this row count
+    // two shared-memory budgets: 110 KB keeps two CTAs (16 warps) per SM; long filters or large decimation
+    // factors need more room per CTA to have at least a tile per warp, and then run one CTA per SM
+    for (int pass = 0; pass < 2; ++pass) {
+        const size_t budget = pass ? 200 * 1024 : 110 * 1024;
+        for (int rows = ART_P_ROWS_MAX; rows >= 1; --rows) {
+            // shifts inside a phase block: consecutive phases advance by M/L samples
+            const int spread = (int) (((long long) (rows * 8 - 1) * M + L - 1) / L) + 2;
+            const int Kp = (k.T + spread + 31) & ~31;
+            for (int Qc = 64; Qc >= QT; Qc -= QT) {
+                ArtPeriodic t = p;
+                t.rowsPerCta = rows; t.Kp = Kp; t.Qc = Qc; t.Wc = (Qc - 1) * M + Kp;
+                if (periodic_smem (t, CV) > budget) continue;
+                // staged input is reused by rows*8 phases, the filters by Qc periods: weigh both, prefer
+                // enough tiles per chunk to keep 8 warps busy
+                const int tiles = rows * (Qc / QT);
+                const int warps = pass ? 16 : 8;
+                double score = (double) rows * 8 * Qc / (rows * 8 + Qc) * (tiles >= warps ? 1.0 : (double) tiles / warps);
+                score *= (double) k.T / Kp;                       // union-window padding is wasted FMAs
+                const int usedRows = (R + rows - 1) / rows * rows;
+                score *= (double) R / usedRows;                   // idle rows in the last phase block
+                if (pass) score *= 0.8;                           // one CTA per SM: no second CTA to hide the staging
+                if (score > bestScore) { bestScore = score; bestRows = rows; bestQc = Qc; }
+                break;                                            // largest Qc that fits for this row count
+            }
         }
     }
     if (!bestRows) return false;
@@ -443,7 +474,7 @@ bool artPlanPeriodic (const ArtClass &k, double ratio, unsigned int maxOutputs, 
     // the once-per-CTA filter fetch is amortised
     const long long perJob = (maxOutputs + L - 1) / L;
     const long long jobsApprox = perJob ? (periods + perJob - 1) / perJob : 1;
-    const long long slots = (long long) smCount * 2;
+    const long long slots = (long long) smCount * (periodic_smem (p, CV) > 110 * 1024 ? 1 : 2);
     int bestChunks = 1;
     double best = -1.0;
     for (int chunks = 1; chunks <= 16; ++chunks) {
@@ -491,11 +522,11 @@ int artPeriodicCtas (const ArtPeriodic &p, unsigned int outputs)
     return (int) (p.PB * ((Q + p.Qblk - 1) / p.Qblk));
 }
 
-template <int CV>
+template <int CV, int THREADS>
 static void launch_periodic (const ArtClass &k, const ArtPeriodic &p, int totalCtas, int numJobs, int numTables,
                              const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream)
 {
-    auto kern = art_sinc_periodic_kernel<CV>;
+    auto kern = art_sinc_periodic_kernel<CV, THREADS>;
     static size_t configured[16] = { 0 };
     int device = 0;
     ART_CUDA_CHECK (cudaGetDevice (&device));
@@ -510,10 +541,10 @@ static void launch_periodic (const ArtClass &k, const ArtPeriodic &p, int totalC
     const int prepBlocks = numTables * p.PB * p.rowsPerCta * 8 + (numJobs * p.PB + 127) / 128 + numJobs * histBlocks;
     art_periodic_prep_kernel<<<prepBlocks, 128, 0, stream>>> (k, p, single, d_jobs, numJobs, numTables, histBlocks);
     ART_CUDA_CHECK (cudaGetLastError ());
-    dim3 grid (totalCtas, (k.C + CV - 1) / CV);
+    const unsigned int grid = (unsigned int) totalCtas * (unsigned int) ((k.C + CV - 1) / CV);
     void *prof;
     artProfileBegin (stream, &prof);
-    kern<<<grid, ART_P_THREADS, smem, stream>>> (k, p, single, d_jobs);
+    kern<<<grid, THREADS, smem, stream>>> (k, p, single, d_jobs);
     artProfileEnd (stream, prof);
     ART_CUDA_CHECK (cudaGetLastError ());
     g_artLaunches += 2;
@@ -523,7 +554,14 @@ void artLaunchPeriodic (const ArtClass &k, const ArtPeriodic &p, int CV, int tot
                         const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream)
 {
     if (totalCtas <= 0) return;
-    if (CV == 4) launch_periodic<4> (k, p, totalCtas, numJobs, numTables, single, d_jobs, stream);
-    else if (CV == 2) launch_periodic<2> (k, p, totalCtas, numJobs, numTables, single, d_jobs, stream);
-    else launch_periodic<1> (k, p, totalCtas, numJobs, numTables, single, d_jobs, stream);
+    const bool big = periodic_smem (p, CV) > 110 * 1024;         // one CTA per SM: give it 16 warps
+#define ART_LP(CVV)                                                                                    \
+    do {                                                                                               \
+        if (big) launch_periodic<CVV, 512> (k, p, totalCtas, numJobs, numTables, single, d_jobs, stream); \
+        else     launch_periodic<CVV, 256> (k, p, totalCtas, numJobs, numTables, single, d_jobs, stream); \
+    } while (0)
+    if (CV == 4) ART_LP (4);
+    else if (CV == 2) ART_LP (2);
+    else ART_LP (1);
+#undef ART_LP
 }

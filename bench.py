@@ -256,6 +256,8 @@ def run_gpu_arm(args):
 
     # ---- timed region: device-resident ------------------------------------------------------------
     launches0 = lib.resampleB200KernelLaunches()
+    gen_0, per_0 = C.c_ulonglong(), C.c_ulonglong()
+    lib.resampleB200PathCounts(C.byref(gen_0), C.byref(per_0))
     lib.resampleB200ProfileEnable(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     out_frames = 0
@@ -276,6 +278,8 @@ def run_gpu_arm(args):
     kern_ms = C.c_double(0.0)
     kern_launches = lib.resampleB200ProfileCollect(C.byref(kern_ms))
     launches = lib.resampleB200KernelLaunches() - launches0
+    gen_n, per_n = C.c_ulonglong(), C.c_ulonglong()
+    lib.resampleB200PathCounts(C.byref(gen_n), C.byref(per_n))
 
     ms_max, total_frames = reduce_over_ranks(dist if world > 1 else None, dev, ms, float(out_frames))
     value = total_frames * CHANNELS / (ms_max * 1e-3) / 1e6
@@ -285,20 +289,29 @@ def run_gpu_arm(args):
 
     # ---- roofline of the convolution kernel ------------------------------------------------------------
     peak, peak_src = load_peaks()
+    periodic = (per_n.value - per_0.value) > 0 and (gen_n.value - gen_0.value) == 0
     per_launch_samples = out_frames * CHANNELS / max(1, kern_launches)
     kern_avg_ms = kern_ms.value / max(1, kern_launches)
     achieved = per_launch_samples * BYTES_PER_OUTPUT_SAMPLE / (kern_avg_ms * 1e-3) / 1e9
-    flops = per_launch_samples * (4 * TAPS + 3) / (kern_avg_ms * 1e-3) / 1e12
+    # the reference's operation count (two T-tap dot products + lerp) and what the kernel executes (the
+    # rational-ratio kernel applies ONE pre-interpolated filter over a 416-tap union window)
+    alg_tflops = per_launch_samples * (4 * TAPS + 3) / (kern_avg_ms * 1e-3) / 1e12
+    exe_tflops = per_launch_samples * (2 * 416 if periodic else 4 * 384) / (kern_avg_ms * 1e-3) / 1e12
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "art_sinc_generic_kernel<interp,float,CV=2>",
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "art_sinc_periodic_kernel<CV=2,256>" if periodic else "art_sinc_generic_kernel<interp,float,CV=2>",
                 "kernel_ms_per_launch": kern_avg_ms, "kernel_share_of_step": kern_ms.value / ms,
                 "algorithmic_bytes_per_output_sample": BYTES_PER_OUTPUT_SAMPLE,
-                "fp32_tflops": flops, "fp32_fma_peak_tflops_at_max_clock": 74.4,
-                "note": "arithmetic intensity 198 flop/B puts this path above the FP32 ridge: FP32 FMA issue binds, not HBM"}
-    prof = ROOT / "profiles" / "r01_ncu_summary.json"
-    if prof.exists():
+                "algorithmic_bytes_per_launch": per_launch_samples * BYTES_PER_OUTPUT_SAMPLE,
+                "fp32_tflops_reference_opcount": alg_tflops, "fp32_tflops_executed": exe_tflops,
+                "fp32_fma_peak_tflops_at_max_clock": 74.4, "fp32_frac_executed": exe_tflops / 74.4,
+                "note": "arithmetic intensity ~200 flop/B puts this path above the FP32 ridge (~11 flop/B): the FP32 FMA "
+                        "pipe binds, not HBM; frac is the HBM-roofline fraction BASELINE.json's metric asks for"}
+    prof = ROOT / "profiles" / ("r01_periodic_final_ncu.json" if periodic else "r01_generic_v2_ncu.json")
+    if prof.exists() and streams == 64 and frames == (1 << 18):
         try:
             roofline["traffic"] = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+            roofline["traffic_source"] = f"profiles/{prof.name} (ncu --set full, same launch geometry)"
         except Exception:
             pass
 

@@ -181,14 +181,35 @@ ART_HD ArtLoopPlan art_plan_loop (const ArtLoopState *s, int numIn, int numOut)
     unsigned int lo = 0, hi = numOut > 0 ? (unsigned int) numOut : 0;
     if (numIn < 0) numIn = 0;
 
-    /* largest N <= numOut with N == 0 or inputs_before(N-1) <= numIn (monotone in N) */
-    if (hi > 0 && art_inputs_before (s, hi - 1) <= numIn)
+    /* largest N <= numOut with N == 0 or inputs_before(N-1) <= numIn (monotone in N).  The answer is
+     * within a couple of units of (I + numIn - T/2 - P) * ratio, so bracket it from that estimate with
+     * doubling steps and bisect only inside the bracket: ~4 predicate evaluations instead of ~log2(numOut). */
+#define ART_OK(N) ((N) == 0 || art_inputs_before (s, (N) - 1) <= numIn)
+    if (hi > 0 && ART_OK (hi))
         lo = hi;
-    else
+    else if (hi > 0) {
+        double est = ((double) s->I + (double) numIn - (double) (s->T / 2) - s->P) * s->ratio;
+        unsigned int g, stepw = 2;
+        if (!(est > 0.0)) est = 0.0;
+        if (est > (double) hi) est = (double) hi;
+        g = (unsigned int) est;
+        if (ART_OK (g)) {
+            /* invariant: ok(lo), !ok(hi) */
+            lo = g;
+            while (lo + stepw < hi && ART_OK (lo + stepw)) { lo += stepw; stepw <<= 1; }
+            if (lo + stepw < hi) hi = lo + stepw;
+        }
+        else {
+            hi = g;
+            while (hi > stepw && !ART_OK (hi - stepw)) { hi -= stepw; stepw <<= 1; }
+            lo = hi > stepw ? hi - stepw : 0;
+        }
         while (hi - lo > 1) {
             unsigned int mid = lo + (hi - lo) / 2;
-            if (art_inputs_before (s, mid - 1) <= numIn) lo = mid; else hi = mid;
+            if (ART_OK (mid)) lo = mid; else hi = mid;
         }
+    }
+#undef ART_OK
 
     p.outputs = lo;
     if (numOut <= 0)

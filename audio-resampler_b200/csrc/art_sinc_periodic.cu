@@ -213,7 +213,7 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
 
     extern __shared__ __align__ (128) unsigned char smem_raw[];
     float *Hs = reinterpret_cast<float *> (smem_raw);            // [rows][NIg][2][32][4]
-    float *xsRaw = Hs + (size_t) p.rowsPerCta * 8 * p.Kp;        // [Wc + 4][CV] (+4: alignment slack of the bulk copy)
+    float *xsBuf = Hs + (size_t) p.rowsPerCta * 8 * p.Kp;        // [Wc + 4][CV] (+4: alignment slack of the bulk copy)
     __shared__ __align__ (8) unsigned long long bars[2];         // [0] filters, [1] input chunk
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -255,28 +255,29 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
     unsigned int xPhase = 0;
     bool filtersReady = false;
 
-    for (int q0 = qStart; q0 < qEnd; q0 += p.Qc) {
+    /* Stage chunk `q0` into buffer `buf`: asynchronously by TMA when it is a plain span of the caller's block
+     * (returns the float offset of sample 0 inside the buffer, >= 0), otherwise cooperatively by all threads
+     * (returns -1 - offset; the caller must __syncthreads before reading). */
+    auto stage = [&] (int q0) -> int {
         const int nq = min (p.Qc, qEnd - q0);
         const long long a = S0 + (long long) M * q0;             // region index of the chunk's first sample
         const int len = (nq - 1) * M + p.Kp;                      // samples per channel
-        __syncthreads ();                                         // previous chunk fully consumed
-
-        int xoff = 0;                                             // float offset of sample 0 inside xsRaw
+        float *xsRaw = xsBuf;
         const float *g = job.in + a * CV;
-        const bool fast = bulkOk && a >= -job.prevAvail && a + len + 4 <= (long long) job.inValid;
-        if (fast) {
+        if (bulkOk && a >= -job.prevAvail && a + len + 4 <= (long long) job.inValid) {
             // align the source down to 16 bytes; the same slack appears in front of the data in shared memory
-            xoff = (int) ((reinterpret_cast<unsigned long long> (g) >> 2) & 3);
+            const int xoff = (int) ((reinterpret_cast<unsigned long long> (g) >> 2) & 3);
             if (tid == 0) {
                 const unsigned int bytes = (unsigned int) (((size_t) len * CV + xoff + 3) & ~(size_t) 3) * sizeof (float);
                 art_mbar_expect_tx (&bars[1], bytes);
                 art_bulk_g2s (xsRaw, g - xoff, bytes, &bars[1]);
             }
+            return xoff;
         }
-        else if (CV > 1 && job.inPlanes == nullptr && job.inCS == 1 && c0 + CV <= k.C &&
-                 a >= -job.prevAvail && a + len <= (long long) job.inValid &&
-                 ((reinterpret_cast<unsigned long long> (job.in + a * job.inFS + c0) & (sizeof (VecT) - 1)) == 0) &&
-                 ((job.inFS * sizeof (float)) & (sizeof (VecT) - 1)) == 0) {
+        if (CV > 1 && job.inPlanes == nullptr && job.inCS == 1 && c0 + CV <= k.C &&
+            a >= -job.prevAvail && a + len <= (long long) job.inValid &&
+            ((reinterpret_cast<unsigned long long> (job.in + a * job.inFS + c0) & (sizeof (VecT) - 1)) == 0) &&
+            ((job.inFS * sizeof (float)) & (sizeof (VecT) - 1)) == 0) {
             // a CV-channel group of a wider interleaved block: one vector load per frame, four in flight
             const float *g0 = job.in + a * job.inFS + c0;
             VecT *dst = reinterpret_cast<VecT *> (xsRaw);
@@ -292,46 +293,67 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
             }
             for (; i < len; i += THREADS)
                 dst[i] = __ldg (reinterpret_cast<const VecT *> (g0 + (long long) i * job.inFS));
+            return -1;
         }
-        else {
-            const int total = len * CV;
-            for (int e = tid; e < total; e += THREADS) {
-                const int i = e / CV, v = e - i * CV;
-                xsRaw[e] = (c0 + v < k.C) ? art_fetch (job, T, c0 + v, a + i) : 0.0f;
-            }
+        const int total = len * CV;
+        for (int e = tid; e < total; e += THREADS) {
+            const int i = e / CV, v = e - i * CV;
+            xsRaw[e] = (c0 + v < k.C) ? art_fetch (job, T, c0 + v, a + i) : 0.0f;
         }
+        return -1;
+    };
+
+    /* (a second buffer with the next chunk's copy in flight was measured: no gain -- the second resident
+     * CTA already covers the copy -- so the shared memory goes to longer chunks instead) */
+    for (int q0 = qStart; q0 < qEnd; q0 += p.Qc) {
+        const int nq = min (p.Qc, qEnd - q0);
+        __syncthreads ();                                          // previous chunk fully consumed
+        const int mine = stage (q0);
         if (!filtersReady) {
             art_mbar_wait (&bars[0], 0);
             filtersReady = true;
         }
-        if (fast) {
+        int xoff = 0;
+        if (mine >= 0) {
             art_mbar_wait (&bars[1], xPhase);
             xPhase ^= 1;
+            xoff = mine;
         }
         else
-            __syncthreads ();
-        const float *xs = xsRaw + xoff;
+            __syncthreads ();                                      // cooperative stores of this chunk are complete
+        const float *xs = xsBuf + xoff;
 
         const int qTiles = (nq + QT - 1) / QT;
         for (int tile = warp; tile < nrows * qTiles; tile += (THREADS / 32)) {
             const int row = tile % nrows, qloc = (tile / nrows) * QT;
 
-            // 64 accumulators as 32 packed pairs: acc2[pp][col] = phases (2pp, 2pp+1) of the row, column col
+            /* 64 accumulators as 32 packed pairs: acc2[pp][col] = phases (2pp, 2pp+1) of the row x column col
+             * (col = period * CV + channel), in SLOT coordinates: a lane may hold its periods and its two
+             * half-rows in a lane-dependent order, because that order is only a matter of which pointer it
+             * loads from.  The lane bits chosen below make the three big stages of the transposing reduction
+             * (56 of 62 shuffles) need no select at all: every lane sends its upper slots and keeps its lower
+             * ones, and the XOR-permuted slot order guarantees partner lanes exchange matching values. */
+            constexpr int QB = CV == 1 ? 3 : (CV == 2 ? 2 : 1);         // period bits of a tile
+            // lane bits (from bit 4 down) are spent on: period bits, then the half-row bit, then the rest
+            const int qmask = (lane >> (5 - QB)) & (QT - 1);            // XOR applied to the period slot index
+            const int hsel = (lane >> (4 - QB)) & 1;                    // 1: this lane's slots 0,1 hold phases 4..7
+
             unsigned long long acc2[4][8];
 #pragma unroll
             for (int a2 = 0; a2 < 4; ++a2)
 #pragma unroll
                 for (int b2 = 0; b2 < 8; ++b2) acc2[a2][b2] = 0ull;
 
-            const float4 *hp = reinterpret_cast<const float4 *> (Hs) + (size_t) row * NIg * 64 + lane;
+            const float4 *hpA = reinterpret_cast<const float4 *> (Hs) + (size_t) row * NIg * 64 + lane + hsel * 32;
+            const float4 *hpB = reinterpret_cast<const float4 *> (Hs) + (size_t) row * NIg * 64 + lane + (1 - hsel) * 32;
             const VecT *xp[QT];
 #pragma unroll
             for (int qq = 0; qq < QT; ++qq)
-                xp[qq] = reinterpret_cast<const VecT *> (xs) + (size_t) min (qloc + qq, p.Qc - 1) * M + lane;
+                xp[qq] = reinterpret_cast<const VecT *> (xs) + (size_t) min (qloc + (qq ^ qmask), p.Qc - 1) * M + lane;
 
 #pragma unroll 2
             for (int i = 0; i < NIg; ++i) {
-                const float4 ha = hp[(i * 2) * 32], hb = hp[(i * 2 + 1) * 32];
+                const float4 ha = hpA[i * 64], hb = hpB[i * 64];
                 unsigned long long h2[4];
                 h2[0] = art_pack2 (ha.x, ha.y); h2[1] = art_pack2 (ha.z, ha.w);
                 h2[2] = art_pack2 (hb.x, hb.y); h2[3] = art_pack2 (hb.z, hb.w);
@@ -348,30 +370,63 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
                     }
                 }
             }
-            float acc[8][8];
+
+            /* flat value index: bit 0 = low/high phase of a pair, bits 1-3 = column slot, bits 4-5 = pair slot */
+            float v[64];
 #pragma unroll
             for (int pp = 0; pp < 4; ++pp)
 #pragma unroll
-                for (int b2 = 0; b2 < 8; ++b2)
-                    art_unpack2 (acc2[pp][b2], acc[2 * pp][b2], acc[2 * pp + 1][b2]);
+                for (int c = 0; c < 8; ++c)
+                    art_unpack2 (acc2[pp][c], v[(pp << 4) | (c << 1)], v[(pp << 4) | (c << 1) | 1]);
 
-            /* reduce across lanes: value index = col * 8 + jj, so that consecutive lanes hold consecutive
-             * phases = consecutive output frames */
+            // stage order: which flat bit each shuffle offset (16, 8, 4, 2, 1) folds away, and whether that
+            // bit was XOR-permuted per lane (select-free) or not
+            constexpr int chBits = CV == 1 ? 0 : (CV == 2 ? 1 : 2);
+            int consumed = 0;
 #pragma unroll
-            for (int halfSel = 0; halfSel < 2; ++halfSel) {
-                float vals[32];
+            for (int stage = 0; stage < 5; ++stage) {
+                const int off = 16 >> stage;
+                int bit;                                        // flat bit folded in this stage
+                bool isFree;
+                if (stage < QB)            { bit = 3 - stage;                 isFree = true; }     // period bits, high to low
+                else if (stage == QB)      { bit = 5;                         isFree = true; }     // half-row (pair bit 1)
+                else if (stage < QB + 1 + chBits) { bit = chBits - (stage - QB - 1);  isFree = false; }   // channel bits
+                else                       { bit = 4;                         isFree = false; }    // pair bit 0
+                const int bmask = 1 << bit;
+                const bool upper = (lane & off) != 0;
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int i = 0; i < 64; ++i) {
+                    if ((i & consumed) != 0 || (i & bmask) != 0) continue;
+                    if (isFree)
+                        v[i] += __shfl_xor_sync (0xffffffffu, v[i | bmask], off);
+                    else {
+                        const float send = upper ? v[i] : v[i | bmask];
+                        const float keep = upper ? v[i | bmask] : v[i];
+                        v[i] = keep + __shfl_xor_sync (0xffffffffu, send, off);
+                    }
+                }
+                consumed |= bmask;
+            }
+
+            /* every lane now owns one phase pair of one column: v[0], v[1] */
+            {
+                int lb = 4;                                     // walk the lane bits in the order they were spent
+                int qa = 0;
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj)
-                        vals[c * 8 + jj] = acc[jj][halfSel * 4 + c];
-                const float total = art_transpose_reduce<32, float> (vals, lane);
-                const int col = halfSel * 4 + (lane >> 3), jj = lane & 7;
-                const int qq = col / CV, v = col - qq * CV;
-                const int j = j0 + row * 8 + jj;
-                const long long nl = (long long) (q0 + qloc + qq) * L + j;        // output index inside the segment
-                if (j < L && qloc + qq < nq && nl < (long long) job.outputs && c0 + v < k.C)
-                    *art_out_ptr (job, c0 + v, (long long) job.nStart + nl) = total;
+                for (int t = 0; t < QB; ++t) qa = (qa << 1) | ((lane >> lb--) & 1);
+                const int pp1 = (lane >> lb--) & 1;
+                int ch = 0;
+#pragma unroll
+                for (int t = 0; t < chBits; ++t) ch = (ch << 1) | ((lane >> lb--) & 1);
+                const int pp0 = lane & 1;
+                const int j = j0 + row * 8 + ((pp1 << 1) | pp0) * 2;
+                const long long nl = (long long) (q0 + qloc + qa) * L + j;          // output index inside the segment
+                if (qloc + qa < nq && c0 + ch < k.C) {
+                    if (j < L && nl < (long long) job.outputs)
+                        *art_out_ptr (job, c0 + ch, (long long) job.nStart + nl) = v[0];
+                    if (j + 1 < L && nl + 1 < (long long) job.outputs)
+                        *art_out_ptr (job, c0 + ch, (long long) job.nStart + nl + 1) = v[1];
+                }
             }
         }
     }

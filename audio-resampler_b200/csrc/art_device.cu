@@ -312,28 +312,42 @@ static void finish_job (ArtDev *dev, const ArtCallPlan &p)
  * are cut into segments for the periodic kernel (see artPeriodicSegmentOutputs). */
 struct ArtLaunchPlan {
     ArtClass k;
-    bool periodic;
+    bool periodic;              // one of the two rational-ratio kernels
+    bool tiled;                 // ... the register-tiled one (art_sinc_periodic2.cu)
     ArtPeriodic per;
+    ArtPeriodic2 per2;
     int CV;
     ArtLaunchGeom g;
     unsigned int segLen;
 };
 
-static bool g_forceGeneric = false, g_envRead = false;
+static bool g_forceGeneric = false, g_useTiled = false, g_envRead = false;
 
 static void plan_launch (ArtDev *lead, double minRatio, bool oneRatio, unsigned int maxOut, unsigned long long totalOut,
                          bool allowPeriodic, ArtLaunchPlan &lp)
 {
     if (!g_envRead) {
         g_forceGeneric = getenv ("ART_B200_GENERIC") != nullptr;     // debugging / A-B measurements
+        // the register-tiled rational-ratio kernel (art_sinc_periodic2.cu) is experimental: correct, but its
+        // single-accumulator summation leaves a thin margin to the 1e-6 bar on long filters and its boundary
+        // staging is not tuned; opt in for measurements only
+        g_useTiled = getenv ("ART_B200_TILED") != nullptr;
         g_envRead = true;
     }
     lp.k = lead->klass;
     lp.periodic = false;
+    lp.tiled = false;
     lp.segLen = 0;
     if (!maxOut)
         return;
     const unsigned int total32 = (unsigned int) (totalOut > 0xffffffffULL ? 0xffffffffULL : totalOut);
+    if (allowPeriodic && oneRatio && !g_forceGeneric && g_useTiled &&
+        artPlanPeriodic2 (lp.k, minRatio, maxOut, lp.per2, lp.CV)) {
+        lp.periodic = lp.tiled = true;
+        lp.per.L = lp.per2.L; lp.per.M = lp.per2.M;
+        lp.segLen = artPeriodicSegmentOutputs (lp.per, minRatio);
+        return;
+    }
     if (allowPeriodic && oneRatio && !g_forceGeneric &&
         artPlanPeriodic (lp.k, minRatio, maxOut, totalOut, lead->smCount, lp.per, lp.CV)) {
         lp.periodic = true;
@@ -368,7 +382,7 @@ static int append_job (const ArtLaunchPlan &lp, const ArtJob &base, std::vector<
         j.tile0 = firstCta + ctas;
         if (at) j.histOut = nullptr;        // one history update per call
         jobs.push_back (j);
-        ctas += artPeriodicCtas (lp.per, j.outputs);
+        ctas += lp.tiled ? artPeriodic2Ctas (lp.per2, lp.CV, j.outputs) : artPeriodicCtas (lp.per, j.outputs);
     }
     return ctas;
 }
@@ -415,7 +429,8 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
         if (lp.periodic) {
             const size_t tableFloats = (size_t) numTables * lp.per.PB * lp.per.rowsPerCta * 8 * lp.per.Kp;
             const size_t tableInts = (size_t) n * lp.per.PB;
-            const size_t bytes = tableFloats * sizeof (float) + tableInts * sizeof (int);
+            const size_t bytes = lp.tiled ? artPeriodic2TableBytes (lp.per2, numTables, n)
+                                          : tableFloats * sizeof (float) + tableInts * sizeof (int);
             void *tables = nullptr;
             const bool persistent = owner && n == 1;
             if (persistent) {
@@ -429,9 +444,15 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
             }
             else
                 ART_CUDA_CHECK (cudaMallocAsync (&tables, bytes, stream));
-            lp.per.Hblk = reinterpret_cast<float *> (tables);
-            lp.per.S0 = reinterpret_cast<int *> (lp.per.Hblk + tableFloats);
-            artLaunchPeriodic (lp.k, lp.per, lp.CV, ctas, n, numTables, jobs[0], d_jobs, stream);
+            if (lp.tiled) {
+                artPeriodic2Carve (lp.per2, tables, numTables, n);
+                artLaunchPeriodic2 (lp.k, lp.per2, lp.CV, ctas, n, numTables, jobs[0], d_jobs, stream);
+            }
+            else {
+                lp.per.Hblk = reinterpret_cast<float *> (tables);
+                lp.per.S0 = reinterpret_cast<int *> (lp.per.Hblk + tableFloats);
+                artLaunchPeriodic (lp.k, lp.per, lp.CV, ctas, n, numTables, jobs[0], d_jobs, stream);
+            }
             ++g_pathLaunches[1];
             if (!persistent)
                 ART_CUDA_CHECK (cudaFreeAsync (tables, stream));

@@ -70,6 +70,16 @@ struct ArtPeriodic {
     int   *S0;           // [jobs][PB]  region index of the block's first tap, period 0
 };
 
+/* register-tiled form of the rational-ratio kernel (art_sinc_periodic2.cu) */
+struct ArtPeriodic2 {
+    int L, M;            // outputs / inputs per period
+    int PB;              // phase tiles of 80 phases
+    int Kt;              // taps per phase tile (union window), multiple of 32
+    float *Hg;           // [tables][PB][Kt][80]  filters of a phase tile, tap-major, zero outside the band
+    int   *D;            // [tables][PB * 80]     window shift of every phase inside its tile, -1 beyond L
+    int   *S0;           // [jobs][PB]            region index of the tile's first tap, period 0
+};
+
 /* Sum NV register values per lane across the warp so that lane L ends up with the total of
  * value (L * NV / 32).  log2(NV) exchange stages halve the value count while consuming one
  * lane bit each; the remaining lane bits are folded with a plain butterfly. */
@@ -142,6 +152,13 @@ unsigned int artPeriodicSegmentOutputs (const ArtPeriodic &p, double ratio);
 int  artPeriodicCtas (const ArtPeriodic &p, unsigned int outputs);
 void artLaunchPeriodic (const ArtClass &k, const ArtPeriodic &p, int CV, int totalCtas, int numJobs, int numTables,
                         const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream);
+
+bool artPlanPeriodic2 (const ArtClass &k, double ratio, unsigned int maxOutputs, ArtPeriodic2 &p, int &CV);
+int  artPeriodic2Ctas (const ArtPeriodic2 &p, int CV, unsigned int outputs);
+size_t artPeriodic2TableBytes (const ArtPeriodic2 &p, int numTables, int numJobs);
+void artPeriodic2Carve (ArtPeriodic2 &p, void *tables, int numTables, int numJobs);
+void artLaunchPeriodic2 (const ArtClass &k, const ArtPeriodic2 &p, int CV, int totalCtas, int numJobs, int numTables,
+                         const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream);
 
 extern unsigned long long g_artLaunches;
 

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <mutex>
 #include <vector>
 #include "art_kernels.cuh"
@@ -72,6 +73,7 @@ extern "C" unsigned long long artDevProfileCollect (double *totalMs)
 /* ---- filter banks are immutable and identical for equal (T, F, coefficients): share them ---- */
 struct ArtBank {
     int device, T, Tp, F, refs;
+    float absSum;
     unsigned long long hash;
     float *d_rows;
     std::vector<float> packed;
@@ -99,6 +101,12 @@ static ArtBank *bank_acquire (int device, int T, int F, const float *const *rows
     ArtBank *b = new ArtBank;
     b->device = device; b->T = T; b->Tp = Tp; b->F = F; b->refs = 1; b->hash = h;
     b->packed.swap (packed);
+    b->absSum = 0.0f;
+    for (int r = 0; r <= F; ++r) {
+        double s = 0.0;
+        for (int t = 0; t < T; ++t) s += fabs ((double) b->packed[(size_t) r * Tp + t]);
+        if (s > b->absSum) b->absSum = (float) s;
+    }
     if (cudaMalloc (&b->d_rows, b->packed.size () * sizeof (float)) != cudaSuccess ||
         cudaMemcpy (b->d_rows, b->packed.data (), b->packed.size () * sizeof (float), cudaMemcpyHostToDevice) != cudaSuccess) {
         fprintf (stderr, "libresampler_b200: cannot place the filter bank on the GPU: %s\n",
@@ -218,6 +226,7 @@ extern "C" ArtDev *artDevCreate (int channels, int taps, int filters, int mode, 
     memset (&k, 0, sizeof k);
     k.bank = dev->bank->d_rows;
     k.T = taps; k.Tp = dev->bank->Tp; k.F = filters; k.C = channels; k.mode = mode;
+    k.absSum = dev->bank->absSum;
     k.sort = getenv ("ART_B200_NOSORT") ? 0 : 1;
     return dev;
 }
@@ -314,6 +323,9 @@ struct ArtLaunchPlan {
     ArtClass k;
     bool periodic;              // one of the two rational-ratio kernels
     bool tiled;                 // ... the register-tiled one (art_sinc_periodic2.cu)
+    bool umma;                  // ... the tensor-core one (art_sinc_umma.cu)
+    ArtUmma um;
+    int smCount;
     ArtPeriodic per;
     ArtPeriodic2 per2;
     int CV;
@@ -337,9 +349,18 @@ static void plan_launch (ArtDev *lead, double minRatio, bool oneRatio, unsigned 
     lp.k = lead->klass;
     lp.periodic = false;
     lp.tiled = false;
+    lp.umma = false;
+    lp.smCount = lead->smCount;
     lp.segLen = 0;
     if (!maxOut)
         return;
+    if (allowPeriodic && oneRatio && !g_forceGeneric && !g_useTiled &&
+        artPlanUmma (lp.k, minRatio, maxOut, totalOut, lead->smCount, lp.um)) {
+        lp.periodic = lp.umma = true;
+        lp.per.L = lp.um.L; lp.per.M = lp.um.M;
+        lp.segLen = artPeriodicSegmentOutputs (lp.per, minRatio);
+        return;
+    }
     const unsigned int total32 = (unsigned int) (totalOut > 0xffffffffULL ? 0xffffffffULL : totalOut);
     if (allowPeriodic && oneRatio && !g_forceGeneric && g_useTiled &&
         artPlanPeriodic2 (lp.k, minRatio, maxOut, lp.per2, lp.CV)) {
@@ -382,7 +403,8 @@ static int append_job (const ArtLaunchPlan &lp, const ArtJob &base, std::vector<
         j.tile0 = firstCta + ctas;
         if (at) j.histOut = nullptr;        // one history update per call
         jobs.push_back (j);
-        ctas += lp.tiled ? artPeriodic2Ctas (lp.per2, lp.CV, j.outputs) : artPeriodicCtas (lp.per, j.outputs);
+        ctas += lp.umma ? artUmmaTiles (lp.um, lp.k.C, j.outputs)
+                        : lp.tiled ? artPeriodic2Ctas (lp.per2, lp.CV, j.outputs) : artPeriodicCtas (lp.per, j.outputs);
     }
     return ctas;
 }
@@ -429,7 +451,8 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
         if (lp.periodic) {
             const size_t tableFloats = (size_t) numTables * lp.per.PB * lp.per.rowsPerCta * 8 * lp.per.Kp;
             const size_t tableInts = (size_t) n * lp.per.PB;
-            const size_t bytes = lp.tiled ? artPeriodic2TableBytes (lp.per2, numTables, n)
+            const size_t bytes = lp.umma ? artUmmaTableBytes (lp.um, numTables, n, ctas)
+                               : lp.tiled ? artPeriodic2TableBytes (lp.per2, numTables, n)
                                           : tableFloats * sizeof (float) + tableInts * sizeof (int);
             void *tables = nullptr;
             const bool persistent = owner && n == 1;
@@ -444,7 +467,11 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
             }
             else
                 ART_CUDA_CHECK (cudaMallocAsync (&tables, bytes, stream));
-            if (lp.tiled) {
+            if (lp.umma) {
+                artUmmaCarve (lp.um, tables, numTables, n);
+                artLaunchUmma (lp.k, lp.um, ctas, n, numTables, lp.smCount, jobs[0], d_jobs, stream);
+            }
+            else if (lp.tiled) {
                 artPeriodic2Carve (lp.per2, tables, numTables, n);
                 artLaunchPeriodic2 (lp.k, lp.per2, lp.CV, ctas, n, numTables, jobs[0], d_jobs, stream);
             }

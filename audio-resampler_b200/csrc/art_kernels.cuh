@@ -54,6 +54,7 @@ struct ArtClass {
     int Wp;          // floats per smem plane
     int numJobs;
     int sort;        // 1: group a tile's outputs by filter row before convolving
+    float absSum;    // max over bank rows of sum |tap|: bounds sum |h| of any interpolated filter
 };
 
 /* rational-ratio kernel: per-launch geometry and the phase tables it reads (art_sinc_periodic.cu) */
@@ -78,6 +79,25 @@ struct ArtPeriodic2 {
     float *Hg;           // [tables][PB][Kt][80]  filters of a phase tile, tap-major, zero outside the band
     int   *D;            // [tables][PB * 80]     window shift of every phase inside its tile, -1 beyond L
     int   *S0;           // [jobs][PB]            region index of the tile's first tap, period 0
+};
+
+/* tensor-core form of the rational-ratio kernel (art_sinc_umma.cu): y[period, phase] as a product of the
+ * input read at stride M (rows = periods) and the banded matrix of pre-interpolated filters, on tcgen05 */
+#define ART_U_MAXK 96
+struct ArtUmma {
+    int L, M;            // outputs / inputs per period
+    int Npad;            // phases rounded up to 16: the N of every MMA
+    int KI;              // k-steps (16 taps) per input period: ceil(M / 16)
+    int numK;            // k-steps per tile
+    int rows;            // rows of the signal operand held per tile: 128 + largest row shift, padded
+    int DH;              // filter quantum is 2^-DH
+    int stages;          // depth of the filter stage ring
+    int tableHalfs;      // fp16 elements per table: numK * 3 * 2 * Npad * 8
+    unsigned short *H;   // [tables][numK][3 splits][2 k-planes][Npad][8]  fp16 bit patterns
+    int *S0;             // [jobs]  region index of tap 0 of phase 0, period 0
+    int *tileExp;        // [tiles] exponent e of the tile's signal quantum 2^e (block maximum <= 2^(e+11))
+    unsigned char ka[ART_U_MAXK], ki[ART_U_MAXK];      // k-step -> (row shift a, 16-tap group i), i outermost
+    unsigned char nA[16];                              // row shifts per 16-tap group
 };
 
 /* Sum NV register values per lane across the warp so that lane L ends up with the total of
@@ -159,6 +179,14 @@ size_t artPeriodic2TableBytes (const ArtPeriodic2 &p, int numTables, int numJobs
 void artPeriodic2Carve (ArtPeriodic2 &p, void *tables, int numTables, int numJobs);
 void artLaunchPeriodic2 (const ArtClass &k, const ArtPeriodic2 &p, int CV, int totalCtas, int numJobs, int numTables,
                          const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream);
+
+bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsigned long long totalOutputs,
+                  int smCount, ArtUmma &u);
+int  artUmmaTiles (const ArtUmma &u, int channels, unsigned int outputs);
+size_t artUmmaTableBytes (const ArtUmma &u, int numTables, int numJobs, int totalTiles);
+void artUmmaCarve (ArtUmma &u, void *tables, int numTables, int numJobs);
+void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int numJobs, int numTables, int smCount,
+                    const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream);
 
 extern unsigned long long g_artLaunches;
 

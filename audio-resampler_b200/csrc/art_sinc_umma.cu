@@ -1,0 +1,845 @@
+/*
+ * art_sinc_umma.cu -- the rational-ratio windowed-sinc kernel on the 5th-generation tensor cores
+ * (tcgen05.mma, accumulators in tensor memory; sm_100a).
+ *
+ * Same reference functions as art_sinc_periodic.cu (resampler.c:523-526, :640-643, :1135-1157,
+ * :1033-1044).  For ratio = L/M output n = L*q + j reads
+ *
+ *      y[q, j] = sum_k x[s_j + M*q + k] * h_j[k]
+ *
+ * which is a dense (periods x taps) by (taps x phases) product once the taps are counted from a
+ * common origin s_0 ("flat" tap index f = k + s_j - s_0, 0 <= f < M + T): D[q, j] = sum_f A[q, f] * B[j, f]
+ * with A[q, f] = x[s_0 + M*q + f] and B[j, f] = h_j[f - (s_j - s_0)] (zero outside the band).
+ *
+ *   operand A (signal)   The flat index is split as f = M*a + b: A[q, M*a + b] = x[s_0 + M*(q + a) + b] is row
+ *                        q + a of the matrix X[r, b] = x[s_0 + M*r + b].  X is held ONCE in shared memory
+ *                        (K-major, no swizzle, stored as 8-tap planes with rows at a 16-byte pitch) and the
+ *                        row shift a is nothing but +16*a bytes on the descriptor's start address -- no
+ *                        im2col copy of the overlapping windows is ever made.
+ *   operand B (filters)  built once per launch by the prep kernel in exactly the shared-memory image of a
+ *                        k-step (16 taps x Npad phases), streamed by TMA bulk copies through a 3-stage ring.
+ *   exact accumulation   Tensor-memory accumulation truncates (measured on B200: -0.15 ulp per MMA, see
+ *                        profiles/microbench/umma_probe.cu), which a chain of ~200 MMAs cannot afford at a
+ *                        1e-6 bar.  Integer-valued fp16 operands whose sums stay below 2^24 accumulate
+ *                        EXACTLY, so both operands are split in fixed point per tile:
+ *                            x = qx * (X1 + 2^-11 x2),   h = qh * (H1 + 2^-11 h2 + 2^-22 h3)
+ *                        X1, H1 integers of magnitude <= 2^11 (exact in fp16), x2/h2/h3 fp16 residuals.  Five
+ *                        MMAs per k-step feed three accumulators: [X1*H1] exact; [X1*h2 + x2*H1] and
+ *                        [X1*h3 + x2*h2] carry 2^-11 and 2^-22 of the weight, where truncation is harmless.
+ *                        The epilogue adds them in fp32 and applies the power-of-two scale.
+ *
+ * Warp roles (one CTA of 608 threads per SM, persistent over tiles of 128 periods x 1 channel):
+ *   warp 0      TMA producer: filter k-steps -> stage ring (cp.async.bulk + mbarrier)
+ *   warps 1-2   MMA issuers, alternating ring slots: 5 x tcgen05.mma (M=128, N=Npad, K=16) per k-step, tcgen05.commit
+ *   warps 3-10  converters: global -> fixed-point split -> operand A, a pair of 8-tap planes at a time
+ *   warps 11-18 epilogue: tcgen05.ld the three accumulators, combine, scale, transpose, store
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cuda_fp16.h>
+#include "art_kernels.cuh"
+#include "art_device.h"
+
+#define ART_U_THREADS 608           /* producer warp + 2 MMA warps + 8 converter warps + 8 epilogue warps */
+#define ART_U_EPI     256           /* epilogue threads */
+#define ART_U_CONV    256           /* converter threads */
+#define ART_U_STAGES  8           /* filter ring depth (fewer when shared memory is short) */
+#define ART_U_MAXKI   12
+#define ART_U_GROUP   2             /* k-steps per ring slot: one wait / commit per slot */
+#define ART_U_ROWS    128           /* periods per tile = M of the MMA */
+#define ART_U_DX      11            /* signal digit: |X1| <= 2^11 */
+
+__device__ __forceinline__ unsigned int u_smem (const void *p) { return (unsigned int) __cvta_generic_to_shared (p); }
+
+__device__ __forceinline__ void u_mbar_init (unsigned int bar, unsigned int count)
+{
+    asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+__device__ __forceinline__ void u_mbar_expect_tx (unsigned int bar, unsigned int bytes)
+{
+    asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void u_mbar_arrive (unsigned int bar)
+{
+    asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void u_mbar_wait (unsigned int bar, unsigned int parity)
+{
+    // the spin limit only turns a lost arrival (a bug) into a trap instead of a hung GPU
+    for (unsigned int spins = 0; spins < (1u << 27); ++spins) {
+        unsigned int done;
+        asm volatile (
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    printf ("libresampler_b200: tensor-core pipeline stalled (block %d, thread %d)\n", blockIdx.x, threadIdx.x);
+    __trap ();
+}
+/* for the roles that wait long (producer, converters, epilogue): sleep between polls, so that their spinning does not
+ * take issue slots and shared-memory atomic bandwidth from the warps that are working */
+__device__ __forceinline__ void u_mbar_wait_relaxed (unsigned int bar, unsigned int parity)
+{
+    for (unsigned int spins = 0; spins < (1u << 24); ++spins) {
+        unsigned int done;
+        asm volatile (
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        __nanosleep (200);
+    }
+    printf ("libresampler_b200: tensor-core pipeline stalled (block %d, thread %d)\n", blockIdx.x, threadIdx.x);
+    __trap ();
+}
+__device__ __forceinline__ void u_bulk_g2s (unsigned int dstSmem, const void *srcGlobal, unsigned int bytes, unsigned int bar)
+{
+    asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                  :: "r"(dstSmem), "l"(srcGlobal), "r"(bytes), "r"(bar) : "memory");
+}
+
+/* shared-memory matrix descriptor: K-major, no swizzle; lbo = bytes between the two 8-tap planes of a
+ * k-step, sbo = bytes between groups of 8 rows (128: rows sit at a uniform 16-byte pitch) */
+__device__ __forceinline__ unsigned long long u_desc (unsigned int addr, unsigned int lbo, unsigned int sbo)
+{
+    return (unsigned long long) ((addr >> 4) & 0x3fff) | ((unsigned long long) ((lbo >> 4) & 0x3fff) << 16) |
+           ((unsigned long long) ((sbo >> 4) & 0x3fff) << 32) | (1ull << 46);
+}
+/* instruction descriptor: fp32 accumulator, fp16 x fp16, both K-major, M x N */
+__device__ __forceinline__ unsigned int u_idesc (int M, int N)
+{
+    return (1u << 4) | ((unsigned int) (N >> 3) << 17) | ((unsigned int) (M >> 4) << 24);
+}
+__device__ __forceinline__ void u_mma (unsigned int tmem, unsigned long long da, unsigned long long db, unsigned int idesc, unsigned int acc)
+{
+    asm volatile ("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                  :: "r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+}
+/* Shared memory is addressed through 32-bit shared-window addresses derived once from the block's base: a generic
+ * pointer costs a read of the cluster CTA id (S2UR SR_CgaCtaId) at every use, which showed up in every store of the converters */
+__device__ __forceinline__ void u_sts16 (unsigned int addr, unsigned short v) { asm volatile ("st.shared.u16 [%0], %1;" :: "r"(addr), "h"(v) : "memory"); }
+__device__ __forceinline__ void u_sts32 (unsigned int addr, unsigned int v) { asm volatile ("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void u_stsf (unsigned int addr, float v) { asm volatile ("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float u_ldsf (unsigned int addr) { float v; asm volatile ("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ unsigned int u_lds32 (unsigned int addr) { unsigned int v; asm volatile ("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ uint2 u_lds64 (unsigned int addr) { uint2 v; asm volatile ("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ void u_sts64 (unsigned int addr, uint2 v) { asm volatile ("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(addr), "r"(v.x), "r"(v.y) : "memory"); }
+
+__device__ __forceinline__ bool u_elect ()
+{
+    unsigned int pred;
+    asm volatile ("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void u_commit (unsigned int bar)
+{
+    asm volatile ("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void u_tmem_ld32 (unsigned int addr, unsigned int (&r)[32])
+{
+    asm volatile ("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                  "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                    "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                  : "r"(addr));
+}
+__device__ __forceinline__ void u_tmem_ld16 (unsigned int addr, unsigned int (&r)[16])
+{
+    asm volatile ("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                  "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                  : "r"(addr));
+}
+
+/* optional role timing (ART_B200_UPROF=1): cycles spent waiting / working per role, summed over CTAs */
+__device__ unsigned long long g_uprof[16];
+#define UCLK() (prof ? clock64 () : 0ll)
+#define UPROF_ADD(slot, cyc) do { if (prof) pacc[slot] += (cyc); } while (0)      /* flushed once per thread at the end */
+
+__device__ __forceinline__ int u_find_job (const ArtJob *jobs, int numJobs, int tile)
+{
+    int lo = 0, hi = numJobs - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].tile0 <= tile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+/* ---- 1. prep: filter operand, per-job origins, history ------------------------------------------ */
+/* One block per (table, phase).  Phase j's interpolated filter h_j (the same float values the FFMA form
+ * uses: (float) (a + f (b - a)) in double, resampler.c:1155-1156 with the lerp folded into the taps) is
+ * cut into fixed-point digits and written in the shared-memory image of every k-step. */
+__global__ void __launch_bounds__ (128)
+art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__ ArtJob single,
+                      const ArtJob *__restrict__ jobs, int numJobs, int numTables, int histBlocksPerJob, int totalTiles, int dbg)
+{
+    const int tableBlocks = numTables * u.Npad;
+    const int originBlocks = (numJobs + 127) / 128;
+    int b = blockIdx.x;
+    const int T = k.T, half = T / 2, F = k.F;
+    if (b < tableBlocks) {
+        if (dbg & 16) return;
+        const int tbl = b / u.Npad, j = b - tbl * u.Npad;
+        const ArtJob &job = jobs ? jobs[jobs[tbl].repJob] : single;
+        __shared__ int sh_row, sh_pass, sh_shift;
+        __shared__ double sh_f;
+        if (threadIdx.x == 0) {
+            ArtLoopState st;
+            st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = T;
+            long long sj = 0, sb = 0;
+            int row = 0, pass = -1;
+            double f = 0.0;
+            for (int which = 0; which < 2; ++which) {               // 0: phase 0 (the origin), 1: this phase
+                const int ph = which ? j : 0;
+                if (ph >= u.L) break;
+                int w;
+                const double pos = art_output_pos (&st, job.nStart + ph, &w);
+                const double whole = floor (pos), fr = pos - whole;
+                const long long s = (long long) whole - half + 1 + (long long) w * 15LL * T - job.origin;
+                if (!which) { sb = s; continue; }
+                sj = s;
+                if (k.mode & ART_MODE_INTERP) {
+                    double phs = fr * F;                             // resampler.c:1149-1152
+                    row = (int) floor (phs);
+                    f = phs - row;
+                    if (row >= F) { row = F - 1; f = 1.0; }
+                }
+                else {
+                    row = (int) floor (fr * F + 0.5);                // resampler.c:1137
+                    if (!(k.mode & ART_MODE_LOWPASS) && row % F == 0)    // resampler.c:1141-1142
+                        pass = half - 1 + (row ? 1 : 0);
+                }
+            }
+            sh_row = row; sh_f = f; sh_pass = pass; sh_shift = (int) (sj - sb);
+        }
+        __syncthreads ();
+        const int row = sh_row, pass = sh_pass, shift = sh_shift;
+        const double f = sh_f;
+        const float *ra = k.bank + (size_t) row * k.Tp, *rb = ra + k.Tp;
+        unsigned short *tab = u.H + (size_t) tbl * u.tableHalfs;
+        const double qinv = (double) (1 << u.DH);
+        for (int kk = threadIdx.x; kk < u.numK * 16; kk += 128) {
+            const int ks = kk >> 4, e16 = kk & 15;
+            const int bb = 16 * u.ki[ks] + e16;
+            const int t = u.ka[ks] * u.M + bb - shift;
+            float h = 0.0f;
+            if (j < u.L && bb < u.M && t >= 0 && t < T) {
+                if (pass >= 0)
+                    h = t == pass ? 1.0f : 0.0f;
+                else if (k.mode & ART_MODE_INTERP) {
+                    const double a = ra[t], c = rb[t];
+                    h = (float) (a + f * (c - a));
+                }
+                else
+                    h = ra[t];
+            }
+            const double v = (double) h * qinv;
+            const double H1 = rint (v);
+            const double r1 = (v - H1) * 2048.0;
+            const __half h2 = __double2half (r1);
+            const double r2 = (r1 - (double) __half2float (h2)) * 2048.0;
+            const __half h3 = __double2half (r2);
+            const __half h1 = __double2half (H1);
+            // [ks][split][plane][Npad][8]
+            const size_t at = (((size_t) ks * 3 * 2 + (e16 >> 3)) * u.Npad + j) * 8 + (e16 & 7);
+            const size_t splitStride = (size_t) 2 * u.Npad * 8;
+            tab[at] = __half_as_ushort (h1);
+            tab[at + splitStride] = __half_as_ushort (h2);
+            tab[at + 2 * splitStride] = __half_as_ushort (h3);
+        }
+        return;
+    }
+    b -= tableBlocks;
+    if (b < originBlocks) {
+        const int seg = b * 128 + threadIdx.x;
+        if (seg >= numJobs) return;
+        const ArtJob &job = jobs ? jobs[seg] : single;
+        ArtLoopState st;
+        st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = T;
+        int w;
+        const double pos = art_output_pos (&st, job.nStart, &w);
+        u.S0[seg] = (int) ((long long) floor (pos) - half + 1 + (long long) w * 15LL * T - job.origin);
+        return;
+    }
+    b -= originBlocks;
+    if (b < totalTiles) {
+        /* block maximum of the samples a tile reads -> exponent of its power-of-two quantum: |x| / 2^e <= 2^11.
+         * One block serves the tiles of all channels of a period block (they read the same frames); blocks whose
+         * index is not a multiple of C return.  (The origin is recomputed: the origin block may run later.) */
+        const int tile = b;
+        if (dbg & 32) { if (threadIdx.x == 0) u.tileExp[tile] = -10; return; }
+        const int seg = jobs ? (numJobs > 1 ? u_find_job (jobs, numJobs, tile) : 0) : 0;
+        const ArtJob &job = jobs ? jobs[seg] : single;
+        const int local = tile - job.tile0;
+        const int C = k.C;
+        if (local % C) return;
+        const int qb = local / C;
+        ArtLoopState st;
+        st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = T;
+        int w;
+        const double pos = art_output_pos (&st, job.nStart, &w);
+        const long long S0 = (long long) floor (pos) - half + 1 + (long long) w * 15LL * T - job.origin;
+        const long long R0 = S0 + (long long) u.M * qb * 128;
+        const int span = u.M * (u.rows - 1) + 16 * u.KI;
+        const bool inside = job.inPlanes == nullptr && R0 >= -job.prevAvail && R0 + span <= (long long) job.inValid;
+        __shared__ float red[4];
+        if (inside && C == 2 && job.inCS == 1 && job.inFS == 2) {
+            // interleaved stereo: the block is one contiguous run; 16-byte loads over its aligned interior
+            const float *p0 = job.in + R0 * 2, *p1 = p0 + (size_t) span * 2;
+            float m0 = 0.0f, m1 = 0.0f;
+            const float *a0 = reinterpret_cast<const float *> ((reinterpret_cast<unsigned long long> (p0) + 15) & ~15ull);
+            const float *a1 = reinterpret_cast<const float *> (reinterpret_cast<unsigned long long> (p1) & ~15ull);
+            const bool odd = ((a0 - p0) & 1) != 0;                          // a0 starts on a right-channel sample
+            for (const float *p = p0 + threadIdx.x; p < a0; p += 128) { const float v = fabsf (*p); if ((p - p0) & 1) m1 = fmaxf (m1, v); else m0 = fmaxf (m0, v); }
+            for (const float *p = a1 + threadIdx.x; p < p1; p += 128) { const float v = fabsf (*p); if ((p - p0) & 1) m1 = fmaxf (m1, v); else m0 = fmaxf (m0, v); }
+            const float4 *q = reinterpret_cast<const float4 *> (a0);
+            const int n4 = (int) ((a1 - a0) >> 2);
+            float e0 = 0.0f, e1 = 0.0f;
+#pragma unroll 8
+            for (int i = threadIdx.x; i < n4; i += 128) {
+                const float4 v = __ldg (q + i);
+                e0 = fmaxf (e0, fmaxf (fabsf (v.x), fabsf (v.z)));
+                e1 = fmaxf (e1, fmaxf (fabsf (v.y), fabsf (v.w)));
+            }
+            m0 = fmaxf (m0, odd ? e1 : e0);
+            m1 = fmaxf (m1, odd ? e0 : e1);
+            for (int c = 0; c < 2; ++c) {
+                float m = c ? m1 : m0;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) m = fmaxf (m, __shfl_xor_sync (0xffffffffu, m, off));
+                __syncthreads ();
+                if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+                __syncthreads ();
+                if (threadIdx.x == 0) {
+                    m = fmaxf (fmaxf (red[0], red[1]), fmaxf (red[2], red[3]));
+                    int e = 0;
+                    if (m > 0.0f) { (void) frexpf (m, &e); e -= 11; e = e < -100 ? -100 : (e > 100 ? 100 : e); }
+                    u.tileExp[tile + c] = e;
+                }
+            }
+            return;
+        }
+        for (int c = 0; c < C; ++c) {
+            float m = 0.0f;
+            {
+                // the part inside the caller's block, then the part that comes from the history; the rest is silence
+                const long long lo = R0 > -job.prevAvail ? R0 : -job.prevAvail;
+                const long long hi = R0 + span < (long long) job.inValid ? R0 + span : (long long) job.inValid;
+                const float *base = job.inPlanes ? job.inPlanes[c] : job.in + (long long) c * job.inCS;
+                const long long fs = job.inFS;
+#pragma unroll 16
+                for (long long i = lo + threadIdx.x; i < hi; i += 128) m = fmaxf (m, fabsf (__ldg (base + i * fs)));
+                const long long hlo = R0 > -job.prevAvail - T ? R0 : -job.prevAvail - T;
+                const long long hhi = R0 + span < -job.prevAvail ? R0 + span : -job.prevAvail;
+                const float *hist = job.hist + (long long) c * T + T + job.prevAvail;
+                for (long long i = hlo + threadIdx.x; i < hhi; i += 128) m = fmaxf (m, fabsf (hist[i]));
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) m = fmaxf (m, __shfl_xor_sync (0xffffffffu, m, off));
+            __syncthreads ();
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+            __syncthreads ();
+            if (threadIdx.x == 0) {
+                m = fmaxf (fmaxf (red[0], red[1]), fmaxf (red[2], red[3]));
+                int e = 0;
+                if (m > 0.0f) { (void) frexpf (m, &e); e -= 11; e = e < -100 ? -100 : (e > 100 ? 100 : e); }    // m < 2^e
+                u.tileExp[tile + c] = e;
+            }
+        }
+        return;
+    }
+    b -= totalTiles;
+    {
+        const int seg = b / histBlocksPerJob, hb = b - seg * histBlocksPerJob;
+        const ArtJob &job = jobs ? jobs[seg] : single;
+        if (!job.histOut) return;
+        const int total = k.C * T;
+        for (int e = hb * 128 + threadIdx.x; e < total; e += histBlocksPerJob * 128) {
+            const int c = e / T, i = e - c * T;
+            job.histOut[e] = art_fetch (job, T, c, job.consumed - T + i);
+        }
+    }
+}
+
+/* ---- 2. the product ------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__ (ART_U_THREADS, 1)
+art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const __grid_constant__ ArtJob single,
+                      const ArtJob *__restrict__ jobs, int totalTiles, int profArg)
+{
+    const int prof = profArg & 1, dbg = profArg >> 4;
+    long long pacc[16] = { 0 };
+    extern __shared__ __align__ (1024) unsigned char smem[];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int L = u.L, M = u.M, Npad = u.Npad, KI = u.KI, numK = u.numK, C = k.C, T = k.T;
+    const unsigned int planeBytes = (unsigned int) u.rows * 16u;
+    const unsigned int splitBytes = planeBytes * 2u * (unsigned int) KI;
+    const unsigned int stageBytes = 3u * 2u * (unsigned int) Npad * 16u;
+    // [operand A: 2 splits][filter stage ring][epilogue transposition scratch][barriers and small tables]
+    unsigned int xcBase;
+    asm volatile ("mov.u32 %0, %1;" : "=r"(xcBase) : "r"(u_smem (smem)));       // opaque: never rematerialised from the generic pointer
+    const unsigned int stBase = xcBase + 2u * splitBytes;
+    const unsigned int scratchBase = stBase + (unsigned int) u.stages * stageBytes;
+    const unsigned int ctl = scratchBase + 8u * 32u * 17u * 4u;
+    const int units = u.stages / ART_U_GROUP;             // ring slots of ART_U_GROUP k-steps
+#define hFullA(s)   (ctl + 8u * (unsigned int) (s))
+#define hEmptyA(s)  (ctl + 64u + 8u * (unsigned int) (s))
+#define pFullA(i)   (ctl + 128u + 8u * (unsigned int) (i))
+#define pEmptyA(i)  (ctl + 224u + 8u * (unsigned int) (i))
+#define accFullA    (ctl + 320u)
+#define accEmptyA   (ctl + 328u)
+#define tmemSlotA   (ctl + 336u)
+#define goA(w)      (ctl + ((w) ? 368u : 344u))                         /* issue token of MMA issuer w */
+#define sScaleA(j)  (ctl + 352u + 4u * (unsigned int) (j))
+#define kTabA(ks)   (ctl + 384u + 8u * (unsigned int) (ks))          /* per k-step: low descriptor word of operand A, flags | plane pair << 8 */
+
+    const int unitsPerTile = (numK + ART_U_GROUP - 1) / ART_U_GROUP;
+    if (tid == 0) {
+        for (int s = 0; s < units; ++s) { u_mbar_init (hFullA (s), 1); u_mbar_init (hEmptyA (s), 1); }
+        for (int i = 0; i < KI; ++i) {
+            // a pair of planes is released by every issuer that used it
+            unsigned int who = 0;
+            for (int ks = 0; ks < numK; ++ks)
+                if (u.ki[ks] == i) who |= 1u << ((ks / ART_U_GROUP) & 1);
+            u_mbar_init (pFullA (i), ART_U_CONV / 32);
+            u_mbar_init (pEmptyA (i), who == 3u ? 2 : 1);
+        }
+        u_mbar_init (accFullA, unitsPerTile > 1 ? 2 : 1);
+        u_mbar_init (accEmptyA, ART_U_EPI / 32);
+        u_mbar_init (goA (0), 1);
+        u_mbar_init (goA (1), 1);
+        asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int ks = tid; ks < numK; ks += ART_U_THREADS) {
+        const unsigned int i = u.ki[ks], a = u.ka[ks];
+        const unsigned int aAddr = xcBase + 2u * i * planeBytes + 16u * a;                 // row shift a = +16 bytes
+        // bit 1: the last k-step of its pair of planes that this k-step's issuer handles
+        const int mine = (ks / ART_U_GROUP) & 1;
+        bool last = true;
+        for (int k2 = ks + 1; k2 < numK && u.ki[k2] == i; ++k2)
+            if (((k2 / ART_U_GROUP) & 1) == mine) last = false;
+        u_sts64 (kTabA (ks), make_uint2 (((aAddr >> 4) & 0x3fffu) | (((planeBytes >> 4) & 0x3fffu) << 16),
+                                         (a == 0 ? 1u : 0u) | (last ? 2u : 0u) | (i << 8)));
+    }
+    if (warp == 0) {
+        asm volatile ("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmemSlotA), "r"(512));
+        asm volatile ("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads ();
+    asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned int tm = u_lds32 (tmemSlotA);
+
+    const ArtJob *const singlePtr = &single;
+    auto jobOf = [=] (int tile) -> const ArtJob & {
+        return jobs ? jobs[k.numJobs > 1 ? u_find_job (jobs, k.numJobs, tile) : 0] : *singlePtr;
+    };
+
+    if (warp == 0) {
+        /* ===== TMA producer: the tile's filter table, two k-steps per copy ===== */
+        if (lane == 0) {
+            unsigned int us = 0, ph = 0;
+            for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
+                const ArtJob &job = jobOf (tile);
+                const unsigned short *tab = u.H + (size_t) job.table * u.tableHalfs;
+                for (int ks = 0; ks < numK; ks += ART_U_GROUP) {
+                    const unsigned int bytes = (unsigned int) (numK - ks < ART_U_GROUP ? numK - ks : ART_U_GROUP) * stageBytes;
+                    long long t0 = UCLK ();
+                    u_mbar_wait_relaxed (hEmptyA (us), ph ^ 1);
+                    UPROF_ADD (0, UCLK () - t0);
+                    if (dbg & 2) { u_mbar_arrive (hFullA (us)); }
+                    else {
+                        u_mbar_expect_tx (hFullA (us), bytes);
+                        u_bulk_g2s (stBase + us * (ART_U_GROUP * stageBytes), tab + (size_t) ks * (stageBytes / 2), bytes, hFullA (us));
+                    }
+                    if (++us == (unsigned int) units) { us = 0; ph ^= 1; }
+                }
+            }
+        }
+    }
+    else if (warp < 3) {
+        /* ===== MMA issuers.  A single thread needs ~460 cycles to issue a k-step whose five MMAs run for 400, so two warps
+         * share the work: ring slots (ART_U_GROUP k-steps) alternate between them.  Each whole warp walks the loop (uniform
+         * control flow) and one elected lane issues.  Every tcgen05.commit costs the tensor pipe ~85 cycles (measured,
+         * profiles/microbench/umma_probe.cu): one per slot, one per issuer and pair of planes, one per issuer and tile ===== */
+        const unsigned int me = (unsigned int) (warp - 1);
+        const unsigned int idesc = u_idesc (ART_U_ROWS, Npad);
+        const unsigned int bSplitU = (2u * (unsigned int) Npad * 16u) >> 4, stageU = stageBytes >> 4;
+        const unsigned long long descHi = ((unsigned long long) (128u >> 4) << 32) | (1ull << 46);      // SBO = 128, version 1
+        const unsigned int bLo0 = ((stBase >> 4) & 0x3fffu) | ((((unsigned int) Npad * 16u >> 4) & 0x3fffu) << 16);
+        const unsigned int aSplitU = splitBytes >> 4;
+        unsigned int us = 0, ph = 0, lt = 0, gw = 0;
+        for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++lt) {
+            long long t1 = UCLK ();
+            // the accumulators are free once the epilogue has drained them (the second issuer starts on the first one's token)
+            if (me == 0) u_mbar_wait (accEmptyA, (lt & 1) ^ 1);
+            long long t2 = UCLK ();
+            if (lane == 0 && me == 0) UPROF_ADD (2, t2 - t1);
+            asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
+            unsigned int unit = 0;
+            for (int ks0 = 0; ks0 < numK; ks0 += ART_U_GROUP, ++unit) {
+                if ((unit & 1u) == me) {
+                    const int cnt = numK - ks0 < ART_U_GROUP ? numK - ks0 : ART_U_GROUP;
+                    long long t0 = UCLK ();
+                    for (int g = 0; g < cnt; ++g)
+                        u_mbar_wait (pFullA (u_lds64 (kTabA (ks0 + g)).y >> 8), lt & 1);   // the converters filled this pair of planes
+                    long long t3 = UCLK ();
+                    u_mbar_wait (hFullA (us), ph);
+                    if (lane == 0 && me == 0) { UPROF_ADD (1, t3 - t0); UPROF_ADD (3, UCLK () - t3); }
+                    // slots are issued strictly in order -- the two issuers pass a token -- so that every accumulator sees its
+                    // MMAs in one fixed order: the truncating accumulation (classes 2 and 3) stays bit-reproducible
+                    if (unit > 0) { u_mbar_wait (goA (me), gw & 1); ++gw; }
+                    asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    long long t4 = UCLK ();
+                    if (u_elect ()) {
+                        for (int g = 0; g < cnt; ++g) {
+                            const int ks = ks0 + g;
+                            const uint2 kt = u_lds64 (kTabA (ks));
+                            const unsigned int aLo = kt.x;
+                            const unsigned int bLo = bLo0 + (us * ART_U_GROUP + (unsigned int) g) * stageU;
+                            const unsigned long long dA1 = descHi | aLo, dA2 = descHi | (aLo + aSplitU);
+                            const unsigned long long dB1 = descHi | bLo, dB2 = descHi | (bLo + bSplitU), dB3 = descHi | (bLo + 2u * bSplitU);
+                            const unsigned int acc = ks > 0;
+                            if (!(dbg & 8)) {
+                            u_mma (tm, dA1, dB1, idesc, acc);                       // X1 * H1   (exact)
+                            u_mma (tm + Npad, dA1, dB2, idesc, acc);                // X1 * h2
+                            u_mma (tm + Npad, dA2, dB1, idesc, 1);                  // x2 * H1
+                            u_mma (tm + 2 * Npad, dA1, dB3, idesc, acc);            // X1 * h3
+                            u_mma (tm + 2 * Npad, dA2, dB2, idesc, 1);              // x2 * h2
+                            }
+                            if (kt.y & 2)
+                                u_commit (pEmptyA (kt.y >> 8));                      // this issuer is done with the pair of planes
+                        }
+                        long long t5 = UCLK ();
+                        u_commit (hEmptyA (us));
+                        if ((int) unit + 1 < unitsPerTile) u_mbar_arrive (goA (me ^ 1u));     // the next slot is the other issuer's
+                        if (me == 0) { UPROF_ADD (11, t5 - t4); UPROF_ADD (12, UCLK () - t5); }
+                    }
+                    __syncwarp ();
+                    if (lane == 0 && me == 0) UPROF_ADD (13, UCLK () - t4);
+                }
+                if (++us == (unsigned int) units) { us = 0; ph ^= 1; }
+            }
+            if (me < unit) {                                                     // this issuer had work in the tile
+                if (u_elect ())
+                    u_commit (accFullA);
+                __syncwarp ();
+            }
+            if (lane == 0 && me == 0) UPROF_ADD (4, UCLK () - t2);
+        }
+    }
+    else if (warp < 11) {
+        /* ===== converters: signal -> fixed-point operand A, one pair of 8-tap planes at a time ===== */
+        const int ctid = tid - 96, cw = ctid >> 5;
+        const int span = M * (u.rows - 1) + 16 * KI;                       // samples the tile touches per channel
+        constexpr int UN = 9;                                               // row pairs per warp: rows <= 144
+        const int r0 = 2 * cw + (lane >> 4);                                // this lane's row in the first pair
+        const int off0 = M * r0 + (lane & 15);                              // its sample offset inside the tile, plane pair 0
+        unsigned int lt = 0;
+        float v[UN], vn[UN];
+        const int nU = (u.rows / 2 - cw + 7) / 8;                           // row pairs this warp owns
+
+        /* what a lane needs to fetch its samples of one tile */
+        /* what a lane needs to fetch its samples of one tile.  Inside the caller's block a sample is base[idx * fs];
+         * tiles that touch the history or run past the end of the input take the same loads from a clamped address
+         * and zero what must read as silence, so that all loads of a plane pair are still issued back to back */
+        struct Src { const float *p, *base, *hist; long long fs, R0, lo, hi; bool fast; };
+        auto source = [&] (int tile) -> Src {
+            Src sc;
+            const ArtJob &job = jobOf (tile);
+            const int seg = (int) (&job - (jobs ? jobs : singlePtr));
+            const int local = tile - job.tile0;
+            const int qb = local / C, c = local - qb * C;
+            sc.R0 = (long long) u.S0[seg] + (long long) M * qb * ART_U_ROWS;
+            sc.lo = -job.prevAvail; sc.hi = job.inValid;
+            sc.fast = sc.R0 >= sc.lo && sc.R0 + span <= sc.hi;
+            sc.fs = job.inFS;
+            sc.base = job.inPlanes ? job.inPlanes[c] : job.in + (long long) c * job.inCS;
+            sc.hist = job.hist + (long long) c * T + T + job.prevAvail;       // hist[idx]: -T - prevAvail <= idx < -prevAvail
+            sc.p = sc.base + (sc.R0 + off0) * sc.fs;
+            return sc;
+        };
+        auto fetch = [&] (const Src &sc, int i, float (&dst)[UN]) {
+            if (sc.fast) {
+                const float *p = sc.p + (long long) (16 * i) * sc.fs;
+                const long long rowStep = (long long) (16 * M) * sc.fs;
+#pragma unroll
+                for (int uu = 0; uu < UN; ++uu) {
+                    dst[uu] = (uu < nU && !(dbg & 1)) ? __ldg (p) : 0.0f;
+                    p += rowStep;
+                }
+            }
+            else {
+                const float *ptr[UN];
+                bool ok[UN];
+#pragma unroll
+                for (int uu = 0; uu < UN; ++uu) {
+                    const long long idx = sc.R0 + off0 + 16 * i + 16 * M * uu;
+                    const bool inBlock = idx >= sc.lo && idx < sc.hi, inHist = idx < sc.lo && idx >= sc.lo - T;
+                    ok[uu] = (inBlock || inHist) && uu < nU;
+                    ptr[uu] = inBlock ? sc.base + idx * sc.fs : (inHist ? sc.hist + idx : sc.hist + sc.lo - 1);
+                }
+#pragma unroll
+                for (int uu = 0; uu < UN; ++uu) dst[uu] = __ldg (ptr[uu]);
+#pragma unroll
+                for (int uu = 0; uu < UN; ++uu) dst[uu] = ok[uu] ? dst[uu] : 0.0f;
+            }
+        };
+
+        Src cur = source (blockIdx.x < totalTiles ? blockIdx.x : 0);
+        if ((int) blockIdx.x < totalTiles) fetch (cur, 0, vn);
+        for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++lt) {
+            const int e = u.tileExp[tile];
+            const float invq = __int_as_float ((127 - e) << 23);
+            if (ctid == 0)
+                u_stsf (sScaleA (lt & 3), __int_as_float ((127 + e) << 23) * __int_as_float ((127 - u.DH) << 23));
+            const bool more = tile + (int) gridDim.x < totalTiles;
+            Src nxt = cur;
+            for (int i = 0; i < KI; ++i) {
+                long long ca = UCLK ();
+#pragma unroll
+                for (int uu = 0; uu < UN; ++uu) v[uu] = vn[uu];
+                // the next pair's loads (of the next tile after the last pair) fly while this pair is converted
+                if (i + 1 < KI) fetch (cur, i + 1, vn);
+                else if (more) { nxt = source (tile + gridDim.x); fetch (nxt, 0, vn); }
+                long long c0t = UCLK ();
+                u_mbar_wait_relaxed (pEmptyA (i), (lt & 1) ^ 1);
+                long long cb = UCLK ();
+                if (ctid == 0) { UPROF_ADD (6, c0t - ca); UPROF_ADD (5, cb - c0t); }
+                const unsigned int dst = xcBase + (unsigned int) (2 * i + ((lane >> 3) & 1)) * planeBytes + (unsigned int) (lane & 7) * 2u +
+                                         (unsigned int) r0 * 16u;
+#pragma unroll
+                for (int uu = 0; uu < UN; ++uu) {
+                    if (uu < nU) {
+                        const float uq = v[uu] * invq;
+                        const float X1 = (uq + 12582912.0f) - 12582912.0f;          // round to nearest integer (|uq| <= 2^11)
+                        const float r = (uq - X1) * 2048.0f;
+                        const __half2 pk = __floats2half2_rn (X1, r);                // one conversion instruction for both digits
+                        const unsigned int bits = *reinterpret_cast<const unsigned int *> (&pk);
+                        u_sts16 (dst + uu * 256, (unsigned short) bits);
+                        u_sts16 (dst + splitBytes + uu * 256, (unsigned short) (bits >> 16));
+                    }
+                }
+                long long cc = UCLK ();
+                asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> tensor-core reads
+                long long cd = UCLK ();
+                __syncwarp ();
+                if (lane == 0) u_mbar_arrive (pFullA (i));                          // one arrival per warp: 256 serialised arrivals cost ~500 cycles
+                if (ctid == 0) { UPROF_ADD (7, cc - cb); UPROF_ADD (14, cd - cc); UPROF_ADD (15, UCLK () - cd); }
+            }
+            cur = nxt;
+        }
+    }
+    else {
+        /* ===== epilogue: accumulators -> output, transposed through shared memory so that a warp stores runs of phases ===== */
+        const int quad = warp & 3;                                          // (warps 11-18: every quarter is served by two warps)
+        const int qslot = (warp - 11) >> 2; (void) qslot;                                          // TMEM lanes 32*quad .. 32*quad+31
+        const unsigned int tmRow = tm + ((unsigned int) (quad * 32) << 16);
+        const unsigned int scratch = scratchBase + (unsigned int) (warp - 11) * (32u * 17u * 4u);
+        const int half16 = lane >> 4, col = lane & 15;
+        unsigned int lt = 0;
+        for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++lt) {
+            const ArtJob &job = jobOf (tile);
+            const int local = tile - job.tile0;
+            const int qb = local / C, c = local - qb * C;
+            long long e0 = UCLK ();
+            u_mbar_wait_relaxed (accFullA, lt & 1);
+            long long e1 = UCLK ();
+            asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const float scale = u_ldsf (sScaleA (lt & 3));
+            // job fields into registers: the output stores below may alias anything as far as the compiler knows
+            const long long outputs = job.outputs, outFS = job.outFS;
+            float *const obase = (job.outPlanes ? job.outPlanes[c] : job.out + (long long) c * job.outCS) + (long long) job.nStart * outFS;
+            const long long q0 = (long long) qb * ART_U_ROWS + quad * 32;    // period of this warp's row 0
+            for (int c0 = 16 * ((warp - 11) >> 2); c0 < ((dbg & 4) ? 0 : Npad); c0 += 32) {
+                unsigned int a1[16], a2[16], a3[16];
+                u_tmem_ld16 (tmRow + (unsigned int) c0, a1);
+                u_tmem_ld16 (tmRow + (unsigned int) (Npad + c0), a2);
+                u_tmem_ld16 (tmRow + (unsigned int) (2 * Npad + c0), a3);
+                asm volatile ("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    u_stsf (scratch + (unsigned int) (lane * 17 + j) * 4u,
+                            ((__uint_as_float (a3[j]) * (1.0f / 4194304.0f) + __uint_as_float (a2[j]) * (1.0f / 2048.0f)) + __uint_as_float (a1[j])) * scale);
+                __syncwarp ();
+                const int ph = c0 + col;                                     // this lane's phase
+                long long nl = (q0 + half16) * L + ph;                       // output index inside the job, rows advance by 2
+                float *op = obase + nl * outFS;
+                const unsigned int sp = scratch + (unsigned int) (half16 * 17 + col) * 4u;
+                const long long step = 2ll * L, ostep = step * outFS;
+                if (ph < L) {
+#pragma unroll 8
+                    for (int rr = 0; rr < 16; ++rr) {
+                        const float y = u_ldsf (sp + (unsigned int) rr * (34u * 4u));
+                        if (nl < outputs) *op = y;
+                        nl += step; op += ostep;
+                    }
+                }
+                __syncwarp ();
+            }
+            asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp ();
+            if (lane == 0) u_mbar_arrive (accEmptyA);
+            if (tid == 11 * 32) { UPROF_ADD (8, e1 - e0); UPROF_ADD (9, UCLK () - e1); UPROF_ADD (10, 1); }
+        }
+    }
+
+    if (prof) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (pacc[i]) atomicAdd (&g_uprof[i], (unsigned long long) pacc[i]);
+    }
+    asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads ();
+    if (warp == 0) {
+        __syncwarp ();
+        asm volatile ("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tm), "r"(512));
+    }
+}
+
+/* ---- host side -------------------------------------------------------------------------------------- */
+
+static size_t umma_smem (const ArtUmma &u)
+{
+    const size_t xc = (size_t) 2 * (2 * u.KI) * u.rows * 16;                 // two splits
+    return xc + (size_t) u.stages * 3 * 2 * u.Npad * 16 + 8 * 32 * 17 * sizeof (float) + 384 + ART_U_MAXK * 8;
+}
+
+bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsigned long long totalOutputs,
+                  int smCount, ArtUmma &u)
+{
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char *e = getenv ("ART_B200_UMMA");
+        enabled = e ? atoi (e) : 1;
+    }
+    if (!enabled) return false;
+    if (k.mode & ART_MODE_PRECISE) return false;                  // double accumulation: generic kernel
+    // the block-scaled fixed point makes the last bit depend on where a tile starts: contexts that promise
+    // chunking-invariant output (no interpolation, resampler.c:1135-1145) keep the FFMA form
+    if (!(k.mode & ART_MODE_INTERP)) return false;
+    int L, M;
+    if (!artRational (ratio, 160, &L, &M)) return false;
+    // short periods are grouped: g periods of L outputs form one row of g*L phases
+    int g = 160 / L;
+    while (g > 1 && (long long) M * g > 176) --g;
+    L *= g; M *= g;
+    if (L < 48 || M > 176) return false;
+    if (maxOutputs < (unsigned) (16 * L)) return false;           // rows of a tile would be mostly idle
+    // enough tiles to occupy the GPU (small calls are latency bound: FFMA kernel)
+    const unsigned long long tiles = (totalOutputs / L / ART_U_ROWS) * (unsigned long long) k.C;
+    if (enabled < 2 && tiles < (unsigned long long) smCount / 2) return false;
+
+    memset (&u, 0, sizeof u);
+    u.L = L; u.M = M;
+    u.Npad = (L + 15) & ~15;
+    u.KI = (M + 15) / 16;
+    if (u.KI > ART_U_MAXKI) return false;
+    const int flatEnd = M + 1 + k.T;                              // taps are counted from phase 0's first tap
+    int n = 0, aMax = 0;
+    for (int i = 0; i < u.KI; ++i)                                // plane pair outermost: its planes are handed
+        for (int a = 0; a * M + 16 * i < flatEnd; ++a) {          // back to the converters after the last shift
+            if (n >= ART_U_MAXK) return false;
+            u.ka[n] = (unsigned char) a; u.ki[n] = (unsigned char) i; ++n;
+            if (a > aMax) aMax = a;
+        }
+    u.numK = n;
+    for (int i = 0; i < u.KI; ++i) {
+        int c = 0;
+        for (int a = 0; a * M + 16 * i < flatEnd; ++a) ++c;
+        u.nA[i] = (unsigned char) c;
+    }
+    // rows: 128 + aMax, even, and 2..6 (mod 8) so that the 16-byte row slots of neighbouring planes fall on different banks
+    int rows = ART_U_ROWS + aMax;
+    while ((rows & 1) || (rows & 7) < 2 || (rows & 7) > 6) ++rows;
+    if (rows > 144) return false;
+    u.rows = rows;
+    // filter quantum: the exact accumulator holds sum X1*H1 with |X1| <= 2^11 and sum |H1| <= absSum * 2^DH + T/2
+    u.DH = 0;
+    for (int dh = 11; dh >= 6; --dh)
+        if ((double) k.absSum * (double) (1 << dh) + 0.5 * k.T < 8191.0) { u.DH = dh; break; }
+    if (!u.DH) return false;
+    u.tableHalfs = u.numK * 3 * 2 * u.Npad * 8;
+    u.stages = ART_U_STAGES;
+    while (u.stages > 2 * ART_U_GROUP && umma_smem (u) > 224 * 1024) u.stages -= ART_U_GROUP;
+    if (umma_smem (u) > 224 * 1024) return false;
+    if (getenv ("ART_B200_TRACE"))
+        fprintf (stderr, "[art] umma L=%d M=%d Npad=%d KI=%d numK=%d rows=%d DH=%d stages=%d smem=%zu\n",
+                 u.L, u.M, u.Npad, u.KI, u.numK, u.rows, u.DH, u.stages, umma_smem (u));
+    return true;
+}
+
+int artUmmaTiles (const ArtUmma &u, int channels, unsigned int outputs)
+{
+    const long long Q = ((long long) outputs + u.L - 1) / u.L;
+    return (int) (((Q + ART_U_ROWS - 1) / ART_U_ROWS) * channels);
+}
+
+static size_t umma_align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
+
+size_t artUmmaTableBytes (const ArtUmma &u, int numTables, int numJobs, int totalTiles)
+{
+    return umma_align16 ((size_t) numTables * u.tableHalfs * sizeof (unsigned short)) + umma_align16 ((size_t) numJobs * sizeof (int)) +
+           (size_t) totalTiles * sizeof (int);
+}
+
+void artUmmaCarve (ArtUmma &u, void *tables, int numTables, int numJobs)
+{
+    unsigned char *p = reinterpret_cast<unsigned char *> (tables);
+    u.H = reinterpret_cast<unsigned short *> (p);
+    p += umma_align16 ((size_t) numTables * u.tableHalfs * sizeof (unsigned short));
+    u.S0 = reinterpret_cast<int *> (p);
+    p += umma_align16 ((size_t) numJobs * sizeof (int));
+    u.tileExp = reinterpret_cast<int *> (p);
+}
+
+void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int numJobs, int numTables, int smCount,
+                    const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream)
+{
+    if (totalTiles <= 0) return;
+    static bool configured[16] = { false };
+    int device = 0;
+    ART_CUDA_CHECK (cudaGetDevice (&device));
+    if (!configured[device & 15]) {
+        ART_CUDA_CHECK (cudaFuncSetAttribute (art_sinc_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        configured[device & 15] = true;
+    }
+    int histBlocks = (k.C * k.T + 127) / 128;
+    if (histBlocks > 32) histBlocks = 32;
+    const int prepBlocks = numTables * u.Npad + (numJobs + 127) / 128 + totalTiles + numJobs * histBlocks;
+    static int prepDbg = -1;
+    if (prepDbg < 0) { const char *d = getenv ("ART_B200_UDBG"); prepDbg = d ? atoi (d) : 0; }
+    art_umma_prep_kernel<<<prepBlocks, 128, 0, stream>>> (k, u, single, d_jobs, numJobs, numTables, histBlocks, totalTiles, prepDbg);
+    ART_CUDA_CHECK (cudaGetLastError ());
+    const int grid = totalTiles < smCount ? totalTiles : smCount;
+    static int roleProf = -1;
+    if (roleProf < 0) {
+        roleProf = getenv ("ART_B200_UPROF") ? 1 : 0;
+        if (const char *d = getenv ("ART_B200_UDBG")) roleProf |= atoi (d) << 4;
+        if (roleProf & 1) atexit ([] () {
+            unsigned long long h[16];
+            cudaDeviceSynchronize ();
+            if (cudaMemcpyFromSymbol (h, g_uprof, sizeof h) != cudaSuccess) return;
+            const double n = h[10] ? (double) h[10] : 1.0;
+            fprintf (stderr, "[art] umma cycles per tile: producer wait-empty %.0f | mma wait-planes %.0f wait-acc %.0f wait-h %.0f tile %.0f | "
+                     "convert wait-planes %.0f | epilogue wait %.0f work %.0f | tiles %.0f | mma issue %.0f commit %.0f region %.0f | convert loads %.0f split %.0f fence %.0f arrive %.0f\n",
+                     h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[8] / n, h[9] / n, n, h[11] / n, h[12] / n, h[13] / n,
+                     h[6] / n, h[7] / n, h[14] / n, h[15] / n);
+        });
+    }
+    void *prof;
+    artProfileBegin (stream, &prof);
+    art_sinc_umma_kernel<<<grid, ART_U_THREADS, umma_smem (u), stream>>> (k, u, single, d_jobs, totalTiles, roleProf);
+    artProfileEnd (stream, prof);
+    ART_CUDA_CHECK (cudaGetLastError ());
+    g_artLaunches += 2;
+}

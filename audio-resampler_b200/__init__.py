@@ -107,6 +107,8 @@ def load() -> C.CDLL:
         "resampleB200Synchronize": (None, [ctx]),
         "resampleB200KernelLaunches": (C.c_ulonglong, []),
         "resampleB200PathCounts": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
+        "resampleB200SetTensorPath": (None, [i32]),
+        "resampleB200TensorLaunches": (C.c_ulonglong, []),
         "resampleB200ProfileEnable": (None, [i32]),
         "resampleB200ProfileCollect": (C.c_ulonglong, [C.POINTER(dbl)]),
         "resampleProcessInterleavedDevice": (ResampleResult, [ctx, vp, i32, vp, i32, dbl, vp]),
@@ -136,7 +138,7 @@ EXPORTED_SYMBOLS = [
     "resampleGetNumFilters", "resampleInterpolationUsed", "resampleReset", "resampleFree",
     "biquad_init", "biquad_lowpass", "biquad_highpass", "biquad_apply_buffer", "biquad_apply_sample",
     "resampleB200SetDevice", "resampleB200GetDeviceCount", "resampleB200Synchronize", "resampleB200KernelLaunches",
-    "resampleB200PathCounts", "resampleB200ProfileEnable", "resampleB200ProfileCollect",
+    "resampleB200PathCounts", "resampleB200SetTensorPath", "resampleB200TensorLaunches", "resampleB200ProfileEnable", "resampleB200ProfileCollect",
     "resampleProcessInterleavedDevice", "resampleProcessDevice", "resampleBatchProcessInterleavedDevice",
     "resampleBatchProcessInterleaved", "resampleProcessBlocksInterleavedDevice", "biquad_apply_cascade_interleaved",
     "biquad_apply_cascade_interleaved_device",

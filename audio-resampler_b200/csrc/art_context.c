@@ -484,5 +484,7 @@ int resampleB200GetDeviceCount (void) { return artDevCount (); }
 void resampleB200Synchronize (Resample *cxt) { artDevSynchronize (cxt->device); }
 unsigned long long resampleB200KernelLaunches (void) { return artDevLaunchCount (); }
 void resampleB200PathCounts (unsigned long long *generic, unsigned long long *periodic) { artDevPathCounts (generic, periodic); }
+unsigned long long resampleB200TensorLaunches (void) { return artDevTensorLaunches (); }
+void resampleB200SetTensorPath (int mode) { artDevSetTensorMode (mode); }
 void resampleB200ProfileEnable (int on) { artDevProfileEnable (on); }
 unsigned long long resampleB200ProfileCollect (double *totalMs) { return artDevProfileCollect (totalMs); }

@@ -16,13 +16,18 @@
 #include "art_device.h"
 
 unsigned long long g_artLaunches = 0;
-static unsigned long long g_pathLaunches[2] = { 0, 0 };        // [0] generic kernel, [1] periodic kernel
+static unsigned long long g_pathLaunches[3] = { 0, 0, 0 };     // [0] generic kernel, [1] periodic FFMA kernels, [2] tensor-core kernel
 
 extern "C" void artDevPathCounts (unsigned long long *generic, unsigned long long *periodic)
 {
     if (generic) *generic = g_pathLaunches[0];
     if (periodic) *periodic = g_pathLaunches[1];
 }
+
+extern "C" unsigned long long artDevTensorLaunches (void) { return g_pathLaunches[2]; }
+
+int g_artTensorMode = -1;          // -1: read ART_B200_UMMA on first use; 0 off, 1 when the launch is large enough, 2 whenever eligible
+extern "C" void artDevSetTensorMode (int mode) { g_artTensorMode = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
 
 extern "C" unsigned long long artDevLaunchCount (void) { return g_artLaunches; }
 
@@ -480,7 +485,7 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
                 lp.per.S0 = reinterpret_cast<int *> (lp.per.Hblk + tableFloats);
                 artLaunchPeriodic (lp.k, lp.per, lp.CV, ctas, n, numTables, jobs[0], d_jobs, stream);
             }
-            ++g_pathLaunches[1];
+            ++g_pathLaunches[lp.umma ? 2 : 1];
             if (!persistent)
                 ART_CUDA_CHECK (cudaFreeAsync (tables, stream));
             anyHist = false;                    // the periodic prep kernel moved the history already

@@ -76,6 +76,8 @@ void artDevSetHistory (ArtDev *dev, const float *hostPlanar);
 /* statistics for bench.py's gpu_launches claim and roofline leg */
 unsigned long long artDevLaunchCount (void);
 void artDevPathCounts (unsigned long long *generic, unsigned long long *periodic);
+unsigned long long artDevTensorLaunches (void);               /* launches of the tensor-core kernel (not counted above) */
+void artDevSetTensorMode (int mode);                          /* 0 never, 1 large launches (default), 2 whenever eligible */
 void artDevProfileEnable (int on);
 unsigned long long artDevProfileCollect (double *totalMs);   /* returns timed launches, clears */
 

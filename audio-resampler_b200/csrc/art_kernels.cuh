@@ -189,6 +189,7 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
                     const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream);
 
 extern unsigned long long g_artLaunches;
+extern int g_artTensorMode;
 
 /* per-kernel event timing, active only after artDevProfileEnable(1) */
 void artProfileBegin (cudaStream_t stream, void **token);

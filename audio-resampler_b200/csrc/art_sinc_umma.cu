@@ -322,7 +322,7 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
                 if (threadIdx.x == 0) {
                     m = fmaxf (fmaxf (red[0], red[1]), fmaxf (red[2], red[3]));
                     int e = 0;
-                    if (m > 0.0f) { (void) frexpf (m, &e); e -= 11; e = e < -100 ? -100 : (e > 100 ? 100 : e); }
+                    if (m > 0.0f) { (void) frexpf (m, &e); e -= 11; e = e < -114 ? -114 : (e > 100 ? 100 : e); }
                     u.tileExp[tile + c] = e;
                 }
             }
@@ -351,7 +351,7 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
             if (threadIdx.x == 0) {
                 m = fmaxf (fmaxf (red[0], red[1]), fmaxf (red[2], red[3]));
                 int e = 0;
-                if (m > 0.0f) { (void) frexpf (m, &e); e -= 11; e = e < -100 ? -100 : (e > 100 ? 100 : e); }    // m < 2^e
+                if (m > 0.0f) { (void) frexpf (m, &e); e -= 11; e = e < -114 ? -114 : (e > 100 ? 100 : e); }    // m < 2^e
                 u.tileExp[tile + c] = e;
             }
         }
@@ -672,14 +672,15 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                             ((__uint_as_float (a3[j]) * (1.0f / 4194304.0f) + __uint_as_float (a2[j]) * (1.0f / 2048.0f)) + __uint_as_float (a1[j])) * scale);
                 __syncwarp ();
                 const int ph = c0 + col;                                     // this lane's phase
-                long long nl = (q0 + half16) * L + ph;                       // output index inside the job, rows advance by 2
+                // half-warps take rows rr and rr + 16: with the row pitch of 17 words their 16 columns fall on disjoint banks
+                long long nl = (q0 + 16 * half16) * L + ph;                  // output index inside the job, rows advance by 1
                 float *op = obase + nl * outFS;
-                const unsigned int sp = scratch + (unsigned int) (half16 * 17 + col) * 4u;
-                const long long step = 2ll * L, ostep = step * outFS;
+                const unsigned int sp = scratch + (unsigned int) (16 * half16 * 17 + col) * 4u;
+                const long long step = L, ostep = step * outFS;
                 if (ph < L) {
 #pragma unroll 8
                     for (int rr = 0; rr < 16; ++rr) {
-                        const float y = u_ldsf (sp + (unsigned int) rr * (34u * 4u));
+                        const float y = u_ldsf (sp + (unsigned int) rr * (17u * 4u));
                         if (nl < outputs) *op = y;
                         nl += step; op += ostep;
                     }
@@ -717,11 +718,11 @@ static size_t umma_smem (const ArtUmma &u)
 bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsigned long long totalOutputs,
                   int smCount, ArtUmma &u)
 {
-    static int enabled = -1;
-    if (enabled < 0) {
+    if (g_artTensorMode < 0) {
         const char *e = getenv ("ART_B200_UMMA");
-        enabled = e ? atoi (e) : 1;
+        g_artTensorMode = e ? atoi (e) : 1;
     }
+    const int enabled = g_artTensorMode;
     if (!enabled) return false;
     if (k.mode & ART_MODE_PRECISE) return false;                  // double accumulation: generic kernel
     // the block-scaled fixed point makes the last bit depend on where a tile starts: contexts that promise
@@ -735,9 +736,10 @@ bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsi
     L *= g; M *= g;
     if (L < 48 || M > 176) return false;
     if (maxOutputs < (unsigned) (16 * L)) return false;           // rows of a tile would be mostly idle
-    // enough tiles to occupy the GPU (small calls are latency bound: FFMA kernel)
-    const unsigned long long tiles = (totalOutputs / L / ART_U_ROWS) * (unsigned long long) k.C;
-    if (enabled < 2 && tiles < (unsigned long long) smCount / 2) return false;
+    // a launch costs this kernel ~25 us whatever its size (filter table + one tile per SM); the FFMA form runs at
+    // ~11 Gsamples/s on a single stream, so it wins below ~0.3 Msamples
+    (void) smCount;
+    if (enabled < 2 && totalOutputs * (unsigned long long) k.C < 300000ull) return false;
 
     memset (&u, 0, sizeof u);
     u.L = L; u.M = M;

@@ -258,6 +258,7 @@ def run_gpu_arm(args):
     launches0 = lib.resampleB200KernelLaunches()
     gen_0, per_0 = C.c_ulonglong(), C.c_ulonglong()
     lib.resampleB200PathCounts(C.byref(gen_0), C.byref(per_0))
+    tensor_0 = lib.resampleB200TensorLaunches()
     lib.resampleB200ProfileEnable(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     out_frames = 0
@@ -280,6 +281,7 @@ def run_gpu_arm(args):
     launches = lib.resampleB200KernelLaunches() - launches0
     gen_n, per_n = C.c_ulonglong(), C.c_ulonglong()
     lib.resampleB200PathCounts(C.byref(gen_n), C.byref(per_n))
+    tensor = (lib.resampleB200TensorLaunches() - tensor_0) > 0
 
     ms_max, total_frames = reduce_over_ranks(dist if world > 1 else None, dev, ms, float(out_frames))
     value = total_frames * CHANNELS / (ms_max * 1e-3) / 1e6
@@ -297,17 +299,40 @@ def run_gpu_arm(args):
     # rational-ratio kernel applies ONE pre-interpolated filter over a 416-tap union window)
     alg_tflops = per_launch_samples * (4 * TAPS + 3) / (kern_avg_ms * 1e-3) / 1e12
     exe_tflops = per_launch_samples * (2 * 416 if periodic else 4 * 384) / (kern_avg_ms * 1e-3) / 1e12
+    kernel = ("art_sinc_umma_kernel (tcgen05.mma, 608 threads, 1 CTA/SM)" if tensor else
+              "art_sinc_periodic_kernel<CV=2,256>" if periodic else "art_sinc_generic_kernel<interp,float,CV=2>")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,
-                "kernel": "art_sinc_periodic_kernel<CV=2,256>" if periodic else "art_sinc_generic_kernel<interp,float,CV=2>",
+                "kernel": kernel,
                 "kernel_ms_per_launch": kern_avg_ms, "kernel_share_of_step": kern_ms.value / ms,
                 "algorithmic_bytes_per_output_sample": BYTES_PER_OUTPUT_SAMPLE,
                 "algorithmic_bytes_per_launch": per_launch_samples * BYTES_PER_OUTPUT_SAMPLE,
-                "fp32_tflops_reference_opcount": alg_tflops, "fp32_tflops_executed": exe_tflops,
-                "fp32_fma_peak_tflops_at_max_clock": 74.4, "fp32_frac_executed": exe_tflops / 74.4,
-                "note": "arithmetic intensity ~200 flop/B puts this path above the FP32 ridge (~11 flop/B): the FP32 FMA "
-                        "pipe binds, not HBM; frac is the HBM-roofline fraction BASELINE.json's metric asks for"}
-    prof = ROOT / "profiles" / ("r01_periodic_final_ncu.json" if periodic else "r01_generic_v2_ncu.json")
+                "fp32_tflops_reference_opcount": alg_tflops}
+    if tensor:
+        # what the tensor pipe executes: per tile of 128 periods x 1 channel, 36 k-steps of 5 MMAs (128 x 160 x 16) --
+        # the fixed-point split (5 digit products) and the band's zero blocks (576 executed taps for 380) included
+        per_stream_out = out_frames / max(1, args.steps) / streams
+        tiles = -(-(-(-per_stream_out // 160)) // 128) * CHANNELS * streams
+        mma_flops = tiles * 36 * 5 * 2.0 * 128 * 160 * 16
+        tens = mma_flops / (kern_avg_ms * 1e-3) / 1e12
+        tpeak = None
+        try:
+            tpeak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("bf16_tflops")
+        except Exception:
+            pass
+        tpeak = tpeak or 1622.6
+        roofline.update({
+            "tensor_tflops_executed": tens, "tensor_peak_tflops": tpeak, "tensor_frac": tens / tpeak,
+            "tensor_peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; fp16 runs at the same rate)",
+            "note": "arithmetic intensity ~200 flop/B puts this path far above the ridge: the kernel is bound by the tensor "
+                    "pipe (issue rate of its MMA warps), not by HBM; frac is the HBM-roofline fraction BASELINE.json's "
+                    "metric asks for, tensor_frac the share of the measured dense fp16/bf16 tensor peak the MMAs reach"})
+    else:
+        roofline.update({
+            "fp32_tflops_executed": exe_tflops, "fp32_fma_peak_tflops_at_max_clock": 74.4, "fp32_frac_executed": exe_tflops / 74.4,
+            "note": "arithmetic intensity ~200 flop/B puts this path above the FP32 ridge (~11 flop/B): the FP32 FMA "
+                    "pipe binds, not HBM; frac is the HBM-roofline fraction BASELINE.json's metric asks for"})
+    prof = ROOT / "profiles" / ("r01_umma_ncu.json" if tensor else "r01_periodic_final_ncu.json" if periodic else "r01_generic_v2_ncu.json")
     if prof.exists() and streams == 64 and frames == (1 << 18):
         try:
             roofline["traffic"] = json.loads(prof.read_text()).get("dram_bytes_per_launch")

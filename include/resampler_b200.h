@@ -26,6 +26,12 @@ void resampleB200Synchronize (Resample *cxt);            /* wait for the context
 unsigned long long resampleB200KernelLaunches (void);    /* kernels launched by this library so far */
 /* how many convolution launches went to the any-ratio kernel and to the rational-ratio kernel */
 void resampleB200PathCounts (unsigned long long *generic, unsigned long long *periodic);
+/* The rational-ratio path has two forms: FFMA kernels, and a tensor-core (tcgen05) kernel used for interpolating contexts
+ * when a launch holds enough work to fill the GPU.  mode 0: never use the tensor-core kernel, 1 (default): when the launch is
+ * large enough, 2: whenever the configuration is eligible (tests).  The environment variable ART_B200_UMMA sets the initial
+ * mode.  TensorLaunches counts its launches (PathCounts' `periodic` counts the FFMA form only). */
+void resampleB200SetTensorPath (int mode);
+unsigned long long resampleB200TensorLaunches (void);
 /* measurement aid: when enabled, every convolution kernel launch is bracketed by CUDA events on its
  * own stream; Collect waits for them, returns how many launches were timed and their summed
  * duration in milliseconds, and clears the list */

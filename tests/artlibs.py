@@ -174,7 +174,34 @@ def load_product() -> C.CDLL:
     so = product_path()
     if not so.exists():
         raise RuntimeError(f"{so} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
-    return bind_reference_api(C.CDLL(str(so), mode=os.RTLD_LOCAL))
+    lib = bind_reference_api(C.CDLL(str(so), mode=os.RTLD_LOCAL))
+    # the extension entry points the tests use (include/resampler_b200.h)
+    ctx = C.POINTER(RefResample)
+    lib.resampleB200SetTensorPath.restype = None
+    lib.resampleB200SetTensorPath.argtypes = [C.c_int]
+    lib.resampleB200TensorLaunches.restype = C.c_ulonglong
+    lib.resampleB200TensorLaunches.argtypes = []
+    lib.resampleBatchProcessInterleaved.restype = None
+    lib.resampleBatchProcessInterleaved.argtypes = [C.POINTER(ctx), C.c_int, C.POINTER(f32p), C.POINTER(C.c_int),
+                                                    C.POINTER(f32p), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(Result)]
+    return lib
+
+
+def batch_process(streams, xs, n_out: int, ratio: float):
+    """resampleBatchProcessInterleaved over product streams: returns [(y, input_used, output_generated)] per stream."""
+    lib, n = streams[0].lib, len(streams)
+    ch = streams[0].channels
+    xs = [np.ascontiguousarray(x, dtype=np.float32).reshape(-1, ch) for x in xs]
+    outs = [np.zeros((max(n_out, 1), ch), np.float32) for _ in range(n)]
+    ctxs = (type(streams[0].ctx) * n)(*[s.ctx for s in streams])
+    ins = (f32p * n)(*[_ptr(x) for x in xs])
+    out_arr = (f32p * n)(*[_ptr(o) for o in outs])
+    nin = (C.c_int * n)(*[x.shape[0] for x in xs])
+    nout = (C.c_int * n)(*([n_out] * n))
+    ratios = (C.c_double * n)(*([ratio] * n))
+    res = (Result * n)()
+    lib.resampleBatchProcessInterleaved(ctxs, n, ins, nin, out_arr, nout, ratios, res)
+    return [(outs[i][:res[i].output_generated].copy(), res[i].input_used, res[i].output_generated) for i in range(n)]
 
 
 # ---------------------------------------------------------------------------

@@ -237,6 +237,7 @@ def test_kernel_selection():
     import os
     lib = A.product()
     lib.resampleB200PathCounts.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    lib.resampleB200SetTensorPath(1)        # default policy: calls of this size stay on the FFMA form
 
     def counts():
         g, p = C.c_ulonglong(), C.c_ulonglong()

@@ -1,0 +1,149 @@
+"""GPU parity tests of the tensor-core (tcgen05) form of the rational-ratio path (art_sinc_umma.cu).
+
+By default the library only takes that kernel when a launch holds enough work to fill the GPU; these tests
+force it (resampleB200SetTensorPath(2)) so that small, oracle-checkable calls run on it too, and check that it
+really ran (resampleB200TensorLaunches).  Same bar as test_gpu_parity.py: counts and position bit-identical,
+samples within 1e-6 * peak(reference).
+"""
+import numpy as np
+import pytest
+
+import artlibs as A
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6
+BH_INTERP = A.SUBSAMPLE_INTERPOLATE | A.BLACKMAN_HARRIS
+
+
+@pytest.fixture(autouse=True)
+def forced_tensor_path():
+    lib = A.product()
+    lib.resampleB200SetTensorPath(2)
+    yield lib
+    lib.resampleB200SetTensorPath(1)
+
+
+def _pair(ch, taps, filters, **kw):
+    return A.product_stream(ch, taps, filters, **kw), A.oracle_stream(ch, taps, filters, **kw)
+
+
+def _check_call(g, o, x, cap, ratio, tol=TOL, **kw):
+    yg, ug, gg = g.process(x, cap, ratio, **kw)
+    yo, uo, go = o.process(x, cap, ratio, **kw)
+    assert (ug, gg) == (uo, go), f"counts differ: gpu {(ug, gg)} oracle {(uo, go)}"
+    assert g.position() == o.position()
+    err = A.peak_error(yg, yo)
+    assert err <= tol, f"max|d|/peak = {err:.3g}"
+    return yg, yo
+
+
+@pytest.mark.parametrize("ch,preset,src,dst,lowpass_hz", [
+    (2, 3, 44100, 48000, 0),            # BASELINE config 2 (metric config): 160/147
+    (1, 1, 44100, 48000, 0),            # BASELINE config 1: short filter, few k-steps
+    (2, 3, 48000, 44100, 20000),        # one stream of BASELINE config 4: 147/160, phases padded to 160
+    (3, 2, 32000, 40000, 0),            # 5/4: 32 periods grouped into one row of 160 phases
+    (5, 1, 8000, 48000, 0),             # 6/1: 26 periods per row, odd channel count
+    (2, 4, 44100, 48000, 0),            # preset -4: 988 taps, 8 row shifts
+])
+def test_configs_on_the_tensor_path(forced_tensor_path, ch, preset, src, dst, lowpass_hz):
+    lib = forced_tensor_path
+    filters, taps = A.PRESETS[preset]
+    g, o = _pair(ch, taps, filters, lowpass_ratio=lowpass_hz * 2.0 / src, flags=BH_INTERP)
+    g.advance(taps / 2); o.advance(taps / 2)
+    ratio = dst / src
+    rng = np.random.default_rng(200 + ch + preset)
+    before = lib.resampleB200TensorLaunches()
+    blocks = 3
+    for b in range(blocks):
+        x = rng.uniform(-0.5, 0.5, (8192, ch)).astype(np.float32)
+        _check_call(g, o, x, int(8192 * ratio) + taps + 10, ratio, flush_after=(b == blocks - 1))
+    assert lib.resampleB200TensorLaunches() - before >= blocks - 1, "the tensor-core kernel did not run"
+
+
+def test_ragged_calls_planar_and_limits(forced_tensor_path):
+    """odd call sizes, output-limited calls, the planar API, and calls too small for the kernel in between"""
+    lib = forced_tensor_path
+    g, o = _pair(2, 380, 380, lowpass_ratio=0.0)
+    g2 = A.product_stream(2, 380, 380, 0.0)
+    rng = np.random.default_rng(31)
+    ratio = 48000 / 44100
+    before = lib.resampleB200TensorLaunches()
+    for n, cap in [(5000, 9000), (1, 10), (12345, 20000), (0, 10), (7000, 3000), (4097, 9000), (30011, 40000)]:
+        x = rng.uniform(-0.5, 0.5, (n, 2)).astype(np.float32)
+        yg, _ = _check_call(g, o, x, cap, ratio)
+        yp, up, mp = g2.process(x, cap, ratio, planar=True)
+        assert np.array_equal(yg, yp), "planar and interleaved calls differ"
+    assert lib.resampleB200TensorLaunches() - before >= 8
+    _check_call(g, o, None, 500, ratio)                                 # flush
+
+
+def test_bit_reproducible(forced_tensor_path):
+    """two issuer warps feed the tensor pipe; the order in which an accumulator sees its MMAs must be fixed"""
+    rng = np.random.default_rng(33)
+    x = rng.uniform(-0.5, 0.5, (50000, 2)).astype(np.float32)
+    outs = []
+    for _ in range(4):
+        g = A.product_stream(2, 380, 380, 0.0)
+        g.advance(190)
+        y, u, m = g.process(x, 60000, 48000 / 44100)
+        outs.append(y)
+    assert all(np.array_equal(outs[0], y) for y in outs[1:])
+
+
+@pytest.mark.parametrize("scale", [1e-30, 3e-5, 1.0, 32768.0, 1e20])
+def test_block_scaling_follows_the_signal(forced_tensor_path, scale):
+    """the fixed-point split is relative to each tile's maximum: any overall level must give the same relative error"""
+    g, o = _pair(2, 380, 380, lowpass_ratio=0.0)
+    g.advance(190); o.advance(190)
+    rng = np.random.default_rng(35)
+    x = (rng.uniform(-0.5, 0.5, (20000, 2)) * scale).astype(np.float32)
+    _check_call(g, o, x, 30000, 48000 / 44100)
+
+
+def test_quiet_passage_after_a_loud_one(forced_tensor_path):
+    """a tile holding full-scale and -120 dB material: the error stays below 1e-6 of the call's peak, and a tile
+    that is quiet throughout keeps its own relative accuracy"""
+    g, o = _pair(1, 380, 380, lowpass_ratio=0.0)
+    g.advance(190); o.advance(190)
+    rng = np.random.default_rng(37)
+    x = rng.uniform(-0.5, 0.5, (60000, 1)).astype(np.float32)
+    x[30000:] *= 1e-6
+    yg, yo = _check_call(g, o, x, 80000, 48000 / 44100)
+    tail_g, tail_o = yg[45000:60000], yo[45000:60000]               # tiles that only hold the quiet part
+    assert A.peak_error(tail_g, tail_o) <= TOL
+
+
+def test_silence_and_impulse(forced_tensor_path):
+    g, o = _pair(2, 380, 380, lowpass_ratio=0.0)
+    g.advance(190); o.advance(190)
+    x = np.zeros((20000, 2), np.float32)
+    yg, yo = _check_call(g, o, x, 30000, 48000 / 44100)
+    assert not yg.any()
+    x[10000, 0] = 1.0
+    x[10001, 1] = -0.75
+    _check_call(g, o, x, 30000, 48000 / 44100)
+
+
+def test_many_streams_batched(forced_tensor_path):
+    """resampleBatchProcessInterleaved: independent streams with DIFFERENT states (tables are per state) and lengths;
+    the host-pointer batch pipelines stream by stream (upload, launch, download), hence one launch per stream"""
+    lib = forced_tensor_path
+    rng = np.random.default_rng(39)
+    ratio = 48000 / 44100
+    n_streams = 5
+    gs = [A.product_stream(2, 380, 380, 0.0) for _ in range(n_streams)]
+    os_ = [A.oracle_stream(2, 380, 380, 0.0) for _ in range(n_streams)]
+    for i, (g, o) in enumerate(zip(gs, os_)):
+        g.advance(190); o.advance(190)
+        if i % 2:                                                   # desynchronise some of the streams
+            x = rng.uniform(-0.5, 0.5, (1000 + 37 * i, 2)).astype(np.float32)
+            g.process(x, 5000, ratio); o.process(x, 5000, ratio)
+    xs = [rng.uniform(-0.5, 0.5, (20000 + 1111 * i, 2)).astype(np.float32) for i in range(n_streams)]
+    before = lib.resampleB200TensorLaunches()
+    ys = A.batch_process(gs, xs, 40000, ratio)
+    assert lib.resampleB200TensorLaunches() - before >= 1
+    for g, o, x, (y, used, made) in zip(gs, os_, xs, ys):
+        yo, uo, mo = o.process(x, 40000, ratio)
+        assert (used, made) == (uo, mo) and g.position() == o.position()
+        assert A.peak_error(y, yo) <= TOL

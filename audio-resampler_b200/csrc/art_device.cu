@@ -542,7 +542,9 @@ extern "C" void artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, 
     reserve (dev, inFloats, outFloats);
 
     // a piece costs ~25 us of launch latency; only cut when its copies take several times that
-    int pieces = (int) (((unsigned long long) plan->outputs * C) >> 20);
+    static int pieceShift = -1;
+    if (pieceShift < 0) { const char *e = getenv ("ART_B200_PIECE_SHIFT"); pieceShift = e ? atoi (e) : 20; }
+    int pieces = (int) (((unsigned long long) plan->outputs * C) >> pieceShift);
     if (pieces < 1 || plan->pre) pieces = 1;
     if (pieces > 8) pieces = 8;
     if (getenv ("ART_B200_NOPIPE")) pieces = 1;

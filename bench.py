@@ -394,22 +394,51 @@ def measure_e2e(lib, pkg, torch, dist, world, dev, streams, frames, cap, args):
     # -- reference-facing API, several host threads -------------------------------------------------
     ctxs = fresh()
 
-    def one(i):
-        lib.resampleB200SetDevice(local)
-        return lib.resampleProcessInterleaved(ctxs[i], xp[i], frames, yp[i], cap, RATIO).output_generated
+    # long-lived host threads, each owning every T-th stream: the call is ~60 us, so per-call Python overhead (futures,
+    # GIL hand-offs of an executor's map) would be a visible part of it
+    import threading
+    T = max(1, min(args.e2e_threads, n))
+    start, done = threading.Barrier(T + 1), threading.Barrier(T + 1)
+    made_by = [0] * T
+    rounds = {"n": 0}
 
-    with ThreadPoolExecutor(args.e2e_threads) as pool:
-        for _ in range(2):
-            list(pool.map(one, range(n)))
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        made = 0
-        for _ in range(steps):
-            made += sum(pool.map(one, range(n)))
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+    def worker(t):
+        lib.resampleB200SetDevice(local)
+        fn = lib.resampleProcessInterleaved
+        mine = [(ctxs[i], xp[i], yp[i]) for i in range(t, n, T)]
+        while True:
+            start.wait()
+            if rounds["n"] < 0:
+                return
+            tot = 0
+            for _ in range(rounds["n"]):
+                for c, xi, yi in mine:
+                    tot += fn(c, xi, frames, yi, cap, RATIO).output_generated
+            made_by[t] = tot
+            done.wait()
+
+    threads = [threading.Thread(target=worker, args=(t,), daemon=True) for t in range(T)]
+    for th in threads:
+        th.start()
+
+    def run_rounds(k):
+        rounds["n"] = k
+        start.wait()
+        done.wait()
+        return sum(made_by)
+
+    run_rounds(2)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    made = run_rounds(steps)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    rounds["n"] = -1
+    start.wait()
+    for th in threads:
+        th.join()
     value = reduce(made, dt)
     per_step_out = made / steps
     for c in ctxs:
@@ -459,8 +488,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=64, help="independent stereo streams per GPU per step")
     ap.add_argument("--frames", type=int, default=1 << 18, help="input frames per stream per step")
-    ap.add_argument("--e2e-streams", type=int, default=16)
-    ap.add_argument("--e2e-threads", type=int, default=4)
+    ap.add_argument("--e2e-streams", type=int, default=64)
+    ap.add_argument("--e2e-threads", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -28,11 +28,12 @@
  *                        [X1*h3 + x2*h2] carry 2^-11 and 2^-22 of the weight, where truncation is harmless.
  *                        The epilogue adds them in fp32 and applies the power-of-two scale.
  *
- * Warp roles (one CTA of 608 threads per SM, persistent over tiles of 128 periods x 1 channel):
+ * Warp roles (one CTA of 640 threads per SM, persistent over tiles of 128 periods x 1 channel):
  *   warp 0      TMA producer: filter k-steps -> stage ring (cp.async.bulk + mbarrier)
  *   warps 1-2   MMA issuers, alternating ring slots: 5 x tcgen05.mma (M=128, N=Npad, K=16) per k-step, tcgen05.commit
- *   warps 3-10  converters: global -> fixed-point split -> operand A, a pair of 8-tap planes at a time
- *   warps 11-18 epilogue: tcgen05.ld the three accumulators, combine, scale, transpose, store
+ *   warps 4-11  converters: global -> fixed-point split -> operand A, a pair of 8-tap planes at a time
+ *   warps 12-19 epilogue: tcgen05.ld the three accumulators into registers (setmaxnreg gives them 136), release tensor
+ *               memory, then transpose through shared memory and store
  */
 #include <cstdio>
 #include <cstdlib>
@@ -41,7 +42,7 @@
 #include "art_kernels.cuh"
 #include "art_device.h"
 
-#define ART_U_THREADS 608           /* producer warp + 2 MMA warps + 8 converter warps + 8 epilogue warps */
+#define ART_U_THREADS 640           /* warpgroup 0: producer + 2 MMA warps (+1 idle); 1-2: converters; 3-4: epilogue */
 #define ART_U_EPI     256           /* epilogue threads */
 #define ART_U_CONV    256           /* converter threads */
 #define ART_U_STAGES  8           /* filter ring depth (fewer when shared memory is short) */
@@ -162,7 +163,16 @@ __device__ __forceinline__ void u_tmem_ld16 (unsigned int addr, unsigned int (&r
 /* optional role timing (ART_B200_UPROF=1): cycles spent waiting / working per role, summed over CTAs */
 __device__ unsigned long long g_uprof[16];
 #define UCLK() (prof ? clock64 () : 0ll)
-#define UPROF_ADD(slot, cyc) do { if (prof) pacc[slot] += (cyc); } while (0)      /* flushed once per thread at the end */
+#define UPROF_ADD(slot, cyc) do { if (prof) pacc[slot] += (unsigned int) (cyc); } while (0)      /* role-local, flushed once per thread */
+#define UPROF_DECL()  unsigned int pacc[16] = { 0 }
+#define UPROF_FLUSH() do { if (prof) { _Pragma ("unroll") for (int i_ = 0; i_ < 16; ++i_) if (pacc[i_]) atomicAdd (&g_uprof[i_], (unsigned long long) pacc[i_]); } } while (0)
+
+__device__ __forceinline__ void u_tmem_ld8 (unsigned int addr, unsigned int (&r)[8])
+{
+    asm volatile ("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                  : "r"(addr));
+}
 
 __device__ __forceinline__ int u_find_job (const ArtJob *jobs, int numJobs, int tile)
 {
@@ -376,7 +386,6 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                       const ArtJob *__restrict__ jobs, int totalTiles, int profArg)
 {
     const int prof = profArg & 1, dbg = profArg >> 4;
-    long long pacc[16] = { 0 };
     extern __shared__ __align__ (1024) unsigned char smem[];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -438,6 +447,8 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
     __syncthreads ();
     asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned int tm = u_lds32 (tmemSlotA);
+    /* Registers follow the work (setmaxnreg, per warpgroup): the epilogue keeps a whole accumulator row block in registers so
+     * that tensor memory is handed back to the MMAs before the slow part (transpose + stores) starts. 128*56 + 256*88 + 256*120 <= 640 * 96 */
 
     const ArtJob *const singlePtr = &single;
     auto jobOf = [=] (int tile) -> const ArtJob & {
@@ -445,8 +456,10 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
     };
 
     if (warp == 0) {
+        asm volatile ("setmaxnreg.dec.sync.aligned.u32 56;");
         /* ===== TMA producer: the tile's filter table, two k-steps per copy ===== */
         if (lane == 0) {
+            UPROF_DECL ();
             unsigned int us = 0, ph = 0;
             for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
                 const ArtJob &job = jobOf (tile);
@@ -464,6 +477,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                     if (++us == (unsigned int) units) { us = 0; ph ^= 1; }
                 }
             }
+            UPROF_FLUSH ();
         }
     }
     else if (warp < 3) {
@@ -471,7 +485,9 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
          * share the work: ring slots (ART_U_GROUP k-steps) alternate between them.  Each whole warp walks the loop (uniform
          * control flow) and one elected lane issues.  Every tcgen05.commit costs the tensor pipe ~85 cycles (measured,
          * profiles/microbench/umma_probe.cu): one per slot, one per issuer and pair of planes, one per issuer and tile ===== */
+        asm volatile ("setmaxnreg.dec.sync.aligned.u32 56;");
         const unsigned int me = (unsigned int) (warp - 1);
+        UPROF_DECL ();
         const unsigned int idesc = u_idesc (ART_U_ROWS, Npad);
         const unsigned int bSplitU = (2u * (unsigned int) Npad * 16u) >> 4, stageU = stageBytes >> 4;
         const unsigned long long descHi = ((unsigned long long) (128u >> 4) << 32) | (1ull << 46);      // SBO = 128, version 1
@@ -536,23 +552,32 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             }
             if (lane == 0 && me == 0) UPROF_ADD (4, UCLK () - t2);
         }
+        UPROF_FLUSH ();
     }
-    else if (warp < 11) {
+    else if (warp < 4) {
+        /* idle: fills warpgroup 0 (register re-allocation is per warpgroup) */
+        asm volatile ("setmaxnreg.dec.sync.aligned.u32 56;");
+    }
+    else if (warp < 12) {
         /* ===== converters: signal -> fixed-point operand A, one pair of 8-tap planes at a time ===== */
-        const int ctid = tid - 96, cw = ctid >> 5;
+        asm volatile ("setmaxnreg.dec.sync.aligned.u32 88;");
+        const int ctid = tid - 128, cw = ctid >> 5;
+        UPROF_DECL ();
         const int span = M * (u.rows - 1) + 16 * KI;                       // samples the tile touches per channel
-        constexpr int UN = 9;                                               // row pairs per warp: rows <= 144
-        const int r0 = 2 * cw + (lane >> 4);                                // this lane's row in the first pair
-        const int off0 = M * r0 + (lane & 15);                              // its sample offset inside the tile, plane pair 0
+        /* a lane converts TWO neighbouring taps of a row per step (one conversion and one 32-bit store per digit for the two);
+         * a warp covers 4 rows x 16 taps, the 8 warps take every 8th group of 4 rows */
+        constexpr int UN = 5;                                               // row groups per warp: rows <= 160
+        const int r0 = 4 * cw + (lane >> 3);                                // this lane's row in the warp's first group
+        const int off0 = M * r0 + 2 * (lane & 7);                           // its first sample's offset inside the tile, plane pair 0
         unsigned int lt = 0;
-        float v[UN], vn[UN];
-        const int nU = (u.rows / 2 - cw + 7) / 8;                           // row pairs this warp owns
+        float v[2 * UN], vn[2 * UN];
+        const int nU = ((u.rows + 3) / 4 - cw + 7) / 8;                     // row groups this warp owns
+        const bool oddRows = (u.rows & 3) != 0;                             // the last group is only half there (rows is even)
 
-        /* what a lane needs to fetch its samples of one tile */
         /* what a lane needs to fetch its samples of one tile.  Inside the caller's block a sample is base[idx * fs];
          * tiles that touch the history or run past the end of the input take the same loads from a clamped address
          * and zero what must read as silence, so that all loads of a plane pair are still issued back to back */
-        struct Src { const float *p, *base, *hist; long long fs, R0, lo, hi; bool fast; };
+        struct Src { const float *p, *base, *hist; long long fs, R0, lo, hi; int e; bool fast; };
         auto source = [&] (int tile) -> Src {
             Src sc;
             const ArtJob &job = jobOf (tile);
@@ -566,67 +591,75 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             sc.base = job.inPlanes ? job.inPlanes[c] : job.in + (long long) c * job.inCS;
             sc.hist = job.hist + (long long) c * T + T + job.prevAvail;       // hist[idx]: -T - prevAvail <= idx < -prevAvail
             sc.p = sc.base + (sc.R0 + off0) * sc.fs;
+            sc.e = u.tileExp[tile];
             return sc;
         };
-        auto fetch = [&] (const Src &sc, int i, float (&dst)[UN]) {
+        auto rowOk = [&] (int uu) -> bool { return uu < nU && r0 + 32 * uu < u.rows; };
+        auto fetch = [&] (const Src &sc, int i, float (&dst)[2 * UN]) {
             if (sc.fast) {
                 const float *p = sc.p + (long long) (16 * i) * sc.fs;
-                const long long rowStep = (long long) (16 * M) * sc.fs;
+                const long long rowStep = (long long) (32 * M) * sc.fs;
 #pragma unroll
                 for (int uu = 0; uu < UN; ++uu) {
-                    dst[uu] = (uu < nU && !(dbg & 1)) ? __ldg (p) : 0.0f;
+                    const bool ok = rowOk (uu) && !(dbg & 1);
+                    dst[2 * uu] = ok ? __ldg (p) : 0.0f;
+                    dst[2 * uu + 1] = ok ? __ldg (p + sc.fs) : 0.0f;
                     p += rowStep;
                 }
             }
             else {
-                const float *ptr[UN];
-                bool ok[UN];
+                const float *ptr[2 * UN];
+                bool ok[2 * UN];
 #pragma unroll
-                for (int uu = 0; uu < UN; ++uu) {
-                    const long long idx = sc.R0 + off0 + 16 * i + 16 * M * uu;
+                for (int e = 0; e < 2 * UN; ++e) {
+                    const long long idx = sc.R0 + off0 + 16 * i + 32 * M * (e >> 1) + (e & 1);
                     const bool inBlock = idx >= sc.lo && idx < sc.hi, inHist = idx < sc.lo && idx >= sc.lo - T;
-                    ok[uu] = (inBlock || inHist) && uu < nU;
-                    ptr[uu] = inBlock ? sc.base + idx * sc.fs : (inHist ? sc.hist + idx : sc.hist + sc.lo - 1);
+                    ok[e] = (inBlock || inHist) && rowOk (e >> 1);
+                    ptr[e] = inBlock ? sc.base + idx * sc.fs : (inHist ? sc.hist + idx : sc.hist + sc.lo - 1);
                 }
 #pragma unroll
-                for (int uu = 0; uu < UN; ++uu) dst[uu] = __ldg (ptr[uu]);
+                for (int e = 0; e < 2 * UN; ++e) dst[e] = __ldg (ptr[e]);
 #pragma unroll
-                for (int uu = 0; uu < UN; ++uu) dst[uu] = ok[uu] ? dst[uu] : 0.0f;
+                for (int e = 0; e < 2 * UN; ++e) dst[e] = ok[e] ? dst[e] : 0.0f;
             }
         };
+        (void) oddRows;
 
         Src cur = source (blockIdx.x < totalTiles ? blockIdx.x : 0);
         if ((int) blockIdx.x < totalTiles) fetch (cur, 0, vn);
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++lt) {
-            const int e = u.tileExp[tile];
+            const int e = cur.e;
             const float invq = __int_as_float ((127 - e) << 23);
             if (ctid == 0)
                 u_stsf (sScaleA (lt & 3), __int_as_float ((127 + e) << 23) * __int_as_float ((127 - u.DH) << 23));
             const bool more = tile + (int) gridDim.x < totalTiles;
             Src nxt = cur;
             for (int i = 0; i < KI; ++i) {
-                long long ca = UCLK ();
 #pragma unroll
-                for (int uu = 0; uu < UN; ++uu) v[uu] = vn[uu];
+                for (int uu = 0; uu < 2 * UN; ++uu) v[uu] = vn[uu];
                 // the next pair's loads (of the next tile after the last pair) fly while this pair is converted
+                // (the next tile's job lookup is a chain of dependent global loads: done early, at the first pair, where
+                //  the converters have a whole tile of slack, not in front of the last pair the MMAs are waiting for)
+                if (i == 0 && more) nxt = source (tile + gridDim.x);
                 if (i + 1 < KI) fetch (cur, i + 1, vn);
-                else if (more) { nxt = source (tile + gridDim.x); fetch (nxt, 0, vn); }
+                else if (more) fetch (nxt, 0, vn);
                 long long c0t = UCLK ();
                 u_mbar_wait_relaxed (pEmptyA (i), (lt & 1) ^ 1);
                 long long cb = UCLK ();
-                if (ctid == 0) { UPROF_ADD (6, c0t - ca); UPROF_ADD (5, cb - c0t); }
-                const unsigned int dst = xcBase + (unsigned int) (2 * i + ((lane >> 3) & 1)) * planeBytes + (unsigned int) (lane & 7) * 2u +
+                if (ctid == 0) UPROF_ADD (5, cb - c0t);
+                // taps 2c, 2c+1 of the pair: plane 2i + (c >> 2), 4 bytes at (c & 3) * 4 of the row's 16-byte slot
+                const unsigned int dst = xcBase + (unsigned int) (2 * i + ((lane >> 2) & 1)) * planeBytes + (unsigned int) (lane & 3) * 4u +
                                          (unsigned int) r0 * 16u;
 #pragma unroll
                 for (int uu = 0; uu < UN; ++uu) {
-                    if (uu < nU) {
-                        const float uq = v[uu] * invq;
-                        const float X1 = (uq + 12582912.0f) - 12582912.0f;          // round to nearest integer (|uq| <= 2^11)
-                        const float r = (uq - X1) * 2048.0f;
-                        const __half2 pk = __floats2half2_rn (X1, r);                // one conversion instruction for both digits
-                        const unsigned int bits = *reinterpret_cast<const unsigned int *> (&pk);
-                        u_sts16 (dst + uu * 256, (unsigned short) bits);
-                        u_sts16 (dst + splitBytes + uu * 256, (unsigned short) (bits >> 16));
+                    if (rowOk (uu)) {
+                        const float ua = v[2 * uu] * invq, ub = v[2 * uu + 1] * invq;
+                        const float Xa = (ua + 12582912.0f) - 12582912.0f;          // round to nearest integer (|u| <= 2^11)
+                        const float Xb = (ub + 12582912.0f) - 12582912.0f;
+                        const float ra = (ua - Xa) * 2048.0f, rb = (ub - Xb) * 2048.0f;
+                        const __half2 p1 = __floats2half2_rn (Xa, Xb), p2 = __floats2half2_rn (ra, rb);      // low half = first tap
+                        u_sts32 (dst + uu * 512, *reinterpret_cast<const unsigned int *> (&p1));
+                        u_sts32 (dst + splitBytes + uu * 512, *reinterpret_cast<const unsigned int *> (&p2));
                     }
                 }
                 long long cc = UCLK ();
@@ -638,14 +671,18 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             }
             cur = nxt;
         }
+        UPROF_FLUSH ();
     }
     else {
-        /* ===== epilogue: accumulators -> output, transposed through shared memory so that a warp stores runs of phases ===== */
-        const int quad = warp & 3;                                          // (warps 11-18: every quarter is served by two warps)
-        const int qslot = (warp - 11) >> 2; (void) qslot;                                          // TMEM lanes 32*quad .. 32*quad+31
+        /* ===== epilogue: accumulators -> registers (tensor memory released) -> transposed through shared memory -> output ===== */
+        asm volatile ("setmaxnreg.inc.sync.aligned.u32 120;");
+        const int quad = warp & 3;                                          // TMEM lanes 32*quad .. 32*quad+31 (a warp may only read quarter warp%4)
+        UPROF_DECL ();
+        const int slot = (warp - 12) >> 2;                                  // every quarter is served by two warps: even / odd 16-column chunks
         const unsigned int tmRow = tm + ((unsigned int) (quad * 32) << 16);
-        const unsigned int scratch = scratchBase + (unsigned int) (warp - 11) * (32u * 17u * 4u);
+        const unsigned int scratch = scratchBase + (unsigned int) (warp - 12) * (32u * 17u * 4u);
         const int half16 = lane >> 4, col = lane & 15;
+        constexpr int NCH = 5;                                              // chunks per warp: Npad <= 160
         unsigned int lt = 0;
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++lt) {
             const ArtJob &job = jobOf (tile);
@@ -656,49 +693,65 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             long long e1 = UCLK ();
             asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
             const float scale = u_ldsf (sScaleA (lt & 3));
+            float y[NCH][16];
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int c0 = 16 * slot + 32 * ch;
+                if (c0 < Npad && !(dbg & 4)) {
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {                        // 8 columns at a time: 24 transient registers
+                        unsigned int a1[8], a2[8], a3[8];
+                        u_tmem_ld8 (tmRow + (unsigned int) (c0 + 8 * hh), a1);
+                        u_tmem_ld8 (tmRow + (unsigned int) (Npad + c0 + 8 * hh), a2);
+                        u_tmem_ld8 (tmRow + (unsigned int) (2 * Npad + c0 + 8 * hh), a3);
+                        asm volatile ("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            y[ch][8 * hh + j] = ((__uint_as_float (a3[j]) * (1.0f / 4194304.0f) + __uint_as_float (a2[j]) * (1.0f / 2048.0f)) +
+                                                 __uint_as_float (a1[j])) * scale;
+                    }
+                }
+            }
+            // the accumulators may be overwritten by the next tile from here on
+            asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp ();
+            if (lane == 0) u_mbar_arrive (accEmptyA);
+            long long e2 = UCLK ();
+
             // job fields into registers: the output stores below may alias anything as far as the compiler knows
             const long long outputs = job.outputs, outFS = job.outFS;
             float *const obase = (job.outPlanes ? job.outPlanes[c] : job.out + (long long) c * job.outCS) + (long long) job.nStart * outFS;
             const long long q0 = (long long) qb * ART_U_ROWS + quad * 32;    // period of this warp's row 0
-            for (int c0 = 16 * ((warp - 11) >> 2); c0 < ((dbg & 4) ? 0 : Npad); c0 += 32) {
-                unsigned int a1[16], a2[16], a3[16];
-                u_tmem_ld16 (tmRow + (unsigned int) c0, a1);
-                u_tmem_ld16 (tmRow + (unsigned int) (Npad + c0), a2);
-                u_tmem_ld16 (tmRow + (unsigned int) (2 * Npad + c0), a3);
-                asm volatile ("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    u_stsf (scratch + (unsigned int) (lane * 17 + j) * 4u,
-                            ((__uint_as_float (a3[j]) * (1.0f / 4194304.0f) + __uint_as_float (a2[j]) * (1.0f / 2048.0f)) + __uint_as_float (a1[j])) * scale);
-                __syncwarp ();
-                const int ph = c0 + col;                                     // this lane's phase
-                // half-warps take rows rr and rr + 16: with the row pitch of 17 words their 16 columns fall on disjoint banks
-                long long nl = (q0 + 16 * half16) * L + ph;                  // output index inside the job, rows advance by 1
-                float *op = obase + nl * outFS;
-                const unsigned int sp = scratch + (unsigned int) (16 * half16 * 17 + col) * 4u;
-                const long long step = L, ostep = step * outFS;
-                if (ph < L) {
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int c0 = 16 * slot + 32 * ch;
+                if (c0 < Npad && !(dbg & 4)) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        u_stsf (scratch + (unsigned int) (lane * 17 + j) * 4u, y[ch][j]);
+                    __syncwarp ();
+                    const int ph = c0 + col;                                 // this lane's phase
+                    // half-warps take rows rr and rr + 16: with the row pitch of 17 words their 16 columns fall on disjoint banks
+                    long long nl = (q0 + 16 * half16) * L + ph;              // output index inside the job, rows advance by 1
+                    float *op = obase + nl * outFS;
+                    const unsigned int sp = scratch + (unsigned int) (16 * half16 * 17 + col) * 4u;
+                    const long long step = L, ostep = step * outFS;
+                    if (ph < L) {
 #pragma unroll 8
-                    for (int rr = 0; rr < 16; ++rr) {
-                        const float y = u_ldsf (sp + (unsigned int) rr * (17u * 4u));
-                        if (nl < outputs) *op = y;
-                        nl += step; op += ostep;
+                        for (int rr = 0; rr < 16; ++rr) {
+                            const float v = u_ldsf (sp + (unsigned int) rr * (17u * 4u));
+                            if (nl < outputs) *op = v;
+                            nl += step; op += ostep;
+                        }
                     }
+                    __syncwarp ();
                 }
-                __syncwarp ();
             }
-            asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp ();
-            if (lane == 0) u_mbar_arrive (accEmptyA);
-            if (tid == 11 * 32) { UPROF_ADD (8, e1 - e0); UPROF_ADD (9, UCLK () - e1); UPROF_ADD (10, 1); }
+            if (tid == 12 * 32) { UPROF_ADD (8, e1 - e0); UPROF_ADD (9, e2 - e1); UPROF_ADD (6, UCLK () - e2); UPROF_ADD (10, 1); }
         }
+        UPROF_FLUSH ();
     }
 
-    if (prof) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (pacc[i]) atomicAdd (&g_uprof[i], (unsigned long long) pacc[i]);
-    }
     asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads ();
     if (warp == 0) {
@@ -812,6 +865,16 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
     int device = 0;
     ART_CUDA_CHECK (cudaGetDevice (&device));
     if (!configured[device & 15]) {
+        // the kernel moves registers between its warpgroups (setmaxnreg: 128 threads down to 56, 256 down to 88, 256 up to 120);
+        // the pool that comes from is threads x registers-per-thread as compiled, so check that it suffices -- a warpgroup
+        // asking for registers that never become free would spin forever
+        cudaFuncAttributes fa;
+        ART_CUDA_CHECK (cudaFuncGetAttributes (&fa, art_sinc_umma_kernel));
+        if (128 * (fa.numRegs - 56) + 256 * (fa.numRegs - 88) < 256 * (120 - fa.numRegs) || fa.numRegs < 88 || fa.numRegs > 120) {
+            fprintf (stderr, "libresampler_b200: art_sinc_umma_kernel was compiled with %d registers per thread: its register re-allocation "
+                     "plan does not hold\n", fa.numRegs);
+            abort ();
+        }
         ART_CUDA_CHECK (cudaFuncSetAttribute (art_sinc_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         configured[device & 15] = true;
     }
@@ -833,7 +896,7 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
             if (cudaMemcpyFromSymbol (h, g_uprof, sizeof h) != cudaSuccess) return;
             const double n = h[10] ? (double) h[10] : 1.0;
             fprintf (stderr, "[art] umma cycles per tile: producer wait-empty %.0f | mma wait-planes %.0f wait-acc %.0f wait-h %.0f tile %.0f | "
-                     "convert wait-planes %.0f | epilogue wait %.0f work %.0f | tiles %.0f | mma issue %.0f commit %.0f region %.0f | convert loads %.0f split %.0f fence %.0f arrive %.0f\n",
+                     "convert wait-planes %.0f | epilogue wait %.0f drain %.0f | tiles %.0f | mma issue %.0f commit %.0f region %.0f | epilogue store %.0f | convert split %.0f fence %.0f arrive %.0f\n",
                      h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[8] / n, h[9] / n, n, h[11] / n, h[12] / n, h[13] / n,
                      h[6] / n, h[7] / n, h[14] / n, h[15] / n);
         });

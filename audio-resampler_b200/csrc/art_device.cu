@@ -26,8 +26,8 @@ extern "C" void artDevPathCounts (unsigned long long *generic, unsigned long lon
 
 extern "C" unsigned long long artDevTensorLaunches (void) { return g_pathLaunches[2]; }
 
-int g_artTensorMode = -1;          // -1: read ART_B200_UMMA on first use; 0 off, 1 when the launch is large enough, 2 whenever eligible
-extern "C" void artDevSetTensorMode (int mode) { g_artTensorMode = mode < 0 ? 0 : (mode > 2 ? 2 : mode); }
+int g_artTensorMode = -1;          // -1: read ART_B200_UMMA on first use; 0 off, 1 when the launch is large enough, 2 whenever eligible, 3 as 1 plus non-interpolating contexts
+extern "C" void artDevSetTensorMode (int mode) { g_artTensorMode = mode < 0 ? 0 : (mode > 3 ? 3 : mode); }
 
 extern "C" unsigned long long artDevLaunchCount (void) { return g_artLaunches; }
 

@@ -779,8 +779,9 @@ bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsi
     if (!enabled) return false;
     if (k.mode & ART_MODE_PRECISE) return false;                  // double accumulation: generic kernel
     // the block-scaled fixed point makes the last bit depend on where a tile starts: contexts that promise
-    // chunking-invariant output (no interpolation, resampler.c:1135-1145) keep the FFMA form
-    if (!(k.mode & ART_MODE_INTERP)) return false;
+    // chunking-invariant output (no interpolation, resampler.c:1135-1145) keep the FFMA form unless the caller
+    // trades that promise for speed (mode 3)
+    if (!(k.mode & ART_MODE_INTERP) && enabled < 3) return false;
     int L, M;
     if (!artRational (ratio, 160, &L, &M)) return false;
     // short periods are grouped: g periods of L outputs form one row of g*L phases
@@ -792,7 +793,7 @@ bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsi
     // a launch costs this kernel ~25 us whatever its size (filter table + one tile per SM); the FFMA form runs at
     // ~11 Gsamples/s on a single stream, so it wins below ~0.3 Msamples
     (void) smCount;
-    if (enabled < 2 && totalOutputs * (unsigned long long) k.C < 300000ull) return false;
+    if (enabled != 2 && totalOutputs * (unsigned long long) k.C < 300000ull) return false;
 
     memset (&u, 0, sizeof u);
     u.L = L; u.M = M;

@@ -28,7 +28,9 @@ unsigned long long resampleB200KernelLaunches (void);    /* kernels launched by 
 void resampleB200PathCounts (unsigned long long *generic, unsigned long long *periodic);
 /* The rational-ratio path has two forms: FFMA kernels, and a tensor-core (tcgen05) kernel used for interpolating contexts
  * when a launch holds enough work to fill the GPU.  mode 0: never use the tensor-core kernel, 1 (default): when the launch is
- * large enough, 2: whenever the configuration is eligible (tests).  The environment variable ART_B200_UMMA sets the initial
+ * large enough, 2: whenever the configuration is eligible (tests), 3: as 1, and also for non-interpolating contexts
+ * (resampleFixedRatioInit): their output then still matches the reference within 1e-6 of peak but is no longer bit-identical
+ * across different call chunkings, which the FFMA form guarantees as the reference does.  The environment variable ART_B200_UMMA sets the initial
  * mode.  TensorLaunches counts its launches (PathCounts' `periodic` counts the FFMA form only). */
 void resampleB200SetTensorPath (int mode);
 unsigned long long resampleB200TensorLaunches (void);

@@ -42,6 +42,7 @@ def run(name, ch, preset, src, dst, streams, frames, lowpass_hz=0, fixed=False, 
         step()
     torch.cuda.synchronize()
     g0, p0 = paths()
+    t0n = lib.resampleB200TensorLaunches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter(); e0.record(st); made = 0
     for _ in range(steps):
@@ -53,7 +54,7 @@ def run(name, ch, preset, src, dst, streams, frames, lowpass_hz=0, fixed=False, 
     byts = 4.0 * (1.0 + 1.0 / ratio)
     print(json.dumps({"config": name, "Gsamples_per_s": round(sps / 1e9, 2), "ms_per_step": round(ms / steps, 3),
                       "wall_ms_per_step": round(wall / steps, 3), "hbm_frac": round(sps * byts / 6553e9, 4),
-                      "kernel": "periodic" if p1 > p0 else "generic", "filters": lib.resampleGetNumFilters(ctxs[0]),
+                      "kernel": "tensor" if lib.resampleB200TensorLaunches() > t0n else "periodic" if p1 > p0 else "generic", "filters": lib.resampleGetNumFilters(ctxs[0]),
                       "interp": bool(lib.resampleInterpolationUsed(ctxs[0]))}), flush=True)
     for c in ctxs:
         lib.resampleFree(c)
@@ -103,6 +104,9 @@ if __name__ == "__main__":
     run("cfg3 64ch -4 96->44.1k lowpass 20k (1 ctx x 2^19)", 64, 4, 96000, 44100, 1, 1 << 19, lowpass_hz=20000)
     run("cfg3 fixed-ratio init (147 filters, auto lowpass)", 64, 4, 96000, 44100, 1, 1 << 19, fixed=True)
     run("cfg4 1024 stereo streams -3 48->44.1k lowpass (2^15 each)", 2, 3, 48000, 44100, 1024, 1 << 15, lowpass_hz=20000)
+    run("cfg4 128 stereo streams -3 48->44.1k lowpass (2^18 each: one GPU's share of 1024, long blocks)", 2, 3, 48000, 44100, 128, 1 << 18, lowpass_hz=20000)
+    run("stereo -4 44.1->48k (64 streams x 2^18)", 2, 4, 44100, 48000, 64, 1 << 18)
+    run("stereo -2 44.1->48k (64 streams x 2^18)", 2, 2, 44100, 48000, 64, 1 << 18)
     run("cfg2 stereo -3 irrational ratio 1.0884 (generic kernel)", 2, 3, 44100, 44100 * 1.08843537, 64, 1 << 18)
     run("stereo -2 1:1.0001 (near unity, generic)", 2, 2, 48000, 48004.8, 64, 1 << 18)
     run_asrc("cfg5 8ch -2 ASRC +/-100ppm, 256 blocks x 4096 frames", 8, 2, 256, 4096)

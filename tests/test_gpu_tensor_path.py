@@ -147,3 +147,24 @@ def test_many_streams_batched(forced_tensor_path):
         yo, uo, mo = o.process(x, 40000, ratio)
         assert (used, made) == (uo, mo) and g.position() == o.position()
         assert A.peak_error(y, yo) <= TOL
+
+
+def test_fixed_ratio_contexts_opt_in(forced_tensor_path):
+    """resampleFixedRatioInit contexts (no interpolation) stay on the FFMA form by default -- it keeps their output
+    bit-identical across call chunkings -- and take the tensor-core kernel only in mode 3"""
+    lib = forced_tensor_path
+    rng = np.random.default_rng(41)
+    x = rng.uniform(-0.5, 0.5, (200000, 2)).astype(np.float32)
+
+    def run():
+        g = A.product_stream(2, 380, 380, flags=7, fixed=(44100, 48000, 0))
+        o = A.oracle_stream(2, 380, 380, flags=7, fixed=(44100, 48000, 0))
+        g.advance(190); o.advance(190)
+        before = lib.resampleB200TensorLaunches()
+        _check_call(g, o, x, 250000, 0.0)
+        return lib.resampleB200TensorLaunches() - before
+
+    lib.resampleB200SetTensorPath(1)
+    assert run() == 0
+    lib.resampleB200SetTensorPath(3)
+    assert run() == 1

@@ -87,7 +87,8 @@ struct ArtPeriodic2 {
 struct ArtUmma {
     int L, M;            // outputs / inputs per period
     int Npad;            // phases rounded up to 16: the N of every MMA
-    int KI;              // k-steps (16 taps) per input period: ceil(M / 16)
+    int KI;              // k-steps (16 taps) per input period: ceil(M / 16) = pairs of 8-tap planes per row
+    int NS;              // plane-pair slots of operand A held in shared memory (a divisor of KI; pair i lives in slot i % NS)
     int numK;            // k-steps per tile
     int rows;            // rows of the signal operand held per tile: 128 + largest row shift, padded
     int DH;              // filter quantum is 2^-DH
@@ -97,7 +98,7 @@ struct ArtUmma {
     int *S0;             // [jobs]  region index of tap 0 of phase 0, period 0
     int *tileExp;        // [tiles] exponent e of the tile's signal quantum 2^e (block maximum <= 2^(e+11))
     unsigned char ka[ART_U_MAXK], ki[ART_U_MAXK];      // k-step -> (row shift a, 16-tap group i), i outermost
-    unsigned char nA[16];                              // row shifts per 16-tap group
+    unsigned char nA[32];                              // row shifts per 16-tap group
 };
 
 /* Sum NV register values per lane across the warp so that lane L ends up with the total of

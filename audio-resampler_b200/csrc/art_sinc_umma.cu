@@ -46,7 +46,8 @@
 #define ART_U_EPI     256           /* epilogue threads */
 #define ART_U_CONV    256           /* converter threads */
 #define ART_U_STAGES  8           /* filter ring depth (fewer when shared memory is short) */
-#define ART_U_MAXKI   12
+#define ART_U_MAXKI   12            /* plane-pair slots (barriers) */
+#define ART_U_MAXPAIRS 32           /* plane pairs per row: M <= 512 */
 #define ART_U_GROUP   2             /* k-steps per ring slot: one wait / commit per slot */
 #define ART_U_ROWS    128           /* periods per tile = M of the MMA */
 #define ART_U_DX      11            /* signal digit: |X1| <= 2^11 */
@@ -338,6 +339,33 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
             }
             return;
         }
+        if (job.inPlanes == nullptr && job.inCS == 1 && job.inFS == C && C <= 128 && (128 % C) == 0) {
+            // interleaved, channel count dividing the block: thread t owns channel t % C and every (128 / C)-th frame, so a
+            // warp reads consecutive floats and every sample is read once for all channels
+            __shared__ unsigned int smaxC[128];
+            const int c = threadIdx.x % C, f0 = threadIdx.x / C, fstep = 128 / C;
+            smaxC[threadIdx.x] = 0u;
+            __syncthreads ();
+            float m = 0.0f;
+            const long long lo = R0 > -job.prevAvail ? R0 : -job.prevAvail;
+            const long long hi = R0 + span < (long long) job.inValid ? R0 + span : (long long) job.inValid;
+            const float *base = job.in + c;
+#pragma unroll 8
+            for (long long i = lo + f0; i < hi; i += fstep) m = fmaxf (m, fabsf (__ldg (base + i * C)));
+            const long long hlo = R0 > -job.prevAvail - T ? R0 : -job.prevAvail - T;
+            const long long hhi = R0 + span < -job.prevAvail ? R0 + span : -job.prevAvail;
+            const float *hist = job.hist + (long long) c * T + T + job.prevAvail;
+            for (long long i = hlo + f0; i < hhi; i += fstep) m = fmaxf (m, fabsf (hist[i]));
+            atomicMax (&smaxC[c], __float_as_uint (m));
+            __syncthreads ();
+            if (threadIdx.x < C) {
+                m = __uint_as_float (smaxC[threadIdx.x]);
+                int e = 0;
+                if (m > 0.0f) { (void) frexpf (m, &e); e -= 11; e = e < -114 ? -114 : (e > 100 ? 100 : e); }
+                u.tileExp[tile + threadIdx.x] = e;
+            }
+            return;
+        }
         for (int c = 0; c < C; ++c) {
             float m = 0.0f;
             {
@@ -389,9 +417,10 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
     extern __shared__ __align__ (1024) unsigned char smem[];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int L = u.L, M = u.M, Npad = u.Npad, KI = u.KI, numK = u.numK, C = k.C, T = k.T;
+    const int L = u.L, M = u.M, Npad = u.Npad, KI = u.KI, NS = u.NS, numK = u.numK, C = k.C, T = k.T;
+    const unsigned int rep = (unsigned int) (KI / NS);    // uses of a plane-pair slot per tile
     const unsigned int planeBytes = (unsigned int) u.rows * 16u;
-    const unsigned int splitBytes = planeBytes * 2u * (unsigned int) KI;
+    const unsigned int splitBytes = planeBytes * 2u * (unsigned int) NS;
     const unsigned int stageBytes = 3u * 2u * (unsigned int) Npad * 16u;
     // [operand A: 2 splits][filter stage ring][epilogue transposition scratch][barriers and small tables]
     unsigned int xcBase;
@@ -414,13 +443,14 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
     const int unitsPerTile = (numK + ART_U_GROUP - 1) / ART_U_GROUP;
     if (tid == 0) {
         for (int s = 0; s < units; ++s) { u_mbar_init (hFullA (s), 1); u_mbar_init (hEmptyA (s), 1); }
-        for (int i = 0; i < KI; ++i) {
-            // a pair of planes is released by every issuer that used it
+        for (int sl = 0; sl < NS; ++sl) {
+            // a pair of planes is released by every issuer that used it (the planner guarantees that the pairs
+            // sharing a slot agree on that)
             unsigned int who = 0;
             for (int ks = 0; ks < numK; ++ks)
-                if (u.ki[ks] == i) who |= 1u << ((ks / ART_U_GROUP) & 1);
-            u_mbar_init (pFullA (i), ART_U_CONV / 32);
-            u_mbar_init (pEmptyA (i), who == 3u ? 2 : 1);
+                if (u.ki[ks] % NS == sl) who |= 1u << ((ks / ART_U_GROUP) & 1);
+            u_mbar_init (pFullA (sl), ART_U_CONV / 32);
+            u_mbar_init (pEmptyA (sl), who == 3u ? 2 : 1);
         }
         u_mbar_init (accFullA, unitsPerTile > 1 ? 2 : 1);
         u_mbar_init (accEmptyA, ART_U_EPI / 32);
@@ -430,14 +460,14 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
     }
     for (int ks = tid; ks < numK; ks += ART_U_THREADS) {
         const unsigned int i = u.ki[ks], a = u.ka[ks];
-        const unsigned int aAddr = xcBase + 2u * i * planeBytes + 16u * a;                 // row shift a = +16 bytes
+        const unsigned int aAddr = xcBase + 2u * (i % (unsigned int) NS) * planeBytes + 16u * a;      // row shift a = +16 bytes
         // bit 1: the last k-step of its pair of planes that this k-step's issuer handles
         const int mine = (ks / ART_U_GROUP) & 1;
         bool last = true;
         for (int k2 = ks + 1; k2 < numK && u.ki[k2] == i; ++k2)
             if (((k2 / ART_U_GROUP) & 1) == mine) last = false;
         u_sts64 (kTabA (ks), make_uint2 (((aAddr >> 4) & 0x3fffu) | (((planeBytes >> 4) & 0x3fffu) << 16),
-                                         (a == 0 ? 1u : 0u) | (last ? 2u : 0u) | (i << 8)));
+                                         (a == 0 ? 1u : 0u) | (last ? 2u : 0u) | ((i % (unsigned int) NS) << 8) | ((i / (unsigned int) NS) << 16)));
     }
     if (warp == 0) {
         asm volatile ("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tmemSlotA), "r"(512));
@@ -506,8 +536,10 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                 if ((unit & 1u) == me) {
                     const int cnt = numK - ks0 < ART_U_GROUP ? numK - ks0 : ART_U_GROUP;
                     long long t0 = UCLK ();
-                    for (int g = 0; g < cnt; ++g)
-                        u_mbar_wait (pFullA (u_lds64 (kTabA (ks0 + g)).y >> 8), lt & 1);   // the converters filled this pair of planes
+                    for (int g = 0; g < cnt; ++g) {
+                        const unsigned int f = u_lds64 (kTabA (ks0 + g)).y;
+                        u_mbar_wait (pFullA ((f >> 8) & 0xffu), (lt * rep + (f >> 16)) & 1);   // the converters filled this pair of planes
+                    }
                     long long t3 = UCLK ();
                     u_mbar_wait (hFullA (us), ph);
                     if (lane == 0 && me == 0) { UPROF_ADD (1, t3 - t0); UPROF_ADD (3, UCLK () - t3); }
@@ -533,7 +565,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                             u_mma (tm + 2 * Npad, dA2, dB2, idesc, 1);              // x2 * h2
                             }
                             if (kt.y & 2)
-                                u_commit (pEmptyA (kt.y >> 8));                      // this issuer is done with the pair of planes
+                                u_commit (pEmptyA ((kt.y >> 8) & 0xffu));            // this issuer is done with the pair of planes
                         }
                         long long t5 = UCLK ();
                         u_commit (hEmptyA (us));
@@ -644,11 +676,12 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                 if (i + 1 < KI) fetch (cur, i + 1, vn);
                 else if (more) fetch (nxt, 0, vn);
                 long long c0t = UCLK ();
-                u_mbar_wait_relaxed (pEmptyA (i), (lt & 1) ^ 1);
+                const unsigned int sl = (unsigned int) i % (unsigned int) NS, use = lt * rep + (unsigned int) i / (unsigned int) NS;
+                u_mbar_wait_relaxed (pEmptyA (sl), (use & 1) ^ 1);
                 long long cb = UCLK ();
                 if (ctid == 0) UPROF_ADD (5, cb - c0t);
                 // taps 2c, 2c+1 of the pair: plane 2i + (c >> 2), 4 bytes at (c & 3) * 4 of the row's 16-byte slot
-                const unsigned int dst = xcBase + (unsigned int) (2 * i + ((lane >> 2) & 1)) * planeBytes + (unsigned int) (lane & 3) * 4u +
+                const unsigned int dst = xcBase + (2u * sl + ((lane >> 2) & 1)) * planeBytes + (unsigned int) (lane & 3) * 4u +
                                          (unsigned int) r0 * 16u;
 #pragma unroll
                 for (int uu = 0; uu < UN; ++uu) {
@@ -666,7 +699,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                 asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> tensor-core reads
                 long long cd = UCLK ();
                 __syncwarp ();
-                if (lane == 0) u_mbar_arrive (pFullA (i));                          // one arrival per warp: 256 serialised arrivals cost ~500 cycles
+                if (lane == 0) u_mbar_arrive (pFullA (sl));                          // one arrival per warp: 256 serialised arrivals cost ~500 cycles
                 if (ctid == 0) { UPROF_ADD (7, cc - cb); UPROF_ADD (14, cd - cc); UPROF_ADD (15, UCLK () - cd); }
             }
             cur = nxt;
@@ -764,7 +797,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
 
 static size_t umma_smem (const ArtUmma &u)
 {
-    const size_t xc = (size_t) 2 * (2 * u.KI) * u.rows * 16;                 // two splits
+    const size_t xc = (size_t) 2 * (2 * u.NS) * u.rows * 16;                 // two splits
     return xc + (size_t) u.stages * 3 * 2 * u.Npad * 16 + 8 * 32 * 17 * sizeof (float) + 384 + ART_U_MAXK * 8;
 }
 
@@ -788,7 +821,7 @@ bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsi
     int g = 160 / L;
     while (g > 1 && (long long) M * g > 176) --g;
     L *= g; M *= g;
-    if (L < 48 || M > 176) return false;
+    if (L < 48 || M > 16 * ART_U_MAXPAIRS) return false;
     if (maxOutputs < (unsigned) (16 * L)) return false;           // rows of a tile would be mostly idle
     // a launch costs this kernel ~25 us whatever its size (filter table + one tile per SM); the FFMA form runs at
     // ~11 Gsamples/s on a single stream, so it wins below ~0.3 Msamples
@@ -799,7 +832,7 @@ bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsi
     u.L = L; u.M = M;
     u.Npad = (L + 15) & ~15;
     u.KI = (M + 15) / 16;
-    if (u.KI > ART_U_MAXKI) return false;
+    if (u.KI > ART_U_MAXPAIRS) return false;
     const int flatEnd = M + 1 + k.T;                              // taps are counted from phase 0's first tap
     int n = 0, aMax = 0;
     for (int i = 0; i < u.KI; ++i)                                // plane pair outermost: its planes are handed
@@ -826,11 +859,25 @@ bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsi
     if (!u.DH) return false;
     u.tableHalfs = u.numK * 3 * 2 * u.Npad * 8;
     u.stages = ART_U_STAGES;
+    // operand A: all KI plane pairs of a row if they fit, else a ring of NS | KI slots -- pairs are used in order, each
+    // for all of its row shifts in a row, so a slot can take pair i + NS as soon as the MMAs of pair i are done.  Slots
+    // shared by several pairs need those pairs to be released by the same issuers (both, i.e. >= 3 k-steps per pair).
+    u.NS = 0;
+    for (int ns = u.KI < ART_U_MAXKI ? u.KI : ART_U_MAXKI; ns >= 1; --ns) {
+        if (u.KI % ns) continue;
+        u.NS = ns;
+        if (umma_smem (u) <= 224 * 1024) break;
+        u.NS = 0;
+    }
+    if (!u.NS) return false;
+    if (u.NS < u.KI)
+        for (int i = 0; i < u.KI; ++i)
+            if (u.nA[i] < 3) return false;
     while (u.stages > 2 * ART_U_GROUP && umma_smem (u) > 224 * 1024) u.stages -= ART_U_GROUP;
     if (umma_smem (u) > 224 * 1024) return false;
     if (getenv ("ART_B200_TRACE"))
-        fprintf (stderr, "[art] umma L=%d M=%d Npad=%d KI=%d numK=%d rows=%d DH=%d stages=%d smem=%zu\n",
-                 u.L, u.M, u.Npad, u.KI, u.numK, u.rows, u.DH, u.stages, umma_smem (u));
+        fprintf (stderr, "[art] umma L=%d M=%d Npad=%d KI=%d NS=%d numK=%d rows=%d DH=%d stages=%d smem=%zu\n",
+                 u.L, u.M, u.Npad, u.KI, u.NS, u.numK, u.rows, u.DH, u.stages, umma_smem (u));
     return true;
 }
 

@@ -45,6 +45,8 @@ def _check_call(g, o, x, cap, ratio, tol=TOL, **kw):
     (3, 2, 32000, 40000, 0),            # 5/4: 32 periods grouped into one row of 160 phases
     (5, 1, 8000, 48000, 0),             # 6/1: 26 periods per row, odd channel count
     (2, 4, 44100, 48000, 0),            # preset -4: 988 taps, 8 row shifts
+    (8, 4, 96000, 44100, 20000),        # BASELINE config 3's shape (8 of its 64 channels): 147/320, operand A as a ring of plane pairs
+    (4, 3, 96000, 48000, 0),            # 1/2: 160 periods per row, M = 320
 ])
 def test_configs_on_the_tensor_path(forced_tensor_path, ch, preset, src, dst, lowpass_hz):
     lib = forced_tensor_path

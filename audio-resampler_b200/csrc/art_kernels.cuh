@@ -96,7 +96,7 @@ struct ArtUmma {
     int tableHalfs;      // fp16 elements per table: numK * 3 * 2 * Npad * 8
     unsigned short *H;   // [tables][numK][3 splits][2 k-planes][Npad][8]  fp16 bit patterns
     int *S0;             // [jobs]  region index of tap 0 of phase 0, period 0
-    int *tileExp;        // [tiles] exponent e of the tile's signal quantum 2^e (block maximum <= 2^(e+11))
+    int *tileExp;        // [tiles] block maximum |x| of the samples a tile reads, as a float bit pattern (-> the tile's quantum)
     unsigned char ka[ART_U_MAXK], ki[ART_U_MAXK];      // k-step -> (row shift a, 16-tap group i), i outermost
     unsigned char nA[32];                              // row shifts per 16-tap group
 };

@@ -283,17 +283,18 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
     }
     b -= originBlocks;
     if (b < totalTiles) {
-        /* block maximum of the samples a tile reads -> exponent of its power-of-two quantum: |x| / 2^e <= 2^11.
-         * One block serves the tiles of all channels of a period block (they read the same frames); blocks whose
-         * index is not a multiple of C return.  (The origin is recomputed: the origin block may run later.) */
+        /* Block maximum of the samples a tile reads (-> its power-of-two quantum, |x| / 2^e <= 2^11, taken by the converters).
+         * tileMax[] holds float bit patterns, zeroed before the launch, raised with atomicMax.  The C tiles of a period block
+         * read the same frames: for interleaved input their C blocks each scan 1/C of the frames for ALL channels (every
+         * sample read once, coalesced); otherwise each block scans its own channel.  (The origin is recomputed here: the
+         * origin block may run later.) */
         const int tile = b;
-        if (dbg & 32) { if (threadIdx.x == 0) u.tileExp[tile] = -10; return; }
+        if (dbg & 32) { if (threadIdx.x == 0) u.tileExp[tile] = __float_as_uint (1.0f); return; }
         const int seg = jobs ? (numJobs > 1 ? u_find_job (jobs, numJobs, tile) : 0) : 0;
         const ArtJob &job = jobs ? jobs[seg] : single;
         const int local = tile - job.tile0;
         const int C = k.C;
-        if (local % C) return;
-        const int qb = local / C;
+        const int qb = local / C, j = local - qb * C;
         ArtLoopState st;
         st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = T;
         int w;
@@ -301,97 +302,78 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
         const long long S0 = (long long) floor (pos) - half + 1 + (long long) w * 15LL * T - job.origin;
         const long long R0 = S0 + (long long) u.M * qb * 128;
         const int span = u.M * (u.rows - 1) + 16 * u.KI;
-        const bool inside = job.inPlanes == nullptr && R0 >= -job.prevAvail && R0 + span <= (long long) job.inValid;
-        __shared__ float red[4];
-        if (inside && C == 2 && job.inCS == 1 && job.inFS == 2) {
-            // interleaved stereo: the block is one contiguous run; 16-byte loads over its aligned interior
-            const float *p0 = job.in + R0 * 2, *p1 = p0 + (size_t) span * 2;
-            float m0 = 0.0f, m1 = 0.0f;
-            const float *a0 = reinterpret_cast<const float *> ((reinterpret_cast<unsigned long long> (p0) + 15) & ~15ull);
-            const float *a1 = reinterpret_cast<const float *> (reinterpret_cast<unsigned long long> (p1) & ~15ull);
-            const bool odd = ((a0 - p0) & 1) != 0;                          // a0 starts on a right-channel sample
-            for (const float *p = p0 + threadIdx.x; p < a0; p += 128) { const float v = fabsf (*p); if ((p - p0) & 1) m1 = fmaxf (m1, v); else m0 = fmaxf (m0, v); }
-            for (const float *p = a1 + threadIdx.x; p < p1; p += 128) { const float v = fabsf (*p); if ((p - p0) & 1) m1 = fmaxf (m1, v); else m0 = fmaxf (m0, v); }
-            const float4 *q = reinterpret_cast<const float4 *> (a0);
-            const int n4 = (int) ((a1 - a0) >> 2);
-            float e0 = 0.0f, e1 = 0.0f;
-#pragma unroll 8
-            for (int i = threadIdx.x; i < n4; i += 128) {
-                const float4 v = __ldg (q + i);
-                e0 = fmaxf (e0, fmaxf (fabsf (v.x), fabsf (v.z)));
-                e1 = fmaxf (e1, fmaxf (fabsf (v.y), fabsf (v.w)));
-            }
-            m0 = fmaxf (m0, odd ? e1 : e0);
-            m1 = fmaxf (m1, odd ? e0 : e1);
-            for (int c = 0; c < 2; ++c) {
-                float m = c ? m1 : m0;
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) m = fmaxf (m, __shfl_xor_sync (0xffffffffu, m, off));
-                __syncthreads ();
-                if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-                __syncthreads ();
-                if (threadIdx.x == 0) {
-                    m = fmaxf (fmaxf (red[0], red[1]), fmaxf (red[2], red[3]));
-                    int e = 0;
-                    if (m > 0.0f) { (void) frexpf (m, &e); e -= 11; e = e < -114 ? -114 : (e > 100 ? 100 : e); }
-                    u.tileExp[tile + c] = e;
-                }
-            }
-            return;
+        // the part inside the caller's block, and the part that comes from the history; the rest is silence
+        const long long lo = R0 > -job.prevAvail ? R0 : -job.prevAvail;
+        const long long hi = R0 + span < (long long) job.inValid ? R0 + span : (long long) job.inValid;
+        const long long hlo = R0 > -job.prevAvail - T ? R0 : -job.prevAvail - T;
+        const long long hhi = R0 + span < -job.prevAvail ? R0 + span : -job.prevAvail;
+        unsigned int *tileMax = reinterpret_cast<unsigned int *> (u.tileExp) + (tile - j);       // entries of this period block
+        __shared__ unsigned int smaxC[128];
+
+        // channel j's stretch of history (planar [C][T])
+        float mh = 0.0f;
+        {
+            const float *hist = job.hist + (long long) j * T + T + job.prevAvail;
+            for (long long i = hlo + threadIdx.x; i < hhi; i += 128) mh = fmaxf (mh, fabsf (hist[i]));
         }
-        if (job.inPlanes == nullptr && job.inCS == 1 && job.inFS == C && C <= 128 && (128 % C) == 0) {
-            // interleaved, channel count dividing the block: thread t owns channel t % C and every (128 / C)-th frame, so a
-            // warp reads consecutive floats and every sample is read once for all channels
-            __shared__ unsigned int smaxC[128];
-            const int c = threadIdx.x % C, f0 = threadIdx.x / C, fstep = 128 / C;
+        const bool interleaved = job.inPlanes == nullptr && job.inCS == 1 && job.inFS == C && C <= 128;
+        if (interleaved) {
+            const long long len = hi > lo ? hi - lo : 0;
+            const long long s0 = lo + len * j / C, s1 = lo + len * (j + 1) / C;        // this block's frames
             smaxC[threadIdx.x] = 0u;
             __syncthreads ();
-            float m = 0.0f;
-            const long long lo = R0 > -job.prevAvail ? R0 : -job.prevAvail;
-            const long long hi = R0 + span < (long long) job.inValid ? R0 + span : (long long) job.inValid;
-            const float *base = job.in + c;
+            if (mh > 0.0f) atomicMax (&smaxC[j], __float_as_uint (mh));
+            const float *p0 = job.in + s0 * C, *p1 = job.in + s1 * C;
+            if (C == 2) {
+                // 16-byte loads over the aligned interior
+                float m0 = 0.0f, m1 = 0.0f;
+                const float *a0 = reinterpret_cast<const float *> ((reinterpret_cast<unsigned long long> (p0) + 15) & ~15ull);
+                const float *a1 = reinterpret_cast<const float *> (reinterpret_cast<unsigned long long> (p1) & ~15ull);
+                if (a1 < a0) { a0 = p1; a1 = p1; }
+                const bool odd = ((a0 - p0) & 1) != 0;                      // a0 starts on a right-channel sample
+                for (const float *p = p0 + threadIdx.x; p < a0 && p < p1; p += 128) { const float v = fabsf (*p); if ((p - p0) & 1) m1 = fmaxf (m1, v); else m0 = fmaxf (m0, v); }
+                for (const float *p = a1 + threadIdx.x; p < p1; p += 128) { const float v = fabsf (*p); if ((p - p0) & 1) m1 = fmaxf (m1, v); else m0 = fmaxf (m0, v); }
+                const float4 *q = reinterpret_cast<const float4 *> (a0);
+                const int n4 = (int) ((a1 - a0) >> 2);
+                float e0 = 0.0f, e1 = 0.0f;
 #pragma unroll 8
-            for (long long i = lo + f0; i < hi; i += fstep) m = fmaxf (m, fabsf (__ldg (base + i * C)));
-            const long long hlo = R0 > -job.prevAvail - T ? R0 : -job.prevAvail - T;
-            const long long hhi = R0 + span < -job.prevAvail ? R0 + span : -job.prevAvail;
-            const float *hist = job.hist + (long long) c * T + T + job.prevAvail;
-            for (long long i = hlo + f0; i < hhi; i += fstep) m = fmaxf (m, fabsf (hist[i]));
-            atomicMax (&smaxC[c], __float_as_uint (m));
-            __syncthreads ();
-            if (threadIdx.x < C) {
-                m = __uint_as_float (smaxC[threadIdx.x]);
-                int e = 0;
-                if (m > 0.0f) { (void) frexpf (m, &e); e -= 11; e = e < -114 ? -114 : (e > 100 ? 100 : e); }
-                u.tileExp[tile + threadIdx.x] = e;
+                for (int i = threadIdx.x; i < n4; i += 128) {
+                    const float4 v = __ldg (q + i);
+                    e0 = fmaxf (e0, fmaxf (fabsf (v.x), fabsf (v.z)));
+                    e1 = fmaxf (e1, fmaxf (fabsf (v.y), fabsf (v.w)));
+                }
+                m0 = fmaxf (m0, odd ? e1 : e0);
+                m1 = fmaxf (m1, odd ? e0 : e1);
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) { m0 = fmaxf (m0, __shfl_xor_sync (0xffffffffu, m0, off)); m1 = fmaxf (m1, __shfl_xor_sync (0xffffffffu, m1, off)); }
+                if ((threadIdx.x & 31) == 0) { atomicMax (&smaxC[0], __float_as_uint (m0)); atomicMax (&smaxC[1], __float_as_uint (m1)); }
             }
+            else if ((128 % C) == 0) {
+                // thread t owns channel t % C and every (128 / C)-th frame: a warp reads consecutive floats
+                const int c = threadIdx.x % C, fstep = 128 / C;
+                float m = 0.0f;
+                const float *base = job.in + c;
+#pragma unroll 8
+                for (long long i = s0 + threadIdx.x / C; i < s1; i += fstep) m = fmaxf (m, fabsf (__ldg (base + i * C)));
+                atomicMax (&smaxC[c], __float_as_uint (m));
+            }
+            else {
+                const long long n = (s1 - s0) * C;
+                for (long long e = threadIdx.x; e < n; e += 128) atomicMax (&smaxC[(int) (e % C)], __float_as_uint (fabsf (__ldg (p0 + e))));
+            }
+            __syncthreads ();
+            if (threadIdx.x < C && smaxC[threadIdx.x]) atomicMax (&tileMax[threadIdx.x], smaxC[threadIdx.x]);
             return;
         }
-        for (int c = 0; c < C; ++c) {
-            float m = 0.0f;
-            {
-                // the part inside the caller's block, then the part that comes from the history; the rest is silence
-                const long long lo = R0 > -job.prevAvail ? R0 : -job.prevAvail;
-                const long long hi = R0 + span < (long long) job.inValid ? R0 + span : (long long) job.inValid;
-                const float *base = job.inPlanes ? job.inPlanes[c] : job.in + (long long) c * job.inCS;
-                const long long fs = job.inFS;
+        {
+            float m = mh;
+            const float *base = job.inPlanes ? job.inPlanes[j] : job.in + (long long) j * job.inCS;
+            const long long fs = job.inFS;
 #pragma unroll 16
-                for (long long i = lo + threadIdx.x; i < hi; i += 128) m = fmaxf (m, fabsf (__ldg (base + i * fs)));
-                const long long hlo = R0 > -job.prevAvail - T ? R0 : -job.prevAvail - T;
-                const long long hhi = R0 + span < -job.prevAvail ? R0 + span : -job.prevAvail;
-                const float *hist = job.hist + (long long) c * T + T + job.prevAvail;
-                for (long long i = hlo + threadIdx.x; i < hhi; i += 128) m = fmaxf (m, fabsf (hist[i]));
-            }
+            for (long long i = lo + threadIdx.x; i < hi; i += 128) m = fmaxf (m, fabsf (__ldg (base + i * fs)));
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) m = fmaxf (m, __shfl_xor_sync (0xffffffffu, m, off));
-            __syncthreads ();
-            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-            __syncthreads ();
-            if (threadIdx.x == 0) {
-                m = fmaxf (fmaxf (red[0], red[1]), fmaxf (red[2], red[3]));
-                int e = 0;
-                if (m > 0.0f) { (void) frexpf (m, &e); e -= 11; e = e < -114 ? -114 : (e > 100 ? 100 : e); }    // m < 2^e
-                u.tileExp[tile + c] = e;
-            }
+            if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax (&tileMax[j], __float_as_uint (m));
         }
         return;
     }
@@ -623,7 +605,12 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             sc.base = job.inPlanes ? job.inPlanes[c] : job.in + (long long) c * job.inCS;
             sc.hist = job.hist + (long long) c * T + T + job.prevAvail;       // hist[idx]: -T - prevAvail <= idx < -prevAvail
             sc.p = sc.base + (sc.R0 + off0) * sc.fs;
-            sc.e = u.tileExp[tile];
+            {
+                const float m = __int_as_float (u.tileExp[tile]);             // block maximum (prep kernel)
+                int e = 0;
+                if (m > 0.0f) { (void) frexpf (m, &e); e -= ART_U_DX; e = e < -114 ? -114 : (e > 100 ? 100 : e); }      // m < 2^(e + 11)
+                sc.e = e;
+            }
             return sc;
         };
         auto rowOk = [&] (int uu) -> bool { return uu < nU && r0 + 32 * uu < u.rows; };
@@ -929,6 +916,7 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
     int histBlocks = (k.C * k.T + 127) / 128;
     if (histBlocks > 32) histBlocks = 32;
     const int prepBlocks = numTables * u.Npad + (numJobs + 127) / 128 + totalTiles + numJobs * histBlocks;
+    ART_CUDA_CHECK (cudaMemsetAsync (u.tileExp, 0, (size_t) totalTiles * sizeof (int), stream));
     static int prepDbg = -1;
     if (prepDbg < 0) { const char *d = getenv ("ART_B200_UDBG"); prepDbg = d ? atoi (d) : 0; }
     art_umma_prep_kernel<<<prepBlocks, 128, 0, stream>>> (k, u, single, d_jobs, numJobs, numTables, histBlocks, totalTiles, prepDbg);

@@ -414,12 +414,119 @@ static int append_job (const ArtLaunchPlan &lp, const ArtJob &base, std::vector<
     return ctas;
 }
 
+
+/* ---- many-channel interleaved blocks on the tensor-core kernel -------------------------------------------
+ * Its tiles are single channels; read straight from an interleaved block of C >= 8 channels every 32-byte sector would
+ * carry one useful sample (and 8 tiles would fetch the same sector), and the epilogue would store 4 bytes per sector.
+ * Such launches go through planar scratch in HBM instead: one coalesced transposition in, one out (+16 bytes of
+ * traffic per sample on a path that sits far below the HBM roofline). */
+struct ArtXpose { const float *src; float *dst; long long frames, pitch; };
+
+__global__ void __launch_bounds__ (256)
+art_deinterleave_kernel (const ArtXpose *__restrict__ g, int C)            // dst[c * pitch + f] = src[f * C + c]
+{
+    __shared__ float t[32][33];
+    const ArtXpose x = g[blockIdx.z];
+    const long long f0 = (long long) blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    if (f0 >= x.frames) return;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const long long f = f0 + r;
+        const int c = c0 + threadIdx.x;
+        t[r][threadIdx.x] = (f < x.frames && c < C) ? __ldg (x.src + f * C + c) : 0.0f;
+    }
+    __syncthreads ();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int c = c0 + r;
+        const long long f = f0 + threadIdx.x;
+        if (c < C && f < x.frames) x.dst[(long long) c * x.pitch + f] = t[threadIdx.x][r];
+    }
+}
+
+__global__ void __launch_bounds__ (256)
+art_interleave_kernel (const ArtXpose *__restrict__ g, int C)              // dst[f * C + c] = src[c * pitch + f]
+{
+    __shared__ float t[32][33];
+    const ArtXpose x = g[blockIdx.z];
+    const long long f0 = (long long) blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    if (f0 >= x.frames) return;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int c = c0 + r;
+        const long long f = f0 + threadIdx.x;
+        t[r][threadIdx.x] = (c < C && f < x.frames) ? __ldg (x.src + (long long) c * x.pitch + f) : 0.0f;
+    }
+    __syncthreads ();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const long long f = f0 + r;
+        const int c = c0 + threadIdx.x;
+        if (f < x.frames && c < C) x.dst[f * C + c] = t[threadIdx.x][r];
+    }
+}
+
 static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cudaStream_t stream, ArtDev *owner = nullptr)
 {
     if (jobs.empty ())
         return;
     const int n = (int) jobs.size ();
     lp.k.numJobs = n;
+
+    // tensor-core kernel on interleaved blocks of many channels: planar scratch (see above).  Segments of one call sit
+    // next to each other in `jobs` and share their pointers: one scratch pair per call.
+    float *scratch = nullptr;
+    ArtXpose *d_xpose = nullptr;
+    std::vector<ArtXpose> xin, xout;
+    long long maxInFrames = 0, maxOutFrames = 0;
+    const int C = lp.k.C;
+    if (lp.umma && ctas > 0 && C >= 8) {
+        bool ok = true;
+        for (const ArtJob &j : jobs)
+            ok &= j.inPlanes == nullptr && j.outPlanes == nullptr && j.inCS == 1 && j.inFS == C && j.outCS == 1 && j.outFS == C && j.prevAvail == 0;
+        if (ok) {
+            size_t floats = 0;
+            std::vector<size_t> inAt, outAt;
+            for (int i = 0; i < n; ) {
+                int e = i;
+                long long outFrames = 0;
+                while (e < n && jobs[e].in == jobs[i].in && jobs[e].out == jobs[i].out) {
+                    const long long end = (long long) jobs[e].nStart + jobs[e].outputs;
+                    if (end > outFrames) outFrames = end;
+                    ++e;
+                }
+                const long long inFrames = jobs[i].inValid > 0 ? jobs[i].inValid : 0;
+                const long long inPitch = (inFrames + 31) & ~31LL, outPitch = (outFrames + 31) & ~31LL;
+                xin.push_back ({ jobs[i].in, nullptr, inFrames, inPitch });
+                xout.push_back ({ nullptr, jobs[i].out, outFrames, outPitch });
+                inAt.push_back (floats); floats += (size_t) C * inPitch;
+                outAt.push_back (floats); floats += (size_t) C * outPitch;
+                if (inFrames > maxInFrames) maxInFrames = inFrames;
+                if (outFrames > maxOutFrames) maxOutFrames = outFrames;
+                for (int q = i; q < e; ++q) jobs[q].table = (int) xin.size () - 1;          // group index, for the rewrite below
+                i = e;
+            }
+            ART_CUDA_CHECK (cudaMallocAsync (&scratch, floats * sizeof (float), stream));
+            for (size_t gi = 0; gi < xin.size (); ++gi) {
+                xin[gi].dst = scratch + inAt[gi];
+                xout[gi].src = scratch + outAt[gi];
+            }
+            for (ArtJob &j : jobs) {
+                const ArtXpose &a = xin[j.table], &b = xout[j.table];
+                j.in = a.dst;  j.inFS = 1;  j.inCS = a.pitch;
+                j.out = const_cast<float *> (b.src); j.outFS = 1; j.outCS = b.pitch;
+            }
+            const size_t ng = xin.size ();
+            std::vector<ArtXpose> both (xin);
+            both.insert (both.end (), xout.begin (), xout.end ());
+            ART_CUDA_CHECK (cudaMallocAsync (&d_xpose, both.size () * sizeof (ArtXpose), stream));
+            ART_CUDA_CHECK (cudaMemcpyAsync (d_xpose, both.data (), both.size () * sizeof (ArtXpose), cudaMemcpyHostToDevice, stream));
+            if (maxInFrames > 0) {
+                const dim3 grid ((unsigned int) ((maxInFrames + 31) / 32), (unsigned int) ((C + 31) / 32), (unsigned int) ng);
+                art_deinterleave_kernel<<<grid, dim3 (32, 8), 0, stream>>> (d_xpose, C);
+                ART_CUDA_CHECK (cudaGetLastError ());
+                ++g_artLaunches;
+            }
+        }
+    }
     bool anyHist = false;
     for (const ArtJob &j : jobs) anyHist |= j.histOut != nullptr;
 
@@ -498,6 +605,17 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
     }
     if (anyHist)
         artLaunchHistory (lp.k, jobs[0], d_jobs, n, stream);
+    if (scratch) {
+        if (maxOutFrames > 0) {
+            const size_t ng = xin.size ();
+            const dim3 grid ((unsigned int) ((maxOutFrames + 31) / 32), (unsigned int) ((C + 31) / 32), (unsigned int) ng);
+            art_interleave_kernel<<<grid, dim3 (32, 8), 0, stream>>> (d_xpose + ng, C);
+            ART_CUDA_CHECK (cudaGetLastError ());
+            ++g_artLaunches;
+        }
+        ART_CUDA_CHECK (cudaFreeAsync (d_xpose, stream));
+        ART_CUDA_CHECK (cudaFreeAsync (scratch, stream));
+    }
     if (d_jobs)
         ART_CUDA_CHECK (cudaFreeAsync (d_jobs, stream));
 }

@@ -397,7 +397,8 @@ def measure_e2e(lib, pkg, torch, dist, world, dev, streams, frames, cap, args):
     # long-lived host threads, each owning every T-th stream: the call is ~60 us, so per-call Python overhead (futures,
     # GIL hand-offs of an executor's map) would be a visible part of it
     import threading
-    T = max(1, min(args.e2e_threads, n))
+    # a host thread spins inside cudaStreamSynchronize: do not oversubscribe the cores when several ranks share the box
+    T = max(1, min(args.e2e_threads, n, max(2, (os.cpu_count() or 16) // max(1, world))))
     start, done = threading.Barrier(T + 1), threading.Barrier(T + 1)
     made_by = [0] * T
     rounds = {"n": 0}
@@ -475,7 +476,7 @@ def measure_e2e(lib, pkg, torch, dist, world, dev, streams, frames, cap, args):
     return {"value": value, "unit": "Msamples/s",
             "h2d_bytes_per_step": int(n * frames * CHANNELS * 4), "d2h_bytes_per_step": int(per_step_out * CHANNELS * 4),
             "api": "resampleProcessInterleaved (host pointers, pinned), "
-                   f"{n} streams x {frames} frames per step, {args.e2e_threads} host threads",
+                   f"{n} streams x {frames} frames per step, {T} host threads",
             "batched_value": batched,
             "batched_api": "resampleBatchProcessInterleaved (host pointers, pinned), one call per step"}
 

@@ -6,6 +6,7 @@
  */
 #include "../../include/resampler_b200.h"
 #include "art_device.h"
+#include "art_extrapolate.h"
 
 #include <math.h>
 #include <stdio.h>
@@ -98,12 +99,9 @@ Resample *resampleInit (int numChannels, int numTaps, int numFilters, double low
         fprintf (stderr, "must be at least 1 channel!\n");
         return NULL;
     }
-    if (flags & EXTRAPOLATE_ENDPOINTS) {
-        static int warned;
-        if (!warned++)
-            fprintf (stderr, "libresampler_b200: EXTRAPOLATE_ENDPOINTS is not implemented yet; endpoints are zero-extended\n");
-        flags &= ~EXTRAPOLATE_ENDPOINTS;
-    }
+    flags &= ~EXTRAPOLATE_PREFILL;
+    if (flags & EXTRAPOLATE_ENDPOINTS)                              /* resampler.c:179-182 */
+        flags |= EXTRAPOLATE_PREFILL;
 
     cxt = calloc (1, sizeof *cxt);
     cxt->lowpassRatio = lowpassRatio;
@@ -179,6 +177,8 @@ void resampleReset (Resample *cxt)                                  /* resampler
     cxt->outputOffset = cxt->numTaps / 2;
     cxt->inputIndex = cxt->numTaps;
     cxt->flags &= ~RESAMPLER_FLUSHED;
+    if (cxt->flags & EXTRAPOLATE_ENDPOINTS)                         /* resampler.c:393-394 */
+        cxt->flags |= EXTRAPOLATE_PREFILL;
 }
 
 void resampleFree (Resample *cxt)                                   /* resampler.c:973-995 */
@@ -245,40 +245,154 @@ static ResampleResult plan_call (Resample *cxt, int numInputFrames, int numOutpu
     return res;
 }
 
-ResampleResult resampleProcessInterleaved (Resample *cxt, const artsample_t *input, int numInputFrames, artsample_t *output, int numOutputFrames, double ratio)
+/* The four single-call entry points differ only in where the samples live. */
+enum { IO_HOST_INTERLEAVED, IO_HOST_PLANAR, IO_DEVICE_INTERLEAVED, IO_DEVICE_PLANAR };
+
+static void run_call (Resample *cxt, int io, const ArtCallPlan *call, const void *in, void *out, void *stream)
 {
+    switch (io) {
+        case IO_HOST_INTERLEAVED:   artDevRunHostInterleaved (cxt->device, call, (const float *) in, (float *) out); break;
+        case IO_HOST_PLANAR:        artDevRunHostPlanar (cxt->device, call, (const float *const *) in, (float *const *) out); break;
+        case IO_DEVICE_INTERLEAVED: artDevRunDeviceInterleaved (cxt->device, call, (const float *) in, (float *) out, stream); break;
+        default:                    artDevRunDevicePlanar (cxt->device, call, (const float *const *) in, (float *const *) out, stream); break;
+    }
+}
+
+/* EXTRAPOLATE_ENDPOINTS (resampler.c:516-522 / :663-698, extrapolator.c): at the end of a stream the T/2 frames the flush
+ * appends are predicted from the last T/2 frames instead of being silence; at its start, when the first output is about
+ * to be produced, the zero history in front of the first sample is replaced by a backward prediction from the samples
+ * received so far.  Both are a few hundred samples of serial work per stream, done on the host (art_extrapolate.c) around
+ * small synchronous transfers; the call itself then runs as any other. */
+static void run_call_with_endpoints (Resample *cxt, int io, ArtCallPlan *call, const void *in, void *out, void *stream, int flushing)
+{
+    const int T = cxt->numTaps, half = T / 2, C = cxt->numChannels;
+    const int onDevice = io == IO_DEVICE_INTERLEAVED || io == IO_DEVICE_PLANAR;
+    const int planar = io == IO_HOST_PLANAR || io == IO_DEVICE_PLANAR;
+    void *st = onDevice ? stream : NULL;
+    float *hist = NULL, *tail = NULL;           /* [C][T] history at call entry; [C][half] predicted flush block (planar) */
+    const float **tailPlanes = NULL;
+    float *tailInterleaved = NULL;
+    int c, i;
+
+    if (flushing || ((cxt->flags & EXTRAPOLATE_PREFILL) && call->outputs)) {
+        hist = malloc (sizeof (float) * (size_t) C * T);
+        artDevGetHistoryOn (cxt->device, hist, st);
+    }
+
+    if (flushing) {                             /* postfillAllChannels, resampler.c:663-685 */
+        float *work = malloc (sizeof (float) * (size_t) T);
+        tail = malloc (sizeof (float) * (size_t) C * half);
+        for (c = 0; c < C; ++c) {
+            memcpy (work, hist + (size_t) c * T + half, sizeof (float) * half);
+            artExtendForward (work, half, half);
+            memcpy (tail + (size_t) c * half, work + half, sizeof (float) * half);
+        }
+        free (work);
+        call->inValid = call->pre;              /* the region's first T/2 frames now hold data */
+    }
+
+    if ((cxt->flags & EXTRAPOLATE_PREFILL) && call->outputs) {          /* prefillAllChannels, resampler.c:691-698 */
+        const long long u0 = art_inputs_before (&call->st, 0);          /* frames pulled in this call before its first output */
+        const long long n0 = (long long) call->st.I - call->pre - T;    /* frames received by earlier calls */
+        const long long have = n0 + call->pre + u0;                     /* inputIndex - numTaps at that moment */
+        cxt->flags &= ~EXTRAPOLATE_PREFILL;
+        if (have >= 8 && have < T && n0 >= 0 && u0 <= call->inValid - (flushing ? call->pre : 0) + 0LL) {
+            float *line = malloc (sizeof (float) * (size_t) T);         /* the ring's first T slots: [have, T) predicted, then ... */
+            float *first = u0 ? malloc (sizeof (float) * (size_t) u0 * C) : NULL;   /* the call's first u0 input frames */
+            if (u0) {
+                if (!onDevice && !planar) memcpy (first, in, sizeof (float) * (size_t) u0 * C);
+                else if (!onDevice)
+                    for (c = 0; c < C; ++c) for (i = 0; i < u0; ++i) first[(size_t) i * C + c] = ((const float *const *) in)[c][i];
+                else if (!planar) artDevFetch (cxt->device, (const float *) in, (size_t) u0 * C, first, st);
+                else {
+                    float *plane = malloc (sizeof (float) * (size_t) u0);
+                    for (c = 0; c < C; ++c) {
+                        artDevFetch (cxt->device, ((const float *const *) in)[c], (size_t) u0, plane, st);
+                        for (i = 0; i < u0; ++i) first[(size_t) i * C + c] = plane[i];
+                    }
+                    free (plane);
+                }
+            }
+            for (c = 0; c < C; ++c) {
+                /* newest `have` samples, oldest first, at the end of `line`: earlier calls, the flush block, this call */
+                float *seq = line + T - have;
+                long long at = 0;
+                for (i = 0; i < n0; ++i) seq[at++] = hist[(size_t) c * T + T - n0 + i];
+                for (i = 0; i < call->pre; ++i) seq[at++] = tail ? tail[(size_t) c * half + i] : 0.0f;
+                for (i = 0; i < u0; ++i) seq[at++] = first[(size_t) i * C + c];
+                artExtendBackward (line + T, (int) have, (int) (T - have));
+                /* line[k], k < T - have, is ring slot have + k: the slots in front of the first real sample.  The history
+                 * at call entry is ring [n0, n0 + T), so they land at history index have - n0 + k */
+                artDevPatchHistory (cxt->device, c, (int) (have - n0), (int) (T - have), line, st);
+            }
+            free (first);
+            free (line);
+        }
+    }
+
+    if (!flushing)
+        run_call (cxt, io, call, in, out, stream);
+    else if (!onDevice) {
+        if (planar) {
+            tailPlanes = malloc (sizeof *tailPlanes * C);
+            for (c = 0; c < C; ++c) tailPlanes[c] = tail + (size_t) c * half;
+            run_call (cxt, io, call, tailPlanes, out, stream);
+        }
+        else {
+            tailInterleaved = malloc (sizeof (float) * (size_t) C * half);
+            for (c = 0; c < C; ++c) for (i = 0; i < half; ++i) tailInterleaved[(size_t) i * C + c] = tail[(size_t) c * half + i];
+            run_call (cxt, io, call, tailInterleaved, out, stream);
+        }
+    }
+    else if (planar) {
+        const float *d_tail = artDevStage (cxt->device, tail, (size_t) C * half, st);
+        tailPlanes = malloc (sizeof *tailPlanes * C);
+        for (c = 0; c < C; ++c) tailPlanes[c] = d_tail + (size_t) c * half;
+        run_call (cxt, io, call, tailPlanes, out, stream);
+    }
+    else {
+        tailInterleaved = malloc (sizeof (float) * (size_t) C * half);
+        for (c = 0; c < C; ++c) for (i = 0; i < half; ++i) tailInterleaved[(size_t) i * C + c] = tail[(size_t) c * half + i];
+        run_call (cxt, io, call, artDevStage (cxt->device, tailInterleaved, (size_t) C * half, st), out, stream);
+    }
+    free (tailPlanes);
+    free (tailInterleaved);
+    free (tail);
+    free (hist);
+}
+
+static ResampleResult process_one (Resample *cxt, int io, const void *in, int numInputFrames, void *out, int numOutputFrames, double ratio, void *stream)
+{
+    const int flushing = numInputFrames < 0 && !(cxt->flags & RESAMPLER_FLUSHED);
     ArtCallPlan call;
     ResampleResult res = plan_call (cxt, numInputFrames, numOutputFrames, ratio, &call);
-    if (call.outputs || call.consumed)
-        artDevRunHostInterleaved (cxt->device, &call, input, output);
+    if (!(call.outputs || call.consumed))
+        return res;
+    if ((cxt->flags & EXTRAPOLATE_ENDPOINTS) && (flushing || (cxt->flags & EXTRAPOLATE_PREFILL)))
+        run_call_with_endpoints (cxt, io, &call, in, out, stream, flushing);
+    else
+        run_call (cxt, io, &call, in, out, stream);
     return res;
+}
+
+ResampleResult resampleProcessInterleaved (Resample *cxt, const artsample_t *input, int numInputFrames, artsample_t *output, int numOutputFrames, double ratio)
+{
+    return process_one (cxt, IO_HOST_INTERLEAVED, input, numInputFrames, output, numOutputFrames, ratio, NULL);
 }
 
 ResampleResult resampleProcess (Resample *cxt, const artsample_t *const *input, int numInputFrames, artsample_t *const *output, int numOutputFrames, double ratio)
 {
-    ArtCallPlan call;
-    ResampleResult res = plan_call (cxt, numInputFrames, numOutputFrames, ratio, &call);
-    if (call.outputs || call.consumed)
-        artDevRunHostPlanar (cxt->device, &call, input, output);
-    return res;
+    return process_one (cxt, IO_HOST_PLANAR, input, numInputFrames, (void *) output, numOutputFrames, ratio, NULL);
 }
 
 ResampleResult resampleProcessInterleavedDevice (Resample *cxt, const float *d_input, int numInputFrames, float *d_output, int numOutputFrames, double ratio, void *stream)
 {
-    ArtCallPlan call;
-    ResampleResult res = plan_call (cxt, numInputFrames, numOutputFrames, ratio, &call);
-    if (call.outputs || call.consumed)
-        artDevRunDeviceInterleaved (cxt->device, &call, d_input, d_output, stream);
-    return res;
+    return process_one (cxt, IO_DEVICE_INTERLEAVED, d_input, numInputFrames, d_output, numOutputFrames, ratio, stream);
 }
 
 ResampleResult resampleProcessDevice (Resample *cxt, const float *const *d_input, int numInputFrames, float *const *d_output, int numOutputFrames, double ratio, void *stream)
 {
-    ArtCallPlan call;
-    ResampleResult res = plan_call (cxt, numInputFrames, numOutputFrames, ratio, &call);
-    if (call.outputs || call.consumed)
-        artDevRunDevicePlanar (cxt->device, &call, d_input, d_output, stream);
-    return res;
+    return process_one (cxt, IO_DEVICE_PLANAR, d_input, numInputFrames, (void *) d_output, numOutputFrames, ratio, stream);
 }
 
 /* resampler.c:741-758 */
@@ -313,6 +427,15 @@ ResampleResult resampleProcessAndFlush (Resample *cxt, const artsample_t *const 
 
 /* ---------------------------------------------------------------- batched extensions */
 
+/* does this call have to go through run_call_with_endpoints? */
+static int needs_endpoint_work (const Resample *cxt, int numInputFrames)
+{
+    if (!(cxt->flags & EXTRAPOLATE_ENDPOINTS))
+        return 0;
+    return (cxt->flags & EXTRAPOLATE_PREFILL) || (numInputFrames < 0 && !(cxt->flags & RESAMPLER_FLUSHED));
+}
+
+
 void resampleBatchProcessInterleavedDevice (Resample *const *cxts, int numContexts,
                                             const float *const *d_inputs, const int *numInputFrames,
                                             float *const *d_outputs, const int *numOutputFrames,
@@ -320,22 +443,38 @@ void resampleBatchProcessInterleavedDevice (Resample *const *cxts, int numContex
 {
     ArtCallPlan *calls;
     ArtDev **devs;
-    int i, live = 0;
+    const float **din;
+    float **dout;
+    int i, n = 0, live = 0;
 
     if (numContexts <= 0)
         return;
     calls = malloc (sizeof *calls * numContexts);
     devs = malloc (sizeof *devs * numContexts);
+    din = malloc (sizeof *din * numContexts);
+    dout = malloc (sizeof *dout * numContexts);
     for (i = 0; i < numContexts; ++i) {
-        ResampleResult r = plan_call (cxts[i], numInputFrames[i], numOutputFrames[i], ratios ? ratios[i] : 0.0, &calls[i]);
-        devs[i] = cxts[i]->device;
+        ResampleResult r;
+        if (needs_endpoint_work (cxts[i], numInputFrames[i])) {     /* stream start / end with extrapolation: on its own */
+            r = process_one (cxts[i], IO_DEVICE_INTERLEAVED, d_inputs ? d_inputs[i] : NULL, numInputFrames[i], d_outputs[i],
+                             numOutputFrames[i], ratios ? ratios[i] : 0.0, stream);
+            if (results) results[i] = r;
+            continue;
+        }
+        r = plan_call (cxts[i], numInputFrames[i], numOutputFrames[i], ratios ? ratios[i] : 0.0, &calls[n]);
+        devs[n] = cxts[i]->device;
+        din[n] = d_inputs ? d_inputs[i] : NULL;
+        dout[n] = d_outputs[i];
         if (results) results[i] = r;
-        live |= calls[i].outputs || calls[i].consumed;
+        live |= calls[n].outputs || calls[n].consumed;
+        ++n;
     }
     if (live)
-        artDevRunBatchInterleaved (devs, calls, numContexts, d_inputs, d_outputs, stream);
+        artDevRunBatchInterleaved (devs, calls, n, din, dout, stream);
     free (calls);
     free (devs);
+    free (din);
+    free (dout);
 }
 
 void resampleBatchProcessInterleaved (Resample *const *cxts, int numContexts,
@@ -345,20 +484,37 @@ void resampleBatchProcessInterleaved (Resample *const *cxts, int numContexts,
 {
     ArtCallPlan *calls;
     ArtDev **devs;
-    int i;
+    const float **hin;
+    float **hout;
+    int i, n = 0;
 
     if (numContexts <= 0)
         return;
     calls = malloc (sizeof *calls * numContexts);
     devs = malloc (sizeof *devs * numContexts);
+    hin = malloc (sizeof *hin * numContexts);
+    hout = malloc (sizeof *hout * numContexts);
     for (i = 0; i < numContexts; ++i) {
-        ResampleResult r = plan_call (cxts[i], numInputFrames[i], numOutputFrames[i], ratios ? ratios[i] : 0.0, &calls[i]);
-        devs[i] = cxts[i]->device;
+        ResampleResult r;
+        if (needs_endpoint_work (cxts[i], numInputFrames[i])) {
+            r = process_one (cxts[i], IO_HOST_INTERLEAVED, inputs ? inputs[i] : NULL, numInputFrames[i], outputs[i],
+                             numOutputFrames[i], ratios ? ratios[i] : 0.0, NULL);
+            if (results) results[i] = r;
+            continue;
+        }
+        r = plan_call (cxts[i], numInputFrames[i], numOutputFrames[i], ratios ? ratios[i] : 0.0, &calls[n]);
+        devs[n] = cxts[i]->device;
+        hin[n] = inputs ? inputs[i] : NULL;
+        hout[n] = outputs[i];
         if (results) results[i] = r;
+        ++n;
     }
-    artDevRunHostBatchInterleaved (devs, calls, numContexts, inputs, outputs);
+    if (n)
+        artDevRunHostBatchInterleaved (devs, calls, n, hin, hout);
     free (calls);
     free (devs);
+    free (hin);
+    free (hout);
 }
 
 int resampleProcessBlocksInterleavedDevice (Resample *cxt, const float *d_input, const int *blockFrames,
@@ -367,8 +523,8 @@ int resampleProcessBlocksInterleavedDevice (Resample *cxt, const float *d_input,
                                             ResampleResult *results, double *positions, void *stream)
 {
     ArtCallPlan *calls;
-    long long *inOff, *outOff, inAt = 0, outAt = 0;
-    int b, done = 0;
+    long long *inOff, *outOff, inAt = 0, outAt = 0, inFirst = 0;
+    int b, done = 0, first = 0;
 
     if (numBlocks <= 0)
         return 0;
@@ -376,7 +532,29 @@ int resampleProcessBlocksInterleavedDevice (Resample *cxt, const float *d_input,
     inOff = malloc (sizeof *inOff * numBlocks);
     outOff = malloc (sizeof *outOff * numBlocks);
 
-    for (b = 0; b < numBlocks; ++b) {
+    /* with endpoint extrapolation the blocks up to the first output go one at a time (the backward prediction needs
+     * their samples on the host); once it is done the rest is one launch */
+    while (done < numBlocks && (cxt->flags & EXTRAPOLATE_ENDPOINTS) && (cxt->flags & EXTRAPOLATE_PREFILL)) {
+        Resample probe = *cxt;
+        ArtCallPlan dry;
+        long long room = (long long) outputCapacityFrames - outAt;
+        ResampleResult r;
+        if (blockFrames[done] < 0 || room <= 0)
+            break;
+        r = plan_call (&probe, blockFrames[done], room > 0x7fffffff ? 0x7fffffff : (int) room, ratios[done], &dry);
+        if ((int) r.input_used != blockFrames[done])
+            break;
+        r = process_one (cxt, IO_DEVICE_INTERLEAVED, d_input + inAt * cxt->numChannels, blockFrames[done],
+                         d_output + outAt * cxt->numChannels, room > 0x7fffffff ? 0x7fffffff : (int) room, ratios[done], stream);
+        inAt += r.input_used;
+        outAt += r.output_generated;
+        if (results) results[done] = r;
+        if (positions) positions[done] = resampleGetPosition (cxt);
+        ++done;
+    }
+    first = done;
+    inFirst = inAt;
+    for (b = first; b < numBlocks; ++b) {
         /* dry-run on a copy of the scalar state: a block that cannot finish is not started */
         Resample probe = *cxt;
         long long room = (long long) outputCapacityFrames - outAt;
@@ -390,7 +568,7 @@ int resampleProcessBlocksInterleavedDevice (Resample *cxt, const float *d_input,
         cxt->outputOffset = probe.outputOffset;
         cxt->inputIndex = probe.inputIndex;
         cxt->flags = probe.flags;
-        inOff[b] = inAt;
+        inOff[b] = inAt - inFirst;       /* relative to the first block of the launch: what precedes it is in the history */
         outOff[b] = outAt;
         inAt += r.input_used;
         outAt += r.output_generated;
@@ -398,8 +576,9 @@ int resampleProcessBlocksInterleavedDevice (Resample *cxt, const float *d_input,
         if (positions) positions[b] = resampleGetPosition (cxt);
         ++done;
     }
-    if (done)
-        artDevRunBlocksInterleaved (cxt->device, calls, done, inOff, outOff, d_input, d_output, stream);
+    if (done > first)
+        artDevRunBlocksInterleaved (cxt->device, calls + first, done - first, inOff + first, outOff + first,
+                                    d_input + inFirst * cxt->numChannels, d_output, stream);
     free (calls);
     free (inOff);
     free (outOff);

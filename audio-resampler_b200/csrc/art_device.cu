@@ -144,6 +144,8 @@ struct ArtDev {
     int cur;
     float *d_in, *d_out;
     size_t inCap, outCap;           // floats
+    float *d_stage;                 // flush block of the endpoint extrapolation (device-pointer calls)
+    size_t stageCap;
     ArtClass klass;
     // host-pointer path: copies in, kernels and copies out run on three streams so that PCIe traffic in
     // both directions overlaps the convolution (created on first use)
@@ -223,6 +225,8 @@ extern "C" ArtDev *artDevCreate (int channels, int taps, int filters, int mode, 
     dev->cur = 0;
     dev->d_in = dev->d_out = nullptr;
     dev->inCap = dev->outCap = 0;
+    dev->d_stage = nullptr;
+    dev->stageCap = 0;
     dev->sIn = dev->sOut = nullptr;
     dev->tableBuf = nullptr;
     dev->tableCap = 0;
@@ -245,6 +249,7 @@ extern "C" void artDevDestroy (ArtDev *dev)
     cudaFree (dev->hist[1]);
     cudaFree (dev->d_in);
     cudaFree (dev->d_out);
+    cudaFree (dev->d_stage);
     cudaFree (dev->tableBuf);
     cudaStreamDestroy (dev->stream);
     if (dev->sIn) { cudaStreamDestroy (dev->sIn); cudaStreamDestroy (dev->sOut); }
@@ -287,6 +292,46 @@ extern "C" void artDevGetHistory (ArtDev *dev, float *hostPlanar)
     use_device (dev);
     ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
     ART_CUDA_CHECK (cudaMemcpy (hostPlanar, dev->hist[dev->cur], sizeof (float) * (size_t) dev->C * dev->T, cudaMemcpyDeviceToHost));
+}
+
+/* ---- endpoint extrapolation support (art_context.c): small synchronous transfers at a stream's start and end ---- */
+extern "C" void artDevGetHistoryOn (ArtDev *dev, float *hostPlanar, void *stream)
+{
+    use_device (dev);
+    cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
+    ART_CUDA_CHECK (cudaMemcpyAsync (hostPlanar, dev->hist[dev->cur], sizeof (float) * (size_t) dev->C * dev->T, cudaMemcpyDeviceToHost, st));
+    ART_CUDA_CHECK (cudaStreamSynchronize (st));
+}
+
+extern "C" void artDevPatchHistory (ArtDev *dev, int channel, int first, int count, const float *values, void *stream)
+{
+    use_device (dev);
+    cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
+    // pageable source: staged by the runtime before the call returns
+    ART_CUDA_CHECK (cudaMemcpyAsync (dev->hist[dev->cur] + (size_t) channel * dev->T + first, values, sizeof (float) * (size_t) count,
+                                     cudaMemcpyHostToDevice, st));
+}
+
+extern "C" void artDevFetch (ArtDev *dev, const float *d_src, size_t floats, float *host, void *stream)
+{
+    use_device (dev);
+    cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
+    ART_CUDA_CHECK (cudaMemcpyAsync (host, d_src, sizeof (float) * floats, cudaMemcpyDeviceToHost, st));
+    ART_CUDA_CHECK (cudaStreamSynchronize (st));
+}
+
+extern "C" float *artDevStage (ArtDev *dev, const float *host, size_t floats, void *stream)
+{
+    use_device (dev);
+    cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
+    if (floats > dev->stageCap) {
+        ART_CUDA_CHECK (cudaStreamSynchronize (st));
+        cudaFree (dev->d_stage);
+        dev->stageCap = floats + 1024;
+        ART_CUDA_CHECK (cudaMalloc (&dev->d_stage, dev->stageCap * sizeof (float)));
+    }
+    ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_stage, host, sizeof (float) * floats, cudaMemcpyHostToDevice, st));
+    return dev->d_stage;
 }
 
 extern "C" void artDevSetHistory (ArtDev *dev, const float *hostPlanar)

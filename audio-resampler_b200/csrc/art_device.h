@@ -72,6 +72,11 @@ void artDevRunBlocksInterleaved (ArtDev *dev, const ArtCallPlan *plans, int coun
 void artDevSynchronize (ArtDev *dev);
 void artDevGetHistory (ArtDev *dev, float *hostPlanar);        /* [channels][taps], for tests/extrapolation */
 void artDevSetHistory (ArtDev *dev, const float *hostPlanar);
+/* endpoint extrapolation: small synchronous transfers at a stream's start and end (stream NULL = the context's own) */
+void artDevGetHistoryOn (ArtDev *dev, float *hostPlanar, void *stream);
+void artDevPatchHistory (ArtDev *dev, int channel, int first, int count, const float *values, void *stream);
+void artDevFetch (ArtDev *dev, const float *d_src, size_t floats, float *host, void *stream);
+float *artDevStage (ArtDev *dev, const float *host, size_t floats, void *stream);     /* returns the device copy */
 
 /* statistics for bench.py's gpu_launches claim and roofline leg */
 unsigned long long artDevLaunchCount (void);

@@ -79,10 +79,6 @@ OracleResampler *oracle_init (int channels, int taps, int phases, double lowpass
         return NULL;
     if (phases < 1 || phases > 1024)                                        /* :132-135 */
         return NULL;
-    if (flags & ORC_EXTRAPOLATE) {
-        fprintf (stderr, "oracle: EXTRAPOLATE_ENDPOINTS is not restated (SURVEY 8f rank 1)\n");
-        return NULL;
-    }
 
     OracleResampler *r = calloc (1, sizeof *r);
     r->channels = channels;
@@ -109,6 +105,7 @@ OracleResampler *oracle_init (int channels, int taps, int phases, double lowpass
 
     r->read_pos = taps / 2;                                                 /* :176-177 */
     r->write_index = taps;
+    if (r->flags & ORC_EXTRAPOLATE) r->flags |= ORC_PREFILL_PENDING;                /* :179-182 */
     return r;
 }
 
@@ -166,6 +163,7 @@ void oracle_reset (OracleResampler *r)
     r->read_pos = r->taps / 2;
     r->write_index = r->taps;
     r->flags &= ~ORC_FLUSHED;
+    if (r->flags & ORC_EXTRAPOLATE) r->flags |= ORC_PREFILL_PENDING;                /* :393-394 */
 }
 
 /* resampleAdvancePosition, resampler.c:927-935 */
@@ -238,6 +236,143 @@ static double sample_at (const OracleResampler *r, const float *line, double whe
 
 /* ------------------------------------------------------------- streaming */
 
+
+/* ---- endpoint extrapolation (extrapolator.c) ---------------------------------------------------------
+ * A 4-coefficient linear predictor is fitted to the known samples by coordinate descent with a halving
+ * step (extrapolator.c:93-170), made stable through its reflection coefficients (:174-194, :244-283),
+ * replaced by "repeat the last sample" or by silence when those predict better (:213-222), and then run
+ * forward to synthesise the missing samples (extrapolator.c:22-43). */
+#define ORC_LPC_ORDER 4
+#define ORC_LPC_MAX_ROUNDS 100000
+
+static double predictor_output (const float *coef, const float *window)        /* sum_c coef[N-1-c] * window[c] */
+{
+    double acc = 0.0;
+    for (int c = 0; c < ORC_LPC_ORDER; ++c)
+        acc += coef[ORC_LPC_ORDER - c - 1] * window[c];
+    return acc;
+}
+
+static void to_reflection (const double *lpc, double *refl)                     /* extrapolator.c:244-272 */
+{
+    double cur[ORC_LPC_ORDER], nxt[ORC_LPC_ORDER];
+    memcpy (cur, lpc, sizeof cur);
+    for (int m = ORC_LPC_ORDER - 1; m >= 0; --m) {
+        refl[m] = cur[m];
+        double den = 1.0 - refl[m] * refl[m];
+        if (fabs (den) < 1e-6) {
+            refl[m] = refl[m] < 0.0 ? -0.9999995 : 0.9999995;
+            den = 1.0 - refl[m] * refl[m];
+        }
+        for (int i = 0; i < m; ++i)
+            nxt[i] = (cur[i] - refl[m] * cur[m - i - 1]) / den;
+        for (int i = 0; i < m; ++i)
+            cur[i] = nxt[i];
+    }
+}
+
+static void from_reflection (const double *refl, double *lpc)                   /* extrapolator.c:276-283 */
+{
+    for (int i = 0; i < ORC_LPC_ORDER; ++i) {
+        lpc[i] = refl[i];
+        for (int j = 0; j < i / 2; ++j) {
+            double keep = lpc[j];
+            lpc[j] += refl[i] * lpc[i - 1 - j];
+            lpc[i - 1 - j] += refl[i] * keep;
+        }
+        if (i & 1)
+            lpc[i >> 1] += lpc[i >> 1] * refl[i];
+    }
+}
+
+static void fit_predictor (const float *x, int count, float *coef)              /* extrapolator.c:93-240 */
+{
+    const int evals = count - ORC_LPC_ORDER;
+    double signal_energy = 0.0, delta_energy = 0.0, best, step = 3.0 / 16.0;
+    double *resid = malloc (sizeof (double) * (evals > 0 ? evals : 1));
+    int rounds = 0, moved = 0;
+
+    memset (coef, 0, sizeof (float) * ORC_LPC_ORDER);
+    for (int i = 0; i < evals; ++i) {                                            /* :101-107 */
+        const float now = x[i + ORC_LPC_ORDER], before = x[i + ORC_LPC_ORDER - 1];
+        delta_energy += (now - before) * (now - before);
+        signal_energy += now * now;
+    }
+    if (signal_energy == 0.0) { free (resid); return; }                          /* :109-112 */
+    best = signal_energy;
+
+    while (best > 0.0 && rounds < ORC_LPC_MAX_ROUNDS) {                          /* :118 */
+        int which;
+        for (int k = 0; k < evals; ++k)                                          /* :121-129 */
+            resid[k] = predictor_output (coef, x + k) + x[k + ORC_LPC_ORDER];
+        for (which = 0; rounds++, which < ORC_LPC_ORDER; which++) {              /* :131 */
+            double down = 0.0, up = 0.0;
+            for (int k = 0; k < evals; ++k) {
+                const double nudge = x[k + ORC_LPC_ORDER - which - 1] * step;
+                down += (resid[k] - nudge) * (resid[k] - nudge);
+                up += (resid[k] + nudge) * (resid[k] + nudge);
+            }
+            if (down < best || up < best) {                                      /* :141-153 */
+                if (down < up) { best = down; coef[which] -= step; }
+                else           { best = up;   coef[which] += step; }
+                moved++;
+                break;
+            }
+        }
+        if (which == ORC_LPC_ORDER) {                                            /* :158-163 */
+            if (step > 3.0 / (1 << 22)) step *= 0.5;
+            else break;
+        }
+    }
+    free (resid);
+
+    if (moved) {                                                                 /* :170-194 */
+        double wide[ORC_LPC_ORDER], refl[ORC_LPC_ORDER];
+        int clipped = 0;
+        for (int i = 0; i < ORC_LPC_ORDER; ++i) wide[i] = coef[i];
+        to_reflection (wide, refl);
+        for (int i = 0; i < ORC_LPC_ORDER; ++i)
+            if (fabs (refl[i]) > 0.9999) { refl[i] = refl[i] < 0.0 ? -0.9999 : 0.9999; clipped++; }
+        if (clipped) {
+            from_reflection (refl, wide);
+            for (int i = 0; i < ORC_LPC_ORDER; ++i) coef[i] = wide[i];
+        }
+    }
+
+    double err = 0.0;                                                            /* :198-209 */
+    for (int k = 0; k < evals; ++k) {
+        const double e = predictor_output (coef, x + k) + x[k + ORC_LPC_ORDER];
+        err += e * e;
+    }
+    if (delta_energy < err && delta_energy < signal_energy) {                    /* :213-222 */
+        memset (coef, 0, sizeof (float) * ORC_LPC_ORDER);
+        coef[0] = -1.0f;
+    }
+    else if (signal_energy <= err)
+        memset (coef, 0, sizeof (float) * ORC_LPC_ORDER);
+}
+
+/* extrapolate_forward, extrapolator.c:22-43: x[0..known) are given, x[known..known+more) are written */
+void oracle_extend_forward (float *x, int known, int more)
+{
+    float coef[ORC_LPC_ORDER];
+    memset (x + known, 0, sizeof (float) * more);
+    fit_predictor (x, known, coef);
+    for (int i = 0; i < more; ++i)
+        x[known + i] = (float) -predictor_output (coef, x + known - ORC_LPC_ORDER + i);
+}
+
+/* extrapolate_reverse, extrapolator.c:49-65: end[-1], end[-2] ... end[-known] are given (newest first when read
+ * backwards), end[-known-1] ... end[-known-more] are written */
+void oracle_extend_backward (float *end, int known, int more)
+{
+    float *flip = calloc ((size_t) known + more, sizeof (float));
+    for (int i = 0; i < known; ++i) flip[i] = end[-1 - i];
+    oracle_extend_forward (flip, known, more);
+    for (int i = known; i < known + more; ++i) end[-1 - i] = flip[i];
+    free (flip);
+}
+
 /* Ring compaction: keep the newest `taps` samples, shift both cursors
  * (resampler.c:497-503 / :614-620 / :667-673). */
 static void compact_ring (OracleResampler *r)
@@ -251,7 +386,7 @@ static void compact_ring (OracleResampler *r)
     r->write_index -= drop;
 }
 
-/* postfillAllChannels, resampler.c:663-685 (zero fill only) */
+/* postfillAllChannels, resampler.c:663-685 */
 static void append_silence (OracleResampler *r)
 {
     const int half = r->taps / 2;
@@ -260,6 +395,8 @@ static void append_silence (OracleResampler *r)
     for (int c = 0; c < r->channels; ++c) {
         float *line = r->ring + (size_t) c * r->ring_len;
         memset (line + r->write_index, 0, sizeof (float) * (r->ring_len - r->write_index));
+        if (r->flags & ORC_EXTRAPOLATE)                                     /* :677-680 */
+            oracle_extend_forward (line + r->write_index - half, half, half);
     }
     r->flags |= ORC_FLUSHED;
     r->write_index += half;
@@ -293,6 +430,13 @@ static OracleResult run (OracleResampler *r, const float *const *in_base, int in
             n_in--;
         }
         else {
+            if (r->flags & ORC_PREFILL_PENDING) {                                   /* :516-522, prefillAllChannels :691-698 */
+                const int have = r->write_index - r->taps;
+                r->flags &= ~ORC_PREFILL_PENDING;
+                if (have >= 8)
+                    for (int c = 0; c < r->channels; ++c)
+                        oracle_extend_backward (r->ring + (size_t) c * r->ring_len + r->write_index, have, r->taps - have);
+            }
             for (int c = 0; c < r->channels; ++c)
                 out_base[c][(size_t) res.output_generated * out_stride] =
                     (float) sample_at (r, r->ring + (size_t) c * r->ring_len, r->read_pos + step);

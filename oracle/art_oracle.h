@@ -88,6 +88,10 @@ void oracle_biquad_run (OracleBiquad *q, float *buf, int count, int stride);
 /* artest.c:744-754 -- the reference's synthetic noise generator (state passed explicitly). */
 void oracle_noise (unsigned long long *state, float *dst, int count);
 
+/* extrapolator.c:22-65, exported for the tests */
+void oracle_extend_forward (float *x, int known, int more);
+void oracle_extend_backward (float *end, int known, int more);
+
 #ifdef __cplusplus
 }
 #endif

@@ -260,3 +260,38 @@ def test_kernel_selection():
     g3, p3 = counts()
     assert (g3 - g2, p3 - p2) == (1, 0)
     assert A.peak_error(y_per, y_prec) <= 3e-7                     # the two kernels, same stream
+
+
+@pytest.mark.parametrize("ch,preset,src,dst,advance", [
+    (2, 3, 44100, 48000, True),         # art's default: extrapolation on, half-filter delay cancelled
+    (1, 1, 48000, 37000, True),
+    (3, 2, 32000, 40000, False),        # no advance: the first output comes after one input frame, nothing to extrapolate from
+    (2, 4, 96000, 44100, True),
+])
+def test_endpoint_extrapolation(ch, preset, src, dst, advance):
+    """EXTRAPOLATE_ENDPOINTS (resampler.c:516-522, :663-698; extrapolator.c): LPC prediction backwards in front of the
+    first sample and forwards behind the last one, instead of silence.  Oracle restatement pinned bit-exactly against the
+    compiled reference (tests/test_oracle_golden.py)."""
+    filters, taps = A.PRESETS[preset]
+    flags = BH_INTERP | A.EXTRAPOLATE_ENDPOINTS
+    ratio = dst / src
+    t = np.arange(40000)[:, None]
+    rng = np.random.default_rng(22)
+    for planar in (False, True):
+        g, o = _pair(ch, taps, filters, lowpass_ratio=0.0, flags=flags)
+        if advance:
+            g.advance(taps / 2); o.advance(taps / 2)
+        at = 0
+        for b, n in enumerate([3000, 4096, 5, 7000]):
+            x = (0.3 * np.sin(2 * np.pi * 0.013 * (t[at:at + n] + 17.0) + np.arange(ch)) + rng.normal(0, 0.02, (n, ch))).astype(np.float32)
+            at += n
+            yg, ug, gg = g.process(x, 20000, ratio, flush_after=(b == 3), planar=planar)
+            yo, uo, go = o.process(x, 20000, ratio, flush_after=(b == 3))
+            assert (ug, gg) == (uo, go)
+            assert A.peak_error(yg, yo) <= TOL
+        # the extrapolated ends are not silence: the first and last outputs continue the sine instead of fading in/out
+        g.reset(); o.reset()
+        x = rng.uniform(-0.5, 0.5, (2000, ch)).astype(np.float32)
+        yg, ug, gg = g.process(x, 20000, ratio, flush_after=True, planar=planar)
+        yo, uo, go = o.process(x, 20000, ratio, flush_after=True)
+        assert (ug, gg) == (uo, go) and A.peak_error(yg, yo) <= TOL

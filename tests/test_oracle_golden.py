@@ -133,3 +133,42 @@ def test_artest_noise_generator_known_prefix():
     """artest.c:744-754 with the reference's seed; first values recorded from the reference build."""
     x, _ = A.artest_noise(4)
     assert np.allclose(x, [0.36142448, -0.19244033, -0.4861091, 0.38178906], atol=1e-8)
+
+
+def test_oracle_extrapolation_matches_the_reference_build():
+    """extrapolator.c restated in oracle/art_oracle.c: bit-identical synthesised samples on random, tonal and drifting
+    inputs, forwards and backwards; and whole streams with EXTRAPOLATE_ENDPOINTS agree with the reference build."""
+    import ctypes as C
+    ref = A.reference()
+    if ref is None:
+        pytest.skip("oracle/_ref/libartref.so is not available")
+    orc = A.oracle()
+    f32p = C.POINTER(C.c_float)
+    orc.oracle_extend_forward.argtypes = [f32p, C.c_int, C.c_int]; orc.oracle_extend_forward.restype = None
+    orc.oracle_extend_backward.argtypes = [f32p, C.c_int, C.c_int]; orc.oracle_extend_backward.restype = None
+    ref.extrapolate_forward.argtypes = [f32p, C.c_int, C.c_int]; ref.extrapolate_forward.restype = C.c_double
+    ref.extrapolate_reverse.argtypes = [f32p, C.c_int, C.c_int]; ref.extrapolate_reverse.restype = C.c_double
+    rng = np.random.default_rng(0)
+    for trial in range(60):
+        known, more = int(rng.integers(8, 500)), int(rng.integers(1, 500))
+        t = np.arange(known + more)
+        x = [rng.uniform(-0.5, 0.5, known + more), 0.4 * np.sin(2 * np.pi * t * rng.uniform(0.001, 0.3)),
+             np.cumsum(rng.normal(0, 0.01, known + more))][trial % 3].astype(np.float32)
+        a, b = x.copy(), x.copy()
+        orc.oracle_extend_forward(a.ctypes.data_as(f32p), known, more)
+        ref.extrapolate_forward(b.ctypes.data_as(f32p), known, more)
+        assert np.array_equal(a, b)
+        a, b = x.copy(), x.copy()
+        orc.oracle_extend_backward(C.cast(a.ctypes.data + 4 * (known + more), f32p), known, more)
+        ref.extrapolate_reverse(C.cast(b.ctypes.data + 4 * (known + more), f32p), known, more)
+        assert np.array_equal(a, b)
+    flags = A.SUBSAMPLE_INTERPOLATE | A.BLACKMAN_HARRIS | A.EXTRAPOLATE_ENDPOINTS
+    for ch, taps, filters, ratio in [(2, 380, 380, 48000 / 44100), (1, 48, 48, 0.77)]:
+        o = A.oracle_stream(ch, taps, filters, 0.0, flags=flags)
+        r = A.reference_stream(ch, taps, filters, 0.0, flags=flags)
+        o.advance(taps / 2); r.advance(taps / 2)
+        for b, n in enumerate([3000, 5, 4096]):
+            x = (0.3 * np.sin(0.07 * np.arange(n)[:, None] + np.arange(ch)) + rng.normal(0, 0.02, (n, ch))).astype(np.float32)
+            yo, uo, mo = o.process(x, 20000, ratio, flush_after=(b == 2))
+            yr, ur, mr = r.process(x, 20000, ratio, flush_after=(b == 2))
+            assert (uo, mo) == (ur, mr) and A.peak_error(yo, yr) <= 3e-7

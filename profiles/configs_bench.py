@@ -96,7 +96,7 @@ def run_asrc(name, ch, preset, blocks, block_frames, steps=10):
     lib.resampleFree(ctx)
 
 
-if __name__ == "__main__" and len(sys.argv) >= 1 and not sys.argv[0].endswith("cfg3_probe.py"):
+if __name__ == "__main__" and len(sys.argv) >= 1 and not sys.argv[0].endswith("_probe.py"):
     run("cfg1 mono -1 44.1->48k (64 streams x 2^20)", 1, 1, 44100, 48000, 64, 1 << 20)
     run("cfg2 stereo -3 44.1->48k (64 streams x 2^18)", 2, 3, 44100, 48000, 64, 1 << 18)
     run("cfg2 single stream x 2^22 frames", 2, 3, 44100, 48000, 1, 1 << 22)

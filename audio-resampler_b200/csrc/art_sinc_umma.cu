@@ -324,37 +324,53 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
             __syncthreads ();
             if (mh > 0.0f) atomicMax (&smaxC[j], __float_as_uint (mh));
             const float *p0 = job.in + s0 * C, *p1 = job.in + s1 * C;
-            if (C == 2) {
-                // 16-byte loads over the aligned interior
-                float m0 = 0.0f, m1 = 0.0f;
+            if (C == 1 || C == 2 || C == 4) {
+                // 16-byte loads over the aligned interior, eight in flight per thread; lane k of a vector is channel (off + k) % C
+                float mk[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
                 const float *a0 = reinterpret_cast<const float *> ((reinterpret_cast<unsigned long long> (p0) + 15) & ~15ull);
                 const float *a1 = reinterpret_cast<const float *> (reinterpret_cast<unsigned long long> (p1) & ~15ull);
                 if (a1 < a0) { a0 = p1; a1 = p1; }
-                const bool odd = ((a0 - p0) & 1) != 0;                      // a0 starts on a right-channel sample
-                for (const float *p = p0 + threadIdx.x; p < a0 && p < p1; p += 128) { const float v = fabsf (*p); if ((p - p0) & 1) m1 = fmaxf (m1, v); else m0 = fmaxf (m0, v); }
-                for (const float *p = a1 + threadIdx.x; p < p1; p += 128) { const float v = fabsf (*p); if ((p - p0) & 1) m1 = fmaxf (m1, v); else m0 = fmaxf (m0, v); }
+                for (const float *p = p0 + threadIdx.x; p < a0 && p < p1; p += 128) atomicMax (&smaxC[(int) ((p - p0) % C)], __float_as_uint (fabsf (*p)));
+                for (const float *p = a1 + threadIdx.x; p < p1; p += 128) atomicMax (&smaxC[(int) ((p - p0) % C)], __float_as_uint (fabsf (*p)));
                 const float4 *q = reinterpret_cast<const float4 *> (a0);
                 const int n4 = (int) ((a1 - a0) >> 2);
-                float e0 = 0.0f, e1 = 0.0f;
-#pragma unroll 8
-                for (int i = threadIdx.x; i < n4; i += 128) {
-                    const float4 v = __ldg (q + i);
-                    e0 = fmaxf (e0, fmaxf (fabsf (v.x), fabsf (v.z)));
-                    e1 = fmaxf (e1, fmaxf (fabsf (v.y), fabsf (v.w)));
-                }
-                m0 = fmaxf (m0, odd ? e1 : e0);
-                m1 = fmaxf (m1, odd ? e0 : e1);
+                for (int i0 = threadIdx.x; i0 < n4; i0 += 8 * 128) {
+                    float4 v[8];
 #pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) { m0 = fmaxf (m0, __shfl_xor_sync (0xffffffffu, m0, off)); m1 = fmaxf (m1, __shfl_xor_sync (0xffffffffu, m1, off)); }
-                if ((threadIdx.x & 31) == 0) { atomicMax (&smaxC[0], __float_as_uint (m0)); atomicMax (&smaxC[1], __float_as_uint (m1)); }
+                    for (int r = 0; r < 8; ++r) {
+                        const int i = i0 + r * 128;
+                        v[r] = i < n4 ? __ldg (q + i) : make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        mk[0] = fmaxf (mk[0], fabsf (v[r].x)); mk[1] = fmaxf (mk[1], fabsf (v[r].y));
+                        mk[2] = fmaxf (mk[2], fabsf (v[r].z)); mk[3] = fmaxf (mk[3], fabsf (v[r].w));
+                    }
+                }
+                const int off = (int) ((a0 - p0) % C);
+#pragma unroll
+                for (int kq = 0; kq < 4; ++kq) {
+                    float m = mk[kq];
+#pragma unroll
+                    for (int sh = 16; sh >= 1; sh >>= 1) m = fmaxf (m, __shfl_xor_sync (0xffffffffu, m, sh));
+                    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax (&smaxC[(off + kq) % C], __float_as_uint (m));
+                }
             }
             else if ((128 % C) == 0) {
-                // thread t owns channel t % C and every (128 / C)-th frame: a warp reads consecutive floats
+                // thread t owns channel t % C and every (128 / C)-th frame: a warp reads consecutive floats; eight loads in flight
                 const int c = threadIdx.x % C, fstep = 128 / C;
                 float m = 0.0f;
                 const float *base = job.in + c;
-#pragma unroll 8
-                for (long long i = s0 + threadIdx.x / C; i < s1; i += fstep) m = fmaxf (m, fabsf (__ldg (base + i * C)));
+                for (long long i0 = s0 + threadIdx.x / C; i0 < s1; i0 += 8 * fstep) {
+                    float v[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const long long i = i0 + (long long) r * fstep;
+                        v[r] = i < s1 ? __ldg (base + i * C) : 0.0f;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) m = fmaxf (m, fabsf (v[r]));
+                }
                 atomicMax (&smaxC[c], __float_as_uint (m));
             }
             else {
@@ -369,8 +385,16 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
             float m = mh;
             const float *base = job.inPlanes ? job.inPlanes[j] : job.in + (long long) j * job.inCS;
             const long long fs = job.inFS;
-#pragma unroll 16
-            for (long long i = lo + threadIdx.x; i < hi; i += 128) m = fmaxf (m, fabsf (__ldg (base + i * fs)));
+            for (long long i0 = lo + threadIdx.x; i0 < hi; i0 += 8 * 128) {
+                float v[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const long long i = i0 + r * 128;
+                    v[r] = i < hi ? __ldg (base + i * fs) : 0.0f;
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) m = fmaxf (m, fabsf (v[r]));
+            }
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) m = fmaxf (m, __shfl_xor_sync (0xffffffffu, m, off));
             if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax (&tileMax[j], __float_as_uint (m));

@@ -170,3 +170,44 @@ def test_fixed_ratio_contexts_opt_in(forced_tensor_path):
     assert run() == 0
     lib.resampleB200SetTensorPath(3)
     assert run() == 1
+
+
+def test_random_streams_tensor_equals_ffma(forced_tensor_path):
+    """Seeded random sweep at sizes the oracle would take minutes for: the tensor-core form against the FFMA form of the
+    same library (mode 0) -- counts and position identical, samples within 3e-7 of peak (both sit within 2e-7 of the
+    oracle on the oracle-sized cases).  Ratios, presets, channel counts, chunkings, flush and extrapolation vary."""
+    lib = forced_tensor_path
+    rng = np.random.default_rng(77)
+    rates = [(44100, 48000), (48000, 44100), (96000, 44100), (32000, 48000), (48000, 32000), (44100, 88200), (22050, 48000),
+             (48000, 96000), (88200, 48000)]
+    ran = 0
+    for trial in range(14):
+        src, dst = rates[int(rng.integers(len(rates)))]
+        preset = int(rng.integers(1, 5))
+        ch = int(rng.choice([1, 2, 2, 3, 4, 8]))
+        filters, taps = A.PRESETS[preset]
+        flags = BH_INTERP | (A.EXTRAPOLATE_ENDPOINTS if trial % 3 == 0 else 0)
+        lowpass = 0.0 if dst >= src else 0.9 * dst / src
+        ratio = dst / src
+        total = int(rng.integers(40000, 120000))
+        cuts = np.sort(rng.integers(1, total, size=int(rng.integers(0, 4))))
+        chunks = np.diff(np.concatenate(([0], cuts, [total]))).tolist()
+        x = (rng.uniform(-0.5, 0.5, (total, ch)) * rng.choice([1.0, 1e-3, 300.0])).astype(np.float32)
+        outs = []
+        for mode in (0, 2):
+            lib.resampleB200SetTensorPath(mode)
+            before = lib.resampleB200TensorLaunches()
+            s = A.product_stream(ch, taps, filters, lowpass_ratio=lowpass, flags=flags)
+            s.advance(taps / 2)
+            ys, at, log = [], 0, []
+            for i, n in enumerate(chunks):
+                cap = int(n * ratio) + taps + 64
+                y, u, m = s.process(x[at:at + n], cap, ratio, flush_after=(i == len(chunks) - 1), planar=bool(trial & 1))
+                ys.append(y); log.append((u, m, s.position())); at += u
+            outs.append((np.concatenate(ys), log, lib.resampleB200TensorLaunches() - before))
+        (y0, log0, n0), (y2, log2, n2) = outs
+        assert log0 == log2, "counts / positions differ between the two forms"
+        assert n0 == 0
+        ran += n2
+        assert A.peak_error(y2, y0) <= 3e-7, (trial, src, dst, preset, ch, A.peak_error(y2, y0))
+    assert ran >= 10, "the sweep hardly reached the tensor-core kernel"

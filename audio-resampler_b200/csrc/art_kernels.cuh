@@ -86,7 +86,8 @@ struct ArtPeriodic2 {
 #define ART_U_MAXK 96
 struct ArtUmma {
     int L, M;            // outputs / inputs per period
-    int Npad;            // phases rounded up to 16: the N of every MMA
+    int G, Lg;           // the L phases are handled in G groups of Lg (tensor memory holds 160 accumulator columns x 3)
+    int Npad;            // phases of a group rounded up to 16: the N of every MMA
     int KI;              // k-steps (16 taps) per input period: ceil(M / 16) = pairs of 8-tap planes per row
     int NS;              // plane-pair slots of operand A held in shared memory (a divisor of KI; pair i lives in slot i % NS)
     int numK;            // k-steps per tile
@@ -94,8 +95,8 @@ struct ArtUmma {
     int DH;              // filter quantum is 2^-DH
     int stages;          // depth of the filter stage ring
     int tableHalfs;      // fp16 elements per table: numK * 3 * 2 * Npad * 8
-    unsigned short *H;   // [tables][numK][3 splits][2 k-planes][Npad][8]  fp16 bit patterns
-    int *S0;             // [jobs]  region index of tap 0 of phase 0, period 0
+    unsigned short *H;   // [tables][G][numK][3 splits][2 k-planes][Npad][8]  fp16 bit patterns
+    int *S0;             // [jobs][G]  region index of tap 0 of the group's first phase, period 0
     int *tileExp;        // [tiles] block maximum |x| of the samples a tile reads, as a float bit pattern (-> the tile's quantum)
     unsigned char ka[ART_U_MAXK], ki[ART_U_MAXK];      // k-step -> (row shift a, 16-tap group i), i outermost
     unsigned char nA[32];                              // row shifts per 16-tap group

@@ -193,13 +193,16 @@ __global__ void __launch_bounds__ (128)
 art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__ ArtJob single,
                       const ArtJob *__restrict__ jobs, int numJobs, int numTables, int histBlocksPerJob, int totalTiles, int dbg)
 {
-    const int tableBlocks = numTables * u.Npad;
-    const int originBlocks = (numJobs + 127) / 128;
+    const int tableBlocks = numTables * u.G * u.Npad;
+    const int originBlocks = (numJobs * u.G + 127) / 128;
     int b = blockIdx.x;
     const int T = k.T, half = T / 2, F = k.F;
     if (b < tableBlocks) {
         if (dbg & 16) return;
-        const int tbl = b / u.Npad, j = b - tbl * u.Npad;
+        const int tg = b / u.Npad, j = b - tg * u.Npad;                 // (table, phase group), phase inside the group
+        const int tbl = tg / u.G, grp = tg - tbl * u.G;
+        const int ph0 = grp * u.Lg, phj = ph0 + j;                      // the group's first phase, this phase
+        const bool live = j < u.Lg && phj < u.L;
         const ArtJob &job = jobs ? jobs[jobs[tbl].repJob] : single;
         __shared__ int sh_row, sh_pass, sh_shift;
         __shared__ double sh_f;
@@ -209,9 +212,9 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
             long long sj = 0, sb = 0;
             int row = 0, pass = -1;
             double f = 0.0;
-            for (int which = 0; which < 2; ++which) {               // 0: phase 0 (the origin), 1: this phase
-                const int ph = which ? j : 0;
-                if (ph >= u.L) break;
+            for (int which = 0; which < 2; ++which) {               // 0: the group's first phase (the origin), 1: this phase
+                const int ph = which ? phj : ph0;
+                if (which && !live) break;
                 int w;
                 const double pos = art_output_pos (&st, job.nStart + ph, &w);
                 const double whole = floor (pos), fr = pos - whole;
@@ -236,14 +239,14 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
         const int row = sh_row, pass = sh_pass, shift = sh_shift;
         const double f = sh_f;
         const float *ra = k.bank + (size_t) row * k.Tp, *rb = ra + k.Tp;
-        unsigned short *tab = u.H + (size_t) tbl * u.tableHalfs;
+        unsigned short *tab = u.H + (size_t) tg * u.tableHalfs;
         const double qinv = (double) (1 << u.DH);
         for (int kk = threadIdx.x; kk < u.numK * 16; kk += 128) {
             const int ks = kk >> 4, e16 = kk & 15;
             const int bb = 16 * u.ki[ks] + e16;
             const int t = u.ka[ks] * u.M + bb - shift;
             float h = 0.0f;
-            if (j < u.L && bb < u.M && t >= 0 && t < T) {
+            if (live && bb < u.M && t >= 0 && t < T) {
                 if (pass >= 0)
                     h = t == pass ? 1.0f : 0.0f;
                 else if (k.mode & ART_MODE_INTERP) {
@@ -271,14 +274,15 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
     }
     b -= tableBlocks;
     if (b < originBlocks) {
-        const int seg = b * 128 + threadIdx.x;
-        if (seg >= numJobs) return;
+        const int e = b * 128 + threadIdx.x;
+        if (e >= numJobs * u.G) return;
+        const int seg = e / u.G, grp = e - seg * u.G;
         const ArtJob &job = jobs ? jobs[seg] : single;
         ArtLoopState st;
         st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = T;
         int w;
-        const double pos = art_output_pos (&st, job.nStart, &w);
-        u.S0[seg] = (int) ((long long) floor (pos) - half + 1 + (long long) w * 15LL * T - job.origin);
+        const double pos = art_output_pos (&st, job.nStart + grp * u.Lg, &w);
+        u.S0[e] = (int) ((long long) floor (pos) - half + 1 + (long long) w * 15LL * T - job.origin);
         return;
     }
     b -= originBlocks;
@@ -294,11 +298,12 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
         const ArtJob &job = jobs ? jobs[seg] : single;
         const int local = tile - job.tile0;
         const int C = k.C;
-        const int qb = local / C, j = local - qb * C;
+        const int qg = local / C, j = local - qg * C;                    // (period block, phase group), channel
+        const int qb = qg / u.G, grp = qg - qb * u.G;
         ArtLoopState st;
         st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = T;
         int w;
-        const double pos = art_output_pos (&st, job.nStart, &w);
+        const double pos = art_output_pos (&st, job.nStart + grp * u.Lg, &w);
         const long long S0 = (long long) floor (pos) - half + 1 + (long long) w * 15LL * T - job.origin;
         const long long R0 = S0 + (long long) u.M * qb * 128;
         const int span = u.M * (u.rows - 1) + 16 * u.KI;
@@ -499,7 +504,8 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             unsigned int us = 0, ph = 0;
             for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
                 const ArtJob &job = jobOf (tile);
-                const unsigned short *tab = u.H + (size_t) job.table * u.tableHalfs;
+                const int grp = ((tile - job.tile0) / C) % u.G;
+                const unsigned short *tab = u.H + ((size_t) job.table * u.G + grp) * u.tableHalfs;
                 for (int ks = 0; ks < numK; ks += ART_U_GROUP) {
                     const unsigned int bytes = (unsigned int) (numK - ks < ART_U_GROUP ? numK - ks : ART_U_GROUP) * stageBytes;
                     long long t0 = UCLK ();
@@ -621,8 +627,9 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             const ArtJob &job = jobOf (tile);
             const int seg = (int) (&job - (jobs ? jobs : singlePtr));
             const int local = tile - job.tile0;
-            const int qb = local / C, c = local - qb * C;
-            sc.R0 = (long long) u.S0[seg] + (long long) M * qb * ART_U_ROWS;
+            const int qg = local / C, c = local - qg * C;
+            const int qb = qg / u.G, grp = qg - qb * u.G;
+            sc.R0 = (long long) u.S0[seg * u.G + grp] + (long long) M * qb * ART_U_ROWS;
             sc.lo = -job.prevAvail; sc.hi = job.inValid;
             sc.fast = sc.R0 >= sc.lo && sc.R0 + span <= sc.hi;
             sc.fs = job.inFS;
@@ -731,7 +738,9 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++lt) {
             const ArtJob &job = jobOf (tile);
             const int local = tile - job.tile0;
-            const int qb = local / C, c = local - qb * C;
+            const int qg = local / C, c = local - qg * C;
+            const int qb = qg / u.G, grp = qg - qb * u.G;
+            const int phases = min (u.Lg, L - grp * u.Lg);                    // phases of this group
             long long e0 = UCLK ();
             u_mbar_wait_relaxed (accFullA, lt & 1);
             long long e1 = UCLK ();
@@ -776,11 +785,11 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                     __syncwarp ();
                     const int ph = c0 + col;                                 // this lane's phase
                     // half-warps take rows rr and rr + 16: with the row pitch of 17 words their 16 columns fall on disjoint banks
-                    long long nl = (q0 + 16 * half16) * L + ph;              // output index inside the job, rows advance by 1
+                    long long nl = (q0 + 16 * half16) * L + grp * u.Lg + ph;  // output index inside the job, rows advance by 1
                     float *op = obase + nl * outFS;
                     const unsigned int sp = scratch + (unsigned int) (16 * half16 * 17 + col) * 4u;
                     const long long step = L, ostep = step * outFS;
-                    if (ph < L) {
+                    if (ph < phases) {
 #pragma unroll 8
                         for (int rr = 0; rr < 16; ++rr) {
                             const float v = u_ldsf (sp + (unsigned int) rr * (17u * 4u));
@@ -827,9 +836,9 @@ bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsi
     // trades that promise for speed (mode 3)
     if (!(k.mode & ART_MODE_INTERP) && enabled < 3) return false;
     int L, M;
-    if (!artRational (ratio, 160, &L, &M)) return false;
+    if (!artRational (ratio, 1024, &L, &M)) return false;
     // short periods are grouped: g periods of L outputs form one row of g*L phases
-    int g = 160 / L;
+    int g = L <= 160 ? 160 / L : 1;
     while (g > 1 && (long long) M * g > 176) --g;
     L *= g; M *= g;
     if (L < 48 || M > 16 * ART_U_MAXPAIRS) return false;
@@ -841,10 +850,13 @@ bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsi
 
     memset (&u, 0, sizeof u);
     u.L = L; u.M = M;
-    u.Npad = (L + 15) & ~15;
+    // tensor memory holds 3 accumulators of at most 160 columns: more phases are handled in G groups, each with its own table
+    u.G = (L + 159) / 160;
+    u.Lg = (L + u.G - 1) / u.G;
+    u.Npad = (u.Lg + 15) & ~15;
     u.KI = (M + 15) / 16;
     if (u.KI > ART_U_MAXPAIRS) return false;
-    const int flatEnd = M + 1 + k.T;                              // taps are counted from phase 0's first tap
+    const int flatEnd = (int) (((long long) u.Lg * M + L - 1) / L) + 2 + k.T;    // taps are counted from the first tap of a group's first phase
     int n = 0, aMax = 0;
     for (int i = 0; i < u.KI; ++i)                                // plane pair outermost: its planes are handed
         for (int a = 0; a * M + 16 * i < flatEnd; ++a) {          // back to the converters after the last shift
@@ -887,22 +899,22 @@ bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsi
     while (u.stages > 2 * ART_U_GROUP && umma_smem (u) > 224 * 1024) u.stages -= ART_U_GROUP;
     if (umma_smem (u) > 224 * 1024) return false;
     if (getenv ("ART_B200_TRACE"))
-        fprintf (stderr, "[art] umma L=%d M=%d Npad=%d KI=%d NS=%d numK=%d rows=%d DH=%d stages=%d smem=%zu\n",
-                 u.L, u.M, u.Npad, u.KI, u.NS, u.numK, u.rows, u.DH, u.stages, umma_smem (u));
+        fprintf (stderr, "[art] umma L=%d M=%d G=%d Npad=%d KI=%d NS=%d numK=%d rows=%d DH=%d stages=%d smem=%zu\n",
+                 u.L, u.M, u.G, u.Npad, u.KI, u.NS, u.numK, u.rows, u.DH, u.stages, umma_smem (u));
     return true;
 }
 
 int artUmmaTiles (const ArtUmma &u, int channels, unsigned int outputs)
 {
     const long long Q = ((long long) outputs + u.L - 1) / u.L;
-    return (int) (((Q + ART_U_ROWS - 1) / ART_U_ROWS) * channels);
+    return (int) (((Q + ART_U_ROWS - 1) / ART_U_ROWS) * channels * u.G);
 }
 
 static size_t umma_align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
 
 size_t artUmmaTableBytes (const ArtUmma &u, int numTables, int numJobs, int totalTiles)
 {
-    return umma_align16 ((size_t) numTables * u.tableHalfs * sizeof (unsigned short)) + umma_align16 ((size_t) numJobs * sizeof (int)) +
+    return umma_align16 ((size_t) numTables * u.G * u.tableHalfs * sizeof (unsigned short)) + umma_align16 ((size_t) numJobs * u.G * sizeof (int)) +
            (size_t) totalTiles * sizeof (int);
 }
 
@@ -910,9 +922,9 @@ void artUmmaCarve (ArtUmma &u, void *tables, int numTables, int numJobs)
 {
     unsigned char *p = reinterpret_cast<unsigned char *> (tables);
     u.H = reinterpret_cast<unsigned short *> (p);
-    p += umma_align16 ((size_t) numTables * u.tableHalfs * sizeof (unsigned short));
+    p += umma_align16 ((size_t) numTables * u.G * u.tableHalfs * sizeof (unsigned short));
     u.S0 = reinterpret_cast<int *> (p);
-    p += umma_align16 ((size_t) numJobs * sizeof (int));
+    p += umma_align16 ((size_t) numJobs * u.G * sizeof (int));
     u.tileExp = reinterpret_cast<int *> (p);
 }
 
@@ -939,7 +951,7 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
     }
     int histBlocks = (k.C * k.T + 127) / 128;
     if (histBlocks > 32) histBlocks = 32;
-    const int prepBlocks = numTables * u.Npad + (numJobs + 127) / 128 + totalTiles + numJobs * histBlocks;
+    const int prepBlocks = numTables * u.G * u.Npad + (numJobs * u.G + 127) / 128 + totalTiles + numJobs * histBlocks;
     ART_CUDA_CHECK (cudaMemsetAsync (u.tileExp, 0, (size_t) totalTiles * sizeof (int), stream));
     static int prepDbg = -1;
     if (prepDbg < 0) { const char *d = getenv ("ART_B200_UDBG"); prepDbg = d ? atoi (d) : 0; }

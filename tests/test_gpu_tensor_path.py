@@ -47,6 +47,8 @@ def _check_call(g, o, x, cap, ratio, tol=TOL, **kw):
     (2, 4, 44100, 48000, 0),            # preset -4: 988 taps, 8 row shifts
     (8, 4, 96000, 44100, 20000),        # BASELINE config 3's shape (8 of its 64 channels): 147/320, operand A as a ring of plane pairs
     (4, 3, 96000, 48000, 0),            # 1/2: 160 periods per row, M = 320
+    (2, 3, 44100, 96000, 0),            # 320/147: two phase groups of 160
+    (1, 2, 8000, 44100, 0),             # 441/80: three phase groups of 147
 ])
 def test_configs_on_the_tensor_path(forced_tensor_path, ch, preset, src, dst, lowpass_hz):
     lib = forced_tensor_path

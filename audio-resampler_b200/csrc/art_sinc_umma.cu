@@ -17,7 +17,8 @@
  *                        row shift a is nothing but +16*a bytes on the descriptor's start address -- no
  *                        im2col copy of the overlapping windows is ever made.
  *   operand B (filters)  built once per launch by the prep kernel in exactly the shared-memory image of a
- *                        k-step (16 taps x Npad phases), streamed by TMA bulk copies through a 3-stage ring.
+ *                        k-step (16 taps x Npad phases), streamed by TMA bulk copies through an 8-slot ring, two k-steps
+ *                        per copy.
  *   exact accumulation   Tensor-memory accumulation truncates (measured on B200: -0.15 ulp per MMA, see
  *                        profiles/microbench/umma_probe.cu), which a chain of ~200 MMAs cannot afford at a
  *                        1e-6 bar.  Integer-valued fp16 operands whose sums stay below 2^24 accumulate
@@ -28,11 +29,16 @@
  *                        [X1*h3 + x2*h2] carry 2^-11 and 2^-22 of the weight, where truncation is harmless.
  *                        The epilogue adds them in fp32 and applies the power-of-two scale.
  *
- * Warp roles (one CTA of 640 threads per SM, persistent over tiles of 128 periods x 1 channel):
+ *   the prep kernel      (same launch sequence) writes the filter operand, the per-job origins, the new history, and the
+ *                        block maximum of every tile's samples (-> q_x).
+ *   generality           long periods: operand A becomes a ring of plane-pair slots; more than 160 phases: groups of
+ *                        phases with their own tables; many interleaved channels: planar scratch (art_device.cu).
+ *
+ * Warp roles (one CTA of 640 threads per SM, persistent over tiles of 128 periods x 1 channel x 1 phase group):
  *   warp 0      TMA producer: filter k-steps -> stage ring (cp.async.bulk + mbarrier)
  *   warps 1-2   MMA issuers, alternating ring slots: 5 x tcgen05.mma (M=128, N=Npad, K=16) per k-step, tcgen05.commit
  *   warps 4-11  converters: global -> fixed-point split -> operand A, a pair of 8-tap planes at a time
- *   warps 12-19 epilogue: tcgen05.ld the three accumulators into registers (setmaxnreg gives them 136), release tensor
+ *   warps 12-19 epilogue: tcgen05.ld the three accumulators into registers (setmaxnreg gives them 120), release tensor
  *               memory, then transpose through shared memory and store
  */
 #include <cstdio>
@@ -141,24 +147,6 @@ __device__ __forceinline__ bool u_elect ()
 __device__ __forceinline__ void u_commit (unsigned int bar)
 {
     asm volatile ("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ void u_tmem_ld32 (unsigned int addr, unsigned int (&r)[32])
-{
-    asm volatile ("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                  "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                    "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                  : "r"(addr));
-}
-__device__ __forceinline__ void u_tmem_ld16 (unsigned int addr, unsigned int (&r)[16])
-{
-    asm volatile ("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                  "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                  : "r"(addr));
 }
 
 /* optional role timing (ART_B200_UPROF=1): cycles spent waiting / working per role, summed over CTAs */
@@ -616,7 +604,6 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
         unsigned int lt = 0;
         float v[2 * UN], vn[2 * UN];
         const int nU = ((u.rows + 3) / 4 - cw + 7) / 8;                     // row groups this warp owns
-        const bool oddRows = (u.rows & 3) != 0;                             // the last group is only half there (rows is even)
 
         /* what a lane needs to fetch its samples of one tile.  Inside the caller's block a sample is base[idx * fs];
          * tiles that touch the history or run past the end of the input take the same loads from a clamped address
@@ -673,7 +660,6 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                 for (int e = 0; e < 2 * UN; ++e) dst[e] = ok[e] ? dst[e] : 0.0f;
             }
         };
-        (void) oddRows;
 
         Src cur = source (blockIdx.x < totalTiles ? blockIdx.x : 0);
         if ((int) blockIdx.x < totalTiles) fetch (cur, 0, vn);

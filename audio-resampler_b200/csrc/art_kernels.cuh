@@ -98,6 +98,8 @@ struct ArtUmma {
     unsigned short *H;   // [tables][G][numK][3 splits][2 k-planes][Npad][8]  fp16 bit patterns
     int *S0;             // [jobs][G]  region index of tap 0 of the group's first phase, period 0
     int *tileExp;        // [tiles] block maximum |x| of the samples a tile reads, as a float bit pattern (-> the tile's quantum)
+    int *tileJob;        // [tiles] index of the job a tile belongs to (written by the prep kernel: the product kernel's roles
+                         //   then find their job with one load instead of a binary search over the job list)
     unsigned char ka[ART_U_MAXK], ki[ART_U_MAXK];      // k-step -> (row shift a, 16-tap group i), i outermost
     unsigned char nA[32];                              // row shifts per 16-tap group
 };

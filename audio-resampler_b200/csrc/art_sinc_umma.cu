@@ -281,8 +281,8 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
          * sample read once, coalesced); otherwise each block scans its own channel.  (The origin is recomputed here: the
          * origin block may run later.) */
         const int tile = b;
-        if (dbg & 32) { if (threadIdx.x == 0) u.tileExp[tile] = __float_as_uint (1.0f); return; }
         const int seg = jobs ? (numJobs > 1 ? u_find_job (jobs, numJobs, tile) : 0) : 0;
+        if (threadIdx.x == 0) u.tileJob[tile] = seg;
         const ArtJob &job = jobs ? jobs[seg] : single;
         const int local = tile - job.tile0;
         const int C = k.C;
@@ -481,7 +481,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
 
     const ArtJob *const singlePtr = &single;
     auto jobOf = [=] (int tile) -> const ArtJob & {
-        return jobs ? jobs[k.numJobs > 1 ? u_find_job (jobs, k.numJobs, tile) : 0] : *singlePtr;
+        return jobs ? jobs[u.tileJob[tile]] : *singlePtr;
     };
 
     if (warp == 0) {
@@ -901,7 +901,7 @@ static size_t umma_align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
 size_t artUmmaTableBytes (const ArtUmma &u, int numTables, int numJobs, int totalTiles)
 {
     return umma_align16 ((size_t) numTables * u.G * u.tableHalfs * sizeof (unsigned short)) + umma_align16 ((size_t) numJobs * u.G * sizeof (int)) +
-           (size_t) totalTiles * sizeof (int);
+           2 * (size_t) totalTiles * sizeof (int);
 }
 
 void artUmmaCarve (ArtUmma &u, void *tables, int numTables, int numJobs)
@@ -912,6 +912,7 @@ void artUmmaCarve (ArtUmma &u, void *tables, int numTables, int numJobs)
     u.S0 = reinterpret_cast<int *> (p);
     p += umma_align16 ((size_t) numJobs * u.G * sizeof (int));
     u.tileExp = reinterpret_cast<int *> (p);
+    u.tileJob = nullptr;            // follows tileExp: set by the launcher, which knows the tile count
 }
 
 void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int numJobs, int numTables, int smCount,
@@ -938,10 +939,12 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
     int histBlocks = (k.C * k.T + 127) / 128;
     if (histBlocks > 32) histBlocks = 32;
     const int prepBlocks = numTables * u.G * u.Npad + (numJobs * u.G + 127) / 128 + totalTiles + numJobs * histBlocks;
+    ArtUmma uu = u;
+    uu.tileJob = u.tileExp + totalTiles;
     ART_CUDA_CHECK (cudaMemsetAsync (u.tileExp, 0, (size_t) totalTiles * sizeof (int), stream));
     static int prepDbg = -1;
     if (prepDbg < 0) { const char *d = getenv ("ART_B200_UDBG"); prepDbg = d ? atoi (d) : 0; }
-    art_umma_prep_kernel<<<prepBlocks, 128, 0, stream>>> (k, u, single, d_jobs, numJobs, numTables, histBlocks, totalTiles, prepDbg);
+    art_umma_prep_kernel<<<prepBlocks, 128, 0, stream>>> (k, uu, single, d_jobs, numJobs, numTables, histBlocks, totalTiles, prepDbg);
     ART_CUDA_CHECK (cudaGetLastError ());
     const int grid = totalTiles < smCount ? totalTiles : smCount;
     static int roleProf = -1;
@@ -961,7 +964,7 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
     }
     void *prof;
     artProfileBegin (stream, &prof);
-    art_sinc_umma_kernel<<<grid, ART_U_THREADS, umma_smem (u), stream>>> (k, u, single, d_jobs, totalTiles, roleProf);
+    art_sinc_umma_kernel<<<grid, ART_U_THREADS, umma_smem (u), stream>>> (k, uu, single, d_jobs, totalTiles, roleProf);
     artProfileEnd (stream, prof);
     ART_CUDA_CHECK (cudaGetLastError ());
     g_artLaunches += 2;

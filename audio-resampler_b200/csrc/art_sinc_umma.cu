@@ -608,7 +608,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
         /* what a lane needs to fetch its samples of one tile.  Inside the caller's block a sample is base[idx * fs];
          * tiles that touch the history or run past the end of the input take the same loads from a clamped address
          * and zero what must read as silence, so that all loads of a plane pair are still issued back to back */
-        struct Src { const float *p, *base, *hist; long long fs, R0, lo, hi; int e; bool fast; };
+        struct Src { const float *p, *p0, *h0, *dummy; long long fs; int loRel, hiRel, e; bool fast; };
         auto source = [&] (int tile) -> Src {
             Src sc;
             const ArtJob &job = jobOf (tile);
@@ -616,13 +616,20 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             const int local = tile - job.tile0;
             const int qg = local / C, c = local - qg * C;
             const int qb = qg / u.G, grp = qg - qb * u.G;
-            sc.R0 = (long long) u.S0[seg * u.G + grp] + (long long) M * qb * ART_U_ROWS;
-            sc.lo = -job.prevAvail; sc.hi = job.inValid;
-            sc.fast = sc.R0 >= sc.lo && sc.R0 + span <= sc.hi;
+            const long long R0 = (long long) u.S0[seg * u.G + grp] + (long long) M * qb * ART_U_ROWS;
+            const long long lo = -job.prevAvail, hi = job.inValid;
+            sc.fast = R0 >= lo && R0 + span <= hi;
             sc.fs = job.inFS;
-            sc.base = job.inPlanes ? job.inPlanes[c] : job.in + (long long) c * job.inCS;
-            sc.hist = job.hist + (long long) c * T + T + job.prevAvail;       // hist[idx]: -T - prevAvail <= idx < -prevAvail
-            sc.p = sc.base + (sc.R0 + off0) * sc.fs;
+            const float *base = job.inPlanes ? job.inPlanes[c] : job.in + (long long) c * job.inCS;
+            const float *hist = job.hist + (long long) c * T + T + job.prevAvail;     // hist[idx]: -T - prevAvail <= idx < -prevAvail
+            // tile-relative coordinates (rel = idx - R0, an int): the boundary path classifies every sample it fetches
+            const long long loR = lo - R0, hiR = hi - R0;
+            sc.loRel = loR < -(1 << 30) ? -(1 << 30) : (loR > (1 << 30) ? (1 << 30) : (int) loR);
+            sc.hiRel = hiR < -(1 << 30) ? -(1 << 30) : (hiR > (1 << 30) ? (1 << 30) : (int) hiR);
+            sc.p0 = base + R0 * sc.fs;
+            sc.h0 = hist + R0;
+            sc.dummy = hist + lo - 1;                                         // any readable address: the newest history sample
+            sc.p = sc.p0 + (long long) off0 * sc.fs;
             {
                 const float m = __int_as_float (u.tileExp[tile]);             // block maximum (prep kernel)
                 int e = 0;
@@ -649,10 +656,10 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                 bool ok[2 * UN];
 #pragma unroll
                 for (int e = 0; e < 2 * UN; ++e) {
-                    const long long idx = sc.R0 + off0 + 16 * i + 32 * M * (e >> 1) + (e & 1);
-                    const bool inBlock = idx >= sc.lo && idx < sc.hi, inHist = idx < sc.lo && idx >= sc.lo - T;
+                    const int rel = off0 + 16 * i + 32 * M * (e >> 1) + (e & 1);
+                    const bool inBlock = rel >= sc.loRel && rel < sc.hiRel, inHist = rel < sc.loRel && rel >= sc.loRel - T;
                     ok[e] = (inBlock || inHist) && rowOk (e >> 1);
-                    ptr[e] = inBlock ? sc.base + idx * sc.fs : (inHist ? sc.hist + idx : sc.hist + sc.lo - 1);
+                    ptr[e] = inBlock ? sc.p0 + (long long) rel * sc.fs : (inHist ? sc.h0 + rel : sc.dummy);
                 }
 #pragma unroll
                 for (int e = 0; e < 2 * UN; ++e) dst[e] = __ldg (ptr[e]);

@@ -530,6 +530,7 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
         if (ok) {
             size_t floats = 0;
             std::vector<size_t> inAt, outAt;
+            std::vector<int> groupOf (n, 0);                     // which call (scratch pair) a segment belongs to
             for (int i = 0; i < n; ) {
                 int e = i;
                 long long outFrames = 0;
@@ -546,7 +547,7 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
                 outAt.push_back (floats); floats += (size_t) C * outPitch;
                 if (inFrames > maxInFrames) maxInFrames = inFrames;
                 if (outFrames > maxOutFrames) maxOutFrames = outFrames;
-                for (int q = i; q < e; ++q) jobs[q].table = (int) xin.size () - 1;          // group index, for the rewrite below
+                for (int q = i; q < e; ++q) groupOf[q] = (int) xin.size () - 1;
                 i = e;
             }
             ART_CUDA_CHECK (cudaMallocAsync (&scratch, floats * sizeof (float), stream));
@@ -554,8 +555,9 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
                 xin[gi].dst = scratch + inAt[gi];
                 xout[gi].src = scratch + outAt[gi];
             }
-            for (ArtJob &j : jobs) {
-                const ArtXpose &a = xin[j.table], &b = xout[j.table];
+            for (int q = 0; q < n; ++q) {
+                ArtJob &j = jobs[q];
+                const ArtXpose &a = xin[groupOf[q]], &b = xout[groupOf[q]];
                 j.in = a.dst;  j.inFS = 1;  j.inCS = a.pitch;
                 j.out = const_cast<float *> (b.src); j.outFS = 1; j.outCS = b.pitch;
             }

@@ -398,7 +398,11 @@ def measure_e2e(lib, pkg, torch, dist, world, dev, streams, frames, cap, args):
     # GIL hand-offs of an executor's map) would be a visible part of it
     import threading
     # a host thread spins inside cudaStreamSynchronize: do not oversubscribe the cores when several ranks share the box
-    T = max(1, min(args.e2e_threads, n, max(2, (os.cpu_count() or 16) // max(1, world))))
+    try:
+        cores = len(os.sched_getaffinity(0))           # what this process may actually use (cgroup / affinity aware)
+    except Exception:
+        cores = os.cpu_count() or 16
+    T = max(1, min(args.e2e_threads, n, max(2, cores // max(1, world))))
     start, done = threading.Barrier(T + 1), threading.Barrier(T + 1)
     made_by = [0] * T
     rounds = {"n": 0}

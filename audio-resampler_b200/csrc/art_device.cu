@@ -372,39 +372,32 @@ static void finish_job (ArtDev *dev, const ArtCallPlan &p)
 struct ArtLaunchPlan {
     ArtClass k;
     bool periodic;              // one of the two rational-ratio kernels
-    bool tiled;                 // ... the register-tiled one (art_sinc_periodic2.cu)
     bool umma;                  // ... the tensor-core one (art_sinc_umma.cu)
     ArtUmma um;
     int smCount;
     ArtPeriodic per;
-    ArtPeriodic2 per2;
     int CV;
     ArtLaunchGeom g;
     unsigned int segLen;
 };
 
-static bool g_forceGeneric = false, g_useTiled = false, g_envRead = false;
+static bool g_forceGeneric = false, g_envRead = false;
 
 static void plan_launch (ArtDev *lead, double minRatio, bool oneRatio, unsigned int maxOut, unsigned long long totalOut,
                          bool allowPeriodic, ArtLaunchPlan &lp)
 {
     if (!g_envRead) {
         g_forceGeneric = getenv ("ART_B200_GENERIC") != nullptr;     // debugging / A-B measurements
-        // the register-tiled rational-ratio kernel (art_sinc_periodic2.cu) is experimental: correct, but its
-        // single-accumulator summation leaves a thin margin to the 1e-6 bar on long filters and its boundary
-        // staging is not tuned; opt in for measurements only
-        g_useTiled = getenv ("ART_B200_TILED") != nullptr;
         g_envRead = true;
     }
     lp.k = lead->klass;
     lp.periodic = false;
-    lp.tiled = false;
     lp.umma = false;
     lp.smCount = lead->smCount;
     lp.segLen = 0;
     if (!maxOut)
         return;
-    if (allowPeriodic && oneRatio && !g_forceGeneric && !g_useTiled &&
+    if (allowPeriodic && oneRatio && !g_forceGeneric &&
         artPlanUmma (lp.k, minRatio, maxOut, totalOut, lead->smCount, lp.um)) {
         lp.periodic = lp.umma = true;
         lp.per.L = lp.um.L; lp.per.M = lp.um.M;
@@ -412,13 +405,6 @@ static void plan_launch (ArtDev *lead, double minRatio, bool oneRatio, unsigned 
         return;
     }
     const unsigned int total32 = (unsigned int) (totalOut > 0xffffffffULL ? 0xffffffffULL : totalOut);
-    if (allowPeriodic && oneRatio && !g_forceGeneric && g_useTiled &&
-        artPlanPeriodic2 (lp.k, minRatio, maxOut, lp.per2, lp.CV)) {
-        lp.periodic = lp.tiled = true;
-        lp.per.L = lp.per2.L; lp.per.M = lp.per2.M;
-        lp.segLen = artPeriodicSegmentOutputs (lp.per, minRatio);
-        return;
-    }
     if (allowPeriodic && oneRatio && !g_forceGeneric &&
         artPlanPeriodic (lp.k, minRatio, maxOut, totalOut, lead->smCount, lp.per, lp.CV)) {
         lp.periodic = true;
@@ -454,7 +440,7 @@ static int append_job (const ArtLaunchPlan &lp, const ArtJob &base, std::vector<
         if (at) j.histOut = nullptr;        // one history update per call
         jobs.push_back (j);
         ctas += lp.umma ? artUmmaTiles (lp.um, lp.k.C, j.outputs)
-                        : lp.tiled ? artPeriodic2Ctas (lp.per2, lp.CV, j.outputs) : artPeriodicCtas (lp.per, j.outputs);
+                        : artPeriodicCtas (lp.per, j.outputs);
     }
     return ctas;
 }
@@ -611,7 +597,6 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
             const size_t tableFloats = (size_t) numTables * lp.per.PB * lp.per.rowsPerCta * 8 * lp.per.Kp;
             const size_t tableInts = (size_t) n * lp.per.PB;
             const size_t bytes = lp.umma ? artUmmaTableBytes (lp.um, numTables, n, ctas)
-                               : lp.tiled ? artPeriodic2TableBytes (lp.per2, numTables, n)
                                           : tableFloats * sizeof (float) + tableInts * sizeof (int);
             void *tables = nullptr;
             const bool persistent = owner && n == 1;
@@ -629,10 +614,6 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
             if (lp.umma) {
                 artUmmaCarve (lp.um, tables, numTables, n);
                 artLaunchUmma (lp.k, lp.um, ctas, n, numTables, lp.smCount, jobs[0], d_jobs, stream);
-            }
-            else if (lp.tiled) {
-                artPeriodic2Carve (lp.per2, tables, numTables, n);
-                artLaunchPeriodic2 (lp.k, lp.per2, lp.CV, ctas, n, numTables, jobs[0], d_jobs, stream);
             }
             else {
                 lp.per.Hblk = reinterpret_cast<float *> (tables);

@@ -71,16 +71,6 @@ struct ArtPeriodic {
     int   *S0;           // [jobs][PB]  region index of the block's first tap, period 0
 };
 
-/* register-tiled form of the rational-ratio kernel (art_sinc_periodic2.cu) */
-struct ArtPeriodic2 {
-    int L, M;            // outputs / inputs per period
-    int PB;              // phase tiles of 80 phases
-    int Kt;              // taps per phase tile (union window), multiple of 32
-    float *Hg;           // [tables][PB][Kt][80]  filters of a phase tile, tap-major, zero outside the band
-    int   *D;            // [tables][PB * 80]     window shift of every phase inside its tile, -1 beyond L
-    int   *S0;           // [jobs][PB]            region index of the tile's first tap, period 0
-};
-
 /* tensor-core form of the rational-ratio kernel (art_sinc_umma.cu): y[period, phase] as a product of the
  * input read at stride M (rows = periods) and the banded matrix of pre-interpolated filters, on tcgen05 */
 #define ART_U_MAXK 96
@@ -176,13 +166,6 @@ unsigned int artPeriodicSegmentOutputs (const ArtPeriodic &p, double ratio);
 int  artPeriodicCtas (const ArtPeriodic &p, unsigned int outputs);
 void artLaunchPeriodic (const ArtClass &k, const ArtPeriodic &p, int CV, int totalCtas, int numJobs, int numTables,
                         const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream);
-
-bool artPlanPeriodic2 (const ArtClass &k, double ratio, unsigned int maxOutputs, ArtPeriodic2 &p, int &CV);
-int  artPeriodic2Ctas (const ArtPeriodic2 &p, int CV, unsigned int outputs);
-size_t artPeriodic2TableBytes (const ArtPeriodic2 &p, int numTables, int numJobs);
-void artPeriodic2Carve (ArtPeriodic2 &p, void *tables, int numTables, int numJobs);
-void artLaunchPeriodic2 (const ArtClass &k, const ArtPeriodic2 &p, int CV, int totalCtas, int numJobs, int numTables,
-                         const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream);
 
 bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsigned long long totalOutputs,
                   int smCount, ArtUmma &u);

@@ -348,7 +348,10 @@ def run_gpu_arm(args):
                                f"{streams} independent stereo streams x {frames} input frames per step per GPU, "
                                "one batched launch", "streams_per_gpu": streams, "frames_per_stream": frames,
                    "l2": f"inputs {streams * frames * CHANNELS * 4 / 2**20:.0f} MiB + outputs per step exceed the 126 MB L2",
-                   "parallelism": f"streams sharded over {world} GPU(s), no data-path collective"},
+                   "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
+                   "arithmetic": ("float32 in, float32 out; tensor-core kernel: block-scaled fixed-point fp16 digit products with exact "
+                                  "fp32 accumulation (within 2e-7 of peak of the reference's float path)" if tensor else
+                                  "float32 FMA")},
         "wall_ms_per_step": wall_ms / args.steps, "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
     }
     if rank == 0:

@@ -299,7 +299,7 @@ def run_gpu_arm(args):
     # rational-ratio kernel applies ONE pre-interpolated filter over a 416-tap union window)
     alg_tflops = per_launch_samples * (4 * TAPS + 3) / (kern_avg_ms * 1e-3) / 1e12
     exe_tflops = per_launch_samples * (2 * 416 if periodic else 4 * 384) / (kern_avg_ms * 1e-3) / 1e12
-    kernel = ("art_sinc_umma_kernel (tcgen05.mma, 608 threads, 1 CTA/SM)" if tensor else
+    kernel = ("art_sinc_umma_kernel (tcgen05.mma, 640 threads, 1 CTA/SM)" if tensor else
               "art_sinc_periodic_kernel<CV=2,256>" if periodic else "art_sinc_generic_kernel<interp,float,CV=2>")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src,

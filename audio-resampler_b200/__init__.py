@@ -106,6 +106,7 @@ def load() -> C.CDLL:
         "resampleB200GetDeviceCount": (i32, []),
         "resampleB200Synchronize": (None, [ctx]),
         "resampleB200KernelLaunches": (C.c_ulonglong, []),
+        "resampleB200LastError": (C.c_char_p, [i32]),
         "resampleB200PathCounts": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
         "resampleB200SetTensorPath": (None, [i32]),
         "resampleB200TensorLaunches": (C.c_ulonglong, []),
@@ -137,7 +138,7 @@ EXPORTED_SYMBOLS = [
     "resampleGetExpectedOutput", "resampleAdvancePosition", "resampleGetLowpassRatio", "resampleGetPosition",
     "resampleGetNumFilters", "resampleInterpolationUsed", "resampleReset", "resampleFree",
     "biquad_init", "biquad_lowpass", "biquad_highpass", "biquad_apply_buffer", "biquad_apply_sample",
-    "resampleB200SetDevice", "resampleB200GetDeviceCount", "resampleB200Synchronize", "resampleB200KernelLaunches",
+    "resampleB200SetDevice", "resampleB200GetDeviceCount", "resampleB200Synchronize", "resampleB200KernelLaunches", "resampleB200LastError",
     "resampleB200PathCounts", "resampleB200SetTensorPath", "resampleB200TensorLaunches", "resampleB200ProfileEnable", "resampleB200ProfileCollect",
     "resampleProcessInterleavedDevice", "resampleProcessDevice", "resampleBatchProcessInterleavedDevice",
     "resampleBatchProcessInterleaved", "resampleProcessBlocksInterleavedDevice", "biquad_apply_cascade_interleaved",

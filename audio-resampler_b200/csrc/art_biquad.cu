@@ -257,15 +257,15 @@ void run_cascade_order (int order, const BqGeom &g, const ArtBiquadStage *d_st, 
 
 }   // namespace
 
-extern "C" void artBiquadRun (ArtBiquadStage *stages, int numStages, int channels, float *buffer,
-                              long long frames, int stride, int onDevice, void *streamPtr)
+extern "C" int artBiquadRun (ArtBiquadStage *stages, int numStages, int channels, float *buffer,
+                             long long frames, int stride, int onDevice, void *streamPtr)
 {
+    ART_GUARD_BEGIN
     if (frames <= 0 || numStages <= 0 || channels <= 0)
-        return;
+        return 0;
     int count = 0;
     if (cudaGetDeviceCount (&count) != cudaSuccess || count == 0) {
-        fprintf (stderr, "libresampler_b200: biquad needs a CUDA device; this library has no CPU path\n");
-        abort ();
+        artRaise ("biquad needs a CUDA device; this library has no CPU path");
     }
     cudaStream_t stream = (cudaStream_t) streamPtr;
     const size_t span = (size_t) (frames - 1) * stride + channels;
@@ -318,4 +318,6 @@ extern "C" void artBiquadRun (ArtBiquadStage *stages, int numStages, int channel
     ART_CUDA_CHECK (cudaFreeAsync (d_stOut, stream));
     if (!onDevice)
         ART_CUDA_CHECK (cudaFreeAsync (d_buf, stream));
+    return 0;
+    ART_GUARD_END (-1)
 }

@@ -248,23 +248,31 @@ static ResampleResult plan_call (Resample *cxt, int numInputFrames, int numOutpu
 /* The four single-call entry points differ only in where the samples live. */
 enum { IO_HOST_INTERLEAVED, IO_HOST_PLANAR, IO_DEVICE_INTERLEAVED, IO_DEVICE_PLANAR };
 
-static void run_call (Resample *cxt, int io, const ArtCallPlan *call, const void *in, void *out, void *stream)
+/* all device work reports failure as non-zero (art_device.h): the message has been printed and is kept for
+ * resampleB200LastError(); the caller of the public API sees a call that consumed and produced nothing */
+static int run_call (Resample *cxt, int io, const ArtCallPlan *call, const void *in, void *out, void *stream)
 {
     switch (io) {
-        case IO_HOST_INTERLEAVED:   artDevRunHostInterleaved (cxt->device, call, (const float *) in, (float *) out); break;
-        case IO_HOST_PLANAR:        artDevRunHostPlanar (cxt->device, call, (const float *const *) in, (float *const *) out); break;
-        case IO_DEVICE_INTERLEAVED: artDevRunDeviceInterleaved (cxt->device, call, (const float *) in, (float *) out, stream); break;
-        default:                    artDevRunDevicePlanar (cxt->device, call, (const float *const *) in, (float *const *) out, stream); break;
+        case IO_HOST_INTERLEAVED:   return artDevRunHostInterleaved (cxt->device, call, (const float *) in, (float *) out);
+        case IO_HOST_PLANAR:        return artDevRunHostPlanar (cxt->device, call, (const float *const *) in, (float *const *) out);
+        case IO_DEVICE_INTERLEAVED: return artDevRunDeviceInterleaved (cxt->device, call, (const float *) in, (float *) out, stream);
+        default:                    return artDevRunDevicePlanar (cxt->device, call, (const float *const *) in, (float *const *) out, stream);
     }
 }
+
+/* the scalar stream state a failed call has to put back */
+typedef struct { double outputOffset; int inputIndex, flags; } ArtSaved;
+static ArtSaved save_state (const Resample *cxt) { ArtSaved s; s.outputOffset = cxt->outputOffset; s.inputIndex = cxt->inputIndex; s.flags = cxt->flags; return s; }
+static void restore_state (Resample *cxt, const ArtSaved *s) { cxt->outputOffset = s->outputOffset; cxt->inputIndex = s->inputIndex; cxt->flags = s->flags; }
 
 /* EXTRAPOLATE_ENDPOINTS (resampler.c:516-522 / :663-698, extrapolator.c): at the end of a stream the T/2 frames the flush
  * appends are predicted from the last T/2 frames instead of being silence; at its start, when the first output is about
  * to be produced, the zero history in front of the first sample is replaced by a backward prediction from the samples
  * received so far.  Both are a few hundred samples of serial work per stream, done on the host (art_extrapolate.c) around
  * small synchronous transfers; the call itself then runs as any other. */
-static void run_call_with_endpoints (Resample *cxt, int io, ArtCallPlan *call, const void *in, void *out, void *stream, int flushing)
+static int run_call_with_endpoints (Resample *cxt, int io, ArtCallPlan *call, const void *in, void *out, void *stream, int flushing)
 {
+    int failed = 0;
     const int T = cxt->numTaps, half = T / 2, C = cxt->numChannels;
     const int onDevice = io == IO_DEVICE_INTERLEAVED || io == IO_DEVICE_PLANAR;
     const int planar = io == IO_HOST_PLANAR || io == IO_DEVICE_PLANAR;
@@ -276,7 +284,10 @@ static void run_call_with_endpoints (Resample *cxt, int io, ArtCallPlan *call, c
 
     if (flushing || ((cxt->flags & EXTRAPOLATE_PREFILL) && call->outputs)) {
         hist = malloc (sizeof (float) * (size_t) C * T);
-        artDevGetHistoryOn (cxt->device, hist, st);
+        if (artDevGetHistoryOn (cxt->device, hist, st)) {
+            free (hist);
+            return -1;
+        }
     }
 
     if (flushing) {                             /* postfillAllChannels, resampler.c:663-685 */
@@ -303,11 +314,11 @@ static void run_call_with_endpoints (Resample *cxt, int io, ArtCallPlan *call, c
                 if (!onDevice && !planar) memcpy (first, in, sizeof (float) * (size_t) u0 * C);
                 else if (!onDevice)
                     for (c = 0; c < C; ++c) for (i = 0; i < u0; ++i) first[(size_t) i * C + c] = ((const float *const *) in)[c][i];
-                else if (!planar) artDevFetch (cxt->device, (const float *) in, (size_t) u0 * C, first, st);
+                else if (!planar) failed |= artDevFetch (cxt->device, (const float *) in, (size_t) u0 * C, first, st);
                 else {
                     float *plane = malloc (sizeof (float) * (size_t) u0);
                     for (c = 0; c < C; ++c) {
-                        artDevFetch (cxt->device, ((const float *const *) in)[c], (size_t) u0, plane, st);
+                        failed |= artDevFetch (cxt->device, ((const float *const *) in)[c], (size_t) u0, plane, st);
                         for (i = 0; i < u0; ++i) first[(size_t) i * C + c] = plane[i];
                     }
                     free (plane);
@@ -323,55 +334,70 @@ static void run_call_with_endpoints (Resample *cxt, int io, ArtCallPlan *call, c
                 artExtendBackward (line + T, (int) have, (int) (T - have));
                 /* line[k], k < T - have, is ring slot have + k: the slots in front of the first real sample.  The history
                  * at call entry is ring [n0, n0 + T), so they land at history index have - n0 + k */
-                artDevPatchHistory (cxt->device, c, (int) (have - n0), (int) (T - have), line, st);
+                failed |= artDevPatchHistory (cxt->device, c, (int) (have - n0), (int) (T - have), line, st);
             }
             free (first);
             free (line);
         }
     }
 
-    if (!flushing)
-        run_call (cxt, io, call, in, out, stream);
+    if (failed)
+        ;
+    else if (!flushing)
+        failed = run_call (cxt, io, call, in, out, stream);
     else if (!onDevice) {
         if (planar) {
             tailPlanes = malloc (sizeof *tailPlanes * C);
             for (c = 0; c < C; ++c) tailPlanes[c] = tail + (size_t) c * half;
-            run_call (cxt, io, call, tailPlanes, out, stream);
+            failed = run_call (cxt, io, call, tailPlanes, out, stream);
         }
         else {
             tailInterleaved = malloc (sizeof (float) * (size_t) C * half);
             for (c = 0; c < C; ++c) for (i = 0; i < half; ++i) tailInterleaved[(size_t) i * C + c] = tail[(size_t) c * half + i];
-            run_call (cxt, io, call, tailInterleaved, out, stream);
+            failed = run_call (cxt, io, call, tailInterleaved, out, stream);
         }
     }
     else if (planar) {
         const float *d_tail = artDevStage (cxt->device, tail, (size_t) C * half, st);
-        tailPlanes = malloc (sizeof *tailPlanes * C);
-        for (c = 0; c < C; ++c) tailPlanes[c] = d_tail + (size_t) c * half;
-        run_call (cxt, io, call, tailPlanes, out, stream);
+        if (!d_tail)
+            failed = -1;
+        else {
+            tailPlanes = malloc (sizeof *tailPlanes * C);
+            for (c = 0; c < C; ++c) tailPlanes[c] = d_tail + (size_t) c * half;
+            failed = run_call (cxt, io, call, tailPlanes, out, stream);
+        }
     }
     else {
+        const float *d_tail;
         tailInterleaved = malloc (sizeof (float) * (size_t) C * half);
         for (c = 0; c < C; ++c) for (i = 0; i < half; ++i) tailInterleaved[(size_t) i * C + c] = tail[(size_t) c * half + i];
-        run_call (cxt, io, call, artDevStage (cxt->device, tailInterleaved, (size_t) C * half, st), out, stream);
+        d_tail = artDevStage (cxt->device, tailInterleaved, (size_t) C * half, st);
+        failed = d_tail ? run_call (cxt, io, call, d_tail, out, stream) : -1;
     }
     free (tailPlanes);
     free (tailInterleaved);
     free (tail);
     free (hist);
+    return failed;
 }
 
 static ResampleResult process_one (Resample *cxt, int io, const void *in, int numInputFrames, void *out, int numOutputFrames, double ratio, void *stream)
 {
     const int flushing = numInputFrames < 0 && !(cxt->flags & RESAMPLER_FLUSHED);
+    const ArtSaved before = save_state (cxt);
     ArtCallPlan call;
     ResampleResult res = plan_call (cxt, numInputFrames, numOutputFrames, ratio, &call);
+    int failed;
     if (!(call.outputs || call.consumed))
         return res;
     if ((cxt->flags & EXTRAPOLATE_ENDPOINTS) && (flushing || (cxt->flags & EXTRAPOLATE_PREFILL)))
-        run_call_with_endpoints (cxt, io, &call, in, out, stream, flushing);
+        failed = run_call_with_endpoints (cxt, io, &call, in, out, stream, flushing);
     else
-        run_call (cxt, io, &call, in, out, stream);
+        failed = run_call (cxt, io, &call, in, out, stream);
+    if (failed) {                               /* nothing consumed, nothing produced, state as before the call */
+        restore_state (cxt, &before);
+        res.input_used = res.output_generated = 0;
+    }
     return res;
 }
 
@@ -445,6 +471,8 @@ void resampleBatchProcessInterleavedDevice (Resample *const *cxts, int numContex
     ArtDev **devs;
     const float **din;
     float **dout;
+    ArtSaved *saved;
+    int *owner;
     int i, n = 0, live = 0;
 
     if (numContexts <= 0)
@@ -453,6 +481,8 @@ void resampleBatchProcessInterleavedDevice (Resample *const *cxts, int numContex
     devs = malloc (sizeof *devs * numContexts);
     din = malloc (sizeof *din * numContexts);
     dout = malloc (sizeof *dout * numContexts);
+    saved = malloc (sizeof *saved * numContexts);
+    owner = malloc (sizeof *owner * numContexts);
     for (i = 0; i < numContexts; ++i) {
         ResampleResult r;
         if (needs_endpoint_work (cxts[i], numInputFrames[i])) {     /* stream start / end with extrapolation: on its own */
@@ -461,6 +491,8 @@ void resampleBatchProcessInterleavedDevice (Resample *const *cxts, int numContex
             if (results) results[i] = r;
             continue;
         }
+        saved[n] = save_state (cxts[i]);
+        owner[n] = i;
         r = plan_call (cxts[i], numInputFrames[i], numOutputFrames[i], ratios ? ratios[i] : 0.0, &calls[n]);
         devs[n] = cxts[i]->device;
         din[n] = d_inputs ? d_inputs[i] : NULL;
@@ -469,12 +501,17 @@ void resampleBatchProcessInterleavedDevice (Resample *const *cxts, int numContex
         live |= calls[n].outputs || calls[n].consumed;
         ++n;
     }
-    if (live)
-        artDevRunBatchInterleaved (devs, calls, n, din, dout, stream);
+    if (live && artDevRunBatchInterleaved (devs, calls, n, din, dout, stream))
+        for (i = 0; i < n; ++i) {               /* the launch failed as a whole */
+            restore_state (cxts[owner[i]], &saved[i]);
+            if (results) results[owner[i]].input_used = results[owner[i]].output_generated = 0;
+        }
     free (calls);
     free (devs);
     free (din);
     free (dout);
+    free (saved);
+    free (owner);
 }
 
 void resampleBatchProcessInterleaved (Resample *const *cxts, int numContexts,
@@ -486,6 +523,8 @@ void resampleBatchProcessInterleaved (Resample *const *cxts, int numContexts,
     ArtDev **devs;
     const float **hin;
     float **hout;
+    ArtSaved *saved;
+    int *owner;
     int i, n = 0;
 
     if (numContexts <= 0)
@@ -494,6 +533,8 @@ void resampleBatchProcessInterleaved (Resample *const *cxts, int numContexts,
     devs = malloc (sizeof *devs * numContexts);
     hin = malloc (sizeof *hin * numContexts);
     hout = malloc (sizeof *hout * numContexts);
+    saved = malloc (sizeof *saved * numContexts);
+    owner = malloc (sizeof *owner * numContexts);
     for (i = 0; i < numContexts; ++i) {
         ResampleResult r;
         if (needs_endpoint_work (cxts[i], numInputFrames[i])) {
@@ -502,6 +543,8 @@ void resampleBatchProcessInterleaved (Resample *const *cxts, int numContexts,
             if (results) results[i] = r;
             continue;
         }
+        saved[n] = save_state (cxts[i]);
+        owner[n] = i;
         r = plan_call (cxts[i], numInputFrames[i], numOutputFrames[i], ratios ? ratios[i] : 0.0, &calls[n]);
         devs[n] = cxts[i]->device;
         hin[n] = inputs ? inputs[i] : NULL;
@@ -509,12 +552,17 @@ void resampleBatchProcessInterleaved (Resample *const *cxts, int numContexts,
         if (results) results[i] = r;
         ++n;
     }
-    if (n)
-        artDevRunHostBatchInterleaved (devs, calls, n, hin, hout);
+    if (n && artDevRunHostBatchInterleaved (devs, calls, n, hin, hout))
+        for (i = 0; i < n; ++i) {
+            restore_state (cxts[owner[i]], &saved[i]);
+            if (results) results[owner[i]].input_used = results[owner[i]].output_generated = 0;
+        }
     free (calls);
     free (devs);
     free (hin);
     free (hout);
+    free (saved);
+    free (owner);
 }
 
 int resampleProcessBlocksInterleavedDevice (Resample *cxt, const float *d_input, const int *blockFrames,
@@ -525,6 +573,7 @@ int resampleProcessBlocksInterleavedDevice (Resample *cxt, const float *d_input,
     ArtCallPlan *calls;
     long long *inOff, *outOff, inAt = 0, outAt = 0, inFirst = 0;
     int b, done = 0, first = 0;
+    ArtSaved atLaunch;
 
     if (numBlocks <= 0)
         return 0;
@@ -554,6 +603,7 @@ int resampleProcessBlocksInterleavedDevice (Resample *cxt, const float *d_input,
     }
     first = done;
     inFirst = inAt;
+    atLaunch = save_state (cxt);
     for (b = first; b < numBlocks; ++b) {
         /* dry-run on a copy of the scalar state: a block that cannot finish is not started */
         Resample probe = *cxt;
@@ -576,9 +626,11 @@ int resampleProcessBlocksInterleavedDevice (Resample *cxt, const float *d_input,
         if (positions) positions[b] = resampleGetPosition (cxt);
         ++done;
     }
-    if (done > first)
-        artDevRunBlocksInterleaved (cxt->device, calls + first, done - first, inOff + first, outOff + first,
-                                    d_input + inFirst * cxt->numChannels, d_output, stream);
+    if (done > first && artDevRunBlocksInterleaved (cxt->device, calls + first, done - first, inOff + first, outOff + first,
+                                                    d_input + inFirst * cxt->numChannels, d_output, stream)) {
+        restore_state (cxt, &atLaunch);         /* the launch failed: the blocks it covered did not happen */
+        done = first;
+    }
     free (calls);
     free (inOff);
     free (outOff);
@@ -661,6 +713,7 @@ int resampleB200SetDevice (int device) { return artDevSelect (device); }
 int resampleB200GetDeviceCount (void) { return artDevCount (); }
 
 void resampleB200Synchronize (Resample *cxt) { artDevSynchronize (cxt->device); }
+const char *resampleB200LastError (int clear) { return artDevLastError (clear); }
 unsigned long long resampleB200KernelLaunches (void) { return artDevLaunchCount (); }
 void resampleB200PathCounts (unsigned long long *generic, unsigned long long *periodic) { artDevPathCounts (generic, periodic); }
 unsigned long long resampleB200TensorLaunches (void) { return artDevTensorLaunches (); }

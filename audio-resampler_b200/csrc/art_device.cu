@@ -10,13 +10,52 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <cstdarg>
 #include <mutex>
 #include <vector>
 #include "art_kernels.cuh"
 #include "art_device.h"
 
-unsigned long long g_artLaunches = 0;
-static unsigned long long g_pathLaunches[3] = { 0, 0, 0 };     // [0] generic kernel, [1] periodic FFMA kernels, [2] tensor-core kernel
+std::atomic<unsigned long long> g_artLaunches { 0 };
+static std::atomic<unsigned long long> g_pathLaunches[3];       // [0] generic kernel, [1] periodic FFMA kernels, [2] tensor-core kernel
+
+/* ---- error model (art_kernels.cuh): message of the last failure on this thread ------------------------------- */
+static thread_local char g_lastError[512];
+static thread_local bool g_hasError = false;
+
+void artNote (const char *what)
+{
+    snprintf (g_lastError, sizeof g_lastError, "%s", what);
+    g_hasError = true;
+    fprintf (stderr, "libresampler_b200: %s\n", g_lastError);
+}
+
+void artRaiseCuda (cudaError_t code, const char *file, int line, const char *expr)
+{
+    char msg[512];
+    const char *base = strrchr (file, '/');
+    snprintf (msg, sizeof msg, "CUDA error %s at %s:%d (%s)", cudaGetErrorString (code), base ? base + 1 : file, line, expr);
+    artNote (msg);
+    throw ArtError { (int) code };
+}
+
+void artRaise (const char *fmt, ...)
+{
+    char msg[512];
+    va_list ap;
+    va_start (ap, fmt);
+    vsnprintf (msg, sizeof msg, fmt, ap);
+    va_end (ap);
+    artNote (msg);
+    throw ArtError { -1 };
+}
+
+extern "C" const char *artDevLastError (int clear)
+{
+    if (!g_hasError) return nullptr;
+    if (clear) g_hasError = false;
+    return g_lastError;
+}
 
 extern "C" void artDevPathCounts (unsigned long long *generic, unsigned long long *periodic)
 {
@@ -59,6 +98,8 @@ extern "C" void artDevProfileEnable (int on) { g_profile = on != 0; }
 
 extern "C" unsigned long long artDevProfileCollect (double *totalMs)
 {
+    if (totalMs) *totalMs = 0.0;
+    ART_GUARD_BEGIN
     std::lock_guard<std::mutex> lock (g_profMutex);
     double sum = 0.0;
     for (auto &p : g_profEvents) {
@@ -73,6 +114,7 @@ extern "C" unsigned long long artDevProfileCollect (double *totalMs)
     g_profEvents.clear ();
     if (totalMs) *totalMs = sum;
     return n;
+    ART_GUARD_END (0)
 }
 
 /* ---- filter banks are immutable and identical for equal (T, F, coefficients): share them ---- */
@@ -140,6 +182,7 @@ struct ArtDev {
     int C, T, F, mode;
     ArtBank *bank;
     cudaStream_t stream;
+    cudaStream_t lastStream;        // where the most recent device-pointer call was enqueued (reset has to wait for it)
     float *hist[2];
     int cur;
     float *d_in, *d_out;
@@ -179,6 +222,7 @@ static void use_device (const ArtDev *dev)
 
 extern "C" ArtDev *artDevCreate (int channels, int taps, int filters, int mode, const float *const *rows)
 {
+    ART_GUARD_BEGIN
     int device = 0, count = 0;
     cudaError_t e = cudaGetDeviceCount (&count);
     if (e != cudaSuccess || count == 0) {
@@ -223,6 +267,7 @@ extern "C" ArtDev *artDevCreate (int channels, int taps, int filters, int mode, 
         ART_CUDA_CHECK (cudaMemset (dev->hist[i], 0, histBytes));
     }
     dev->cur = 0;
+    dev->lastStream = nullptr;
     dev->d_in = dev->d_out = nullptr;
     dev->inCap = dev->outCap = 0;
     dev->d_stage = nullptr;
@@ -238,6 +283,7 @@ extern "C" ArtDev *artDevCreate (int channels, int taps, int filters, int mode, 
     k.absSum = dev->bank->absSum;
     k.sort = getenv ("ART_B200_NOSORT") ? 0 : 1;
     return dev;
+    ART_GUARD_END (nullptr)
 }
 
 extern "C" void artDevDestroy (ArtDev *dev)
@@ -258,11 +304,19 @@ extern "C" void artDevDestroy (ArtDev *dev)
     delete dev;
 }
 
-extern "C" void artDevReset (ArtDev *dev)
+extern "C" int artDevReset (ArtDev *dev)
 {
+    ART_GUARD_BEGIN
     use_device (dev);
+    // device-pointer calls run on the caller's stream and write the history: wait for the last one before clearing it
+    // (a stream the caller has destroyed since has nothing pending: its error is dropped)
+    if (dev->lastStream && dev->lastStream != dev->stream && cudaStreamSynchronize (dev->lastStream) != cudaSuccess)
+        (void) cudaGetLastError ();
+    dev->lastStream = nullptr;
     ART_CUDA_CHECK (cudaMemsetAsync (dev->hist[dev->cur], 0, sizeof (float) * (size_t) dev->C * dev->T, dev->stream));
     ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+    return 0;
+    ART_GUARD_END (-1)
 }
 
 extern "C" int artDevDeviceIndex (const ArtDev *dev) { return dev->device; }
@@ -281,47 +335,63 @@ extern "C" int artDevCount (void)
     return cudaGetDeviceCount (&n) == cudaSuccess ? n : 0;
 }
 
-extern "C" void artDevSynchronize (ArtDev *dev)
+extern "C" int artDevSynchronize (ArtDev *dev)
 {
+    ART_GUARD_BEGIN
     use_device (dev);
     ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+    return 0;
+    ART_GUARD_END (-1)
 }
 
-extern "C" void artDevGetHistory (ArtDev *dev, float *hostPlanar)
+extern "C" int artDevGetHistory (ArtDev *dev, float *hostPlanar)
 {
+    ART_GUARD_BEGIN
     use_device (dev);
     ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
     ART_CUDA_CHECK (cudaMemcpy (hostPlanar, dev->hist[dev->cur], sizeof (float) * (size_t) dev->C * dev->T, cudaMemcpyDeviceToHost));
+    return 0;
+    ART_GUARD_END (-1)
 }
 
 /* ---- endpoint extrapolation support (art_context.c): small synchronous transfers at a stream's start and end ---- */
-extern "C" void artDevGetHistoryOn (ArtDev *dev, float *hostPlanar, void *stream)
+extern "C" int artDevGetHistoryOn (ArtDev *dev, float *hostPlanar, void *stream)
 {
+    ART_GUARD_BEGIN
     use_device (dev);
     cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
     ART_CUDA_CHECK (cudaMemcpyAsync (hostPlanar, dev->hist[dev->cur], sizeof (float) * (size_t) dev->C * dev->T, cudaMemcpyDeviceToHost, st));
     ART_CUDA_CHECK (cudaStreamSynchronize (st));
+    return 0;
+    ART_GUARD_END (-1)
 }
 
-extern "C" void artDevPatchHistory (ArtDev *dev, int channel, int first, int count, const float *values, void *stream)
+extern "C" int artDevPatchHistory (ArtDev *dev, int channel, int first, int count, const float *values, void *stream)
 {
+    ART_GUARD_BEGIN
     use_device (dev);
     cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
     // pageable source: staged by the runtime before the call returns
     ART_CUDA_CHECK (cudaMemcpyAsync (dev->hist[dev->cur] + (size_t) channel * dev->T + first, values, sizeof (float) * (size_t) count,
                                      cudaMemcpyHostToDevice, st));
+    return 0;
+    ART_GUARD_END (-1)
 }
 
-extern "C" void artDevFetch (ArtDev *dev, const float *d_src, size_t floats, float *host, void *stream)
+extern "C" int artDevFetch (ArtDev *dev, const float *d_src, size_t floats, float *host, void *stream)
 {
+    ART_GUARD_BEGIN
     use_device (dev);
     cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
     ART_CUDA_CHECK (cudaMemcpyAsync (host, d_src, sizeof (float) * floats, cudaMemcpyDeviceToHost, st));
     ART_CUDA_CHECK (cudaStreamSynchronize (st));
+    return 0;
+    ART_GUARD_END (-1)
 }
 
 extern "C" float *artDevStage (ArtDev *dev, const float *host, size_t floats, void *stream)
 {
+    ART_GUARD_BEGIN
     use_device (dev);
     cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
     if (floats > dev->stageCap) {
@@ -332,13 +402,17 @@ extern "C" float *artDevStage (ArtDev *dev, const float *host, size_t floats, vo
     }
     ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_stage, host, sizeof (float) * floats, cudaMemcpyHostToDevice, st));
     return dev->d_stage;
+    ART_GUARD_END (nullptr)
 }
 
-extern "C" void artDevSetHistory (ArtDev *dev, const float *hostPlanar)
+extern "C" int artDevSetHistory (ArtDev *dev, const float *hostPlanar)
 {
+    ART_GUARD_BEGIN
     use_device (dev);
     ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
     ART_CUDA_CHECK (cudaMemcpy (dev->hist[dev->cur], hostPlanar, sizeof (float) * (size_t) dev->C * dev->T, cudaMemcpyHostToDevice));
+    return 0;
+    ART_GUARD_END (-1)
 }
 
 /* ---- job construction ----------------------------------------------------------------------------- */
@@ -454,45 +528,61 @@ static int append_job (const ArtLaunchPlan &lp, const ArtJob &base, std::vector<
 struct ArtXpose { const float *src; float *dst; long long frames, pitch; };
 
 __global__ void __launch_bounds__ (256)
-art_deinterleave_kernel (const ArtXpose *__restrict__ g, int C)            // dst[c * pitch + f] = src[f * C + c]
+art_deinterleave_kernel (const ArtXpose *__restrict__ g, int C, int groups)            // dst[c * pitch + f] = src[f * C + c]
 {
     __shared__ float t[32][33];
-    const ArtXpose x = g[blockIdx.z];
-    const long long f0 = (long long) blockIdx.x * 32;
-    const int c0 = blockIdx.y * 32;
-    if (f0 >= x.frames) return;
-    for (int r = threadIdx.y; r < 32; r += 8) {
-        const long long f = f0 + r;
-        const int c = c0 + threadIdx.x;
-        t[r][threadIdx.x] = (f < x.frames && c < C) ? __ldg (x.src + f * C + c) : 0.0f;
-    }
-    __syncthreads ();
-    for (int r = threadIdx.y; r < 32; r += 8) {
-        const int c = c0 + r;
-        const long long f = f0 + threadIdx.x;
-        if (c < C && f < x.frames) x.dst[(long long) c * x.pitch + f] = t[threadIdx.x][r];
+    for (int z = blockIdx.z; z < groups; z += gridDim.z) {
+        const ArtXpose x = g[z];
+        const long long f0 = (long long) blockIdx.x * 32;
+        const int c0 = blockIdx.y * 32;
+        if (f0 >= x.frames) continue;
+        for (int r = threadIdx.y; r < 32; r += 8) {
+            const long long f = f0 + r;
+            const int c = c0 + threadIdx.x;
+            t[r][threadIdx.x] = (f < x.frames && c < C) ? __ldg (x.src + f * C + c) : 0.0f;
+        }
+        __syncthreads ();
+        for (int r = threadIdx.y; r < 32; r += 8) {
+            const int c = c0 + r;
+            const long long f = f0 + threadIdx.x;
+            if (c < C && f < x.frames) x.dst[(long long) c * x.pitch + f] = t[threadIdx.x][r];
+        }
+        __syncthreads ();
     }
 }
 
 __global__ void __launch_bounds__ (256)
-art_interleave_kernel (const ArtXpose *__restrict__ g, int C)              // dst[f * C + c] = src[c * pitch + f]
+art_interleave_kernel (const ArtXpose *__restrict__ g, int C, int groups)              // dst[f * C + c] = src[c * pitch + f]
 {
     __shared__ float t[32][33];
-    const ArtXpose x = g[blockIdx.z];
-    const long long f0 = (long long) blockIdx.x * 32;
-    const int c0 = blockIdx.y * 32;
-    if (f0 >= x.frames) return;
-    for (int r = threadIdx.y; r < 32; r += 8) {
-        const int c = c0 + r;
-        const long long f = f0 + threadIdx.x;
-        t[r][threadIdx.x] = (c < C && f < x.frames) ? __ldg (x.src + (long long) c * x.pitch + f) : 0.0f;
+    for (int z = blockIdx.z; z < groups; z += gridDim.z) {
+        const ArtXpose x = g[z];
+        const long long f0 = (long long) blockIdx.x * 32;
+        const int c0 = blockIdx.y * 32;
+        if (f0 >= x.frames) continue;
+        for (int r = threadIdx.y; r < 32; r += 8) {
+            const int c = c0 + r;
+            const long long f = f0 + threadIdx.x;
+            t[r][threadIdx.x] = (c < C && f < x.frames) ? __ldg (x.src + (long long) c * x.pitch + f) : 0.0f;
+        }
+        __syncthreads ();
+        for (int r = threadIdx.y; r < 32; r += 8) {
+            const long long f = f0 + r;
+            const int c = c0 + threadIdx.x;
+            if (f < x.frames && c < C) x.dst[f * C + c] = t[threadIdx.x][r];
+        }
+        __syncthreads ();
     }
-    __syncthreads ();
-    for (int r = threadIdx.y; r < 32; r += 8) {
-        const long long f = f0 + r;
-        const int c = c0 + threadIdx.x;
-        if (f < x.frames && c < C) x.dst[f * C + c] = t[threadIdx.x][r];
-    }
+}
+
+/* region index of the first input frame that output n of a job reads (the start of its window) */
+static long long first_frame_read (const ArtJob &j, int T, unsigned int n)
+{
+    ArtLoopState st;
+    st.P = j.P; st.ratio = j.ratio; st.I = j.I; st.T = T;
+    int w;
+    const double pos = art_output_pos (&st, n, &w);
+    return (long long) floor (pos) - T / 2 + 1 + (long long) w * 15LL * T - j.origin;
 }
 
 static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cudaStream_t stream, ArtDev *owner = nullptr)
@@ -519,33 +609,48 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
             std::vector<int> groupOf (n, 0);                     // which call (scratch pair) a segment belongs to
             for (int i = 0; i < n; ) {
                 int e = i;
-                long long outFrames = 0;
+                long long outFrames = 0, outFirst = -1, inFirst = -1;
                 while (e < n && jobs[e].in == jobs[i].in && jobs[e].out == jobs[i].out) {
                     const long long end = (long long) jobs[e].nStart + jobs[e].outputs;
                     if (end > outFrames) outFrames = end;
+                    if (jobs[e].outputs) {
+                        // a piece of a pipelined host call starts at nStart > 0: frames before that belong to earlier pieces
+                        // (already on their way to the host) and must neither be transposed in nor written back
+                        if (outFirst < 0 || (long long) jobs[e].nStart < outFirst) outFirst = jobs[e].nStart;
+                        const long long s0 = first_frame_read (jobs[e], lp.k.T, jobs[e].nStart);
+                        if (inFirst < 0 || s0 < inFirst) inFirst = s0;
+                    }
+                    if (jobs[e].histOut) {
+                        const long long h0 = (long long) jobs[e].consumed - lp.k.T;
+                        if (inFirst < 0 || h0 < inFirst) inFirst = h0;
+                    }
                     ++e;
                 }
+                if (outFirst < 0) outFirst = 0;
+                inFirst = inFirst < 64 ? 0 : ((inFirst - 32) & ~31LL);            // a margin, and whole 128-byte lines
                 const long long inFrames = jobs[i].inValid > 0 ? jobs[i].inValid : 0;
+                if (inFirst > inFrames) inFirst = inFrames;
                 const long long inPitch = (inFrames + 31) & ~31LL, outPitch = (outFrames + 31) & ~31LL;
-                xin.push_back ({ jobs[i].in, nullptr, inFrames, inPitch });
-                xout.push_back ({ nullptr, jobs[i].out, outFrames, outPitch });
+                // src/dst are offset so that scratch index f still means frame f of the call
+                xin.push_back ({ jobs[i].in + inFirst * C, reinterpret_cast<float *> (inFirst), inFrames - inFirst, inPitch });
+                xout.push_back ({ reinterpret_cast<const float *> (outFirst), jobs[i].out + outFirst * C, outFrames - outFirst, outPitch });
                 inAt.push_back (floats); floats += (size_t) C * inPitch;
                 outAt.push_back (floats); floats += (size_t) C * outPitch;
-                if (inFrames > maxInFrames) maxInFrames = inFrames;
-                if (outFrames > maxOutFrames) maxOutFrames = outFrames;
+                if (inFrames - inFirst > maxInFrames) maxInFrames = inFrames - inFirst;
+                if (outFrames - outFirst > maxOutFrames) maxOutFrames = outFrames - outFirst;
                 for (int q = i; q < e; ++q) groupOf[q] = (int) xin.size () - 1;
                 i = e;
             }
             ART_CUDA_CHECK (cudaMallocAsync (&scratch, floats * sizeof (float), stream));
-            for (size_t gi = 0; gi < xin.size (); ++gi) {
-                xin[gi].dst = scratch + inAt[gi];
-                xout[gi].src = scratch + outAt[gi];
-            }
             for (int q = 0; q < n; ++q) {
                 ArtJob &j = jobs[q];
-                const ArtXpose &a = xin[groupOf[q]], &b = xout[groupOf[q]];
-                j.in = a.dst;  j.inFS = 1;  j.inCS = a.pitch;
-                j.out = const_cast<float *> (b.src); j.outFS = 1; j.outCS = b.pitch;
+                const int gi = groupOf[q];
+                j.in = scratch + inAt[gi];   j.inFS = 1;  j.inCS = xin[gi].pitch;
+                j.out = scratch + outAt[gi]; j.outFS = 1; j.outCS = xout[gi].pitch;
+            }
+            for (size_t gi = 0; gi < xin.size (); ++gi) {              // the offsets parked in dst / src above
+                xin[gi].dst = scratch + inAt[gi] + reinterpret_cast<long long> (xin[gi].dst);
+                xout[gi].src = scratch + outAt[gi] + reinterpret_cast<long long> (xout[gi].src);
             }
             const size_t ng = xin.size ();
             std::vector<ArtXpose> both (xin);
@@ -553,8 +658,8 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
             ART_CUDA_CHECK (cudaMallocAsync (&d_xpose, both.size () * sizeof (ArtXpose), stream));
             ART_CUDA_CHECK (cudaMemcpyAsync (d_xpose, both.data (), both.size () * sizeof (ArtXpose), cudaMemcpyHostToDevice, stream));
             if (maxInFrames > 0) {
-                const dim3 grid ((unsigned int) ((maxInFrames + 31) / 32), (unsigned int) ((C + 31) / 32), (unsigned int) ng);
-                art_deinterleave_kernel<<<grid, dim3 (32, 8), 0, stream>>> (d_xpose, C);
+                const dim3 grid ((unsigned int) ((maxInFrames + 31) / 32), (unsigned int) ((C + 31) / 32), (unsigned int) (ng < 65535 ? ng : 65535));
+                art_deinterleave_kernel<<<grid, dim3 (32, 8), 0, stream>>> (d_xpose, C, (int) ng);
                 ART_CUDA_CHECK (cudaGetLastError ());
                 ++g_artLaunches;
             }
@@ -631,13 +736,18 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
             ++g_pathLaunches[0];
         }
     }
-    if (anyHist)
-        artLaunchHistory (lp.k, jobs[0], d_jobs, n, stream);
+    if (anyHist) {
+        // usually one job carries the history update (the last block of an ASRC sequence, a single call): pass it by value
+        int carriers = 0, which = 0;
+        for (int i = 0; i < n; ++i) if (jobs[i].histOut) { ++carriers; which = i; }
+        if (carriers == 1) artLaunchHistory (lp.k, jobs[which], nullptr, 1, stream);
+        else artLaunchHistory (lp.k, jobs[0], d_jobs, n, stream);
+    }
     if (scratch) {
         if (maxOutFrames > 0) {
             const size_t ng = xin.size ();
-            const dim3 grid ((unsigned int) ((maxOutFrames + 31) / 32), (unsigned int) ((C + 31) / 32), (unsigned int) ng);
-            art_interleave_kernel<<<grid, dim3 (32, 8), 0, stream>>> (d_xpose + ng, C);
+            const dim3 grid ((unsigned int) ((maxOutFrames + 31) / 32), (unsigned int) ((C + 31) / 32), (unsigned int) (ng < 65535 ? ng : 65535));
+            art_interleave_kernel<<<grid, dim3 (32, 8), 0, stream>>> (d_xpose + ng, C, (int) ng);
             ART_CUDA_CHECK (cudaGetLastError ());
             ++g_artLaunches;
         }
@@ -680,8 +790,9 @@ static void reserve (ArtDev *dev, size_t inFloats, size_t outFloats)
  * needs the input frames up to art_inputs_before(last output of c), so its upload, its kernels and its
  * download form a three-stage pipeline across pieces.  The samples are the same as for one big launch:
  * every output is evaluated from (P, I, n) alone. */
-extern "C" void artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, const float *in, float *out)
+extern "C" int artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, const float *in, float *out)
 {
+    ART_GUARD_BEGIN
     use_device (dev);
     const size_t C = dev->C;
     const size_t inFloats = (size_t) plan->inValid * C, outFloats = (size_t) plan->outputs * C;
@@ -706,7 +817,7 @@ extern "C" void artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, 
         if (outFloats)
             ART_CUDA_CHECK (cudaMemcpyAsync (out, dev->d_out, outFloats * sizeof (float), cudaMemcpyDeviceToHost, dev->stream));
         ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
-        return;
+        return 0;
     }
 
     host_pipe_init (dev, 2 * (size_t) pieces);
@@ -747,18 +858,21 @@ extern "C" void artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, 
     finish_job (dev, *plan);
     ART_CUDA_CHECK (cudaStreamSynchronize (dev->sOut));
     ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+    return 0;
+    ART_GUARD_END (-1)
 }
 
 /* Many contexts, host memory, interleaved: the same three-stage pipeline over groups of contexts -- a
  * group's uploads, one launch for the group, its downloads (group size 1 measured best on B200: 64 us
  * per 2 MB stereo stream against a PCIe floor of 42 us). */
-extern "C" void artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
+extern "C" int artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
                                            const float *const *d_in, float *const *d_out, void *stream);
 
-extern "C" void artDevRunHostBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
+extern "C" int artDevRunHostBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
                                                const float *const *in, float *const *out)
 {
-    if (count <= 0) return;
+    ART_GUARD_BEGIN
+    if (count <= 0) return 0;
     ArtDev *lead = devs[0];
     use_device (lead);
     const int group = 1;                   // measured: larger groups coarsen the pipeline more than they save
@@ -772,10 +886,8 @@ extern "C" void artDevRunHostBatchInterleaved (ArtDev *const *devs, const ArtCal
         for (int i = i0; i < i1; ++i) {
             ArtDev *dev = devs[i];
             const ArtCallPlan &p = plans[i];
-            if (dev->device != lead->device) {
-                fprintf (stderr, "libresampler_b200: a batch must live on one GPU\n");
-                abort ();
-            }
+            if (dev->device != lead->device)
+                artRaise ("a batch must live on one GPU");
             const size_t inFloats = (size_t) p.inValid * C, outFloats = (size_t) p.outputs * C;
             reserve (dev, inFloats, outFloats);
             dIn[i] = dev->d_in;
@@ -785,7 +897,8 @@ extern "C" void artDevRunHostBatchInterleaved (ArtDev *const *devs, const ArtCal
         }
         ART_CUDA_CHECK (cudaEventRecord (lead->events[2 * g], lead->sIn));
         ART_CUDA_CHECK (cudaStreamWaitEvent (lead->stream, lead->events[2 * g], 0));
-        artDevRunBatchInterleaved (devs + i0, plans + i0, i1 - i0, dIn.data () + i0, dOut.data () + i0, lead->stream);
+        if (artDevRunBatchInterleaved (devs + i0, plans + i0, i1 - i0, dIn.data () + i0, dOut.data () + i0, lead->stream))
+            throw ArtError { -1 };
         ART_CUDA_CHECK (cudaEventRecord (lead->events[2 * g + 1], lead->stream));
         ART_CUDA_CHECK (cudaStreamWaitEvent (lead->sOut, lead->events[2 * g + 1], 0));
         for (int i = i0; i < i1; ++i) {
@@ -796,10 +909,13 @@ extern "C" void artDevRunHostBatchInterleaved (ArtDev *const *devs, const ArtCal
     }
     ART_CUDA_CHECK (cudaStreamSynchronize (lead->sOut));
     ART_CUDA_CHECK (cudaStreamSynchronize (lead->stream));
+    return 0;
+    ART_GUARD_END (-1)
 }
 
-extern "C" void artDevRunHostPlanar (ArtDev *dev, const ArtCallPlan *plan, const float *const *in, float *const *out)
+extern "C" int artDevRunHostPlanar (ArtDev *dev, const ArtCallPlan *plan, const float *const *in, float *const *out)
 {
+    ART_GUARD_BEGIN
     use_device (dev);
     const size_t C = dev->C;
     const size_t nin = plan->inValid, nout = plan->outputs;
@@ -814,25 +930,33 @@ extern "C" void artDevRunHostPlanar (ArtDev *dev, const ArtCallPlan *plan, const
     for (size_t c = 0; c < C && nout; ++c)
         ART_CUDA_CHECK (cudaMemcpyAsync (out[c], dev->d_out + c * nout, nout * sizeof (float), cudaMemcpyDeviceToHost, dev->stream));
     ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+    return 0;
+    ART_GUARD_END (-1)
 }
 
 /* ---- device-memory entry points ------------------------------------------------------------------------ */
 
-extern "C" void artDevRunDeviceInterleaved (ArtDev *dev, const ArtCallPlan *plan, const float *d_in, float *d_out, void *stream)
+extern "C" int artDevRunDeviceInterleaved (ArtDev *dev, const ArtCallPlan *plan, const float *d_in, float *d_out, void *stream)
 {
+    ART_GUARD_BEGIN
     use_device (dev);
     cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
+    dev->lastStream = st;
     ArtJob job;
     fill_job (dev, *plan, job);
     job.in = d_in;   job.inFS = dev->C;  job.inCS = 1;
     job.out = d_out; job.outFS = dev->C; job.outCS = 1;
     run_single (dev, *plan, job, st);
+    return 0;
+    ART_GUARD_END (-1)
 }
 
-extern "C" void artDevRunDevicePlanar (ArtDev *dev, const ArtCallPlan *plan, const float *const *d_in, float *const *d_out, void *stream)
+extern "C" int artDevRunDevicePlanar (ArtDev *dev, const ArtCallPlan *plan, const float *const *d_in, float *const *d_out, void *stream)
 {
+    ART_GUARD_BEGIN
     use_device (dev);
     cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
+    dev->lastStream = st;
     const int C = dev->C;
     ArtJob job;
     fill_job (dev, *plan, job);
@@ -861,14 +985,17 @@ extern "C" void artDevRunDevicePlanar (ArtDev *dev, const ArtCallPlan *plan, con
     run_single (dev, *plan, job, st);
     if (table)
         ART_CUDA_CHECK (cudaFreeAsync (table, st));
+    return 0;
+    ART_GUARD_END (-1)
 }
 
 /* ---- many contexts, one launch ----------------------------------------------------------------------------- */
 
-extern "C" void artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
+extern "C" int artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
                                            const float *const *d_in, float *const *d_out, void *stream)
 {
-    if (count <= 0) return;
+    ART_GUARD_BEGIN
+    if (count <= 0) return 0;
     ArtDev *lead = devs[0];
     use_device (lead);
     cudaStream_t st = stream ? (cudaStream_t) stream : lead->stream;
@@ -878,10 +1005,8 @@ extern "C" void artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPla
     unsigned int maxOut = 0;
     unsigned long long totalOut = 0;
     for (int i = 0; i < count; ++i) {
-        if (devs[i]->bank != lead->bank || devs[i]->C != lead->C || devs[i]->mode != lead->mode || devs[i]->device != lead->device) {
-            fprintf (stderr, "libresampler_b200: a batch must hold contexts of one configuration on one GPU\n");
-            abort ();
-        }
+        if (devs[i]->bank != lead->bank || devs[i]->C != lead->C || devs[i]->mode != lead->mode || devs[i]->device != lead->device)
+            artRaise ("a batch must hold contexts of one configuration on one GPU");
         if (plans[i].st.ratio != plans[0].st.ratio) oneRatio = false;
         if (plans[i].st.ratio < minRatio) minRatio = plans[i].st.ratio;
         if (plans[i].outputs > maxOut) maxOut = plans[i].outputs;
@@ -898,22 +1023,27 @@ extern "C" void artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPla
         fill_job (devs[i], plans[i], j);
         j.in = d_in ? d_in[i] : nullptr;  j.inFS = lead->C;  j.inCS = 1;
         j.out = d_out[i];                 j.outFS = lead->C; j.outCS = 1;
+        devs[i]->lastStream = st;
         ctas += append_job (lp, j, jobs, ctas);
     }
     dispatch (lp, jobs, ctas, st, count == 1 ? lead : nullptr);
     for (int i = 0; i < count; ++i)
         finish_job (devs[i], plans[i]);
+    return 0;
+    ART_GUARD_END (-1)
 }
 
 /* ---- consecutive blocks of one stream, one launch (ASRC) ------------------------------------------------------ */
 
-extern "C" void artDevRunBlocksInterleaved (ArtDev *dev, const ArtCallPlan *plans, int count,
+extern "C" int artDevRunBlocksInterleaved (ArtDev *dev, const ArtCallPlan *plans, int count,
                                             const long long *inOffset, const long long *outOffset,
                                             const float *d_in, float *d_out, void *stream)
 {
-    if (count <= 0) return;
+    ART_GUARD_BEGIN
+    if (count <= 0) return 0;
     use_device (dev);
     cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
+    dev->lastStream = st;
     const int C = dev->C;
 
     double minRatio = plans[0].st.ratio;
@@ -956,4 +1086,6 @@ extern "C" void artDevRunBlocksInterleaved (ArtDev *dev, const ArtCallPlan *plan
     dispatch (lp, jobs, ctas, st);
     if (totalIn)
         dev->cur ^= 1;
+    return 0;
+    ART_GUARD_END (-1)
 }

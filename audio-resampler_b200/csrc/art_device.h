@@ -10,8 +10,10 @@
  *                16*T ring of resampler.c:139,171-174), the filter bank, the convolution.
  *
  * There is no CPU implementation of any of these: when no usable CUDA device exists
- * artDevCreate() reports the CUDA error and returns NULL, and every later entry point
- * aborts on a CUDA error rather than returning silence.
+ * artDevCreate() reports the CUDA error and returns NULL.  Later failures (a CUDA error, an
+ * allocation that does not fit, an unsupported request) never take the process down: the
+ * entry point prints the message once, keeps it for artDevLastError(), and returns non-zero
+ * (NULL for the pointer-valued ones); the caller's buffers are then unspecified.
  */
 #ifndef ART_DEVICE_H
 #define ART_DEVICE_H
@@ -42,41 +44,44 @@ enum {
 
 ArtDev *artDevCreate (int channels, int taps, int filters, int mode, const float *const *rows);
 void    artDevDestroy (ArtDev *dev);
-void    artDevReset (ArtDev *dev);                   /* zero the history (resampler.c:387-388) */
+int     artDevReset (ArtDev *dev);                   /* zero the history (resampler.c:387-388) */
 int     artDevDeviceIndex (const ArtDev *dev);
 int     artDevSelect (int device);                   /* cudaSetDevice; 0 on success            */
 int     artDevCount (void);                          /* usable CUDA devices, 0 when none       */
 
 /* Host-memory entry points: stage in, run, stage out, synchronise. */
-void artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, const float *in, float *out);
-void artDevRunHostPlanar (ArtDev *dev, const ArtCallPlan *plan, const float *const *in, float *const *out);
-void artDevRunHostBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
+int  artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, const float *in, float *out);
+int  artDevRunHostPlanar (ArtDev *dev, const ArtCallPlan *plan, const float *const *in, float *const *out);
+int  artDevRunHostBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
                                     const float *const *in, float *const *out);
 
 /* Device-memory entry points: enqueue on `stream` (a cudaStream_t, NULL = the context's
  * own stream) and return without synchronising. */
-void artDevRunDeviceInterleaved (ArtDev *dev, const ArtCallPlan *plan, const float *d_in, float *d_out, void *stream);
-void artDevRunDevicePlanar (ArtDev *dev, const ArtCallPlan *plan, const float *const *d_in, float *const *d_out, void *stream);
+int  artDevRunDeviceInterleaved (ArtDev *dev, const ArtCallPlan *plan, const float *d_in, float *d_out, void *stream);
+int  artDevRunDevicePlanar (ArtDev *dev, const ArtCallPlan *plan, const float *const *d_in, float *const *d_out, void *stream);
 
 /* Many contexts of one configuration in a single launch (device memory, interleaved). */
-void artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
+int  artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
                                 const float *const *d_in, float *const *d_out, void *stream);
 
 /* Consecutive blocks of ONE stream, each with its own ratio (ASRC), in a single launch.
  * Block b reads d_in + inOffset[b]*channels; the frames before it in the same buffer are
  * its history.  Only valid when every block consumed all of its input. */
-void artDevRunBlocksInterleaved (ArtDev *dev, const ArtCallPlan *plans, int count,
+int  artDevRunBlocksInterleaved (ArtDev *dev, const ArtCallPlan *plans, int count,
                                  const long long *inOffset, const long long *outOffset,
                                  const float *d_in, float *d_out, void *stream);
 
-void artDevSynchronize (ArtDev *dev);
-void artDevGetHistory (ArtDev *dev, float *hostPlanar);        /* [channels][taps], for tests/extrapolation */
-void artDevSetHistory (ArtDev *dev, const float *hostPlanar);
+int  artDevSynchronize (ArtDev *dev);
+int  artDevGetHistory (ArtDev *dev, float *hostPlanar);        /* [channels][taps], for tests/extrapolation */
+int  artDevSetHistory (ArtDev *dev, const float *hostPlanar);
 /* endpoint extrapolation: small synchronous transfers at a stream's start and end (stream NULL = the context's own) */
-void artDevGetHistoryOn (ArtDev *dev, float *hostPlanar, void *stream);
-void artDevPatchHistory (ArtDev *dev, int channel, int first, int count, const float *values, void *stream);
-void artDevFetch (ArtDev *dev, const float *d_src, size_t floats, float *host, void *stream);
+int  artDevGetHistoryOn (ArtDev *dev, float *hostPlanar, void *stream);
+int  artDevPatchHistory (ArtDev *dev, int channel, int first, int count, const float *values, void *stream);
+int  artDevFetch (ArtDev *dev, const float *d_src, size_t floats, float *host, void *stream);
 float *artDevStage (ArtDev *dev, const float *host, size_t floats, void *stream);     /* returns the device copy */
+
+/* message of the last failure on the calling thread, or NULL; clear != 0 forgets it */
+const char *artDevLastError (int clear);
 
 /* statistics for bench.py's gpu_launches claim and roofline leg */
 unsigned long long artDevLaunchCount (void);
@@ -96,7 +101,7 @@ typedef struct {
 /* buffer: host or device memory holding frames*stride floats; channel c of stage-set s uses
  * stages[s*channels + c] and samples buffer[c + f*stride].  States are read from and written
  * back to `stages` (host memory).  onDevice selects the address space of `buffer`. */
-void artBiquadRun (ArtBiquadStage *stages, int numStages, int channels, float *buffer,
+int  artBiquadRun (ArtBiquadStage *stages, int numStages, int channels, float *buffer,
                    long long frames, int stride, int onDevice, void *stream);
 
 #ifdef __cplusplus

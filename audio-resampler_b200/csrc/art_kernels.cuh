@@ -23,6 +23,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <exception>
+#include <atomic>
 #include "art_plan.h"
 
 struct ArtJob {
@@ -175,19 +177,28 @@ void artUmmaCarve (ArtUmma &u, void *tables, int numTables, int numJobs);
 void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int numJobs, int numTables, int smCount,
                     const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream);
 
-extern unsigned long long g_artLaunches;
+extern std::atomic<unsigned long long> g_artLaunches;
 extern int g_artTensorMode;
 
 /* per-kernel event timing, active only after artDevProfileEnable(1) */
 void artProfileBegin (cudaStream_t stream, void **token);
 void artProfileEnd (cudaStream_t stream, void *token);
 
+/* Error model: no CUDA failure may take the caller's process down.  A failed runtime call (or an unsupported request)
+ * records a message (artDevLastError), prints it once to stderr -- as the reference does for its own init errors,
+ * resampler.c:127-135 -- and unwinds to the extern "C" entry point, which reports failure to art_context.c. */
+struct ArtError { int code; };
+[[noreturn]] void artRaiseCuda (cudaError_t code, const char *file, int line, const char *expr);
+[[noreturn]] void artRaise (const char *fmt, ...);
+
 #define ART_CUDA_CHECK(expr)                                                                  \
     do {                                                                                      \
         cudaError_t e_ = (expr);                                                              \
-        if (e_ != cudaSuccess) {                                                              \
-            fprintf (stderr, "libresampler_b200: CUDA error %s at %s:%d (%s)\n",             \
-                     cudaGetErrorString (e_), __FILE__, __LINE__, #expr);                     \
-            abort ();                                                                         \
-        }                                                                                     \
+        if (e_ != cudaSuccess)                                                                \
+            artRaiseCuda (e_, __FILE__, __LINE__, #expr);                                     \
     } while (0)
+
+/* every extern "C" entry point of the CUDA translation units is bracketed by these */
+#define ART_GUARD_BEGIN try {
+#define ART_GUARD_END(onError) } catch (const ArtError &) { return onError; } catch (const std::exception &e_) { artNote (e_.what ()); return onError; }
+void artNote (const char *what);

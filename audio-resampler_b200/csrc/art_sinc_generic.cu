@@ -424,15 +424,17 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
 }
 
 /* ---- history: the newest T consumed samples of every channel ------------------------------- */
-__global__ void art_history_kernel (const ArtClass k, const __grid_constant__ ArtJob single, const ArtJob *__restrict__ jobs)
+__global__ void art_history_kernel (const ArtClass k, const __grid_constant__ ArtJob single, const ArtJob *__restrict__ jobs, int numJobs)
 {
-    const ArtJob &job = jobs ? jobs[blockIdx.y] : single;
-    if (!job.histOut)
-        return;
     const int total = k.C * k.T;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-        const int c = e / k.T, i = e - c * k.T;
-        job.histOut[e] = art_fetch (job, k.T, c, job.consumed - k.T + i);
+    for (int jb = blockIdx.y; jb < numJobs; jb += gridDim.y) {            // grid.y is capped at 65535
+        const ArtJob &job = jobs ? jobs[jb] : single;
+        if (!job.histOut)
+            continue;
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+            const int c = e / k.T, i = e - c * k.T;
+            job.histOut[e] = art_fetch (job, k.T, c, job.consumed - k.T + i);
+        }
     }
 }
 
@@ -485,9 +487,7 @@ void artPlanGenericGeometry (ArtClass &k, double minRatio, unsigned int maxOutpu
             if (score > bestScore) { bestScore = score; bestNB = NB; bestCg = Cg; }
         }
     if (!bestNB) {
-        fprintf (stderr, "libresampler_b200: ratio %g needs a %d-float window per output; unsupported\n",
-                 minRatio, plane_floats (1, minRatio, k.Tp));
-        abort ();
+        artRaise ("ratio %g needs a %d-float window per output; unsupported", minRatio, plane_floats (1, minRatio, k.Tp));
     }
     k.NB = bestNB;
     k.Cg = bestCg;
@@ -538,8 +538,9 @@ void artLaunchGeneric (const ArtClass &k, const ArtLaunchGeom &g, const ArtJob &
 void artLaunchHistory (const ArtClass &k, const ArtJob &single, const ArtJob *d_jobs, int numJobs, cudaStream_t stream)
 {
     const int total = k.C * k.T;
-    dim3 grid ((total + 255) / 256 > 64 ? 64 : (total + 255) / 256, numJobs);
-    art_history_kernel<<<grid, 256, 0, stream>>> (k, single, d_jobs);
+    if (!d_jobs) numJobs = 1;
+    dim3 grid ((total + 255) / 256 > 64 ? 64 : (total + 255) / 256, numJobs < 65535 ? numJobs : 65535);
+    art_history_kernel<<<grid, 256, 0, stream>>> (k, single, d_jobs, numJobs);
     ART_CUDA_CHECK (cudaGetLastError ());
     ++g_artLaunches;
 }

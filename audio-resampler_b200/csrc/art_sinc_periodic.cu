@@ -543,7 +543,8 @@ bool artPlanPeriodic (const ArtClass &k, double ratio, unsigned int maxOutputs, 
     }
     p.Qblk = p.Qc * bestChunks;
 
-    // experiment knobs (profiling only): ART_P_ROWS / ART_P_QC / ART_P_CHUNKS override the choice
+    // experiment knobs (measurement builds only): ART_P_ROWS / ART_P_QC / ART_P_CHUNKS override the choice
+#ifdef ART_B200_ABLATE
     if (const char *e = getenv ("ART_P_ROWS")) {
         p.rowsPerCta = atoi (e);
         const int spread = (int) (((long long) (p.rowsPerCta * 8 - 1) * M + L - 1) / L) + 2;
@@ -551,9 +552,12 @@ bool artPlanPeriodic (const ArtClass &k, double ratio, unsigned int maxOutputs, 
         p.PB = (R + p.rowsPerCta - 1) / p.rowsPerCta;
     }
     if (const char *e = getenv ("ART_P_QC")) p.Qc = atoi (e);
+#endif
     p.Wc = (p.Qc - 1) * M + p.Kp;
     p.Qblk = p.Qc * bestChunks;
+#ifdef ART_B200_ABLATE
     if (const char *e = getenv ("ART_P_CHUNKS")) p.Qblk = p.Qc * atoi (e);
+#endif
     if (periodic_smem (p, CV) > 200 * 1024) return false;
     if (getenv ("ART_B200_TRACE"))
         fprintf (stderr, "[art] periodic L=%d M=%d rows=%d Kp=%d Qc=%d Qblk=%d PB=%d CV=%d smem=%zu\n",

@@ -186,7 +186,9 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
     int b = blockIdx.x;
     const int T = k.T, half = T / 2, F = k.F;
     if (b < tableBlocks) {
+#ifdef ART_B200_ABLATE
         if (dbg & 16) return;
+#endif
         const int tg = b / u.Npad, j = b - tg * u.Npad;                 // (table, phase group), phase inside the group
         const int tbl = tg / u.G, grp = tg - tbl * u.G;
         const int ph0 = grp * u.Lg, phj = ph0 + j;                      // the group's first phase, this phase
@@ -412,7 +414,12 @@ __global__ void __launch_bounds__ (ART_U_THREADS, 1)
 art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const __grid_constant__ ArtJob single,
                       const ArtJob *__restrict__ jobs, int totalTiles, int profArg)
 {
-    const int prof = profArg & 1, dbg = profArg >> 4;
+    const int prof = profArg & 1;
+#ifdef ART_B200_ABLATE              /* measurement builds only: bits that SKIP work (wrong results by construction) */
+    const int dbg = profArg >> 4;
+#else
+    constexpr int dbg = 0;
+#endif
     extern __shared__ __align__ (1024) unsigned char smem[];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -936,9 +943,7 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
         cudaFuncAttributes fa;
         ART_CUDA_CHECK (cudaFuncGetAttributes (&fa, art_sinc_umma_kernel));
         if (128 * (fa.numRegs - 56) + 256 * (fa.numRegs - 88) < 256 * (120 - fa.numRegs) || fa.numRegs < 88 || fa.numRegs > 120) {
-            fprintf (stderr, "libresampler_b200: art_sinc_umma_kernel was compiled with %d registers per thread: its register re-allocation "
-                     "plan does not hold\n", fa.numRegs);
-            abort ();
+            artRaise ("art_sinc_umma_kernel was compiled with %d registers per thread: its register re-allocation plan does not hold", fa.numRegs);
         }
         ART_CUDA_CHECK (cudaFuncSetAttribute (art_sinc_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         configured[device & 15] = true;
@@ -950,14 +955,21 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
     uu.tileJob = u.tileExp + totalTiles;
     ART_CUDA_CHECK (cudaMemsetAsync (u.tileExp, 0, (size_t) totalTiles * sizeof (int), stream));
     static int prepDbg = -1;
-    if (prepDbg < 0) { const char *d = getenv ("ART_B200_UDBG"); prepDbg = d ? atoi (d) : 0; }
+    if (prepDbg < 0) {
+        prepDbg = 0;
+#ifdef ART_B200_ABLATE
+        if (const char *d = getenv ("ART_B200_UDBG")) prepDbg = atoi (d);
+#endif
+    }
     art_umma_prep_kernel<<<prepBlocks, 128, 0, stream>>> (k, uu, single, d_jobs, numJobs, numTables, histBlocks, totalTiles, prepDbg);
     ART_CUDA_CHECK (cudaGetLastError ());
     const int grid = totalTiles < smCount ? totalTiles : smCount;
     static int roleProf = -1;
     if (roleProf < 0) {
         roleProf = getenv ("ART_B200_UPROF") ? 1 : 0;
+#ifdef ART_B200_ABLATE
         if (const char *d = getenv ("ART_B200_UDBG")) roleProf |= atoi (d) << 4;
+#endif
         if (roleProf & 1) atexit ([] () {
             unsigned long long h[16];
             cudaDeviceSynchronize ();

@@ -7,6 +7,10 @@
  * but take DEVICE pointers, enqueue on a CUDA stream and return without synchronising.
  * `stream` is a cudaStream_t passed as void* (NULL = the context's private stream); no CUDA
  * or torch type appears in any signature.
+ *
+ * Stream discipline: the calls on ONE context must be ordered -- use one stream per context, or
+ * synchronise between streams yourself (the context's history and its filter tables are written
+ * by every call).  resampleReset() waits for the stream the context last ran on.
  */
 #ifndef ART_B200_EXT_H
 #define ART_B200_EXT_H
@@ -24,6 +28,12 @@ int  resampleB200SetDevice (int device);                 /* 0 on success */
 int  resampleB200GetDeviceCount (void);
 void resampleB200Synchronize (Resample *cxt);            /* wait for the context's private stream */
 unsigned long long resampleB200KernelLaunches (void);    /* kernels launched by this library so far */
+/* Error reporting.  The reference API has no error codes (resampler.h:64-78): init returns NULL after a message on stderr,
+ * process calls "never fail".  Here a process call can fail (CUDA error, out of device memory, a batch that mixes
+ * configurations): the library then prints the message once, leaves the context's position where it was, reports
+ * input_used = output_generated = 0 -- and never aborts the caller's process.  LastError returns the message of the most
+ * recent failure on the calling thread (NULL when there was none); clear != 0 forgets it. */
+const char *resampleB200LastError (int clear);
 /* how many convolution launches went to the any-ratio kernel and to the rational-ratio kernel */
 void resampleB200PathCounts (unsigned long long *generic, unsigned long long *periodic);
 /* The rational-ratio path has two forms: FFMA kernels, and a tensor-core (tcgen05) kernel used for interpolating contexts

@@ -194,6 +194,7 @@ struct ArtDev {
     // both directions overlaps the convolution (created on first use)
     cudaStream_t sIn, sOut;
     std::vector<cudaEvent_t> events;
+    cudaEvent_t doneEvent;          // blocking-sync event: large host calls sleep on it instead of spinning on the stream
     // phase tables of single-job periodic launches: reused from call to call (calls on one context are
     // stream-ordered), so the latency path has no allocation in it
     void *tableBuf;
@@ -211,6 +212,22 @@ static void host_pipe_init (ArtDev *dev, size_t events)
         ART_CUDA_CHECK (cudaEventCreateWithFlags (&e, cudaEventDisableTiming));
         dev->events.push_back (e);
     }
+}
+
+/* Wait for a host call's last transfer.  cudaStreamSynchronize spins a core (the runtime's default schedule); that is the
+ * lowest latency for a 50-us call, but a process that keeps several large calls in flight from several threads -- and eight
+ * such processes on one host -- would burn every core on polling.  Calls that move more than ~1 MB sleep on an event
+ * created with cudaEventBlockingSync instead: the wake-up costs a few microseconds against >= 50 us of transfer. */
+static void wait_for (ArtDev *dev, cudaStream_t stream, size_t bytesMoved)
+{
+    if (bytesMoved < (1u << 20)) {
+        ART_CUDA_CHECK (cudaStreamSynchronize (stream));
+        return;
+    }
+    if (!dev->doneEvent)
+        ART_CUDA_CHECK (cudaEventCreateWithFlags (&dev->doneEvent, cudaEventBlockingSync | cudaEventDisableTiming));
+    ART_CUDA_CHECK (cudaEventRecord (dev->doneEvent, stream));
+    ART_CUDA_CHECK (cudaEventSynchronize (dev->doneEvent));
 }
 
 static void use_device (const ArtDev *dev)
@@ -273,6 +290,7 @@ extern "C" ArtDev *artDevCreate (int channels, int taps, int filters, int mode, 
     dev->d_stage = nullptr;
     dev->stageCap = 0;
     dev->sIn = dev->sOut = nullptr;
+    dev->doneEvent = nullptr;
     dev->tableBuf = nullptr;
     dev->tableCap = 0;
 
@@ -300,6 +318,7 @@ extern "C" void artDevDestroy (ArtDev *dev)
     cudaStreamDestroy (dev->stream);
     if (dev->sIn) { cudaStreamDestroy (dev->sIn); cudaStreamDestroy (dev->sOut); }
     for (cudaEvent_t e : dev->events) cudaEventDestroy (e);
+    if (dev->doneEvent) cudaEventDestroy (dev->doneEvent);
     bank_release (dev->bank);
     delete dev;
 }
@@ -816,7 +835,7 @@ extern "C" int artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, c
         run_single (dev, *plan, job, dev->stream);
         if (outFloats)
             ART_CUDA_CHECK (cudaMemcpyAsync (out, dev->d_out, outFloats * sizeof (float), cudaMemcpyDeviceToHost, dev->stream));
-        ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+        wait_for (dev, dev->stream, (inFloats + outFloats) * sizeof (float));
         return 0;
     }
 
@@ -856,8 +875,8 @@ extern "C" int artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, c
                                              cudaMemcpyDeviceToHost, dev->sOut));
     }
     finish_job (dev, *plan);
-    ART_CUDA_CHECK (cudaStreamSynchronize (dev->sOut));
-    ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+    // the last download was enqueued after everything else of this call (sOut waits for the last kernel)
+    wait_for (dev, dev->sOut, (inFloats + outFloats) * sizeof (float));
     return 0;
     ART_GUARD_END (-1)
 }
@@ -907,8 +926,9 @@ extern "C" int artDevRunHostBatchInterleaved (ArtDev *const *devs, const ArtCall
                 ART_CUDA_CHECK (cudaMemcpyAsync (out[i], devs[i]->d_out, outFloats * sizeof (float), cudaMemcpyDeviceToHost, lead->sOut));
         }
     }
-    ART_CUDA_CHECK (cudaStreamSynchronize (lead->sOut));
-    ART_CUDA_CHECK (cudaStreamSynchronize (lead->stream));
+    // sOut's last download waits for the last launch, which waits for the last upload
+    wait_for (lead, lead->sOut, (size_t) 1 << 20);
+    ART_CUDA_CHECK (cudaStreamSynchronize (lead->stream));      // (already idle: only the history kernels of the last group can trail)
     return 0;
     ART_GUARD_END (-1)
 }
@@ -929,7 +949,7 @@ extern "C" int artDevRunHostPlanar (ArtDev *dev, const ArtCallPlan *plan, const 
     run_single (dev, *plan, job, dev->stream);
     for (size_t c = 0; c < C && nout; ++c)
         ART_CUDA_CHECK (cudaMemcpyAsync (out[c], dev->d_out + c * nout, nout * sizeof (float), cudaMemcpyDeviceToHost, dev->stream));
-    ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
+    wait_for (dev, dev->stream, (nin + nout) * C * sizeof (float));
     return 0;
     ART_GUARD_END (-1)
 }

@@ -184,7 +184,135 @@ def load_product() -> C.CDLL:
     lib.resampleBatchProcessInterleaved.restype = None
     lib.resampleBatchProcessInterleaved.argtypes = [C.POINTER(ctx), C.c_int, C.POINTER(f32p), C.POINTER(C.c_int),
                                                     C.POINTER(f32p), C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(Result)]
+    # device-pointer entry points: device addresses travel as integers
+    vp = C.c_void_p
+    lib.resampleProcessInterleavedDevice.restype = Result
+    lib.resampleProcessInterleavedDevice.argtypes = [ctx, vp, C.c_int, vp, C.c_int, C.c_double, vp]
+    lib.resampleProcessDevice.restype = Result
+    lib.resampleProcessDevice.argtypes = [ctx, C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_int, C.c_double, vp]
+    lib.resampleBatchProcessInterleavedDevice.restype = None
+    lib.resampleBatchProcessInterleavedDevice.argtypes = [C.POINTER(ctx), C.c_int, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(vp),
+                                                          C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(Result), vp]
+    lib.resampleProcessBlocksInterleavedDevice.restype = C.c_int
+    lib.resampleProcessBlocksInterleavedDevice.argtypes = [ctx, vp, C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int, vp, C.c_int,
+                                                           C.POINTER(Result), C.POINTER(C.c_double), vp]
+    lib.resampleB200PathCounts.restype = None
+    lib.resampleB200PathCounts.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    lib.resampleB200LastError.restype = C.c_char_p
+    lib.resampleB200LastError.argtypes = [C.c_int]
+    lib.resampleB200Synchronize.restype = None
+    lib.resampleB200Synchronize.argtypes = [ctx]
     return lib
+
+
+def path_counts(lib):
+    """(generic, periodic FFMA, tensor) convolution launches so far"""
+    g, p = C.c_ulonglong(), C.c_ulonglong()
+    lib.resampleB200PathCounts(C.byref(g), C.byref(p))
+    return g.value, p.value, lib.resampleB200TensorLaunches()
+
+
+# ---------------------------------------------------------------------------
+# device-pointer entry points (include/resampler_b200.h): torch only provides the device memory and the stream
+
+def _cuda():
+    import torch
+    return torch
+
+
+def device_batch_process(streams, xs, n_out, ratios, use_stream=True):
+    """resampleBatchProcessInterleavedDevice: ONE launch over all contexts.  xs[i] is (frames, ch) float32 or None for
+    a flush (numInputFrames = -1).  Returns [(y, input_used, output_generated)]."""
+    torch = _cuda()
+    lib, n, ch = streams[0].lib, len(streams), streams[0].channels
+    st = torch.cuda.Stream() if use_stream else None
+    dx, nin = [], []
+    for x in xs:
+        if x is None:
+            dx.append(None); nin.append(-1)
+        else:
+            x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, ch)
+            dx.append(torch.from_numpy(x).cuda() if x.size else torch.empty((1, ch), device="cuda"))
+            nin.append(x.shape[0])
+    caps = [n_out] * n if np.isscalar(n_out) else list(n_out)
+    dy = [torch.full((max(c, 1), ch), float("nan"), device="cuda", dtype=torch.float32) for c in caps]
+    torch.cuda.synchronize()
+    ctxs = (type(streams[0].ctx) * n)(*[s.ctx for s in streams])
+    ins = (C.c_void_p * n)(*[t.data_ptr() if t is not None else None for t in dx])
+    outs = (C.c_void_p * n)(*[t.data_ptr() for t in dy])
+    nin_a = (C.c_int * n)(*nin)
+    nout_a = (C.c_int * n)(*caps)
+    rat = (C.c_double * n)(*([ratios] * n if np.isscalar(ratios) else list(ratios)))
+    res = (Result * n)()
+    lib.resampleBatchProcessInterleavedDevice(ctxs, n, ins, nin_a, outs, nout_a, rat, res, C.c_void_p(st.cuda_stream) if st else None)
+    if st:
+        st.synchronize()
+    else:
+        for s in streams:
+            lib.resampleB200Synchronize(s.ctx)
+    torch.cuda.synchronize()
+    return [(dy[i][:res[i].output_generated].cpu().numpy(), res[i].input_used, res[i].output_generated) for i in range(n)]
+
+
+def device_blocks_process(stream, x, block_frames, ratios, capacity):
+    """resampleProcessBlocksInterleavedDevice: consecutive blocks of one stream in one launch.
+    Returns (y, blocks_done, [(input_used, output_generated)], [positions])."""
+    torch = _cuda()
+    lib, ch = stream.lib, stream.channels
+    x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, ch)
+    nb = len(block_frames)
+    dxt = torch.from_numpy(x).cuda()
+    dyt = torch.full((max(capacity, 1), ch), float("nan"), device="cuda", dtype=torch.float32)
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    bf = (C.c_int * nb)(*[int(b) for b in block_frames])
+    rt = (C.c_double * nb)(*[float(r) for r in ratios])
+    res = (Result * nb)()
+    pos = (C.c_double * nb)()
+    done = lib.resampleProcessBlocksInterleavedDevice(stream.ctx, dxt.data_ptr(), bf, rt, nb, dyt.data_ptr(), capacity, res, pos,
+                                                      C.c_void_p(st.cuda_stream))
+    st.synchronize()
+    made = sum(res[i].output_generated for i in range(done))
+    return (dyt[:made].cpu().numpy(), done, [(res[i].input_used, res[i].output_generated) for i in range(done)],
+            [pos[i] for i in range(done)])
+
+
+def device_process(stream, x, n_out, ratio, planar=False, scattered=False):
+    """resampleProcessInterleavedDevice / resampleProcessDevice (planar; `scattered` puts every plane in its own
+    allocation at irregular distances, so the library needs its per-channel pointer table)."""
+    torch = _cuda()
+    lib, ch = stream.lib, stream.channels
+    st = torch.cuda.Stream()
+    if x is None:
+        n_in = -1
+    else:
+        x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, ch)
+        n_in = x.shape[0]
+    if not planar:
+        dxt = torch.from_numpy(x).cuda() if x is not None and x.size else None
+        dyt = torch.full((max(n_out, 1), ch), float("nan"), device="cuda", dtype=torch.float32)
+        torch.cuda.synchronize()
+        res = lib.resampleProcessInterleavedDevice(stream.ctx, dxt.data_ptr() if dxt is not None else None, n_in, dyt.data_ptr(), n_out,
+                                                   ratio, C.c_void_p(st.cuda_stream))
+        st.synchronize()
+        return dyt[:res.output_generated].cpu().numpy(), res.input_used, res.output_generated
+    if scattered:
+        pad = [torch.empty(17 + 13 * c, device="cuda") for c in range(ch)]           # keeps the planes at irregular distances
+        din = [torch.from_numpy(np.ascontiguousarray(x[:, c])).cuda() for c in range(ch)] if x is not None else None
+        dout = [torch.full((max(n_out, 1) + 5 * c,), float("nan"), device="cuda", dtype=torch.float32) for c in range(ch)]
+        del pad
+    else:
+        tin = torch.from_numpy(np.ascontiguousarray(x.T)).cuda() if x is not None else None
+        tout = torch.full((ch, max(n_out, 1)), float("nan"), device="cuda", dtype=torch.float32)
+        din = [tin[c] for c in range(ch)] if tin is not None else None
+        dout = [tout[c] for c in range(ch)]
+    torch.cuda.synchronize()
+    in_arr = (C.c_void_p * ch)(*[t.data_ptr() for t in din]) if din is not None else None
+    out_arr = (C.c_void_p * ch)(*[t.data_ptr() for t in dout])
+    res = lib.resampleProcessDevice(stream.ctx, in_arr, n_in, out_arr, n_out, ratio, C.c_void_p(st.cuda_stream))
+    st.synchronize()
+    y = np.stack([dout[c][:res.output_generated].cpu().numpy() for c in range(ch)], axis=1) if res.output_generated else np.zeros((0, ch), np.float32)
+    return y, res.input_used, res.output_generated
 
 
 def batch_process(streams, xs, n_out: int, ratio: float):

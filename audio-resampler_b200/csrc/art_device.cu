@@ -11,6 +11,7 @@
 #include <cstring>
 #include <cmath>
 #include <cstdarg>
+#include <sched.h>
 #include <mutex>
 #include <vector>
 #include "art_kernels.cuh"
@@ -218,16 +219,31 @@ static void host_pipe_init (ArtDev *dev, size_t events)
  * lowest latency for a 50-us call, but a process that keeps several large calls in flight from several threads -- and eight
  * such processes on one host -- would burn every core on polling.  Calls that move more than ~1 MB sleep on an event
  * created with cudaEventBlockingSync instead: the wake-up costs a few microseconds against >= 50 us of transfer. */
+static int g_waitMode = -1;         // ART_B200_WAIT: 0 spin (cudaStreamSynchronize), 1 sleep on a blocking-sync event, 2 poll + sched_yield
+
 static void wait_for (ArtDev *dev, cudaStream_t stream, size_t bytesMoved)
 {
-    if (bytesMoved < (1u << 20)) {
+    if (g_waitMode < 0) {
+        const char *e = getenv ("ART_B200_WAIT");
+        g_waitMode = !e ? 2 : (!strcmp (e, "spin") ? 0 : (!strcmp (e, "block") ? 1 : 2));
+    }
+    if (bytesMoved < (1u << 20) || g_waitMode == 0) {
         ART_CUDA_CHECK (cudaStreamSynchronize (stream));
         return;
     }
     if (!dev->doneEvent)
         ART_CUDA_CHECK (cudaEventCreateWithFlags (&dev->doneEvent, cudaEventBlockingSync | cudaEventDisableTiming));
     ART_CUDA_CHECK (cudaEventRecord (dev->doneEvent, stream));
-    ART_CUDA_CHECK (cudaEventSynchronize (dev->doneEvent));
+    if (g_waitMode == 1) {
+        ART_CUDA_CHECK (cudaEventSynchronize (dev->doneEvent));
+        return;
+    }
+    for (;;) {                                  // poll, but hand the core to whoever else is runnable between polls
+        const cudaError_t q = cudaEventQuery (dev->doneEvent);
+        if (q == cudaSuccess) return;
+        if (q != cudaErrorNotReady) ART_CUDA_CHECK (q);
+        sched_yield ();
+    }
 }
 
 static void use_device (const ArtDev *dev)
@@ -628,7 +644,7 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
             std::vector<int> groupOf (n, 0);                     // which call (scratch pair) a segment belongs to
             for (int i = 0; i < n; ) {
                 int e = i;
-                long long outFrames = 0, outFirst = -1, inFirst = -1;
+                long long outFrames = 0, outFirst = -1, inFirst = (1LL << 62);    // inFirst may legitimately be negative (history)
                 while (e < n && jobs[e].in == jobs[i].in && jobs[e].out == jobs[i].out) {
                     const long long end = (long long) jobs[e].nStart + jobs[e].outputs;
                     if (end > outFrames) outFrames = end;
@@ -637,11 +653,11 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
                         // (already on their way to the host) and must neither be transposed in nor written back
                         if (outFirst < 0 || (long long) jobs[e].nStart < outFirst) outFirst = jobs[e].nStart;
                         const long long s0 = first_frame_read (jobs[e], lp.k.T, jobs[e].nStart);
-                        if (inFirst < 0 || s0 < inFirst) inFirst = s0;
+                        if (s0 < inFirst) inFirst = s0;
                     }
                     if (jobs[e].histOut) {
                         const long long h0 = (long long) jobs[e].consumed - lp.k.T;
-                        if (inFirst < 0 || h0 < inFirst) inFirst = h0;
+                        if (h0 < inFirst) inFirst = h0;
                     }
                     ++e;
                 }

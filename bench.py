@@ -374,15 +374,6 @@ def kernel_name(before, after):
     return "tensor" if d[2] else "periodic" if d[1] else "generic"
 
 
-class OracleState(C.Structure):
-    """public head of oracle/art_oracle.h's OracleResampler: lets the parity check put the oracle into the exact state
-    (outputOffset, inputIndex, ring contents) a product context had before the launch that is being checked"""
-    _fields_ = [("channels", C.c_int), ("taps", C.c_int), ("phases", C.c_int), ("flags", C.c_int),
-                ("ring_len", C.c_int), ("write_index", C.c_int), ("read_pos", C.c_double),
-                ("fixed_ratio", C.c_double), ("lowpass_ratio", C.c_double),
-                ("bank", C.POINTER(C.c_float)), ("ring", C.POINTER(C.c_float))]
-
-
 def parity_check(torch, batch: DeviceBatch, snapshots, last_ring: int, check_frames: int = 12000):
     """The last timed launch of `batch` against the oracle, for the streams in `snapshots` = {stream: (outputOffset,
     inputIndex)} taken right before that launch.  The oracle is put into the same state, given the last T frames the stream
@@ -393,7 +384,7 @@ def parity_check(torch, batch: DeviceBatch, snapshots, last_ring: int, check_fra
     worst, checked = 0.0, 0
     for s, (P, I) in snapshots.items():
         o = A.oracle_stream(w.ch, w.taps, w.filters, w.lowpass_hz * 2.0 / w.src, flags=FLAGS)
-        st = C.cast(o.ctx, C.POINTER(OracleState)).contents
+        st = C.cast(o.ctx, C.POINTER(A.OracleState)).contents       # the oracle's public head: put it into the context's state
         tail = batch.x[prev_ring, s, w.frames - w.taps:, :].cpu().numpy()                 # [T][ch]
         st.write_index, st.read_pos = int(I), float(P)
         for c in range(w.ch):

@@ -56,7 +56,7 @@ def run(up, down, reps):
 
 
 run(True, True, 2)
-reps = 12
+reps = 120                                      # ~0.4 s per one-way test, ~0.4 s duplex: sustained, not a burst
 t_up, t_down, t_both = run(True, False, reps), run(False, True, reps), run(True, True, reps)
 up_b, down_b = K * nin * 4, K * nout * 4
 if rank == 0:

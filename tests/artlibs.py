@@ -486,6 +486,29 @@ def product():
     return _cache["product"]
 
 
+class OracleState(C.Structure):
+    """public head of OracleResampler (oracle/art_oracle.h)"""
+    _fields_ = [("channels", C.c_int), ("taps", C.c_int), ("phases", C.c_int), ("flags", C.c_int),
+                ("ring_len", C.c_int), ("write_index", C.c_int), ("read_pos", C.c_double),
+                ("fixed_ratio", C.c_double), ("lowpass_ratio", C.c_double),
+                ("bank", f32p), ("ring", f32p)]
+
+
+def oracle_compact_ring(o):
+    """Move the newest T samples of every channel to the front of the oracle's ring and shift its indices accordingly
+    (what resampler.c:497-503 does when the ring is full, done here at an arbitrary fill level): the stream is unchanged."""
+    st = C.cast(o.ctx, C.POINTER(OracleState)).contents
+    T, I = st.taps, st.write_index
+    drop = I - T
+    for c in range(st.channels):
+        base = c * st.ring_len
+        vals = [st.ring[base + drop + i] for i in range(T)]
+        for i in range(T):
+            st.ring[base + i] = vals[i]
+    st.write_index = T
+    st.read_pos -= drop
+
+
 def oracle_stream(*a, **k): return _OracleStream(oracle(), *a, **k)
 def reference_stream(*a, **k): return _ApiStream(reference(), *a, **k)
 def product_stream(*a, **k): return _ApiStream(product(), *a, **k)

@@ -208,7 +208,7 @@ def test_single_context_device_calls(lib, mode, ratio):
     o = A.oracle_stream(ch, taps, filters, 0.0)
     for s in gs + [o]:
         s.advance(taps / 2)
-    for n, cap in [(9000, 12000), (1, 10), (0, 10), (12000, 4000), (8000, 12000), (None, 2000), (100, 200)]:
+    for n, cap in [(9000, 12000), (1, 10), (0, 10), (12000, 4000), (8200, 12000), (None, 2000), (100, 200)]:
         x = None if n is None else rng.uniform(-0.5, 0.5, (n, ch)).astype(np.float32)
         yo, uo, mo = o.process(x, cap, ratio)
         outs = []

@@ -124,6 +124,31 @@ def test_ragged_and_limited_calls():
     _check_call(g, o, x, 500, ratio)
 
 
+def test_flush_when_the_reference_ring_is_nearly_full():
+    """A divergence from the reference that is deliberate.  postfillAllChannels (resampler.c:667-673) compacts the ring when
+    fewer than T/2 slots are free by moving slots [15T, 16T) to the front -- but the newest sample then sits at
+    inputIndex - 15T < T, so the windows of the flush outputs start BEFORE the buffer: the reference (and the oracle, which
+    restates it) read out of bounds and return heap garbage (seen: 1e21..1e32).  The library has the true history on the
+    device and returns what the reference evidently intends.  Checked against the oracle after a proper compaction of its
+    ring (newest T samples to the front) right before the flush; counts and position are identical either way."""
+    g, o = _pair(2, 380, 380, lowpass_ratio=0.0)
+    g.advance(190); o.advance(190)
+    rng = np.random.default_rng(9)
+    ratio = 0.7071067811865476
+    # 380 + 22658 - 3 * 5700 = 5938: 142 free slots < T/2 when the flush arrives
+    for n in (9000, 13658):
+        x = rng.uniform(-0.5, 0.5, (n, 2)).astype(np.float32)
+        _check_call(g, o, x, 20000, ratio)
+    A.oracle_compact_ring(o)
+    assert g.position() == o.position()
+    yg, ug, mg = g.process(None, 2000, ratio)
+    yo, uo, mo = o.process(None, 2000, ratio)
+    # the compaction above shifted the oracle's indices by another amount than the reference's own would have: positions
+    # agree to rounding (1e-13), not to the bit, in this one test
+    assert (ug, mg) == (uo, mo) == (0, 134) and abs(g.position() - o.position()) < 1e-9
+    assert np.max(np.abs(yo)) < 2.0 and A.peak_error(yg, yo) <= TOL
+
+
 def test_long_call_with_many_ring_compactions():
     """one call of 200k frames at preset -1: the reference compacts its ring ~280 times inside it."""
     g, o = _pair(2, 48, 48, lowpass_ratio=0.9)

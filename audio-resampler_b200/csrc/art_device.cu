@@ -11,7 +11,7 @@
 #include <cstring>
 #include <cmath>
 #include <cstdarg>
-#include <sched.h>
+#include <time.h>
 #include <mutex>
 #include <vector>
 #include "art_kernels.cuh"
@@ -219,7 +219,7 @@ static void host_pipe_init (ArtDev *dev, size_t events)
  * lowest latency for a 50-us call, but a process that keeps several large calls in flight from several threads -- and eight
  * such processes on one host -- would burn every core on polling.  Calls that move more than ~1 MB sleep on an event
  * created with cudaEventBlockingSync instead: the wake-up costs a few microseconds against >= 50 us of transfer. */
-static int g_waitMode = -1;         // ART_B200_WAIT: 0 spin (cudaStreamSynchronize), 1 sleep on a blocking-sync event, 2 poll + sched_yield
+static int g_waitMode = -1;         // ART_B200_WAIT: 0 spin (cudaStreamSynchronize), 1 sleep on a blocking-sync event, 2 (default) poll briefly, then sleep
 
 static void wait_for (ArtDev *dev, cudaStream_t stream, size_t bytesMoved)
 {
@@ -234,16 +234,21 @@ static void wait_for (ArtDev *dev, cudaStream_t stream, size_t bytesMoved)
     if (!dev->doneEvent)
         ART_CUDA_CHECK (cudaEventCreateWithFlags (&dev->doneEvent, cudaEventBlockingSync | cudaEventDisableTiming));
     ART_CUDA_CHECK (cudaEventRecord (dev->doneEvent, stream));
-    if (g_waitMode == 1) {
-        ART_CUDA_CHECK (cudaEventSynchronize (dev->doneEvent));
-        return;
+    if (g_waitMode == 2) {
+        // a lone call finishes within ~100 us: polling catches it without a sleep/wake-up; calls queued behind the transfers of
+        // other threads or other processes (measured at 8 GPUs: ~3 ms per 2 MB call, the host's memory system is the limit,
+        // profiles/r02_e2e_scale_n8.txt) fall through to the sleeping wait instead of burning a core each
+        timespec t0, t;
+        clock_gettime (CLOCK_MONOTONIC, &t0);
+        for (;;) {
+            const cudaError_t q = cudaEventQuery (dev->doneEvent);
+            if (q == cudaSuccess) return;
+            if (q != cudaErrorNotReady) ART_CUDA_CHECK (q);
+            clock_gettime (CLOCK_MONOTONIC, &t);
+            if ((t.tv_sec - t0.tv_sec) * 1000000000LL + (t.tv_nsec - t0.tv_nsec) > 500000LL) break;
+        }
     }
-    for (;;) {                                  // poll, but hand the core to whoever else is runnable between polls
-        const cudaError_t q = cudaEventQuery (dev->doneEvent);
-        if (q == cudaSuccess) return;
-        if (q != cudaErrorNotReady) ART_CUDA_CHECK (q);
-        sched_yield ();
-    }
+    ART_CUDA_CHECK (cudaEventSynchronize (dev->doneEvent));
 }
 
 static void use_device (const ArtDev *dev)

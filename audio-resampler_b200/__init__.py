@@ -109,6 +109,7 @@ def load() -> C.CDLL:
         "resampleB200LastError": (C.c_char_p, [i32]),
         "resampleB200PathCounts": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
         "resampleB200SetTensorPath": (None, [i32]),
+        "resampleB200SetTensorDigits": (None, [i32]),
         "resampleB200TensorLaunches": (C.c_ulonglong, []),
         "resampleB200ProfileEnable": (None, [i32]),
         "resampleB200ProfileCollect": (C.c_ulonglong, [C.POINTER(dbl)]),
@@ -139,7 +140,7 @@ EXPORTED_SYMBOLS = [
     "resampleGetNumFilters", "resampleInterpolationUsed", "resampleReset", "resampleFree",
     "biquad_init", "biquad_lowpass", "biquad_highpass", "biquad_apply_buffer", "biquad_apply_sample",
     "resampleB200SetDevice", "resampleB200GetDeviceCount", "resampleB200Synchronize", "resampleB200KernelLaunches", "resampleB200LastError",
-    "resampleB200PathCounts", "resampleB200SetTensorPath", "resampleB200TensorLaunches", "resampleB200ProfileEnable", "resampleB200ProfileCollect",
+    "resampleB200PathCounts", "resampleB200SetTensorPath", "resampleB200SetTensorDigits", "resampleB200TensorLaunches", "resampleB200ProfileEnable", "resampleB200ProfileCollect",
     "resampleProcessInterleavedDevice", "resampleProcessDevice", "resampleBatchProcessInterleavedDevice",
     "resampleBatchProcessInterleaved", "resampleProcessBlocksInterleavedDevice", "biquad_apply_cascade_interleaved",
     "biquad_apply_cascade_interleaved_device",

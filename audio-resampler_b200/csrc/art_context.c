@@ -718,5 +718,6 @@ unsigned long long resampleB200KernelLaunches (void) { return artDevLaunchCount 
 void resampleB200PathCounts (unsigned long long *generic, unsigned long long *periodic) { artDevPathCounts (generic, periodic); }
 unsigned long long resampleB200TensorLaunches (void) { return artDevTensorLaunches (); }
 void resampleB200SetTensorPath (int mode) { artDevSetTensorMode (mode); }
+void resampleB200SetTensorDigits (int digits) { artDevSetTensorDigits (digits); }
 void resampleB200ProfileEnable (int on) { artDevProfileEnable (on); }
 unsigned long long resampleB200ProfileCollect (double *totalMs) { return artDevProfileCollect (totalMs); }

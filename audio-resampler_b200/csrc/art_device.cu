@@ -69,6 +69,8 @@ extern "C" unsigned long long artDevTensorLaunches (void) { return g_pathLaunche
 int g_artTensorMode = -1;          // -1: read ART_B200_UMMA on first use; 0 off, 1 when the launch is large enough, 2 whenever eligible, 3 as 1 plus non-interpolating contexts
 extern "C" void artDevSetTensorMode (int mode) { g_artTensorMode = mode < 0 ? 0 : (mode > 3 ? 3 : mode); }
 
+extern "C" void artDevSetTensorDigits (int digits) { g_artTensorDigits = digits == 2 ? 2 : 3; }
+
 extern "C" unsigned long long artDevLaunchCount (void) { return g_artLaunches; }
 
 /* ---- optional per-kernel timing (bench.py's roofline leg): CUDA events recorded on the launching

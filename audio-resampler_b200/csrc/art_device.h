@@ -88,6 +88,7 @@ unsigned long long artDevLaunchCount (void);
 void artDevPathCounts (unsigned long long *generic, unsigned long long *periodic);
 unsigned long long artDevTensorLaunches (void);               /* launches of the tensor-core kernel (not counted above) */
 void artDevSetTensorMode (int mode);                          /* 0 never, 1 large launches (default), 2 whenever eligible */
+void artDevSetTensorDigits (int digits);                      /* signal digits of the tensor-core form: 3 (default) or 2 */
 void artDevProfileEnable (int on);
 unsigned long long artDevProfileCollect (double *totalMs);   /* returns timed launches, clears */
 

@@ -83,13 +83,15 @@ struct ArtUmma {
     int KI;              // k-steps (16 taps) per input period: ceil(M / 16) = pairs of 8-tap planes per row
     int NS;              // plane-pair slots of operand A held in shared memory (a divisor of KI; pair i lives in slot i % NS)
     int numK;            // k-steps per tile
-    int rows;            // rows of the signal operand held per tile: 128 + largest row shift, padded
+    int cg;              // channels per tile (1, 2, 4): MMA row = cg * period + channel
+    int periods;         // periods per tile incl. the largest row shift: 128 / cg + aMax
+    int digits;          // signal digits (2 or 3): splits of operand A, 5 or 6 MMAs per k-step
+    int rows;            // 16-byte row slots of a plane of the signal operand: cg * periods, padded
     int DH;              // filter quantum is 2^-DH
     int stages;          // depth of the filter stage ring
     int tableHalfs;      // fp16 elements per table: numK * 3 * 2 * Npad * 8
     unsigned short *H;   // [tables][G][numK][3 splits][2 k-planes][Npad][8]  fp16 bit patterns
     int *S0;             // [jobs][G]  region index of tap 0 of the group's first phase, period 0
-    int *tileExp;        // [tiles] block maximum |x| of the samples a tile reads, as a float bit pattern (-> the tile's quantum)
     int *tileJob;        // [tiles] index of the job a tile belongs to (written by the prep kernel: the product kernel's roles
                          //   then find their job with one load instead of a binary search over the job list)
     unsigned char ka[ART_U_MAXK], ki[ART_U_MAXK];      // k-step -> (row shift a, 16-tap group i), i outermost
@@ -179,6 +181,7 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
 
 extern std::atomic<unsigned long long> g_artLaunches;
 extern int g_artTensorMode;
+extern int g_artTensorDigits;
 
 /* per-kernel event timing, active only after artDevProfileEnable(1) */
 void artProfileBegin (cudaStream_t stream, void **token);

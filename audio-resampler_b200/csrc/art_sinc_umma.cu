@@ -57,6 +57,7 @@
 #define ART_U_GROUP   2             /* k-steps per ring slot: one wait / commit per slot */
 #define ART_U_ROWS    128           /* periods per tile = M of the MMA */
 #define ART_U_DX      11            /* signal digit: |X1| <= 2^11 */
+#define ART_U_SCRATCH (32u * 9u * 4u)  /* epilogue transposition scratch per warp: 32 rows x 8 columns, pitch 9 words */
 
 __device__ __forceinline__ unsigned int u_smem (const void *p) { return (unsigned int) __cvta_generic_to_shared (p); }
 
@@ -173,6 +174,63 @@ __device__ __forceinline__ int u_find_job (const ArtJob *jobs, int numJobs, int 
     return lo;
 }
 
+/* Block maximum of the samples one tile reads (-> its quantum), this warp's share: warp `wi` of `nw` takes every nw-th
+ * 512-byte run.  Non-finite samples are left out: they then convert to Inf / NaN digits and poison exactly the outputs whose
+ * windows hold them, as they do in the reference's float arithmetic.  BATCH 16-byte loads are in flight per lane. */
+template <int BATCH>
+__device__ __forceinline__ float u_scan_tile (const ArtJob &job, int CGT, int c0, long long R0, long long R1, int T, int wi, int nw, int lane)
+{
+    const float inf = __int_as_float (0x7f800000);
+    float m = 0.0f;
+#define U_TAKE(x) do { const float v_ = fabsf (x); m = fmaxf (m, v_ < inf ? v_ : 0.0f); } while (0)
+    const long long lo = -job.prevAvail, hi = job.inValid;
+    const long long a = R0 > lo ? R0 : lo, b = R1 < hi ? R1 : hi;
+    const int stride = nw * 32;
+    auto span = [&] (const float *base, long long n) {                     // n contiguous floats, all of them the tile's
+        long long head = (long long) (((16u - (unsigned int) (reinterpret_cast<unsigned long long> (base) & 15u)) & 15u) >> 2);
+        if (head > n) head = n;
+        const long long n4 = (n - head) >> 2;
+        const float4 *q = reinterpret_cast<const float4 *> (base + head);
+        for (long long i0 = wi * 32 + lane; i0 < n4; i0 += (long long) BATCH * stride) {
+            float4 v[BATCH];
+#pragma unroll
+            for (int r = 0; r < BATCH; ++r) {
+                const long long i = i0 + (long long) r * stride;
+                v[r] = i < n4 ? __ldg (q + i) : make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+            }
+#pragma unroll
+            for (int r = 0; r < BATCH; ++r) { U_TAKE (v[r].x); U_TAKE (v[r].y); U_TAKE (v[r].z); U_TAKE (v[r].w); }
+        }
+        if (wi == 0) {                                                      // the unaligned ends
+            for (long long e = lane; e < head; e += 32) U_TAKE (__ldg (base + e));
+            for (long long e = head + 4 * n4 + lane; e < n; e += 32) U_TAKE (__ldg (base + e));
+        }
+    };
+    if (b > a) {
+        const long long fs = job.inFS;
+        if (!job.inPlanes && job.inCS == 1 && fs == CGT)                    // the frames hold exactly the tile's channels
+            span (job.in + c0 + a * fs, (b - a) * fs);
+        else
+            for (int cc = 0; cc < CGT; ++cc) {
+                const float *base = (job.inPlanes ? job.inPlanes[c0 + cc] : job.in + (long long) (c0 + cc) * job.inCS) + a * fs;
+                if (fs == 1) span (base, b - a);
+                else
+                    for (long long i = wi * 32 + lane; i < b - a; i += stride) U_TAKE (__ldg (base + i * fs));
+            }
+    }
+    {   // the stretch that comes from the history (tiles at the start of a call)
+        const long long hlo = R0 > lo - T ? R0 : lo - T, hhi = R1 < lo ? R1 : lo;
+        for (int cc = 0; cc < CGT; ++cc) {
+            const float *hist = job.hist + (long long) (c0 + cc) * T + T + job.prevAvail;
+            for (long long i = hlo + wi * 32 + lane; i < hhi; i += stride) U_TAKE (hist[i]);
+        }
+    }
+#undef U_TAKE
+#pragma unroll
+    for (int sh = 16; sh >= 1; sh >>= 1) m = fmaxf (m, __shfl_xor_sync (0xffffffffu, m, sh));
+    return m;
+}
+
 /* ---- 1. prep: filter operand, per-job origins, history ------------------------------------------ */
 /* One block per (table, phase).  Phase j's interpolated filter h_j (the same float values the FFMA form
  * uses: (float) (a + f (b - a)) in double, resampler.c:1155-1156 with the lerp folded into the taps) is
@@ -276,127 +334,15 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
         return;
     }
     b -= originBlocks;
-    if (b < totalTiles) {
-        /* Block maximum of the samples a tile reads (-> its power-of-two quantum, |x| / 2^e <= 2^11, taken by the converters).
-         * tileMax[] holds float bit patterns, zeroed before the launch, raised with atomicMax.  The C tiles of a period block
-         * read the same frames: for interleaved input their C blocks each scan 1/C of the frames for ALL channels (every
-         * sample read once, coalesced); otherwise each block scans its own channel.  (The origin is recomputed here: the
-         * origin block may run later.) */
-        const int tile = b;
-        const int seg = jobs ? (numJobs > 1 ? u_find_job (jobs, numJobs, tile) : 0) : 0;
-        if (threadIdx.x == 0) u.tileJob[tile] = seg;
-        const ArtJob &job = jobs ? jobs[seg] : single;
-        const int local = tile - job.tile0;
-        const int C = k.C;
-        const int qg = local / C, j = local - qg * C;                    // (period block, phase group), channel
-        const int qb = qg / u.G, grp = qg - qb * u.G;
-        ArtLoopState st;
-        st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = T;
-        int w;
-        const double pos = art_output_pos (&st, job.nStart + grp * u.Lg, &w);
-        const long long S0 = (long long) floor (pos) - half + 1 + (long long) w * 15LL * T - job.origin;
-        const long long R0 = S0 + (long long) u.M * qb * 128;
-        const int span = u.M * (u.rows - 1) + 16 * u.KI;
-        // the part inside the caller's block, and the part that comes from the history; the rest is silence
-        const long long lo = R0 > -job.prevAvail ? R0 : -job.prevAvail;
-        const long long hi = R0 + span < (long long) job.inValid ? R0 + span : (long long) job.inValid;
-        const long long hlo = R0 > -job.prevAvail - T ? R0 : -job.prevAvail - T;
-        const long long hhi = R0 + span < -job.prevAvail ? R0 + span : -job.prevAvail;
-        unsigned int *tileMax = reinterpret_cast<unsigned int *> (u.tileExp) + (tile - j);       // entries of this period block
-        __shared__ unsigned int smaxC[128];
-
-        // channel j's stretch of history (planar [C][T])
-        float mh = 0.0f;
-        {
-            const float *hist = job.hist + (long long) j * T + T + job.prevAvail;
-            for (long long i = hlo + threadIdx.x; i < hhi; i += 128) mh = fmaxf (mh, fabsf (hist[i]));
-        }
-        const bool interleaved = job.inPlanes == nullptr && job.inCS == 1 && job.inFS == C && C <= 128;
-        if (interleaved) {
-            const long long len = hi > lo ? hi - lo : 0;
-            const long long s0 = lo + len * j / C, s1 = lo + len * (j + 1) / C;        // this block's frames
-            smaxC[threadIdx.x] = 0u;
-            __syncthreads ();
-            if (mh > 0.0f) atomicMax (&smaxC[j], __float_as_uint (mh));
-            const float *p0 = job.in + s0 * C, *p1 = job.in + s1 * C;
-            if (C == 1 || C == 2 || C == 4) {
-                // 16-byte loads over the aligned interior, eight in flight per thread; lane k of a vector is channel (off + k) % C
-                float mk[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
-                const float *a0 = reinterpret_cast<const float *> ((reinterpret_cast<unsigned long long> (p0) + 15) & ~15ull);
-                const float *a1 = reinterpret_cast<const float *> (reinterpret_cast<unsigned long long> (p1) & ~15ull);
-                if (a1 < a0) { a0 = p1; a1 = p1; }
-                for (const float *p = p0 + threadIdx.x; p < a0 && p < p1; p += 128) atomicMax (&smaxC[(int) ((p - p0) % C)], __float_as_uint (fabsf (*p)));
-                for (const float *p = a1 + threadIdx.x; p < p1; p += 128) atomicMax (&smaxC[(int) ((p - p0) % C)], __float_as_uint (fabsf (*p)));
-                const float4 *q = reinterpret_cast<const float4 *> (a0);
-                const int n4 = (int) ((a1 - a0) >> 2);
-                for (int i0 = threadIdx.x; i0 < n4; i0 += 8 * 128) {
-                    float4 v[8];
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        const int i = i0 + r * 128;
-                        v[r] = i < n4 ? __ldg (q + i) : make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
-                    }
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        mk[0] = fmaxf (mk[0], fabsf (v[r].x)); mk[1] = fmaxf (mk[1], fabsf (v[r].y));
-                        mk[2] = fmaxf (mk[2], fabsf (v[r].z)); mk[3] = fmaxf (mk[3], fabsf (v[r].w));
-                    }
-                }
-                const int off = (int) ((a0 - p0) % C);
-#pragma unroll
-                for (int kq = 0; kq < 4; ++kq) {
-                    float m = mk[kq];
-#pragma unroll
-                    for (int sh = 16; sh >= 1; sh >>= 1) m = fmaxf (m, __shfl_xor_sync (0xffffffffu, m, sh));
-                    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax (&smaxC[(off + kq) % C], __float_as_uint (m));
-                }
-            }
-            else if ((128 % C) == 0) {
-                // thread t owns channel t % C and every (128 / C)-th frame: a warp reads consecutive floats; eight loads in flight
-                const int c = threadIdx.x % C, fstep = 128 / C;
-                float m = 0.0f;
-                const float *base = job.in + c;
-                for (long long i0 = s0 + threadIdx.x / C; i0 < s1; i0 += 8 * fstep) {
-                    float v[8];
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        const long long i = i0 + (long long) r * fstep;
-                        v[r] = i < s1 ? __ldg (base + i * C) : 0.0f;
-                    }
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) m = fmaxf (m, fabsf (v[r]));
-                }
-                atomicMax (&smaxC[c], __float_as_uint (m));
-            }
-            else {
-                const long long n = (s1 - s0) * C;
-                for (long long e = threadIdx.x; e < n; e += 128) atomicMax (&smaxC[(int) (e % C)], __float_as_uint (fabsf (__ldg (p0 + e))));
-            }
-            __syncthreads ();
-            if (threadIdx.x < C && smaxC[threadIdx.x]) atomicMax (&tileMax[threadIdx.x], smaxC[threadIdx.x]);
-            return;
-        }
-        {
-            float m = mh;
-            const float *base = job.inPlanes ? job.inPlanes[j] : job.in + (long long) j * job.inCS;
-            const long long fs = job.inFS;
-            for (long long i0 = lo + threadIdx.x; i0 < hi; i0 += 8 * 128) {
-                float v[8];
-#pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    const long long i = i0 + r * 128;
-                    v[r] = i < hi ? __ldg (base + i * fs) : 0.0f;
-                }
-#pragma unroll
-                for (int r = 0; r < 8; ++r) m = fmaxf (m, fabsf (v[r]));
-            }
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) m = fmaxf (m, __shfl_xor_sync (0xffffffffu, m, off));
-            if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax (&tileMax[j], __float_as_uint (m));
-        }
+    const int tileJobBlocks = (totalTiles + 127) / 128;
+    if (b < tileJobBlocks) {
+        // tile -> job: the product kernel's roles then find their job with one load instead of a binary search
+        const int tile = b * 128 + threadIdx.x;
+        if (tile < totalTiles)
+            u.tileJob[tile] = jobs ? (numJobs > 1 ? u_find_job (jobs, numJobs, tile) : 0) : 0;
         return;
     }
-    b -= totalTiles;
+    b -= tileJobBlocks;
     {
         const int seg = b / histBlocksPerJob, hb = b - seg * histBlocksPerJob;
         const ArtJob &job = jobs ? jobs[seg] : single;
@@ -410,6 +356,11 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
 }
 
 /* ---- 2. the product ------------------------------------------------------------------------------- */
+/* CGT = channels per tile (1, 2 or 4).  A tile's 128 MMA rows are ART_U_ROWS / CGT periods x CGT channels with the channel
+ * fastest: physical row CGT * r + cc of the signal operand is period r of channel c0 + cc, and the row shift a of a k-step is
+ * +16 * CGT * a bytes on the descriptor.  The converters then read all CGT channels of a frame with ONE vector load (an
+ * interleaved stereo block wastes no half sectors), and the epilogue's stores cover whole frames. */
+template <int CGT>
 __global__ void __launch_bounds__ (ART_U_THREADS, 1)
 art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const __grid_constant__ ArtJob single,
                       const ArtJob *__restrict__ jobs, int totalTiles, int profArg)
@@ -424,16 +375,19 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = u.L, M = u.M, Npad = u.Npad, KI = u.KI, NS = u.NS, numK = u.numK, C = k.C, T = k.T;
+    const int CG = C / CGT;                                 // channel groups: tiles per (period block, phase group)
+    constexpr int PR = ART_U_ROWS / CGT;                    // periods per tile
+    const int digits = u.digits;                            // signal digits: 2, or 3 (one more MMA per k-step)
     const unsigned int rep = (unsigned int) (KI / NS);    // uses of a plane-pair slot per tile
     const unsigned int planeBytes = (unsigned int) u.rows * 16u;
     const unsigned int splitBytes = planeBytes * 2u * (unsigned int) NS;
     const unsigned int stageBytes = 3u * 2u * (unsigned int) Npad * 16u;
-    // [operand A: 2 splits][filter stage ring][epilogue transposition scratch][barriers and small tables]
+    // [operand A: `digits` splits][filter stage ring][epilogue transposition scratch][barriers and small tables]
     unsigned int xcBase;
     asm volatile ("mov.u32 %0, %1;" : "=r"(xcBase) : "r"(u_smem (smem)));       // opaque: never rematerialised from the generic pointer
-    const unsigned int stBase = xcBase + 2u * splitBytes;
+    const unsigned int stBase = xcBase + (unsigned int) digits * splitBytes;
     const unsigned int scratchBase = stBase + (unsigned int) u.stages * stageBytes;
-    const unsigned int ctl = scratchBase + 8u * 32u * 17u * 4u;
+    const unsigned int ctl = scratchBase + 8u * ART_U_SCRATCH;
     const int units = u.stages / ART_U_GROUP;             // ring slots of ART_U_GROUP k-steps
 #define hFullA(s)   (ctl + 8u * (unsigned int) (s))
 #define hEmptyA(s)  (ctl + 64u + 8u * (unsigned int) (s))
@@ -445,33 +399,28 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
 #define goA(w)      (ctl + ((w) ? 368u : 344u))                         /* issue token of MMA issuer w */
 #define sScaleA(j)  (ctl + 352u + 4u * (unsigned int) (j))
 #define kTabA(ks)   (ctl + 384u + 8u * (unsigned int) (ks))          /* per k-step: low descriptor word of operand A, flags | plane pair << 8 */
+#define scanFullA(s)  (ctl + 384u + 8u * ART_U_MAXK + 8u * (unsigned int) (s))          /* tile maxima, ring of 4: written by the epilogue warps ... */
+#define scanEmptyA(s) (ctl + 384u + 8u * ART_U_MAXK + 32u + 8u * (unsigned int) (s))    /* ... three tiles ahead, read by the converters */
+#define sPartA(s, w)  (ctl + 384u + 8u * ART_U_MAXK + 64u + 32u * (unsigned int) (s) + 4u * (unsigned int) (w))
 
     const int unitsPerTile = (numK + ART_U_GROUP - 1) / ART_U_GROUP;
     if (tid == 0) {
-        for (int s = 0; s < units; ++s) { u_mbar_init (hFullA (s), 1); u_mbar_init (hEmptyA (s), 1); }
+        // a ring slot is free when BOTH issuers' MMAs that read it have completed (each commits to it)
+        for (int s = 0; s < units; ++s) { u_mbar_init (hFullA (s), 1); u_mbar_init (hEmptyA (s), 2); }
         for (int sl = 0; sl < NS; ++sl) {
-            // a pair of planes is released by every issuer that used it (the planner guarantees that the pairs
-            // sharing a slot agree on that)
-            unsigned int who = 0;
-            for (int ks = 0; ks < numK; ++ks)
-                if (u.ki[ks] % NS == sl) who |= 1u << ((ks / ART_U_GROUP) & 1);
             u_mbar_init (pFullA (sl), ART_U_CONV / 32);
-            u_mbar_init (pEmptyA (sl), who == 3u ? 2 : 1);
+            u_mbar_init (pEmptyA (sl), 1);                 // released by the relay warp once the slot's last k-step has completed
         }
-        u_mbar_init (accFullA, unitsPerTile > 1 ? 2 : 1);
+        u_mbar_init (accFullA, 2);
         u_mbar_init (accEmptyA, ART_U_EPI / 32);
-        u_mbar_init (goA (0), 1);
-        u_mbar_init (goA (1), 1);
+        for (int sl = 0; sl < 4; ++sl) { u_mbar_init (scanFullA (sl), ART_U_EPI / 32); u_mbar_init (scanEmptyA (sl), ART_U_CONV / 32); }
         asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int ks = tid; ks < numK; ks += ART_U_THREADS) {
         const unsigned int i = u.ki[ks], a = u.ka[ks];
-        const unsigned int aAddr = xcBase + 2u * (i % (unsigned int) NS) * planeBytes + 16u * a;      // row shift a = +16 bytes
-        // bit 1: the last k-step of its pair of planes that this k-step's issuer handles
-        const int mine = (ks / ART_U_GROUP) & 1;
-        bool last = true;
-        for (int k2 = ks + 1; k2 < numK && u.ki[k2] == i; ++k2)
-            if (((k2 / ART_U_GROUP) & 1) == mine) last = false;
+        const unsigned int aAddr = xcBase + 2u * (i % (unsigned int) NS) * planeBytes + 16u * (unsigned int) CGT * a;      // row shift a = +16 * CGT bytes
+        // bit 1: the last k-step of its pair of planes (the k-steps of a pair are consecutive)
+        const bool last = ks + 1 >= numK || u.ki[ks + 1] != i;
         u_sts64 (kTabA (ks), make_uint2 (((aAddr >> 4) & 0x3fffu) | (((planeBytes >> 4) & 0x3fffu) << 16),
                                          (a == 0 ? 1u : 0u) | (last ? 2u : 0u) | ((i % (unsigned int) NS) << 8) | ((i / (unsigned int) NS) << 16)));
     }
@@ -490,6 +439,20 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
     auto jobOf = [=] (int tile) -> const ArtJob & {
         return jobs ? jobs[u.tileJob[tile]] : *singlePtr;
     };
+    /* tile -> (period block, phase group, first channel): tiles of a job run channel group fastest, then phase group */
+    struct Where { int seg, qb, grp, c0; };
+    auto whereIs = [=] (const ArtJob &job, int tile) -> Where {
+        Where w;
+        w.seg = (int) (&job - (jobs ? jobs : singlePtr));
+        const int local = tile - job.tile0;
+        const int qg = local / CG;
+        w.c0 = (local - qg * CG) * CGT;
+        w.qb = qg / u.G;
+        w.grp = qg - w.qb * u.G;
+        return w;
+    };
+    const int periods = u.periods;                                          // periods of a tile incl. the row shifts: PR + aMax
+    const int span = M * (periods - 1) + 16 * KI;                           // samples the tile touches per channel
 
     if (warp == 0) {
         asm volatile ("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -499,7 +462,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             unsigned int us = 0, ph = 0;
             for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
                 const ArtJob &job = jobOf (tile);
-                const int grp = ((tile - job.tile0) / C) % u.G;
+                const int grp = ((tile - job.tile0) / CG) % u.G;
                 const unsigned short *tab = u.H + ((size_t) job.table * u.G + grp) * u.tableHalfs;
                 for (int ks = 0; ks < numK; ks += ART_U_GROUP) {
                     const unsigned int bytes = (unsigned int) (numK - ks < ART_U_GROUP ? numK - ks : ART_U_GROUP) * stageBytes;
@@ -518,10 +481,13 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
         }
     }
     else if (warp < 3) {
-        /* ===== MMA issuers.  A single thread needs ~460 cycles to issue a k-step whose five MMAs run for 400, so two warps
-         * share the work: ring slots (ART_U_GROUP k-steps) alternate between them.  Each whole warp walks the loop (uniform
-         * control flow) and one elected lane issues.  Every tcgen05.commit costs the tensor pipe ~85 cycles (measured,
-         * profiles/microbench/umma_probe.cu): one per slot, one per issuer and pair of planes, one per issuer and tile ===== */
+        /* ===== MMA issuers.  One thread needs 70-90 cycles to issue a tcgen05.mma that executes in 80, so a single issuer
+         * leaves the tensor pipe waiting.  Two warps issue CONCURRENTLY, split by accumulator: issuer 0 feeds [X1*H1] and
+         * [X1*h2 + x2*H1], issuer 1 feeds [X1*h3 + x2*h2 (+ x3*H1)].  Every accumulator sees its MMAs from one thread in program
+         * order, so the truncating accumulation of the lower classes stays bit-reproducible without any hand-off between
+         * the two.  Each whole warp walks the loop (uniform control flow) and one elected lane issues.  tcgen05.commit is not
+         * free (~85 cycles of the pipe, profiles/microbench/umma_probe.cu): one per issuer and ring slot, one per issuer and
+         * tile; plane pairs are released by the relay warp below instead ===== */
         asm volatile ("setmaxnreg.dec.sync.aligned.u32 56;");
         const unsigned int me = (unsigned int) (warp - 1);
         UPROF_DECL ();
@@ -530,163 +496,204 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
         const unsigned long long descHi = ((unsigned long long) (128u >> 4) << 32) | (1ull << 46);      // SBO = 128, version 1
         const unsigned int bLo0 = ((stBase >> 4) & 0x3fffu) | ((((unsigned int) Npad * 16u >> 4) & 0x3fffu) << 16);
         const unsigned int aSplitU = splitBytes >> 4;
-        unsigned int us = 0, ph = 0, lt = 0, gw = 0;
+        unsigned int us = 0, ph = 0, lt = 0;
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++lt) {
             long long t1 = UCLK ();
-            // the accumulators are free once the epilogue has drained them (the second issuer starts on the first one's token)
-            if (me == 0) u_mbar_wait (accEmptyA, (lt & 1) ^ 1);
+            u_mbar_wait (accEmptyA, (lt & 1) ^ 1);                            // the epilogue has drained the accumulators
             long long t2 = UCLK ();
             if (lane == 0 && me == 0) UPROF_ADD (2, t2 - t1);
             asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
-            unsigned int unit = 0;
-            for (int ks0 = 0; ks0 < numK; ks0 += ART_U_GROUP, ++unit) {
-                if ((unit & 1u) == me) {
-                    const int cnt = numK - ks0 < ART_U_GROUP ? numK - ks0 : ART_U_GROUP;
-                    long long t0 = UCLK ();
-                    for (int g = 0; g < cnt; ++g) {
-                        const unsigned int f = u_lds64 (kTabA (ks0 + g)).y;
-                        u_mbar_wait (pFullA ((f >> 8) & 0xffu), (lt * rep + (f >> 16)) & 1);   // the converters filled this pair of planes
-                    }
-                    long long t3 = UCLK ();
-                    u_mbar_wait (hFullA (us), ph);
-                    if (lane == 0 && me == 0) { UPROF_ADD (1, t3 - t0); UPROF_ADD (3, UCLK () - t3); }
-                    // slots are issued strictly in order -- the two issuers pass a token -- so that every accumulator sees its
-                    // MMAs in one fixed order: the truncating accumulation (classes 2 and 3) stays bit-reproducible
-                    if (unit > 0) { u_mbar_wait (goA (me), gw & 1); ++gw; }
-                    asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    long long t4 = UCLK ();
-                    if (u_elect ()) {
-                        for (int g = 0; g < cnt; ++g) {
-                            const int ks = ks0 + g;
-                            const uint2 kt = u_lds64 (kTabA (ks));
-                            const unsigned int aLo = kt.x;
-                            const unsigned int bLo = bLo0 + (us * ART_U_GROUP + (unsigned int) g) * stageU;
-                            const unsigned long long dA1 = descHi | aLo, dA2 = descHi | (aLo + aSplitU);
-                            const unsigned long long dB1 = descHi | bLo, dB2 = descHi | (bLo + bSplitU), dB3 = descHi | (bLo + 2u * bSplitU);
-                            const unsigned int acc = ks > 0;
-                            if (!(dbg & 8)) {
-                            u_mma (tm, dA1, dB1, idesc, acc);                       // X1 * H1   (exact)
-                            u_mma (tm + Npad, dA1, dB2, idesc, acc);                // X1 * h2
-                            u_mma (tm + Npad, dA2, dB1, idesc, 1);                  // x2 * H1
-                            u_mma (tm + 2 * Npad, dA1, dB3, idesc, acc);            // X1 * h3
-                            u_mma (tm + 2 * Npad, dA2, dB2, idesc, 1);              // x2 * h2
-                            }
-                            if (kt.y & 2)
-                                u_commit (pEmptyA ((kt.y >> 8) & 0xffu));            // this issuer is done with the pair of planes
-                        }
-                        long long t5 = UCLK ();
-                        u_commit (hEmptyA (us));
-                        if ((int) unit + 1 < unitsPerTile) u_mbar_arrive (goA (me ^ 1u));     // the next slot is the other issuer's
-                        if (me == 0) { UPROF_ADD (11, t5 - t4); UPROF_ADD (12, UCLK () - t5); }
-                    }
-                    __syncwarp ();
-                    if (lane == 0 && me == 0) UPROF_ADD (13, UCLK () - t4);
+            for (int ks0 = 0; ks0 < numK; ks0 += ART_U_GROUP) {
+                const int cnt = numK - ks0 < ART_U_GROUP ? numK - ks0 : ART_U_GROUP;
+                long long t0 = UCLK ();
+                for (int g = 0; g < cnt; ++g) {
+                    const unsigned int f = u_lds64 (kTabA (ks0 + g)).y;
+                    u_mbar_wait (pFullA ((f >> 8) & 0xffu), (lt * rep + (f >> 16)) & 1);   // the converters filled this pair of planes
                 }
+                long long t3 = UCLK ();
+                u_mbar_wait (hFullA (us), ph);
+                if (lane == 0 && me == 0) { UPROF_ADD (1, t3 - t0); UPROF_ADD (3, UCLK () - t3); }
+                asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
+                long long t4 = UCLK ();
+                if (u_elect ()) {
+                    for (int g = 0; g < cnt; ++g) {
+                        const int ks = ks0 + g;
+                        const unsigned int aLo = u_lds32 (kTabA (ks));
+                        const unsigned int bLo = bLo0 + (us * ART_U_GROUP + (unsigned int) g) * stageU;
+                        const unsigned long long dA1 = descHi | aLo, dA2 = descHi | (aLo + aSplitU);
+                        const unsigned long long dB1 = descHi | bLo, dB2 = descHi | (bLo + bSplitU);
+                        const unsigned int acc = ks > 0;
+                        if (!(dbg & 8)) {
+                            if (me == 0) {
+                                u_mma (tm, dA1, dB1, idesc, acc);                       // X1 * H1   (exact)
+                                u_mma (tm + Npad, dA1, dB2, idesc, acc);                // X1 * h2
+                                u_mma (tm + Npad, dA2, dB1, idesc, 1);                  // x2 * H1
+                            }
+                            else {
+                                u_mma (tm + 2 * Npad, dA1, descHi | (bLo + 2u * bSplitU), idesc, acc);      // X1 * h3
+                                u_mma (tm + 2 * Npad, dA2, dB2, idesc, 1);              // x2 * h2
+                                if (digits == 3)
+                                    u_mma (tm + 2 * Npad, descHi | (aLo + 2u * aSplitU), dB1, idesc, 1);    // x3 * H1
+                            }
+                        }
+                    }
+                    long long t5 = UCLK ();
+                    u_commit (hEmptyA (us));
+                    if (me == 0) { UPROF_ADD (11, t5 - t4); UPROF_ADD (12, UCLK () - t5); }
+                }
+                __syncwarp ();
+                if (lane == 0 && me == 0) UPROF_ADD (13, UCLK () - t4);
                 if (++us == (unsigned int) units) { us = 0; ph ^= 1; }
             }
-            if (me < unit) {                                                     // this issuer had work in the tile
-                if (u_elect ())
-                    u_commit (accFullA);
-                __syncwarp ();
-            }
+            if (u_elect ())
+                u_commit (accFullA);
+            __syncwarp ();
             if (lane == 0 && me == 0) UPROF_ADD (4, UCLK () - t2);
         }
         UPROF_FLUSH ();
     }
     else if (warp < 4) {
-        /* idle: fills warpgroup 0 (register re-allocation is per warpgroup) */
+        /* ===== relay: a pair of planes may be overwritten once the MMAs of its last k-step have completed, which the ring
+         * slot's barrier already reports (both issuers commit to it).  This warp follows those completions in order and
+         * passes them on to the converters -- a plain mbarrier arrive instead of ~20 more tcgen05.commit per tile ===== */
         asm volatile ("setmaxnreg.dec.sync.aligned.u32 56;");
+        if (lane == 0) {
+            unsigned int us = 0, ph = 0;
+            for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
+                for (int ks0 = 0; ks0 < numK; ks0 += ART_U_GROUP) {
+                    const int cnt = numK - ks0 < ART_U_GROUP ? numK - ks0 : ART_U_GROUP;
+                    u_mbar_wait (hEmptyA (us), ph);
+                    for (int g = 0; g < cnt; ++g) {
+                        const unsigned int f = u_lds64 (kTabA (ks0 + g)).y;
+                        if (f & 2u) u_mbar_arrive (pEmptyA ((f >> 8) & 0xffu));
+                    }
+                    if (++us == (unsigned int) units) { us = 0; ph ^= 1; }
+                }
+            }
+        }
     }
     else if (warp < 12) {
         /* ===== converters: signal -> fixed-point operand A, one pair of 8-tap planes at a time ===== */
         asm volatile ("setmaxnreg.dec.sync.aligned.u32 88;");
         const int ctid = tid - 128, cw = ctid >> 5;
         UPROF_DECL ();
-        const int span = M * (u.rows - 1) + 16 * KI;                       // samples the tile touches per channel
-        /* a lane converts TWO neighbouring taps of a row per step (one conversion and one 32-bit store per digit for the two);
-         * a warp covers 4 rows x 16 taps, the 8 warps take every 8th group of 4 rows */
-        constexpr int UN = 5;                                               // row groups per warp: rows <= 160
-        const int r0 = 4 * cw + (lane >> 3);                                // this lane's row in the warp's first group
+        /* a lane converts TWO neighbouring taps of a period, for all CGT channels of the tile (one conversion and one 32-bit
+         * store per digit and channel for the two); a warp covers 4 periods x 16 taps, the 8 warps take every 8th group of 4 */
+        constexpr int UN = CGT == 1 ? 5 : (CGT == 2 ? 3 : 2);               // period groups per warp: periods <= 160 / 96 / 64
+        constexpr int NV = 2 * UN * CGT;
+        const int r0 = 4 * cw + (lane >> 3);                                // this lane's period in the warp's first group
         const int off0 = M * r0 + 2 * (lane & 7);                           // its first sample's offset inside the tile, plane pair 0
         unsigned int lt = 0;
-        float v[2 * UN], vn[2 * UN];
-        const int nU = ((u.rows + 3) / 4 - cw + 7) / 8;                     // row groups this warp owns
+        float v[NV], vn[NV];                                                 // [(group * 2 + tap) * CGT + channel]
 
         /* what a lane needs to fetch its samples of one tile.  Inside the caller's block a sample is base[idx * fs];
          * tiles that touch the history or run past the end of the input take the same loads from a clamped address
          * and zero what must read as silence, so that all loads of a plane pair are still issued back to back */
-        struct Src { const float *p, *p0, *h0, *dummy; long long fs; int loRel, hiRel, e; bool fast; };
+        struct Src { const float *pc[CGT]; const float *h0, *dummy; long long fs; int loRel, hiRel; bool fast, vec; };
         auto source = [&] (int tile) -> Src {
             Src sc;
             const ArtJob &job = jobOf (tile);
-            const int seg = (int) (&job - (jobs ? jobs : singlePtr));
-            const int local = tile - job.tile0;
-            const int qg = local / C, c = local - qg * C;
-            const int qb = qg / u.G, grp = qg - qb * u.G;
-            const long long R0 = (long long) u.S0[seg * u.G + grp] + (long long) M * qb * ART_U_ROWS;
+            const Where w = whereIs (job, tile);
+            const long long R0 = (long long) u.S0[w.seg * u.G + w.grp] + (long long) M * w.qb * PR;
             const long long lo = -job.prevAvail, hi = job.inValid;
             sc.fast = R0 >= lo && R0 + span <= hi;
             sc.fs = job.inFS;
-            const float *base = job.inPlanes ? job.inPlanes[c] : job.in + (long long) c * job.inCS;
-            const float *hist = job.hist + (long long) c * T + T + job.prevAvail;     // hist[idx]: -T - prevAvail <= idx < -prevAvail
+#pragma unroll
+            for (int cc = 0; cc < CGT; ++cc)
+                sc.pc[cc] = (job.inPlanes ? job.inPlanes[w.c0 + cc] : job.in + (long long) (w.c0 + cc) * job.inCS) + R0 * sc.fs;
+            // all channels of a frame from one load: interleaved with the tile's channels adjacent and the vector aligned
+            sc.vec = CGT > 1 && job.inPlanes == nullptr && job.inCS == 1 && (sc.fs % CGT) == 0 &&
+                     (reinterpret_cast<unsigned long long> (job.in + w.c0) & (4u * CGT - 1u)) == 0;
+            const float *hist = job.hist + (long long) w.c0 * T + T + job.prevAvail;     // hist[idx]: -T - prevAvail <= idx < -prevAvail (+ cc * T)
             // tile-relative coordinates (rel = idx - R0, an int): the boundary path classifies every sample it fetches
             const long long loR = lo - R0, hiR = hi - R0;
             sc.loRel = loR < -(1 << 30) ? -(1 << 30) : (loR > (1 << 30) ? (1 << 30) : (int) loR);
             sc.hiRel = hiR < -(1 << 30) ? -(1 << 30) : (hiR > (1 << 30) ? (1 << 30) : (int) hiR);
-            sc.p0 = base + R0 * sc.fs;
             sc.h0 = hist + R0;
             sc.dummy = hist + lo - 1;                                         // any readable address: the newest history sample
-            sc.p = sc.p0 + (long long) off0 * sc.fs;
-            {
-                const float m = __int_as_float (u.tileExp[tile]);             // block maximum (prep kernel)
-                int e = 0;
-                if (m > 0.0f) { (void) frexpf (m, &e); e -= ART_U_DX; e = e < -114 ? -114 : (e > 100 ? 100 : e); }      // m < 2^(e + 11)
-                sc.e = e;
-            }
             return sc;
         };
-        auto rowOk = [&] (int uu) -> bool { return uu < nU && r0 + 32 * uu < u.rows; };
-        auto fetch = [&] (const Src &sc, int i, float (&dst)[2 * UN]) {
+        /* the tile's block maximum -> its power-of-two quantum.  The epilogue warps scan every tile three tiles ahead of its
+         * conversion (each leaves its share of the maximum in the ring slot) */
+        auto quantum = [&] (unsigned int kk) -> int {
+            const unsigned int slot = kk & 3u;
+            u_mbar_wait_relaxed (scanFullA (slot), (kk >> 2) & 1u);
+            unsigned int bits = lane < ART_U_EPI / 32 ? u_lds32 (sPartA (slot, lane)) : 0u;
+#pragma unroll
+            for (int sh = 4; sh >= 1; sh >>= 1) bits = max (bits, __shfl_xor_sync (0xffffffffu, bits, sh));
+            bits = __shfl_sync (0xffffffffu, bits, 0);
+            __syncwarp ();
+            if (lane == 0) u_mbar_arrive (scanEmptyA (slot));
+            const float m = __uint_as_float (bits);
+            int e = 0;
+            if (m > 0.0f) { (void) frexpf (m, &e); e -= ART_U_DX; e = e < -114 ? -114 : (e > 116 ? 116 : e); }      // m < 2^(e + 11): every finite float fits
+            return e;
+        };
+        auto rowOk = [&] (int uu) -> bool { return r0 + 32 * uu < periods; };
+        auto fetch = [&] (const Src &sc, int i, float (&dst)[NV]) {
             if (sc.fast) {
-                const float *p = sc.p + (long long) (16 * i) * sc.fs;
-                const long long rowStep = (long long) (32 * M) * sc.fs;
+                const long long at = (long long) (off0 + 16 * i) * sc.fs, rowStep = (long long) (32 * M) * sc.fs;
 #pragma unroll
                 for (int uu = 0; uu < UN; ++uu) {
                     const bool ok = rowOk (uu) && !(dbg & 1);
-                    dst[2 * uu] = ok ? __ldg (p) : 0.0f;
-                    dst[2 * uu + 1] = ok ? __ldg (p + sc.fs) : 0.0f;
-                    p += rowStep;
+                    const long long o = at + uu * rowStep;
+                    if (CGT == 2 && sc.vec) {
+                        const float2 a = ok ? __ldg (reinterpret_cast<const float2 *> (sc.pc[0] + o)) : make_float2 (0.0f, 0.0f);
+                        const float2 b = ok ? __ldg (reinterpret_cast<const float2 *> (sc.pc[0] + o + sc.fs)) : make_float2 (0.0f, 0.0f);
+                        dst[(2 * uu) * CGT] = a.x; dst[(2 * uu) * CGT + (CGT > 1)] = a.y;
+                        dst[(2 * uu + 1) * CGT] = b.x; dst[(2 * uu + 1) * CGT + (CGT > 1)] = b.y;
+                    }
+                    else if (CGT == 4 && sc.vec) {
+                        const float4 a = ok ? __ldg (reinterpret_cast<const float4 *> (sc.pc[0] + o)) : make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+                        const float4 b = ok ? __ldg (reinterpret_cast<const float4 *> (sc.pc[0] + o + sc.fs)) : make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+                        dst[(2 * uu) * CGT] = a.x; dst[(2 * uu) * CGT + (CGT > 1)] = a.y; dst[(2 * uu) * CGT + 2 * (CGT > 2)] = a.z; dst[(2 * uu) * CGT + 3 * (CGT > 2)] = a.w;
+                        dst[(2 * uu + 1) * CGT] = b.x; dst[(2 * uu + 1) * CGT + (CGT > 1)] = b.y; dst[(2 * uu + 1) * CGT + 2 * (CGT > 2)] = b.z; dst[(2 * uu + 1) * CGT + 3 * (CGT > 2)] = b.w;
+                    }
+                    else {
+#pragma unroll
+                        for (int cc = 0; cc < CGT; ++cc) {
+                            dst[(2 * uu) * CGT + cc] = ok ? __ldg (sc.pc[cc] + o) : 0.0f;
+                            dst[(2 * uu + 1) * CGT + cc] = ok ? __ldg (sc.pc[cc] + o + sc.fs) : 0.0f;
+                        }
+                    }
                 }
             }
             else {
-                const float *ptr[2 * UN];
-                bool ok[2 * UN];
+                // boundary tiles: one plane-pair group at a time keeps the pointer set small
 #pragma unroll
-                for (int e = 0; e < 2 * UN; ++e) {
-                    const int rel = off0 + 16 * i + 32 * M * (e >> 1) + (e & 1);
-                    const bool inBlock = rel >= sc.loRel && rel < sc.hiRel, inHist = rel < sc.loRel && rel >= sc.loRel - T;
-                    ok[e] = (inBlock || inHist) && rowOk (e >> 1);
-                    ptr[e] = inBlock ? sc.p0 + (long long) rel * sc.fs : (inHist ? sc.h0 + rel : sc.dummy);
+                for (int uu = 0; uu < UN; ++uu) {
+                    const float *ptr[2 * CGT];
+                    bool ok[2 * CGT];
+#pragma unroll
+                    for (int e = 0; e < 2 * CGT; ++e) {
+                        const int tap = e / CGT, cc = e - tap * CGT;
+                        const int rel = off0 + 16 * i + 32 * M * uu + tap;
+                        const bool inBlock = rel >= sc.loRel && rel < sc.hiRel, inHist = rel < sc.loRel && rel >= sc.loRel - T;
+                        ok[e] = (inBlock || inHist) && rowOk (uu);
+                        ptr[e] = inBlock ? sc.pc[cc] + (long long) rel * sc.fs : (inHist ? sc.h0 + (long long) cc * T + rel : sc.dummy);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 2 * CGT; ++e) dst[2 * uu * CGT + e] = __ldg (ptr[e]);
+#pragma unroll
+                    for (int e = 0; e < 2 * CGT; ++e) dst[2 * uu * CGT + e] = ok[e] ? dst[2 * uu * CGT + e] : 0.0f;
                 }
-#pragma unroll
-                for (int e = 0; e < 2 * UN; ++e) dst[e] = __ldg (ptr[e]);
-#pragma unroll
-                for (int e = 0; e < 2 * UN; ++e) dst[e] = ok[e] ? dst[e] : 0.0f;
             }
         };
 
         Src cur = source (blockIdx.x < totalTiles ? blockIdx.x : 0);
         if ((int) blockIdx.x < totalTiles) fetch (cur, 0, vn);
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++lt) {
-            const int e = cur.e;
+            const int e = quantum (lt);
             const float invq = __int_as_float ((127 - e) << 23);
+            const unsigned long long invq2 = art_pack2 (invq, invq), magic2 = art_pack2 (12582912.0f, 12582912.0f),
+                                     neg2 = art_pack2 (-1.0f, -1.0f), k2048 = art_pack2 (2048.0f, 2048.0f);
             if (ctid == 0)
                 u_stsf (sScaleA (lt & 3), __int_as_float ((127 + e) << 23) * __int_as_float ((127 - u.DH) << 23));
             const bool more = tile + (int) gridDim.x < totalTiles;
             Src nxt = cur;
             for (int i = 0; i < KI; ++i) {
 #pragma unroll
-                for (int uu = 0; uu < 2 * UN; ++uu) v[uu] = vn[uu];
+                for (int uu = 0; uu < NV; ++uu) v[uu] = vn[uu];
                 // the next pair's loads (of the next tile after the last pair) fly while this pair is converted
                 // (the next tile's job lookup is a chain of dependent global loads: done early, at the first pair, where
                 //  the converters have a whole tile of slack, not in front of the last pair the MMAs are waiting for)
@@ -698,27 +705,50 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                 u_mbar_wait_relaxed (pEmptyA (sl), (use & 1) ^ 1);
                 long long cb = UCLK ();
                 if (ctid == 0) UPROF_ADD (5, cb - c0t);
-                // taps 2c, 2c+1 of the pair: plane 2i + (c >> 2), 4 bytes at (c & 3) * 4 of the row's 16-byte slot
+                // taps 2c, 2c+1 of the pair: plane 2i + (c >> 2), 4 bytes at (c & 3) * 4 of the row's 16-byte slot; row = CGT * period + channel
                 const unsigned int dst = xcBase + (2u * sl + ((lane >> 2) & 1)) * planeBytes + (unsigned int) (lane & 3) * 4u +
-                                         (unsigned int) r0 * 16u;
+                                         (unsigned int) (CGT * r0) * 16u;
 #pragma unroll
                 for (int uu = 0; uu < UN; ++uu) {
                     if (rowOk (uu)) {
-                        const float ua = v[2 * uu] * invq, ub = v[2 * uu + 1] * invq;
-                        const float Xa = (ua + 12582912.0f) - 12582912.0f;          // round to nearest integer (|u| <= 2^11)
-                        const float Xb = (ub + 12582912.0f) - 12582912.0f;
-                        const float ra = (ua - Xa) * 2048.0f, rb = (ub - Xb) * 2048.0f;
-                        const __half2 p1 = __floats2half2_rn (Xa, Xb), p2 = __floats2half2_rn (ra, rb);      // low half = first tap
-                        u_sts32 (dst + uu * 512, *reinterpret_cast<const unsigned int *> (&p1));
-                        u_sts32 (dst + splitBytes + uu * 512, *reinterpret_cast<const unsigned int *> (&p2));
+#pragma unroll
+                        for (int cc = 0; cc < CGT; ++cc) {
+                            // both taps at once in packed fp32 (fma.rn.f32x2): u = x / q;  X = rint (u) by the 1.5 * 2^23 trick (|u| <= 2^11);
+                            // r = (u - X) * 2^11.  Every step is exact or rounds exactly as the scalar form would (x / q is a power-of-two scaling)
+                            const unsigned long long x2 = art_pack2 (v[(2 * uu) * CGT + cc], v[(2 * uu + 1) * CGT + cc]);
+                            unsigned long long t2 = magic2, nX = magic2, d2 = 0ull, r2 = 0ull;
+                            art_ffma2 (t2, x2, invq2);                                   // u + magic
+                            art_ffma2 (nX, t2, neg2);                                    // magic - (u + magic) = -X
+                            d2 = nX; art_ffma2 (d2, x2, invq2);                          // u - X
+                            art_ffma2 (r2, d2, k2048);                                   // (u - X) * 2^11
+                            float nXa, nXb, ra, rb;
+                            art_unpack2 (nX, nXa, nXb);
+                            art_unpack2 (r2, ra, rb);
+                            const __half2 n1 = __floats2half2_rn (nXa, nXb), p2 = __floats2half2_rn (ra, rb);     // low half = first tap
+                            const unsigned int at = dst + (unsigned int) (uu * 512 * CGT + cc * 16);
+                            u_sts32 (at, *reinterpret_cast<const unsigned int *> (&n1) ^ 0x80008000u);            // X = -(-X)
+                            u_sts32 (at + splitBytes, *reinterpret_cast<const unsigned int *> (&p2));
+                            if (digits == 3) {
+                                // third digit: what the fp16 rounding of the second one dropped (11 more bits): every sample keeps >= 22
+                                // significant bits whatever the tile's maximum is
+                                const float2 back = __half22float2 (p2);
+                                unsigned long long e2 = r2, r3 = 0ull;
+                                art_ffma2 (e2, art_pack2 (back.x, back.y), neg2);          // r - fp16 (r)
+                                art_ffma2 (r3, e2, k2048);
+                                float ea, eb;
+                                art_unpack2 (r3, ea, eb);
+                                const __half2 p3 = __floats2half2_rn (ea, eb);
+                                u_sts32 (at + 2u * splitBytes, *reinterpret_cast<const unsigned int *> (&p3));
+                            }
+                        }
                     }
                 }
-                long long cc = UCLK ();
+                long long cc_ = UCLK ();
                 asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> tensor-core reads
                 long long cd = UCLK ();
                 __syncwarp ();
                 if (lane == 0) u_mbar_arrive (pFullA (sl));                          // one arrival per warp: 256 serialised arrivals cost ~500 cycles
-                if (ctid == 0) { UPROF_ADD (7, cc - cb); UPROF_ADD (14, cd - cc); UPROF_ADD (15, UCLK () - cd); }
+                if (ctid == 0) { UPROF_ADD (7, cc_ - cb); UPROF_ADD (14, cd - cc_); UPROF_ADD (15, UCLK () - cd); }
             }
             cur = nxt;
         }
@@ -731,15 +761,37 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
         UPROF_DECL ();
         const int slot = (warp - 12) >> 2;                                  // every quarter is served by two warps: even / odd 16-column chunks
         const unsigned int tmRow = tm + ((unsigned int) (quad * 32) << 16);
-        const unsigned int scratch = scratchBase + (unsigned int) (warp - 12) * (32u * 17u * 4u);
-        const int half16 = lane >> 4, col = lane & 15;
+        const unsigned int scratch = scratchBase + (unsigned int) (warp - 12) * ART_U_SCRATCH;
         constexpr int NCH = 5;                                              // chunks per warp: Npad <= 160
+        /* ---- the tile scanner: block maximum of the samples tile number kk of this CTA will read.  A separate pass over the input
+         * in front of the kernel costs more than these eight warps lose to it (both measured, round 2); they look three tiles
+         * ahead, which also pulls that tile's samples into L2 before the converters ask for them ---- */
+        const int ew = warp - 12;
+        auto scanTile = [&] (int tile, unsigned int kk) {
+            const unsigned int sslot = kk & 3u;
+            u_mbar_wait_relaxed (scanEmptyA (sslot), ((kk >> 2) & 1u) ^ 1u);
+            const ArtJob &job = jobOf (tile);
+            const Where w = whereIs (job, tile);
+            const long long R0 = (long long) u.S0[w.seg * u.G + w.grp] + (long long) M * w.qb * PR;
+            const float m = u_scan_tile<12> (job, CGT, w.c0, R0, R0 + span, T, ew, ART_U_EPI / 32, lane);
+            if (lane == 0) {
+                u_sts32 (sPartA (sslot, ew), __float_as_uint (m));
+                u_mbar_arrive (scanFullA (sslot));
+            }
+            __syncwarp ();
+        };
+        for (int ahead = 0; ahead < 3; ++ahead)
+            if ((long long) blockIdx.x + (long long) ahead * gridDim.x < totalTiles)
+                scanTile (blockIdx.x + ahead * gridDim.x, (unsigned int) ahead);
+        // store mapping after the transposition: a lane owns channel lane % CGT and phase (lane / CGT) % 8 of period lane / (8 * CGT):
+        // one store instruction covers 4 / CGT periods x 8 phases x CGT channels, i.e. whole frames, 32 bytes or more per period
+        const int scc = lane % CGT, sjj = (lane / CGT) & 7, spp = lane / (8 * CGT);
+        constexpr int PPI = 4 / CGT;
         unsigned int lt = 0;
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++lt) {
             const ArtJob &job = jobOf (tile);
-            const int local = tile - job.tile0;
-            const int qg = local / C, c = local - qg * C;
-            const int qb = qg / u.G, grp = qg - qb * u.G;
+            const Where w = whereIs (job, tile);
+            const int grp = w.grp;
             const int phases = min (u.Lg, L - grp * u.Lg);                    // phases of this group
             long long e0 = UCLK ();
             u_mbar_wait_relaxed (accFullA, lt & 1);
@@ -771,36 +823,47 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             if (lane == 0) u_mbar_arrive (accEmptyA);
             long long e2 = UCLK ();
 
-            // job fields into registers: the output stores below may alias anything as far as the compiler knows
-            const long long outputs = job.outputs, outFS = job.outFS;
-            float *const obase = (job.outPlanes ? job.outPlanes[c] : job.out + (long long) c * job.outCS) + (long long) job.nStart * outFS;
-            const long long q0 = (long long) qb * ART_U_ROWS + quad * 32;    // period of this warp's row 0
+            // Output addressing in 32-bit arithmetic relative to one 64-bit pointer per tile: element (period p, phase ph) of this
+            // lane's channel sits at tb[(p * L + ph) * outFS]; `room` is how many of the job's outputs lie at or after the tile's first
+            const long long first = ((long long) w.qb * PR + (quad * 32) / CGT) * L + (long long) grp * u.Lg;      // job-relative index of (warp's period 0, phase 0)
+            const long long left = (long long) job.outputs - first;
+            const int room = left < 0 ? 0 : (left > 0x3fffffff ? 0x3fffffff : (int) left);
+            const int ofs = (int) job.outFS;
+            float *const tb = (job.outPlanes ? job.outPlanes[w.c0 + scc] : job.out + (long long) (w.c0 + scc) * job.outCS) +
+                              ((long long) job.nStart + first) * job.outFS;
+            const int stepN = PPI * L;                                        // outputs between the periods of successive store instructions
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
                 const int c0 = 16 * slot + 32 * ch;
                 if (c0 < Npad && !(dbg & 4)) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        u_stsf (scratch + (unsigned int) (lane * 17 + j) * 4u, y[ch][j]);
-                    __syncwarp ();
-                    const int ph = c0 + col;                                 // this lane's phase
-                    // half-warps take rows rr and rr + 16: with the row pitch of 17 words their 16 columns fall on disjoint banks
-                    long long nl = (q0 + 16 * half16) * L + grp * u.Lg + ph;  // output index inside the job, rows advance by 1
-                    float *op = obase + nl * outFS;
-                    const unsigned int sp = scratch + (unsigned int) (16 * half16 * 17 + col) * 4u;
-                    const long long step = L, ostep = step * outFS;
-                    if (ph < phases) {
-#pragma unroll 8
-                        for (int rr = 0; rr < 16; ++rr) {
-                            const float v = u_ldsf (sp + (unsigned int) rr * (17u * 4u));
-                            if (nl < outputs) *op = v;
-                            nl += step; op += ostep;
+                    for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            u_stsf (scratch + (unsigned int) (lane * 9 + j) * 4u, y[ch][8 * hh + j]);
+                        __syncwarp ();
+                        const int ph = c0 + 8 * hh + sjj;                    // this lane's phase
+                        const unsigned int sp = scratch + (unsigned int) ((CGT * spp + scc) * 9 + sjj) * 4u;
+                        float vv[8];
+#pragma unroll
+                        for (int it = 0; it < 8; ++it)                       // 32 / CGT periods per warp, PPI per instruction
+                            vv[it] = u_ldsf (sp + (unsigned int) it * (unsigned int) (CGT * PPI * 9 * 4));
+                        int nl = spp * L + ph;                                // output index relative to `first`
+                        if (ph < phases) {
+#pragma unroll
+                            for (int it = 0; it < 8; ++it) {
+                                if (nl < room) tb[nl * ofs] = vv[it];
+                                nl += stepN;
+                            }
                         }
+                        __syncwarp ();
                     }
-                    __syncwarp ();
                 }
             }
-            if (tid == 12 * 32) { UPROF_ADD (8, e1 - e0); UPROF_ADD (9, e2 - e1); UPROF_ADD (6, UCLK () - e2); UPROF_ADD (10, 1); }
+            long long e3 = UCLK ();
+            if ((long long) tile + 3LL * gridDim.x < totalTiles)
+                scanTile (tile + 3 * gridDim.x, lt + 3u);
+            if (tid == 12 * 32) { UPROF_ADD (8, e1 - e0); UPROF_ADD (9, e2 - e1); UPROF_ADD (6, e3 - e2); UPROF_ADD (10, 1); UPROF_ADD (2, UCLK () - e3); }
         }
         UPROF_FLUSH ();
     }
@@ -815,11 +878,15 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
 
 /* ---- host side -------------------------------------------------------------------------------------- */
 
+int g_artTensorDigits = -1;        // signal digits of the tensor-core form: 3 (default) or 2; ART_B200_DIGITS sets the initial value
+
 static size_t umma_smem (const ArtUmma &u)
 {
-    const size_t xc = (size_t) 2 * (2 * u.NS) * u.rows * 16;                 // two splits
-    return xc + (size_t) u.stages * 3 * 2 * u.Npad * 16 + 8 * 32 * 17 * sizeof (float) + 384 + ART_U_MAXK * 8;
+    const size_t xc = (size_t) u.digits * (2 * u.NS) * u.rows * 16;          // one split per signal digit
+    return xc + (size_t) u.stages * 3 * 2 * u.Npad * 16 + 8 * ART_U_SCRATCH + 384 + ART_U_MAXK * 8 + 64 + 4 * 32;
 }
+
+#define ART_U_SMEM_MAX (227 * 1024)
 
 bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsigned long long totalOutputs,
                   int smCount, ArtUmma &u)
@@ -827,6 +894,10 @@ bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsi
     if (g_artTensorMode < 0) {
         const char *e = getenv ("ART_B200_UMMA");
         g_artTensorMode = e ? atoi (e) : 1;
+    }
+    if (g_artTensorDigits < 0) {
+        const char *e = getenv ("ART_B200_DIGITS");
+        g_artTensorDigits = e && atoi (e) == 2 ? 2 : 3;
     }
     const int enabled = g_artTensorMode;
     if (!enabled) return false;
@@ -850,6 +921,7 @@ bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsi
 
     memset (&u, 0, sizeof u);
     u.L = L; u.M = M;
+    u.digits = g_artTensorDigits;
     // tensor memory holds 3 accumulators of at most 160 columns: more phases are handled in G groups, each with its own table
     u.G = (L + 159) / 160;
     u.Lg = (L + u.G - 1) / u.G;
@@ -870,44 +942,52 @@ bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsi
         for (int a = 0; a * M + 16 * i < flatEnd; ++a) ++c;
         u.nA[i] = (unsigned char) c;
     }
-    // rows: 128 + aMax, even, and 2..6 (mod 8) so that the 16-byte row slots of neighbouring planes fall on different banks
-    int rows = ART_U_ROWS + aMax;
-    while ((rows & 1) || (rows & 7) < 2 || (rows & 7) > 6) ++rows;
-    if (rows > 144) return false;
-    u.rows = rows;
     // filter quantum: the exact accumulator holds sum X1*H1 with |X1| <= 2^11 and sum |H1| <= absSum * 2^DH + T/2
     u.DH = 0;
     for (int dh = 11; dh >= 6; --dh)
         if ((double) k.absSum * (double) (1 << dh) + 0.5 * k.T < 8191.0) { u.DH = dh; break; }
     if (!u.DH) return false;
     u.tableHalfs = u.numK * 3 * 2 * u.Npad * 8;
-    u.stages = ART_U_STAGES;
-    // operand A: all KI plane pairs of a row if they fit, else a ring of NS | KI slots -- pairs are used in order, each
-    // for all of its row shifts in a row, so a slot can take pair i + NS as soon as the MMAs of pair i are done.  Slots
-    // shared by several pairs need those pairs to be released by the same issuers (both, i.e. >= 3 k-steps per pair).
-    u.NS = 0;
-    for (int ns = u.KI < ART_U_MAXKI ? u.KI : ART_U_MAXKI; ns >= 1; --ns) {
-        if (u.KI % ns) continue;
-        u.NS = ns;
-        if (umma_smem (u) <= 224 * 1024) break;
+
+    // channels per tile: the 128 MMA rows are 128 / cg periods x cg channels (channel fastest), so that the converters read
+    // whole frames of an interleaved block and the epilogue stores whole frames; more channels go through planar scratch
+    // (art_device.cu) one channel per tile.  Fewer when the row shifts no longer fit the operand.
+    for (int cg = (k.C == 4 ? 4 : ((k.C == 2 || k.C == 6) ? 2 : 1)); cg >= 1; cg >>= 1) {
+        u.cg = cg;
+        u.periods = ART_U_ROWS / cg + aMax;
+        // rows: cg * periods, padded so that the 16-byte row slots a warp of converters writes into the two planes of a pair
+        // fall on different banks (plane pitch = rows * 16 bytes)
+        int rows = cg * u.periods;
+        if (cg == 1) while ((rows & 1) || (rows & 7) < 2 || (rows & 7) > 6) ++rows;
+        else if (cg == 2) while (!(rows & 1)) ++rows;
+        else while ((rows & 7) == 0 || (rows & 7) == 4) ++rows;
+        if (rows > 144) continue;
+        u.rows = rows;
+        u.stages = ART_U_STAGES;
+        // operand A: all KI plane pairs of a row if they fit, else a ring of NS | KI slots -- pairs are used in order, each
+        // for all of its row shifts in a row, so a slot can take pair i + NS as soon as the MMAs of pair i are done.
+        // The filter ring shrinks to 4 k-steps before the operand gives up a slot.
         u.NS = 0;
+        for (int ns = u.KI < ART_U_MAXKI ? u.KI : ART_U_MAXKI; ns >= 1 && !u.NS; --ns) {
+            if (u.KI % ns) continue;
+            u.NS = ns;
+            for (u.stages = ART_U_STAGES; u.stages > 2 * ART_U_GROUP && umma_smem (u) > ART_U_SMEM_MAX; u.stages -= ART_U_GROUP) { }
+            if (umma_smem (u) > ART_U_SMEM_MAX) u.NS = 0;
+        }
+        if (!u.NS) continue;
+        if (getenv ("ART_B200_TRACE"))
+            fprintf (stderr, "[art] umma L=%d M=%d G=%d Npad=%d KI=%d NS=%d numK=%d cg=%d rows=%d DH=%d digits=%d stages=%d smem=%zu\n",
+                     u.L, u.M, u.G, u.Npad, u.KI, u.NS, u.numK, u.cg, u.rows, u.DH, u.digits, u.stages, umma_smem (u));
+        return true;
     }
-    if (!u.NS) return false;
-    if (u.NS < u.KI)
-        for (int i = 0; i < u.KI; ++i)
-            if (u.nA[i] < 3) return false;
-    while (u.stages > 2 * ART_U_GROUP && umma_smem (u) > 224 * 1024) u.stages -= ART_U_GROUP;
-    if (umma_smem (u) > 224 * 1024) return false;
-    if (getenv ("ART_B200_TRACE"))
-        fprintf (stderr, "[art] umma L=%d M=%d G=%d Npad=%d KI=%d NS=%d numK=%d rows=%d DH=%d stages=%d smem=%zu\n",
-                 u.L, u.M, u.G, u.Npad, u.KI, u.NS, u.numK, u.rows, u.DH, u.stages, umma_smem (u));
-    return true;
+    return false;
 }
 
 int artUmmaTiles (const ArtUmma &u, int channels, unsigned int outputs)
 {
     const long long Q = ((long long) outputs + u.L - 1) / u.L;
-    return (int) (((Q + ART_U_ROWS - 1) / ART_U_ROWS) * channels * u.G);
+    const int pr = ART_U_ROWS / u.cg;
+    return (int) (((Q + pr - 1) / pr) * (channels / u.cg) * u.G);
 }
 
 static size_t umma_align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
@@ -915,7 +995,7 @@ static size_t umma_align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
 size_t artUmmaTableBytes (const ArtUmma &u, int numTables, int numJobs, int totalTiles)
 {
     return umma_align16 ((size_t) numTables * u.G * u.tableHalfs * sizeof (unsigned short)) + umma_align16 ((size_t) numJobs * u.G * sizeof (int)) +
-           2 * (size_t) totalTiles * sizeof (int);
+           (size_t) totalTiles * sizeof (int);
 }
 
 void artUmmaCarve (ArtUmma &u, void *tables, int numTables, int numJobs)
@@ -925,14 +1005,13 @@ void artUmmaCarve (ArtUmma &u, void *tables, int numTables, int numJobs)
     p += umma_align16 ((size_t) numTables * u.G * u.tableHalfs * sizeof (unsigned short));
     u.S0 = reinterpret_cast<int *> (p);
     p += umma_align16 ((size_t) numJobs * u.G * sizeof (int));
-    u.tileExp = reinterpret_cast<int *> (p);
-    u.tileJob = nullptr;            // follows tileExp: set by the launcher, which knows the tile count
+    u.tileJob = reinterpret_cast<int *> (p);
 }
 
-void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int numJobs, int numTables, int smCount,
-                    const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream)
+template <int CGT>
+static void umma_launch_one (const ArtClass &k, const ArtUmma &u, int totalTiles, int grid, const ArtJob &single, const ArtJob *d_jobs,
+                             int roleProf, cudaStream_t stream)
 {
-    if (totalTiles <= 0) return;
     static bool configured[16] = { false };
     int device = 0;
     ART_CUDA_CHECK (cudaGetDevice (&device));
@@ -941,19 +1020,26 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
         // the pool that comes from is threads x registers-per-thread as compiled, so check that it suffices -- a warpgroup
         // asking for registers that never become free would spin forever
         cudaFuncAttributes fa;
-        ART_CUDA_CHECK (cudaFuncGetAttributes (&fa, art_sinc_umma_kernel));
-        if (128 * (fa.numRegs - 56) + 256 * (fa.numRegs - 88) < 256 * (120 - fa.numRegs) || fa.numRegs < 88 || fa.numRegs > 120) {
+        ART_CUDA_CHECK (cudaFuncGetAttributes (&fa, art_sinc_umma_kernel<CGT>));
+        if (128 * (fa.numRegs - 56) + 256 * (fa.numRegs - 88) < 256 * (120 - fa.numRegs) || fa.numRegs < 88 || fa.numRegs > 120)
             artRaise ("art_sinc_umma_kernel was compiled with %d registers per thread: its register re-allocation plan does not hold", fa.numRegs);
-        }
-        ART_CUDA_CHECK (cudaFuncSetAttribute (art_sinc_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        ART_CUDA_CHECK (cudaFuncSetAttribute (art_sinc_umma_kernel<CGT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ART_U_SMEM_MAX));
         configured[device & 15] = true;
     }
+    void *prof;
+    artProfileBegin (stream, &prof);
+    art_sinc_umma_kernel<CGT><<<grid, ART_U_THREADS, umma_smem (u), stream>>> (k, u, single, d_jobs, totalTiles, roleProf);
+    artProfileEnd (stream, prof);
+    ART_CUDA_CHECK (cudaGetLastError ());
+}
+
+void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int numJobs, int numTables, int smCount,
+                    const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream)
+{
+    if (totalTiles <= 0) return;
     int histBlocks = (k.C * k.T + 127) / 128;
     if (histBlocks > 32) histBlocks = 32;
-    const int prepBlocks = numTables * u.G * u.Npad + (numJobs * u.G + 127) / 128 + totalTiles + numJobs * histBlocks;
-    ArtUmma uu = u;
-    uu.tileJob = u.tileExp + totalTiles;
-    ART_CUDA_CHECK (cudaMemsetAsync (u.tileExp, 0, (size_t) totalTiles * sizeof (int), stream));
+    const int prepBlocks = numTables * u.G * u.Npad + (numJobs * u.G + 127) / 128 + (totalTiles + 127) / 128 + numJobs * histBlocks;
     static int prepDbg = -1;
     if (prepDbg < 0) {
         prepDbg = 0;
@@ -961,6 +1047,7 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
         if (const char *d = getenv ("ART_B200_UDBG")) prepDbg = atoi (d);
 #endif
     }
+    const ArtUmma &uu = u;
     art_umma_prep_kernel<<<prepBlocks, 128, 0, stream>>> (k, uu, single, d_jobs, numJobs, numTables, histBlocks, totalTiles, prepDbg);
     ART_CUDA_CHECK (cudaGetLastError ());
     const int grid = totalTiles < smCount ? totalTiles : smCount;
@@ -975,16 +1062,14 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
             cudaDeviceSynchronize ();
             if (cudaMemcpyFromSymbol (h, g_uprof, sizeof h) != cudaSuccess) return;
             const double n = h[10] ? (double) h[10] : 1.0;
-            fprintf (stderr, "[art] umma cycles per tile: producer wait-empty %.0f | mma wait-planes %.0f wait-acc %.0f wait-h %.0f tile %.0f | "
+            fprintf (stderr, "[art] umma cycles per tile: producer wait-empty %.0f | mma wait-planes %.0f wait-acc+scan %.0f wait-h %.0f tile %.0f | "
                      "convert wait-planes %.0f | epilogue wait %.0f drain %.0f | tiles %.0f | mma issue %.0f commit %.0f region %.0f | epilogue store %.0f | convert split %.0f fence %.0f arrive %.0f\n",
                      h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[8] / n, h[9] / n, n, h[11] / n, h[12] / n, h[13] / n,
                      h[6] / n, h[7] / n, h[14] / n, h[15] / n);
         });
     }
-    void *prof;
-    artProfileBegin (stream, &prof);
-    art_sinc_umma_kernel<<<grid, ART_U_THREADS, umma_smem (u), stream>>> (k, uu, single, d_jobs, totalTiles, roleProf);
-    artProfileEnd (stream, prof);
-    ART_CUDA_CHECK (cudaGetLastError ());
+    if (u.cg == 4)      umma_launch_one<4> (k, uu, totalTiles, grid, single, d_jobs, roleProf, stream);
+    else if (u.cg == 2) umma_launch_one<2> (k, uu, totalTiles, grid, single, d_jobs, roleProf, stream);
+    else                umma_launch_one<1> (k, uu, totalTiles, grid, single, d_jobs, roleProf, stream);
     g_artLaunches += 2;
 }

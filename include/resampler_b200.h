@@ -44,6 +44,16 @@ void resampleB200PathCounts (unsigned long long *generic, unsigned long long *pe
  * mode.  TensorLaunches counts its launches (PathCounts' `periodic` counts the FFMA form only). */
 void resampleB200SetTensorPath (int mode);
 unsigned long long resampleB200TensorLaunches (void);
+/* Arithmetic of the tensor-core form.  A tile (128 MMA rows: 128 / c periods of c = 1, 2 or 4 channels, 0.1-0.4 s of signal) is
+ * converted to fixed point relative to ITS maximum and cut into fp16 digits of 11 bits.
+ *   3 digits (default): every sample keeps >= 22 significant bits of its own magnitude, whatever else the tile holds: the output is
+ *                       within float rounding (observed <= 3e-7) of the reference relative to the LOCAL signal level, like the
+ *                       reference's own float arithmetic and this library's FFMA kernels.  Six MMAs per 16 taps.
+ *   2 digits:           samples are exact to 2^-24 of the TILE's maximum -- below the quantisation step of 24-bit PCM, but a passage
+ *                       60 dB under the loudest sample of its tile is only accurate to ~5e-5 of its own level.  Five MMAs per 16
+ *                       taps, ~15 % faster.
+ * The environment variable ART_B200_DIGITS sets the initial value. */
+void resampleB200SetTensorDigits (int digits);
 /* measurement aid: when enabled, every convolution kernel launch is bracketed by CUDA events on its
  * own stream; Collect waits for them, returns how many launches were timed and their summed
  * duration in milliseconds, and clears the list */

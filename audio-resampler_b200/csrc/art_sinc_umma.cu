@@ -152,6 +152,8 @@ __device__ __forceinline__ void u_commit (unsigned int bar)
 
 /* optional role timing (ART_B200_UPROF=1): cycles spent waiting / working per role, summed over CTAs */
 __device__ unsigned long long g_uprof[16];
+__device__ unsigned long long g_utime[160][4];         // per CTA (last launch): globaltimer at entry, first MMA issue, last accFull commit, exit
+__device__ __forceinline__ unsigned long long u_gtime () { unsigned long long t; asm volatile ("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define UCLK() (prof ? clock64 () : 0ll)
 #define UPROF_ADD(slot, cyc) do { if (prof) pacc[slot] += (unsigned int) (cyc); } while (0)      /* role-local, flushed once per thread */
 #define UPROF_DECL()  unsigned int pacc[16] = { 0 }
@@ -374,6 +376,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
     extern __shared__ __align__ (1024) unsigned char smem[];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (prof && tid == 0 && blockIdx.x < 160) g_utime[blockIdx.x][0] = u_gtime ();
     const int L = u.L, M = u.M, Npad = u.Npad, KI = u.KI, NS = u.NS, numK = u.numK, C = k.C, T = k.T;
     const int CG = C / CGT;                                 // channel groups: tiles per (period block, phase group)
     constexpr int PR = ART_U_ROWS / CGT;                    // periods per tile
@@ -515,6 +518,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                 if (lane == 0 && me == 0) { UPROF_ADD (1, t3 - t0); UPROF_ADD (3, UCLK () - t3); }
                 asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
                 long long t4 = UCLK ();
+                if (prof && me == 0 && lane == 0 && lt == 0 && ks0 == 0 && blockIdx.x < 160) g_utime[blockIdx.x][1] = u_gtime ();
                 if (u_elect ()) {
                     for (int g = 0; g < cnt; ++g) {
                         const int ks = ks0 + g;
@@ -548,6 +552,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             if (u_elect ())
                 u_commit (accFullA);
             __syncwarp ();
+            if (prof && me == 0 && lane == 0 && blockIdx.x < 160) g_utime[blockIdx.x][2] = u_gtime ();
             if (lane == 0 && me == 0) UPROF_ADD (4, UCLK () - t2);
         }
         UPROF_FLUSH ();
@@ -696,7 +701,8 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                 for (int uu = 0; uu < NV; ++uu) v[uu] = vn[uu];
                 // the next pair's loads (of the next tile after the last pair) fly while this pair is converted
                 // (the next tile's job lookup is a chain of dependent global loads: done early, at the first pair, where
-                //  the converters have a whole tile of slack, not in front of the last pair the MMAs are waiting for)
+                //  the converters have a whole tile of slack, not in front of the last pair the MMAs are waiting for).
+                // (Two pairs ahead was tried: the extra registers spill and the conversion slows down by more than the loads gain.)
                 if (i == 0 && more) nxt = source (tile + gridDim.x);
                 if (i + 1 < KI) fetch (cur, i + 1, vn);
                 else if (more) fetch (nxt, 0, vn);
@@ -773,7 +779,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             const ArtJob &job = jobOf (tile);
             const Where w = whereIs (job, tile);
             const long long R0 = (long long) u.S0[w.seg * u.G + w.grp] + (long long) M * w.qb * PR;
-            const float m = u_scan_tile<12> (job, CGT, w.c0, R0, R0 + span, T, ew, ART_U_EPI / 32, lane);
+            const float m = u_scan_tile<20> (job, CGT, w.c0, R0, R0 + span, T, ew, ART_U_EPI / 32, lane);
             if (lane == 0) {
                 u_sts32 (sPartA (sslot, ew), __float_as_uint (m));
                 u_mbar_arrive (scanFullA (sslot));
@@ -849,7 +855,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                         for (int it = 0; it < 8; ++it)                       // 32 / CGT periods per warp, PPI per instruction
                             vv[it] = u_ldsf (sp + (unsigned int) it * (unsigned int) (CGT * PPI * 9 * 4));
                         int nl = spp * L + ph;                                // output index relative to `first`
-                        if (ph < phases) {
+                        if (ph < phases && !(dbg & 32)) {
 #pragma unroll
                             for (int it = 0; it < 8; ++it) {
                                 if (nl < room) tb[nl * ofs] = vv[it];
@@ -870,6 +876,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
 
     asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads ();
+    if (prof && tid == 0 && blockIdx.x < 160) g_utime[blockIdx.x][3] = u_gtime ();
     if (warp == 0) {
         __syncwarp ();
         asm volatile ("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tm), "r"(512));
@@ -1062,6 +1069,19 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
             cudaDeviceSynchronize ();
             if (cudaMemcpyFromSymbol (h, g_uprof, sizeof h) != cudaSuccess) return;
             const double n = h[10] ? (double) h[10] : 1.0;
+            unsigned long long tl[160][4];
+            if (cudaMemcpyFromSymbol (tl, g_utime, sizeof tl) == cudaSuccess) {
+                unsigned long long t0 = ~0ull, t3 = 0;
+                for (int i = 0; i < 148; ++i) { if (tl[i][0] && tl[i][0] < t0) t0 = tl[i][0]; if (tl[i][3] > t3) t3 = tl[i][3]; }
+                double a1 = 0, a2 = 0, a3 = 0, m1 = 0, m2 = 0, m3 = 0, e0 = 0; int nn = 0;
+                double lo3 = 1e30;
+                for (int i = 0; i < 148; ++i) if (tl[i][0]) {
+                    const double s = (double) (tl[i][0] - t0), f = (double) (tl[i][1] - t0), l = (double) (tl[i][2] - t0), x = (double) (tl[i][3] - t0);
+                    e0 += s; a1 += f; a2 += l; a3 += x; if (f > m1) m1 = f; if (l > m2) m2 = l; if (x > m3) m3 = x; if (x < lo3) lo3 = x; ++nn;
+                }
+                if (nn) fprintf (stderr, "[art] umma timeline of the last launch (us from first CTA entry; avg / max over %d CTAs): entry %.1f | first MMA %.1f / %.1f | last MMA commit %.1f / %.1f | exit %.1f / %.1f (min %.1f)\n",
+                                 nn, e0 / nn / 1e3, a1 / nn / 1e3, m1 / 1e3, a2 / nn / 1e3, m2 / 1e3, a3 / nn / 1e3, m3 / 1e3, lo3 / 1e3);
+            }
             fprintf (stderr, "[art] umma cycles per tile: producer wait-empty %.0f | mma wait-planes %.0f wait-acc+scan %.0f wait-h %.0f tile %.0f | "
                      "convert wait-planes %.0f | epilogue wait %.0f drain %.0f | tiles %.0f | mma issue %.0f commit %.0f region %.0f | epilogue store %.0f | convert split %.0f fence %.0f arrive %.0f\n",
                      h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[8] / n, h[9] / n, n, h[11] / n, h[12] / n, h[13] / n,

@@ -493,6 +493,15 @@ def run_gpu_arm(args):
     ms_s_max, tot_s = reduce_over_ranks(dist if world > 1 else None, dev, ms_s, float(made))
     strict_value = tot_s * w.ch / (ms_s_max * 1e-3) / 1e6
 
+    # ---- the tensor-core kernel with two signal digits (the round-1 arithmetic: exact to 2^-24 of a tile's peak) -----------------
+    two_digit_value = None
+    if tensor:
+        lib.resampleB200SetTensorDigits(2)
+        made, ms_2 = time_launches(torch, batch, work_stream, 20, warm=3)
+        lib.resampleB200SetTensorDigits(3)
+        ms_2_max, tot_2 = reduce_over_ranks(dist if world > 1 else None, dev, ms_2, float(made))
+        two_digit_value = tot_2 * w.ch / (ms_2_max * 1e-3) / 1e6
+
     # ---- roofline of the convolution kernel ------------------------------------------------------------------------------------
     bpos = w.bytes_per_output_sample
     per_launch_samples = out_frames * w.ch / max(1, kern_launches)
@@ -510,11 +519,11 @@ def run_gpu_arm(args):
                 "fp32_tflops_reference_opcount": alg_tflops,
                 "timed": "inside the sustained region (clocks as in `clocks`)"}
     if tensor:
-        # what the tensor pipe executes: per tile of 128 periods x 1 channel, 36 k-steps of 5 MMAs (128 x 160 x 16) --
-        # the fixed-point split (5 digit products) and the band's zero blocks (576 executed taps for 380) included
+        # what the tensor pipe executes: per tile of 128 rows (64 periods x 2 channels), 36 k-steps of 6 MMAs (128 x 160 x 16) --
+        # the fixed-point split (6 digit products) and the band's zero blocks (576 executed taps for 380) included
         per_stream_out = out_frames / max(1, total_launches) / streams
         tiles = -(-(-(-per_stream_out // 160)) // 128) * w.ch * streams
-        mma_flops = tiles * 36 * 5 * 2.0 * 128 * 160 * 16
+        mma_flops = tiles * 36 * 6 * 2.0 * 128 * 160 * 16
         tens = mma_flops / (kern_avg_ms * 1e-3) / 1e12
         tpeak_b = peaks.get("bf16_tflops") or 1622.6
         tpeak_s = peaks.get("bf16_tflops_sustained") or tpeak_b
@@ -532,7 +541,7 @@ def run_gpu_arm(args):
                     "pipe binds, not HBM; frac is the HBM-roofline fraction BASELINE.json's metric asks for"})
     for cand in ("r02_umma_ncu.json", "r01_umma_ncu.json") if tensor else ("r01_periodic_final_ncu.json",) if periodic else ("r01_generic_v2_ncu.json",):
         prof = ROOT / "profiles" / cand
-        if prof.exists() and streams == 64 and frames == (1 << 18):
+        if prof.exists() and streams in (64, 74) and frames == (1 << 18):
             try:
                 roofline["traffic"] = json.loads(prof.read_text()).get("dram_bytes_per_launch")
                 roofline["traffic_source"] = f"profiles/{prof.name} (ncu --set full, same launch geometry)"
@@ -561,12 +570,15 @@ def run_gpu_arm(args):
                          f"{streams * batch.cap * w.ch * 4 / 2**20:.0f} MiB out: every launch touches buffers larger than the 126 MB L2 that "
                          "three other launches have used since",
                    "parallelism": f"streams sharded over {world} GPU(s), no data-path collective",
-                   "arithmetic": ("float32 in, float32 out; tensor-core kernel: block-scaled fixed-point fp16 digit products with exact "
-                                  "fp32 accumulation (within 2^-24 of the peak of each 0.43 s block; strict_fp32_value is the FFMA form)" if tensor else
+                   "arithmetic": ("float32 in, float32 out; tensor-core kernel: fixed-point fp16 digit products (3 signal x 3 filter digits, 6 MMAs per 16 taps) "
+                                  "with exact fp32 accumulation of the leading term: every sample keeps >= 22 bits of its own magnitude (float accuracy "
+                                  "relative to the local signal level); strict_fp32_value is the FFMA form, two_digit_value the round-1 arithmetic" if tensor else
                                   "float32 FMA")},
         "timed_region_s": ms_max * 1e-3, "wall_ms_per_step": wall_ms / args.steps,
         "burst_value": burst_value, "burst": "20 launches (~5 ms) on the cold GPU before the sustained region",
         "strict_fp32_value": strict_value, "strict_fp32_kernel": strict_kernel,
+        "two_digit_value": two_digit_value,
+        "two_digit": "resampleB200SetTensorDigits(2): five MMAs per 16 taps instead of six; exact to 2^-24 of a tile's peak instead of 2^-22 of every sample",
         "clocks": clock_summary, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "parity_check": parity, "configs": configs,
     }
@@ -755,7 +767,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=64, help="independent stereo streams per GPU")
+    ap.add_argument("--streams", type=int, default=74,
+                    help="independent stereo streams per GPU (74 x 28 tiles of 64 periods = 2072 = 14 per SM: no partial last wave)")
     ap.add_argument("--frames", type=int, default=1 << 18, help="input frames per stream per block (= per launch)")
     ap.add_argument("--launches-per-step", type=int, default=192, help="blocks every stream advances by in one step")
     ap.add_argument("--e2e-streams", type=int, default=64)

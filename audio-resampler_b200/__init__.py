@@ -42,7 +42,7 @@ class Resample(C.Structure):
                 ("tempFilter", C.c_void_p), ("outputOffset", C.c_double), ("fixedRatio", C.c_double),
                 ("lowpassRatio", C.c_double), ("subsample", C.c_void_p),
                 ("buffers", C.c_void_p), ("filters", C.POINTER(C.POINTER(C.c_float))),
-                ("device", C.c_void_p)]
+                ("device", C.c_void_p), ("prefilterLead", C.c_int), ("prefilterTaps", C.c_void_p), ("plainDevice", C.c_void_p)]
 
 
 class BiquadCoefficients(C.Structure):
@@ -110,6 +110,7 @@ def load() -> C.CDLL:
         "resampleB200PathCounts": (None, [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]),
         "resampleB200SetTensorPath": (None, [i32]),
         "resampleB200SetTensorDigits": (None, [i32]),
+        "resampleB200AttachPrefilter": (i32, [ctx, C.POINTER(Biquad), i32]),
         "resampleB200TensorLaunches": (C.c_ulonglong, []),
         "resampleB200ProfileEnable": (None, [i32]),
         "resampleB200ProfileCollect": (C.c_ulonglong, [C.POINTER(dbl)]),
@@ -140,7 +141,7 @@ EXPORTED_SYMBOLS = [
     "resampleGetNumFilters", "resampleInterpolationUsed", "resampleReset", "resampleFree",
     "biquad_init", "biquad_lowpass", "biquad_highpass", "biquad_apply_buffer", "biquad_apply_sample",
     "resampleB200SetDevice", "resampleB200GetDeviceCount", "resampleB200Synchronize", "resampleB200KernelLaunches", "resampleB200LastError",
-    "resampleB200PathCounts", "resampleB200SetTensorPath", "resampleB200SetTensorDigits", "resampleB200TensorLaunches", "resampleB200ProfileEnable", "resampleB200ProfileCollect",
+    "resampleB200PathCounts", "resampleB200SetTensorPath", "resampleB200SetTensorDigits", "resampleB200AttachPrefilter", "resampleB200TensorLaunches", "resampleB200ProfileEnable", "resampleB200ProfileCollect",
     "resampleProcessInterleavedDevice", "resampleProcessDevice", "resampleBatchProcessInterleavedDevice",
     "resampleBatchProcessInterleaved", "resampleProcessBlocksInterleavedDevice", "biquad_apply_cascade_interleaved",
     "biquad_apply_cascade_interleaved_device",

@@ -75,6 +75,15 @@ static float **design_bank (int taps, int filters, double lowpass, int flags)
 
 /* ------------------------------------------------------------------------------ init */
 
+static int device_mode (int flags)
+{
+    int mode = 0;
+    if (flags & SUBSAMPLE_INTERPOLATE)   mode |= ART_MODE_INTERP;
+    if (flags & INCLUDE_LOWPASS)         mode |= ART_MODE_LOWPASS;
+    if (flags & EXTEND_CONVOLUTION_MATH) mode |= ART_MODE_PRECISE;   /* resampler.c:191-196 */
+    return mode;
+}
+
 Resample *resampleInit (int numChannels, int numTaps, int numFilters, double lowpassRatio, int flags)
 {
     Resample *cxt;
@@ -114,11 +123,8 @@ Resample *resampleInit (int numChannels, int numTaps, int numFilters, double low
     cxt->outputOffset = numTaps / 2;                                /* resampler.c:176-177 */
     cxt->inputIndex = numTaps;
 
-    if (flags & SUBSAMPLE_INTERPOLATE)   mode |= ART_MODE_INTERP;
-    if (flags & INCLUDE_LOWPASS)         mode |= ART_MODE_LOWPASS;
-    if (flags & EXTEND_CONVOLUTION_MATH) mode |= ART_MODE_PRECISE;   /* resampler.c:191-196 */
-
-    cxt->device = artDevCreate (numChannels, numTaps, numFilters, mode, (const float *const *) cxt->filters);
+    mode = device_mode (flags);
+    cxt->device = artDevCreate (numChannels, numTaps, 0, numFilters, mode, (const float *const *) cxt->filters);
     if (!cxt->device) {
         resampleFree (cxt);
         return NULL;
@@ -188,12 +194,105 @@ void resampleFree (Resample *cxt)                                   /* resampler
         return;
     if (cxt->device)
         artDevDestroy (cxt->device);
+    if (cxt->plainDevice)
+        artDevDestroy (cxt->plainDevice);
+    free (cxt->prefilterTaps);
     if (cxt->filters) {
         for (r = 0; r <= cxt->numFilters; ++r)
             free (cxt->filters[r]);
         free (cxt->filters);
     }
     free (cxt);
+}
+
+/* ------------------------------------------------------------------- fused pre-filter */
+
+/* include/resampler_b200.h: fold a cascade of biquad sections (biquad.c:51-74 coefficients, :106-163 recursion) into the bank */
+int resampleB200AttachPrefilter (Resample *cxt, const Biquad *sections, int numSections)
+{
+    enum { MAXLEN = 1024 };
+    double *g, *tmp, total = 0.0, tail;
+    float **rows;
+    ArtDev *fresh;
+    int s, n, d, r, m, k, len, lead, T, Tk, mode = ART_MODE_LOWPASS;        /* never the pass-through shortcut (resampler.c:1141-1142) */
+
+    if (!cxt || !sections || numSections < 1 || numSections > 16)
+        return -1;
+    T = cxt->numTaps;
+    if (cxt->prefilterLead) {
+        fprintf (stderr, "libresampler_b200: a pre-filter is already attached\n");
+        return -1;
+    }
+    if (cxt->flags & EXTRAPOLATE_ENDPOINTS) {
+        fprintf (stderr, "libresampler_b200: a fused pre-filter cannot be combined with EXTRAPOLATE_ENDPOINTS (the reference extrapolates the filtered signal)\n");
+        return -1;
+    }
+    if (cxt->inputIndex != T || (cxt->flags & RESAMPLER_FLUSHED)) {
+        fprintf (stderr, "libresampler_b200: attach the pre-filter before the first input (or right after resampleReset)\n");
+        return -1;
+    }
+    for (s = 0; s < numSections; ++s)
+        for (d = 0; d < 4; ++d)
+            if (sections[s].x[d] != 0.0f || sections[s].y[d] != 0.0f) {
+                fprintf (stderr, "libresampler_b200: pre-filter sections must be in their initial (zero) state\n");
+                return -1;
+            }
+
+    /* impulse response of the cascade, in double, from the float coefficients the sections hold */
+    g = calloc (MAXLEN, sizeof *g);
+    tmp = calloc (MAXLEN, sizeof *tmp);
+    g[0] = 1.0;
+    for (s = 0; s < numSections; ++s) {
+        const Biquad *q = &sections[s];
+        memcpy (tmp, g, sizeof *g * MAXLEN);
+        for (n = 0; n < MAXLEN; ++n) {
+            double y = (double) q->a[0] * tmp[n];
+            for (d = 1; d <= q->order && d <= 4; ++d)
+                if (n >= d)
+                    y += (double) q->a[d] * tmp[n - d] - (double) q->b[d] * g[n - d];
+            g[n] = y;
+        }
+    }
+    for (n = 0; n < MAXLEN; ++n) total += fabs (g[n]);
+    /* shortest length (a multiple of 32: rows stay 128-byte aligned) that leaves less than 1e-9 of the response's mass behind */
+    for (len = 32, tail = total; len < MAXLEN; len += 32) {
+        tail = 0.0;
+        for (n = len; n < MAXLEN; ++n) tail += fabs (g[n]);
+        if (tail <= 1e-9 * total) break;
+    }
+    free (tmp);
+    if (!(total > 0.0) || len >= MAXLEN || T + len > 1024) {
+        fprintf (stderr, "libresampler_b200: the pre-filter's impulse response is too long to fold into %d taps (needs %d more)\n", T, len);
+        free (g);
+        return -1;
+    }
+    lead = len;                                 /* h'[m] = sum_k g[k] * row[m + k], m = -(len - 1) .. T - 1, plus one zero tap in front */
+    Tk = T + lead;
+
+    rows = calloc ((size_t) cxt->numFilters + 1, sizeof *rows);
+    for (r = 0; r <= cxt->numFilters; ++r) {
+        const float *row = cxt->filters[r];
+        rows[r] = calloc (Tk, sizeof (float));
+        for (m = -lead + 1; m < T; ++m) {
+            double acc = 0.0;
+            for (k = m < 0 ? -m : 0; k < len && m + k < T; ++k)
+                acc += g[k] * (double) row[m + k];
+            rows[r][m + lead] = (float) acc;
+        }
+    }
+    mode |= device_mode (cxt->flags);
+    fresh = artDevCreate (cxt->numChannels, Tk, lead, cxt->numFilters, mode, (const float *const *) rows);
+    for (r = 0; r <= cxt->numFilters; ++r) free (rows[r]);
+    free (rows);
+    if (!fresh) {
+        free (g);
+        return -1;
+    }
+    artDevDestroy (cxt->device);
+    cxt->device = fresh;
+    cxt->prefilterLead = lead;
+    cxt->prefilterTaps = g;
+    return 0;
 }
 
 /* ------------------------------------------------------------------- the control loop */
@@ -381,6 +480,43 @@ static int run_call_with_endpoints (Resample *cxt, int io, ArtCallPlan *call, co
     return failed;
 }
 
+/* Flush of a stream with a folded-in pre-filter.  The reference pads the FILTERED signal with T/2 zeros (the caller's biquads never
+ * see the padding, art.c:1011-1017 / resampler.c:663-685); padding the raw signal instead would let the cascade ring on into the
+ * last outputs.  So, for this one call per stream: take the raw history (T + lead frames), filter its newest T frames on the host,
+ * and run the flush on a device context that holds the UNFUSED bank with that filtered history. */
+static int run_flush_prefiltered (Resample *cxt, int io, const ArtCallPlan *call, void *out, void *stream)
+{
+    const int T = cxt->numTaps, lead = cxt->prefilterLead, Tk = T + lead, C = cxt->numChannels;
+    const int onDevice = io == IO_DEVICE_INTERLEAVED || io == IO_DEVICE_PLANAR;
+    float *raw = malloc (sizeof (float) * (size_t) C * Tk), *filtered = malloc (sizeof (float) * (size_t) C * T);
+    ArtDev *fused = cxt->device;
+    int c, i, k, failed;
+
+    failed = artDevGetHistoryOn (fused, raw, onDevice ? stream : NULL);
+    if (!failed && !cxt->plainDevice) {
+        cxt->plainDevice = artDevCreate (C, T, 0, cxt->numFilters, device_mode (cxt->flags), (const float *const *) cxt->filters);
+        failed = cxt->plainDevice == NULL;
+    }
+    if (!failed) {
+        for (c = 0; c < C; ++c)
+            for (i = 0; i < T; ++i) {
+                double acc = 0.0;
+                for (k = 0; k < lead; ++k)
+                    acc += cxt->prefilterTaps[k] * (double) raw[(size_t) c * Tk + lead + i - k];
+                filtered[(size_t) c * T + i] = (float) acc;
+            }
+        failed = artDevSetHistory (cxt->plainDevice, filtered);
+    }
+    if (!failed) {                                  /* (artDevSetHistory is synchronous: the history is in place for any stream) */
+        cxt->device = cxt->plainDevice;
+        failed = run_call (cxt, io, call, NULL, out, stream);
+        cxt->device = fused;
+    }
+    free (raw);
+    free (filtered);
+    return failed;
+}
+
 static ResampleResult process_one (Resample *cxt, int io, const void *in, int numInputFrames, void *out, int numOutputFrames, double ratio, void *stream)
 {
     const int flushing = numInputFrames < 0 && !(cxt->flags & RESAMPLER_FLUSHED);
@@ -392,6 +528,8 @@ static ResampleResult process_one (Resample *cxt, int io, const void *in, int nu
         return res;
     if ((cxt->flags & EXTRAPOLATE_ENDPOINTS) && (flushing || (cxt->flags & EXTRAPOLATE_PREFILL)))
         failed = run_call_with_endpoints (cxt, io, &call, in, out, stream, flushing);
+    else if (flushing && cxt->prefilterLead)
+        failed = run_flush_prefiltered (cxt, io, &call, out, stream);
     else
         failed = run_call (cxt, io, &call, in, out, stream);
     if (failed) {                               /* nothing consumed, nothing produced, state as before the call */
@@ -456,6 +594,8 @@ ResampleResult resampleProcessAndFlush (Resample *cxt, const artsample_t *const 
 /* does this call have to go through run_call_with_endpoints? */
 static int needs_endpoint_work (const Resample *cxt, int numInputFrames)
 {
+    if (cxt->prefilterLead && numInputFrames < 0 && !(cxt->flags & RESAMPLER_FLUSHED))
+        return 1;                               /* the flush of a pre-filtered stream runs on its own (run_flush_prefiltered) */
     if (!(cxt->flags & EXTRAPOLATE_ENDPOINTS))
         return 0;
     return (cxt->flags & EXTRAPOLATE_PREFILL) || (numInputFrames < 0 && !(cxt->flags & RESAMPLER_FLUSHED));

@@ -260,7 +260,7 @@ static void use_device (const ArtDev *dev)
         ART_CUDA_CHECK (cudaSetDevice (dev->device));
 }
 
-extern "C" ArtDev *artDevCreate (int channels, int taps, int filters, int mode, const float *const *rows)
+extern "C" ArtDev *artDevCreate (int channels, int taps, int lead, int filters, int mode, const float *const *rows)
 {
     ART_GUARD_BEGIN
     int device = 0, count = 0;
@@ -321,6 +321,7 @@ extern "C" ArtDev *artDevCreate (int channels, int taps, int filters, int mode, 
     memset (&k, 0, sizeof k);
     k.bank = dev->bank->d_rows;
     k.T = taps; k.Tp = dev->bank->Tp; k.F = filters; k.C = channels; k.mode = mode;
+    k.Tref = taps - lead; k.lead = lead;
     k.absSum = dev->bank->absSum;
     k.sort = getenv ("ART_B200_NOSORT") ? 0 : 1;
     return dev;
@@ -618,13 +619,13 @@ art_interleave_kernel (const ArtXpose *__restrict__ g, int C, int groups)       
 }
 
 /* region index of the first input frame that output n of a job reads (the start of its window) */
-static long long first_frame_read (const ArtJob &j, int T, unsigned int n)
+static long long first_frame_read (const ArtJob &j, const ArtClass &k, unsigned int n)
 {
     ArtLoopState st;
-    st.P = j.P; st.ratio = j.ratio; st.I = j.I; st.T = T;
+    st.P = j.P; st.ratio = j.ratio; st.I = j.I; st.T = k.Tref;
     int w;
     const double pos = art_output_pos (&st, n, &w);
-    return (long long) floor (pos) - T / 2 + 1 + (long long) w * 15LL * T - j.origin;
+    return (long long) floor (pos) - (k.Tref / 2 + k.lead) + 1 + (long long) w * 15LL * k.Tref - j.origin;
 }
 
 static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cudaStream_t stream, ArtDev *owner = nullptr)
@@ -659,7 +660,7 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
                         // a piece of a pipelined host call starts at nStart > 0: frames before that belong to earlier pieces
                         // (already on their way to the host) and must neither be transposed in nor written back
                         if (outFirst < 0 || (long long) jobs[e].nStart < outFirst) outFirst = jobs[e].nStart;
-                        const long long s0 = first_frame_read (jobs[e], lp.k.T, jobs[e].nStart);
+                        const long long s0 = first_frame_read (jobs[e], lp.k, jobs[e].nStart);
                         if (s0 < inFirst) inFirst = s0;
                     }
                     if (jobs[e].histOut) {

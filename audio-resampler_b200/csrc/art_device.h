@@ -42,7 +42,9 @@ enum {
     ART_MODE_PRECISE = 4        /* EXTEND_CONVOLUTION_MATH: double accumulation             */
 };
 
-ArtDev *artDevCreate (int channels, int taps, int filters, int mode, const float *const *rows);
+/* rows: (filters + 1) rows of `taps` floats.  `lead` of those taps lie in front of the reference's window (a pre-filter folded into
+ * the bank, art_context.c): the control loop then runs on taps - lead, the history holds `taps` frames per channel. */
+ArtDev *artDevCreate (int channels, int taps, int lead, int filters, int mode, const float *const *rows);
 void    artDevDestroy (ArtDev *dev);
 int     artDevReset (ArtDev *dev);                   /* zero the history (resampler.c:387-388) */
 int     artDevDeviceIndex (const ArtDev *dev);

@@ -50,7 +50,10 @@ struct ArtJob {
 
 struct ArtClass {
     const float *bank;
-    int T, Tp, F, C, mode;
+    int T, Tp, F, C, mode;   // T = taps of a bank row = depth of the history (Tref + lead)
+    int Tref;        // numTaps of the reference context: what the control loop's position arithmetic (art_plan.h) runs on
+    int lead;        // taps in front of the reference's window: a folded-in pre-filter (art_context.c) extends every filter into the
+                     //   past, so a window starts at floor (pos) - Tref / 2 + 1 - lead and has T taps
     int NB;          // output frames per tile
     int Cg;          // channels per CTA (smem planes; a multiple of the CV the kernel was built for)
     int Wp;          // floats per smem plane

@@ -272,11 +272,11 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
     const unsigned int n0 = job.nStart + t0;                      // call-relative index of the tile's first output
     const int c0 = cgroup * k.Cg;
     const int nc = min (k.Cg, k.C - c0);
-    const int T = k.T, half = T / 2, F = k.F;
+    const int T = k.T, Tref = k.Tref, half = Tref / 2 + k.lead, F = k.F;          // T taps per row; positions run on Tref
 
     ArtLoopState st;
-    st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = T;
-    const long long D = 15LL * T;
+    st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = Tref;
+    const long long D = 15LL * Tref;
 
     for (int i = tid; i < nkeysPad; i += ART_G_THREADS) {
         binEnd[i] = 0;
@@ -286,7 +286,7 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
         int w;
         (void) art_output_pos (&st, n0, &w);
         sh_w0 = w;
-        sh_base0 = art_ring_base (st.P, T, w);
+        sh_base0 = art_ring_base (st.P, Tref, w);
     }
     __syncthreads ();
     const int w0 = sh_w0;

@@ -101,7 +101,7 @@ __device__ __forceinline__ void art_phase_table_block (const ArtClass &k, const 
                                                         const ArtJob *__restrict__ jobs, int j, int tbl)
 {
     const ArtJob &job = jobs ? jobs[jobs[tbl].repJob] : single;
-    const int T = k.T, half = T / 2, F = k.F;
+    const int T = k.T, Tref = k.Tref, half = Tref / 2 + k.lead, F = k.F;          // T taps per row; positions run on Tref
     const int perBlock = p.rowsPerCta * 8;
     const int pb = j / perBlock, jj = j - pb * perBlock, jb = pb * perBlock;
     __shared__ int sh_row, sh_pass, sh_shift;
@@ -109,7 +109,7 @@ __device__ __forceinline__ void art_phase_table_block (const ArtClass &k, const 
 
     if (threadIdx.x == 0) {
         ArtLoopState st;
-        st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = T;
+        st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = Tref;
         long long sj = 0, sb = 0;
         int row = 0, pass = -1;
         double f = 0.0;
@@ -119,7 +119,7 @@ __device__ __forceinline__ void art_phase_table_block (const ArtClass &k, const 
             int w;
             const double pos = art_output_pos (&st, job.nStart + ph, &w);
             const double whole = floor (pos), fr = pos - whole;
-            const long long s = (long long) whole - half + 1 + (long long) w * 15LL * T - job.origin;
+            const long long s = (long long) whole - half + 1 + (long long) w * 15LL * Tref - job.origin;
             if (!which) { sb = s; continue; }
             sj = s;
             if (k.mode & ART_MODE_INTERP) {
@@ -182,10 +182,10 @@ art_periodic_prep_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
         const int seg = e / p.PB, pb = e - seg * p.PB;
         const ArtJob &job = jobs ? jobs[seg] : single;
         ArtLoopState st;
-        st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = k.T;
+        st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = k.Tref;
         int w;
         const double pos = art_output_pos (&st, job.nStart + pb * p.rowsPerCta * 8, &w);
-        p.S0[e] = (int) ((long long) floor (pos) - k.T / 2 + 1 + (long long) w * 15LL * k.T - job.origin);
+        p.S0[e] = (int) ((long long) floor (pos) - (k.Tref / 2 + k.lead) + 1 + (long long) w * 15LL * k.Tref - job.origin);
         return;
     }
     b -= originBlocks;

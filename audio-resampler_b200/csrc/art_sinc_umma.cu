@@ -244,7 +244,7 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
     const int tableBlocks = numTables * u.G * u.Npad;
     const int originBlocks = (numJobs * u.G + 127) / 128;
     int b = blockIdx.x;
-    const int T = k.T, half = T / 2, F = k.F;
+    const int T = k.T, Tref = k.Tref, half = Tref / 2 + k.lead, F = k.F;          // T taps per row; positions run on Tref
     if (b < tableBlocks) {
 #ifdef ART_B200_ABLATE
         if (dbg & 16) return;
@@ -258,7 +258,7 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
         __shared__ double sh_f;
         if (threadIdx.x == 0) {
             ArtLoopState st;
-            st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = T;
+            st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = Tref;
             long long sj = 0, sb = 0;
             int row = 0, pass = -1;
             double f = 0.0;
@@ -268,7 +268,7 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
                 int w;
                 const double pos = art_output_pos (&st, job.nStart + ph, &w);
                 const double whole = floor (pos), fr = pos - whole;
-                const long long s = (long long) whole - half + 1 + (long long) w * 15LL * T - job.origin;
+                const long long s = (long long) whole - half + 1 + (long long) w * 15LL * Tref - job.origin;
                 if (!which) { sb = s; continue; }
                 sj = s;
                 if (k.mode & ART_MODE_INTERP) {
@@ -280,7 +280,7 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
                 else {
                     row = (int) floor (fr * F + 0.5);                // resampler.c:1137
                     if (!(k.mode & ART_MODE_LOWPASS) && row % F == 0)    // resampler.c:1141-1142
-                        pass = half - 1 + (row ? 1 : 0);
+                        pass = half - 1 + (row ? 1 : 0);                 // (never with a folded-in pre-filter: that sets ART_MODE_LOWPASS)
                 }
             }
             sh_row = row; sh_f = f; sh_pass = pass; sh_shift = (int) (sj - sb);
@@ -329,10 +329,10 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
         const int seg = e / u.G, grp = e - seg * u.G;
         const ArtJob &job = jobs ? jobs[seg] : single;
         ArtLoopState st;
-        st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = T;
+        st.P = job.P; st.ratio = job.ratio; st.I = job.I; st.T = Tref;
         int w;
         const double pos = art_output_pos (&st, job.nStart + grp * u.Lg, &w);
-        u.S0[e] = (int) ((long long) floor (pos) - half + 1 + (long long) w * 15LL * T - job.origin);
+        u.S0[e] = (int) ((long long) floor (pos) - half + 1 + (long long) w * 15LL * Tref - job.origin);
         return;
     }
     b -= originBlocks;

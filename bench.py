@@ -315,7 +315,15 @@ class DeviceBatch:
             self.bres = (pkg.ResampleResult * nb)()
             self.bpos = (C.c_double * nb)()
         self.stages = None
-        if w.biquad:                              # art.c:848-851: two lowpass sections per channel at 0.45 * dst/src ahead of a downsampler
+        if w.biquad == "fused":                   # the same two sections folded into the context's filter bank (resampleB200AttachPrefilter)
+            co = pkg.BiquadCoefficients()
+            lib.biquad_lowpass(C.byref(co), 0.45 * w.dst / w.src)
+            sec = (pkg.Biquad * 2)()
+            for q in sec:
+                lib.biquad_init(C.byref(q), C.byref(co), 1.0)
+            for c in self.ctxs:
+                assert lib.resampleB200AttachPrefilter(c, sec, 2) == 0
+        elif w.biquad:                            # art.c:848-851: two lowpass sections per channel at 0.45 * dst/src ahead of a downsampler
             co = pkg.BiquadCoefficients()
             lib.biquad_lowpass(C.byref(co), 0.45 * w.dst / w.src)
             self.bq = [[(pkg.Biquad * w.ch)() for _ in range(2)] for _ in range(n)]
@@ -607,8 +615,10 @@ def measure_configs(lib, pkg, torch, dist, world, rank, dev, stream, peak, args)
         ("cfg1 mono preset -1 44.1->48k", Workload("cfg1", 1, 1, 44100, 48000, 64, 1 << 20), 10),
         ("cfg2 stereo preset -3 44.1->48k (metric config)", Workload("cfg2", 2, 3, 44100, 48000, 64, 1 << 18), 10),
         ("cfg2 via resampleFixedRatioInit (art.c:827: 160 filters, no interpolation)", Workload("cfg2f", 2, 3, 44100, 48000, 64, 1 << 18, fixed=True), 6),
-        (f"cfg3 {ch3} of 64 ch per GPU, preset -4 96->44.1k, lowpass 20 kHz, two-stage biquad pre-filter (art.c:848-851)",
-         Workload("cfg3", ch3, 4, 96000, 44100, 1, 1 << 19, lowpass_hz=20000, biquad=True), 6),
+        (f"cfg3 {ch3} of 64 ch per GPU, preset -4 96->44.1k, lowpass 20 kHz, two-stage biquad pre-filter (art.c:848-851) folded into the bank",
+         Workload("cfg3", ch3, 4, 96000, 44100, 1, 1 << 19, lowpass_hz=20000, biquad="fused"), 6),
+        (f"cfg3 with the pre-filter as separate biquad_apply_cascade_interleaved_device calls (the reference's call pattern)",
+         Workload("cfg3sep", ch3, 4, 96000, 44100, 1, 1 << 19, lowpass_hz=20000, biquad=True), 4),
         (f"cfg3 without the biquad pre-filter", Workload("cfg3nb", ch3, 4, 96000, 44100, 1, 1 << 19, lowpass_hz=20000), 6),
         (f"cfg4 {n4} of 1024 stereo contexts per GPU, preset -3 48->44.1k lowpass 20 kHz, 2^15-frame blocks",
          Workload("cfg4s", 2, 3, 48000, 44100, n4, 1 << 15, lowpass_hz=20000), 6),

@@ -49,6 +49,9 @@ typedef struct resample {
     double (*subsample)(struct resample *cxt, artsample_t *source, double offset);   /* always NULL here */
     artsample_t **buffers, **filters;
     void *device;                               /* private: the CUDA side of the context */
+    int prefilterLead;                          /* private: taps a folded-in pre-filter adds in front of every window (resampler_b200.h) */
+    double *prefilterTaps;                      /* private: its impulse response (prefilterLead taps) */
+    void *plainDevice;                          /* private: device context with the unfused bank, used for the flush of a pre-filtered stream */
 } Resample;
 
 #ifdef __cplusplus

@@ -94,6 +94,20 @@ int resampleProcessBlocksInterleavedDevice (Resample *cxt, const float *d_input,
                                             float *d_output, int outputCapacityFrames,
                                             ResampleResult *results, double *positions, void *stream);
 
+/* Fused pre-filter.  art.c runs a cascade of biquad lowpass sections over the input block in front of a downsampling resampler
+ * (art.c:848-851, :1011-1017): three more passes over memory on a GPU.  A cascade whose impulse response has died out within a
+ * few hundred samples -- every lowpass art.c designs: 32 taps reach 1e-10 at 0.45 * 44.1 / 96 -- is a short FIR filter, and
+ * (resampling filter) o (FIR) is again a bank of FIR filters: this call convolves every row of the context's bank with the
+ * cascade's impulse response (in double, from the float coefficients biquad_init stored) and from then on the context resamples
+ * AND pre-filters in one pass -- zero extra bytes, a few per cent more taps.  The caller then skips its own biquad_apply_buffer
+ * calls.  Counts and positions are unchanged (the control loop still runs on numTaps); samples agree with "reference biquads,
+ * then reference resampler" within 1e-6 of peak (the reference's float32 recursion itself sits 1.6e-7 from the exact response).
+ * `sections` are numSections initialised Biquad structs (biquad_init) in zero state, applied in order to every channel.
+ * Returns 0 on success; non-zero (with a message, context unchanged) when the stream has already consumed input, when
+ * EXTRAPOLATE_ENDPOINTS is set (the reference extrapolates the FILTERED signal), or when the response is too long
+ * (numTaps + its length > 1024). */
+int resampleB200AttachPrefilter (Resample *cxt, const Biquad *sections, int numSections);
+
 /* The cascade art.c applies around the resampler (art.c:1011-1017, :1052-1058): numStages sets of
  * numChannels Biquads over one interleaved buffer, in ONE pass over memory.  stages[s] points at
  * the caller's array of numChannels Biquad structs for stage s (e.g. lowpass1, lowpass2). */

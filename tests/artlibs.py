@@ -179,6 +179,8 @@ def load_product() -> C.CDLL:
     ctx = C.POINTER(RefResample)
     lib.resampleB200SetTensorPath.restype = None
     lib.resampleB200SetTensorPath.argtypes = [C.c_int]
+    lib.resampleB200AttachPrefilter.restype = C.c_int
+    lib.resampleB200AttachPrefilter.argtypes = [ctx, C.POINTER(Biquad), C.c_int]
     lib.resampleB200SetTensorDigits.restype = None
     lib.resampleB200SetTensorDigits.argtypes = [C.c_int]
     lib.resampleB200TensorLaunches.restype = C.c_ulonglong

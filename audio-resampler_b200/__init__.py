@@ -49,6 +49,13 @@ class BiquadCoefficients(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("a0", "a1", "a2", "a3", "a4", "b1", "b2", "b3", "b4")]
 
 
+class Decimate(C.Structure):
+    """Leading public fields of the decimator context (decimator.h:43-51)."""
+    _fields_ = [("numChannels", C.c_int), ("outputBits", C.c_int), ("outputBytes", C.c_int), ("dither_type", C.c_int),
+                ("flags", C.c_int), ("outputGain", C.c_double), ("feedback", C.POINTER(C.c_float)),
+                ("tpdf_generators", C.POINTER(C.c_uint32)), ("noise_shapers", C.c_void_p)]
+
+
 class Biquad(C.Structure):
     _fields_ = [("a", C.c_float * 5), ("b", C.c_float * 5), ("x", C.c_float * 4), ("y", C.c_float * 4),
                 ("order", C.c_int), ("index", C.c_int)]
@@ -124,6 +131,16 @@ def load() -> C.CDLL:
                                                    C.POINTER(ResampleResult)]),
         "resampleProcessBlocksInterleavedDevice": (i32, [ctx, vp, C.POINTER(i32), C.POINTER(dbl), i32, vp, i32,
                                                           C.POINTER(ResampleResult), C.POINTER(dbl), vp]),
+        # include/decimator.h
+        "floatIntegersLE": (None, [vp, dbl, i32, i32, i32, f32p, i32]),
+        "floatIntegersLEDevice": (None, [vp, dbl, i32, i32, i32, vp, i32, vp]),
+        "decimateInit": (C.POINTER(Decimate), [i32, i32, i32, dbl, i32, i32]),
+        "decimateProcessLE": (i32, [C.POINTER(Decimate), f32pp, i32, C.POINTER(vp)]),
+        "decimateProcessInterleavedLE": (i32, [C.POINTER(Decimate), f32p, i32, vp]),
+        "decimateProcessInterleavedLEDevice": (i32, [C.POINTER(Decimate), vp, i32, vp, vp]),
+        "decimateBatchProcessInterleavedLE": (i32, [C.POINTER(C.POINTER(Decimate)), i32, C.POINTER(f32p), C.POINTER(i32), C.POINTER(vp), C.POINTER(i32)]),
+        "decimateBatchProcessInterleavedLEDevice": (i32, [C.POINTER(C.POINTER(Decimate)), i32, C.POINTER(vp), C.POINTER(i32), C.POINTER(vp), C.POINTER(i32), vp]),
+        "decimateFree": (None, [C.POINTER(Decimate)]),
         "biquad_apply_cascade_interleaved": (None, [C.POINTER(C.POINTER(Biquad)), i32, i32, f32p, i32]),
         "biquad_apply_cascade_interleaved_device": (None, [C.POINTER(C.POINTER(Biquad)), i32, i32, vp, i32, vp]),
     }
@@ -145,4 +162,6 @@ EXPORTED_SYMBOLS = [
     "resampleProcessInterleavedDevice", "resampleProcessDevice", "resampleBatchProcessInterleavedDevice",
     "resampleBatchProcessInterleaved", "resampleProcessBlocksInterleavedDevice", "biquad_apply_cascade_interleaved",
     "biquad_apply_cascade_interleaved_device",
+    "floatIntegersLE", "floatIntegersLEDevice", "decimateInit", "decimateProcessLE", "decimateProcessInterleavedLE",
+    "decimateProcessInterleavedLEDevice", "decimateBatchProcessInterleavedLE", "decimateBatchProcessInterleavedLEDevice", "decimateFree",
 ]

@@ -107,6 +107,29 @@ typedef struct {
 int  artBiquadRun (ArtBiquadStage *stages, int numStages, int channels, float *buffer,
                    long long frames, int stride, int onDevice, void *stream);
 
+/* ---- float <-> integer stages (decimator.c), art_decimate.cu ---------------------------------------------------- */
+/* one channel of one context: where its samples are, its conversion parameters and its state (in and out) */
+typedef struct {
+    const float   *in;          /* first sample of the channel; host or device memory as the call says        */
+    unsigned char *out;         /* first output byte of the channel                                            */
+    int   inStride, outStride;  /* floats between samples; BYTES between output samples                        */
+    int   frames, context;
+    int   bits, bytes, pad;     /* outputBits, outputBytes, leading zero bytes of the container                */
+    float scaler;               /* (1 << bits) / 2 * gain                                                      */
+    int   dither, ditherType, shaping;
+    unsigned int rng;           /* tpdf generator                                                              */
+    float feedback;
+    float a[5], b[5], x[4], y[4];   /* noise shaper: coefficients, delayed input / output newest first          */
+    int   order;
+    int   clips;                /* out: samples clipped                                                        */
+} ArtDecLane;
+
+/* lanes: host array (read and updated); channelsHint: numChannels of the first context.  Host buffers are staged through
+ * device memory laid out per lane.  Returns non-zero on failure. */
+int artDecimateRun (ArtDecLane *lanes, int numLanes, int numContexts, int channelsHint, int onDevice, void *stream);
+int artFloatIntegersRun (const unsigned char *input, double gain, int bits, int bytes, int stride, float *output, int count,
+                         int onDevice, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

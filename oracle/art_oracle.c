@@ -619,3 +619,147 @@ void oracle_noise (unsigned long long *state, float *dst, int count)
     }
     *state = s;
 }
+
+/* ------------------------------------------------------- float <-> integer stage */
+/* decimator.c: what sits either side of the resampling path in art.c (:996 floatIntegersLE in front,
+ * :1066 decimateProcessInterleavedLE behind).  One strided per-channel core serves the planar and the
+ * interleaved entry points; channel state lives in one struct per channel. */
+
+/* biquad_apply_sample, biquad.c:78-102 */
+static float shaper_step (OracleBiquad *q, float in)
+{
+    float acc = in * q->a[0];
+    int cur = q->cursor & 3;
+    for (int d = q->order; d >= 1; --d) {
+        int slot = (cur - (d - 1)) & 3;
+        acc += (q->xh[slot] * q->a[d]) - (q->b[d] * q->yh[slot]);
+    }
+    q->cursor = cur = (cur + 1) & 3;
+    q->xh[cur] = in;
+    q->yh[cur] = acc;
+    return acc;
+}
+
+/* shaper_init, decimator.c:383-402: N(z) -> the decoupled H(z) form */
+static void shaper_from_nz (OracleBiquad *q, const double n[9])
+{
+    OracleBiquadCoeffs c;
+    memset (&c, 0, sizeof c);
+    c.a0 = n[5] - n[1]; c.a1 = n[6] - n[2]; c.a2 = n[7] - n[3]; c.a3 = n[8] - n[4];
+    c.b1 = n[5]; c.b2 = n[6]; c.b3 = n[7]; c.b4 = n[8];
+    oracle_biquad_init (q, &c, 1.0);
+}
+
+/* the generator step of tpdf_dither / decimateInit's seeding, decimator.c:47-49, :361-365 */
+static unsigned int lcg15 (unsigned int x) { return ((x << 4) - x) ^ 1u; }
+
+OracleDecimator *oracle_decimate_init (int channels, int bits, int bytes, double gain, int rate, int flags)
+{
+    static const double ath[5][9] = {            /* decimator.c:68-77, Gesemann's ATH curves */
+        { 1.0, -0.780459, +0.569358, -0.348221, +0.466316, +0.950797, +0.282052, +0.004337, +1.76209e-5 },
+        { 1.0, -1.1474, 0.5383, -0.3530, 0.3475, 1.0587, 0.0676, -0.6054, -0.2738 },
+        { 1.0, -1.3344, 0.7455, -0.4602, 0.4363, 0.9030, 0.0116, -0.5853, -0.2571 },
+        { 1.0, -2.150679, +2.1402057, -1.042712, +0.206838, +0.67433, +1.017047, +0.4028633, +0.098656 },
+        { 1.0, -2.16994, +2.01986, -0.894857, +0.1557738, +0.517789, +1.1062189, +0.4825786, +0.244994 } };
+    static const int ath_rate[5] = { 32000, 44100, 48000, 88200, 96000 };
+    static const double order1[9] = { 1, -1, 0, 0, 0, 0, 0, 0, 0 }, order2[9] = { 1, -2, 1, 0, 0, 0, 0, 0, 0 },
+                        order3[9] = { 1, -3, 3, -1, 0, 0, 0, 0, 0 };
+    OracleDecimator *d = calloc (1, sizeof *d);
+    d->channels = channels; d->bits = bits; d->bytes = bytes; d->gain = gain; d->flags = flags;
+    d->lane = calloc (channels, sizeof *d->lane);
+    if (flags & 0x7) {                            /* DITHER_ENABLED: per-channel seeds are consecutive BYTES of one generator (:41-52) */
+        unsigned int r = 0x31415926u;
+        for (int c = 0; c < channels; ++c) {
+            unsigned int seed = 0;
+            for (int b = 0; b < 4; ++b) {
+                seed |= (r >> 24) << (8 * b);     /* little-endian assembly of the byte stream */
+                r = lcg15 (lcg15 (lcg15 (r)));
+            }
+            d->lane[c].rng = seed;
+        }
+        d->dither = (flags & 0x1) ? -1 : ((flags & 0x4) ? 1 : 0);       /* highpass, lowpass, flat (:54-59) */
+    }
+    if (flags & 0xf00)                            /* SHAPING_ENABLED (:62-90) */
+        for (int c = 0; c < channels; ++c) {
+            const double *nz = order1;
+            if (flags & 0x800) {
+                for (int k = 0; k < 5; ++k) if (rate == ath_rate[k]) nz = ath[k];
+            }
+            else if (flags & 0x100) nz = order1;
+            else if (flags & 0x200) nz = order2;
+            else if (flags & 0x400) nz = order3;
+            shaper_from_nz (&d->lane[c].shaper, nz);
+        }
+    return d;
+}
+
+void oracle_decimate_free (OracleDecimator *d)
+{
+    if (d) { free (d->lane); free (d); }
+}
+
+/* tpdf_dither, decimator.c:361-373 */
+static double tpdf (unsigned int *gen, int type)
+{
+    unsigned int r = lcg15 (lcg15 (*gen));
+    unsigned int first = type ? (*gen ^ (unsigned int) (type >> 31)) : ~r;
+    r = lcg15 (lcg15 (lcg15 (r)));
+    *gen = r;
+    return (((first >> 1) + (r >> 1)) / 2147483648.0) - 1.0;
+}
+
+/* one channel: decimator.c:170-199 (= :243-272, :301-333) */
+static int decimate_channel (OracleDecimator *d, int c, const float *in, int in_stride, int frames, unsigned char *out, int out_stride_bytes)
+{
+    const float scaler = (1 << d->bits) / 2.0 * d->gain;
+    const int pad = d->bytes - ((d->bits + 7) / 8);
+    const int bias = (d->bits <= 8) * 128, top = (1 << (d->bits - 1)) - 1, bottom = ~top, shl = (24 - d->bits) % 8;
+    int clips = 0;
+    for (int i = 0; i < frames; ++i, in += in_stride, out += out_stride_bytes) {
+        const float dith = (d->flags & 0x7) ? tpdf (&d->lane[c].rng, d->dither) : 0.0;
+        const float code = (*in * scaler) - d->lane[c].feedback;
+        int v = floor (code + dith + 0.5);
+        unsigned char *o = out;
+        if (d->flags & 0xf00)
+            d->lane[c].feedback = shaper_step (&d->lane[c].shaper, v - code);
+        if (v > top) { v = top; ++clips; }
+        else if (v < bottom) { v = bottom; ++clips; }
+        for (int j = 0; j < pad; ++j) *o++ = 0;
+        v = ((unsigned int) v << shl) + bias;
+        *o++ = v;
+        if (d->bits > 8) { *o++ = v >> 8; if (d->bits > 16) *o++ = v >> 16; }
+    }
+    return clips;
+}
+
+int oracle_decimate_interleaved (OracleDecimator *d, const float *in, int frames, unsigned char *out)
+{
+    int clips = 0;
+    for (int c = 0; c < d->channels; ++c)
+        clips += decimate_channel (d, c, in + c, d->channels, frames, out + c * d->bytes, d->channels * d->bytes);
+    return clips;
+}
+
+int oracle_decimate_planar (OracleDecimator *d, const float *const *in, int frames, unsigned char *const *out)
+{
+    int clips = 0;
+    for (int c = 0; c < d->channels; ++c)
+        clips += decimate_channel (d, c, in[c], 1, frames, out[c], d->bytes);
+    return clips;
+}
+
+/* floatIntegersLE, decimator.c:416-450 */
+void oracle_float_integers (const unsigned char *in, double gain, int bits, int bytes, int stride, float *out, int count)
+{
+    const int used = (bits + 7) / 8;
+    const float g = bits <= 8 ? gain / 128.0 : (bits <= 16 ? gain / 32768.0 : gain / 8388608.0);
+    in += bytes - used;
+    for (int i = 0; i < count; ++i, in += (size_t) stride * bytes) {
+        int v;
+        if (bits <= 8) v = (int) in[0] - 128;
+        else if (bits <= 16) v = (short) (in[0] | (in[1] << 8));
+        else if (bits <= 24) v = in[0] | (in[1] << 8) | ((int) (signed char) in[2] << 16);
+        else continue;                            /* the reference does nothing above 24 bits */
+        *out++ = v * g;
+    }
+}

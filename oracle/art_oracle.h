@@ -85,6 +85,26 @@ void oracle_biquad_highpass (OracleBiquadCoeffs *c, double frequency);
 void oracle_biquad_init (OracleBiquad *q, const OracleBiquadCoeffs *c, double gain);
 void oracle_biquad_run (OracleBiquad *q, float *buf, int count, int stride);
 
+/* decimator.c: float -> integer with TPDF dither and noise shaping (decimateInit :29-100, decimateProcess*LE :112-291),
+ * and its lossless inverse floatIntegersLE (:416-450).  Flag values are decimator.h:29-41. */
+typedef struct {
+    unsigned int rng;           /* "tpdf_generators[ch]" */
+    float        feedback;      /* "feedback[ch]"        */
+    OracleBiquad shaper;        /* "noise_shapers[ch]"   */
+} OracleDecimatorLane;
+
+typedef struct {
+    int    channels, bits, bytes, flags, dither;
+    double gain;
+    OracleDecimatorLane *lane;
+} OracleDecimator;
+
+OracleDecimator *oracle_decimate_init (int channels, int bits, int bytes, double gain, int rate, int flags);
+void oracle_decimate_free (OracleDecimator *d);
+int  oracle_decimate_interleaved (OracleDecimator *d, const float *in, int frames, unsigned char *out);
+int  oracle_decimate_planar (OracleDecimator *d, const float *const *in, int frames, unsigned char *const *out);
+void oracle_float_integers (const unsigned char *in, double gain, int bits, int bytes, int stride, float *out, int count);
+
 /* artest.c:744-754 -- the reference's synthetic noise generator (state passed explicitly). */
 void oracle_noise (unsigned long long *state, float *dst, int count);
 

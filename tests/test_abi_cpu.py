@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     declared = set()
     for header in (ROOT / "include").glob("*.h"):
         text = re.sub(r"/\*.*?\*/", "", header.read_text(), flags=re.S)
-        declared |= set(re.findall(r"\b((?:resample|biquad_)\w+)\s*\(", text))
+        declared |= set(re.findall(r"\b((?:resample|biquad_|decimate|floatIntegers)\w+)\s*\(", text))
     assert declared, "no prototypes found in include/"
     assert declared == set(pkg.EXPORTED_SYMBOLS)
     for name in declared:

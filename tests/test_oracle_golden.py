@@ -172,3 +172,62 @@ def test_oracle_extrapolation_matches_the_reference_build():
             yo, uo, mo = o.process(x, 20000, ratio, flush_after=(b == 2))
             yr, ur, mr = r.process(x, 20000, ratio, flush_after=(b == 2))
             assert (uo, mo) == (ur, mr) and A.peak_error(yo, yr) <= 3e-7
+
+
+# ---------------------------------------------------------------------------------------------- decimator.c
+DECIMATE_FLAGS = [0, 0x1, 0x2, 0x4, 0x100, 0x200, 0x400, 0x800, 0x2 | 0x800, 0x1 | 0x200, 0x4 | 0x100]
+
+
+def _bind_decimators():
+    ol, ref = A.oracle(), A.reference()
+    ol.oracle_decimate_init.restype = C.c_void_p
+    ol.oracle_decimate_init.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]
+    ol.oracle_decimate_free.argtypes = [C.c_void_p]
+    ol.oracle_decimate_interleaved.argtypes = [C.c_void_p, A.f32p, C.c_int, C.c_char_p]
+    ol.oracle_decimate_interleaved.restype = C.c_int
+    ol.oracle_float_integers.argtypes = [C.c_char_p, C.c_double, C.c_int, C.c_int, C.c_int, A.f32p, C.c_int]
+    ol.oracle_float_integers.restype = None
+    if ref is not None:
+        ref.decimateInit.restype = C.c_void_p
+        ref.decimateInit.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]
+        ref.decimateFree.argtypes = [C.c_void_p]
+        ref.decimateProcessInterleavedLE.argtypes = [C.c_void_p, A.f32p, C.c_int, C.c_char_p]
+        ref.decimateProcessInterleavedLE.restype = C.c_int
+        ref.decimateProcessLE.argtypes = [C.c_void_p, C.POINTER(A.f32p), C.c_int, C.POINTER(C.c_char_p)]
+        ref.decimateProcessLE.restype = C.c_int
+        ref.floatIntegersLE.argtypes = [C.c_char_p, C.c_double, C.c_int, C.c_int, C.c_int, A.f32p, C.c_int]
+        ref.floatIntegersLE.restype = None
+    return ol, ref
+
+
+@pytest.mark.skipif(A.reference() is None, reason="oracle/_ref/libartref.so not built")
+@pytest.mark.parametrize("flags", DECIMATE_FLAGS)
+def test_oracle_decimator_is_bit_identical_to_the_reference(flags):
+    """decimateInit / decimateProcessInterleavedLE (decimator.c:29-100, :205-291) in every dither / shaping mode, 8-, 16- and
+    24-bit output (24 in a 32-bit container too), gains that clip, two calls in a row (state carries over)"""
+    ol, ref = _bind_decimators()
+    rng = np.random.default_rng(flags + 5)
+    for ch, bits, bytes_, gain, rate in [(2, 16, 2, 1.0, 44100), (1, 8, 1, 0.9, 48000), (3, 24, 3, 1.3, 96000), (2, 24, 4, 1.0, 32000), (5, 12, 2, 2.5, 12345)]:
+        r = ref.decimateInit(ch, bits, bytes_, gain, rate, flags)
+        o = ol.oracle_decimate_init(ch, bits, bytes_, gain, rate, flags)
+        for n in (777, 1, 2500):
+            x = rng.uniform(-1.0, 1.0, (n, ch)).astype(np.float32)
+            br, bo = C.create_string_buffer(n * ch * bytes_ + 8), C.create_string_buffer(n * ch * bytes_ + 8)
+            cr = ref.decimateProcessInterleavedLE(r, x.ctypes.data_as(A.f32p), n, br)
+            co = ol.oracle_decimate_interleaved(o, x.ctypes.data_as(A.f32p), n, bo)
+            assert cr == co, (ch, bits, flags, "clipped sample counts differ")
+            assert br.raw == bo.raw, (ch, bits, flags, "bytes differ")
+        ref.decimateFree(r); ol.oracle_decimate_free(o)
+
+
+@pytest.mark.skipif(A.reference() is None, reason="oracle/_ref/libartref.so not built")
+def test_oracle_float_integers_is_bit_identical_to_the_reference():
+    ol, ref = _bind_decimators()
+    rng = np.random.default_rng(9)
+    for bits, bytes_, stride, gain in [(8, 1, 1, 1.0), (16, 2, 1, 1.0), (16, 2, 3, 0.5), (24, 3, 1, 1.0), (24, 4, 2, 1.7), (20, 3, 1, 1.0), (12, 2, 1, 1.0)]:
+        n = 1000
+        raw = rng.integers(0, 256, n * stride * bytes_ + 16, dtype=np.uint8).tobytes()
+        a, b = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        ref.floatIntegersLE(raw, gain, bits, bytes_, stride, a.ctypes.data_as(A.f32p), n)
+        ol.oracle_float_integers(raw, gain, bits, bytes_, stride, b.ctypes.data_as(A.f32p), n)
+        assert np.array_equal(a, b), (bits, bytes_, stride)

@@ -10,7 +10,7 @@ With the defaults a step is ~50 ms of GPU work and the timed region of 20 steps 
 (clocks and power sampled inside the region only); a 20-launch burst on the cold GPU is reported beside it.
 
   value             sustained whole-job output samples/s, inputs resident in HBM (CUDA events, max over ranks)
-  burst_value       the same launch timed for ~5 ms on a cold GPU (what round 1 reported)
+  burst_value       20 launches on the cold GPU, before the sustained region (round 1 reported a burst)
   strict_fp32_value the same workload with the tensor-core kernel switched off (FFMA kernels: fp32 accuracy relative to
                     every 380-tap window; the tensor-core form is exact to 2^-24 of a 0.43 s block's peak)
   e2e               the same metric through the reference-facing host-pointer API (resampleProcessInterleaved,
@@ -143,7 +143,8 @@ class Workload:
     """One configuration of the path: `streams` contexts of `ch` channels, blocks of `frames` input frames per launch."""
 
     def __init__(self, name, ch, preset, src, dst, streams, frames, lowpass_hz=0, fixed=False, biquad=False,
-                 asrc_blocks=0, ratio=None):
+                 asrc_blocks=0, ratio=None, tensor_mode=1):
+        self.tensor_mode = tensor_mode                  # resampleB200SetTensorPath while this workload runs (3: also fixed-ratio contexts)
         self.name, self.ch, self.preset, self.src, self.dst = name, ch, preset, src, dst
         self.streams, self.frames, self.lowpass_hz, self.fixed, self.biquad = streams, frames, lowpass_hz, fixed, biquad
         self.asrc_blocks = asrc_blocks                  # > 0: one stream, asrc_blocks blocks of `frames` per launch, ratio swept
@@ -549,17 +550,19 @@ def run_gpu_arm(args):
                     "pipe binds, not HBM; frac is the HBM-roofline fraction BASELINE.json's metric asks for"})
     for cand in ("r02_umma_ncu.json", "r01_umma_ncu.json") if tensor else ("r01_periodic_final_ncu.json",) if periodic else ("r01_generic_v2_ncu.json",):
         prof = ROOT / "profiles" / cand
-        if prof.exists() and streams in (64, 74) and frames == (1 << 18):
+        if prof.exists():
             try:
                 roofline["traffic"] = json.loads(prof.read_text()).get("dram_bytes_per_launch")
-                roofline["traffic_source"] = f"profiles/{prof.name} (ncu --set full, same launch geometry)"
+                roofline["traffic_source"] = (f"profiles/{prof.name} (ncu --set full of this kernel on 64 streams x 2^18 frames, scaled by "
+                                              "the launch's algorithmic bytes)")
+                roofline["traffic"] = roofline["traffic"] * (per_launch_samples * bpos) / (64 * 285344 * 2 * bpos)
                 break
             except Exception:
                 pass
     batch.close()
 
     # ---- end to end through the host-pointer API -----------------------------------------------------------------------------
-    e2e = measure_e2e(lib, pkg, torch, dist, world, dev, streams, frames, args) if not args.no_e2e else None
+    e2e = measure_e2e(lib, pkg, torch, dist, world, dev, streams, args.e2e_frames, args) if not args.no_e2e else None
 
     # ---- every BASELINE config and preset ------------------------------------------------------------------------------------------
     configs = None
@@ -583,7 +586,7 @@ def run_gpu_arm(args):
                                   "relative to the local signal level); strict_fp32_value is the FFMA form, two_digit_value the round-1 arithmetic" if tensor else
                                   "float32 FMA")},
         "timed_region_s": ms_max * 1e-3, "wall_ms_per_step": wall_ms / args.steps,
-        "burst_value": burst_value, "burst": "20 launches (~5 ms) on the cold GPU before the sustained region",
+        "burst_value": burst_value, "burst": "20 launches on the cold GPU before the sustained region",
         "strict_fp32_value": strict_value, "strict_fp32_kernel": strict_kernel,
         "two_digit_value": two_digit_value,
         "two_digit": "resampleB200SetTensorDigits(2): five MMAs per 16 taps instead of six; exact to 2^-24 of a tile's peak instead of 2^-22 of every sample",
@@ -615,6 +618,8 @@ def measure_configs(lib, pkg, torch, dist, world, rank, dev, stream, peak, args)
         ("cfg1 mono preset -1 44.1->48k", Workload("cfg1", 1, 1, 44100, 48000, 64, 1 << 20), 10),
         ("cfg2 stereo preset -3 44.1->48k (metric config)", Workload("cfg2", 2, 3, 44100, 48000, 64, 1 << 18), 10),
         ("cfg2 via resampleFixedRatioInit (art.c:827: 160 filters, no interpolation)", Workload("cfg2f", 2, 3, 44100, 48000, 64, 1 << 18, fixed=True), 6),
+        ("cfg2 via resampleFixedRatioInit, tensor-core kernel by opt-in (resampleB200SetTensorPath(3): output no longer bit-identical across call chunkings)",
+         Workload("cfg2ft", 2, 3, 44100, 48000, 64, 1 << 18, fixed=True, tensor_mode=3), 8),
         (f"cfg3 {ch3} of 64 ch per GPU, preset -4 96->44.1k, lowpass 20 kHz, two-stage biquad pre-filter (art.c:848-851) folded into the bank",
          Workload("cfg3", ch3, 4, 96000, 44100, 1, 1 << 19, lowpass_hz=20000, biquad="fused"), 6),
         (f"cfg3 with the pre-filter as separate biquad_apply_cascade_interleaved_device calls (the reference's call pattern)",
@@ -638,7 +643,9 @@ def measure_configs(lib, pkg, torch, dist, world, rank, dev, stream, peak, args)
         ring = 2 if w.streams * w.frames * max(1, w.asrc_blocks) * w.ch * 4 > (64 << 20) else 4
         b = DeviceBatch(lib, pkg, torch, dev, w, ring, 777 + rank, stream)
         p0 = path_counts(lib)
+        lib.resampleB200SetTensorPath(w.tensor_mode)
         made, ms = time_launches(torch, b, stream, launches, warm=2)
+        lib.resampleB200SetTensorPath(1)
         kern = kernel_name(p0, path_counts(lib))
         ms_max, tot = reduce_over_ranks(dist if world > 1 else None, dev, ms, float(made))
         gs = tot * w.ch / (ms_max * 1e-3) / 1e9
@@ -779,10 +786,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=74,
                     help="independent stereo streams per GPU (74 x 28 tiles of 64 periods = 2072 = 14 per SM: no partial last wave)")
-    ap.add_argument("--frames", type=int, default=1 << 18, help="input frames per stream per block (= per launch)")
-    ap.add_argument("--launches-per-step", type=int, default=192, help="blocks every stream advances by in one step")
+    ap.add_argument("--frames", type=int, default=1 << 20,
+                    help="input frames per stream per block (= per launch): 23.8 s of audio; 74 streams x 112 tiles = 56 tiles per SM")
+    ap.add_argument("--launches-per-step", type=int, default=56, help="blocks every stream advances by in one step (~0.9 ms each)")
     ap.add_argument("--e2e-streams", type=int, default=64)
     ap.add_argument("--e2e-threads", type=int, default=8)
+    ap.add_argument("--e2e-frames", type=int, default=1 << 18, help="input frames per host call in the end-to-end leg")
     ap.add_argument("--e2e-steps", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config table")

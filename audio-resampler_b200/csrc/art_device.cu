@@ -500,7 +500,7 @@ struct ArtLaunchPlan {
 
 static bool g_forceGeneric = false, g_envRead = false;
 
-static void plan_launch (ArtDev *lead, double minRatio, bool oneRatio, unsigned int maxOut, unsigned long long totalOut,
+static void plan_launch (ArtDev *lead, double minRatio, double maxRatio, bool oneRatio, unsigned int maxOut, unsigned long long totalOut,
                          bool allowPeriodic, ArtLaunchPlan &lp)
 {
     if (!g_envRead) {
@@ -527,6 +527,12 @@ static void plan_launch (ArtDev *lead, double minRatio, bool oneRatio, unsigned 
         lp.periodic = true;
         lp.segLen = artPeriodicSegmentOutputs (lp.per, minRatio);
         return;
+    }
+    // asynchronous sample-rate conversion: ratios within a few hundred ppm of 1.  The read position then advances by almost exactly
+    // one sample per output, the filter-row pair changes every 1 / (|1/r - 1| * F) outputs, and runs of consecutive outputs share it
+    {
+        const double dLo = fabs (1.0 / minRatio - 1.0), dHi = fabs (1.0 / maxRatio - 1.0), d = dLo > dHi ? dLo : dHi;
+        lp.k.unity = (lp.k.mode & ART_MODE_INTERP) && !(lp.k.mode & ART_MODE_PRECISE) && d * lp.k.F <= 0.125 && !getenv ("ART_B200_NOUNITY");
     }
     artPlanGenericGeometry (lp.k, minRatio, total32, lead->smCount, lp.g);
 }
@@ -804,7 +810,7 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
 static void run_single (ArtDev *dev, const ArtCallPlan &p, ArtJob &job, cudaStream_t stream)
 {
     ArtLaunchPlan lp;
-    plan_launch (dev, p.st.ratio, true, p.outputs, p.outputs, true, lp);
+    plan_launch (dev, p.st.ratio, p.st.ratio, true, p.outputs, p.outputs, true, lp);
     std::vector<ArtJob> jobs;
     const int ctas = append_job (lp, job, jobs, 0);
     dispatch (lp, jobs, ctas, stream, dev);
@@ -865,7 +871,7 @@ extern "C" int artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, c
 
     host_pipe_init (dev, 2 * (size_t) pieces);
     ArtLaunchPlan lp;
-    plan_launch (dev, plan->st.ratio, true, plan->outputs / pieces + 1, plan->outputs, true, lp);
+    plan_launch (dev, plan->st.ratio, plan->st.ratio, true, plan->outputs / pieces + 1, plan->outputs, true, lp);
     long long uploaded = 0;
     for (int c = 0; c < pieces; ++c) {
         const unsigned int n0 = (unsigned int) ((unsigned long long) plan->outputs * c / pieces);
@@ -1044,7 +1050,7 @@ extern "C" int artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPlan
     use_device (lead);
     cudaStream_t st = stream ? (cudaStream_t) stream : lead->stream;
 
-    double minRatio = plans[0].st.ratio;
+    double minRatio = plans[0].st.ratio, maxRatio = plans[0].st.ratio;
     bool oneRatio = true;
     unsigned int maxOut = 0;
     unsigned long long totalOut = 0;
@@ -1053,12 +1059,13 @@ extern "C" int artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPlan
             artRaise ("a batch must hold contexts of one configuration on one GPU");
         if (plans[i].st.ratio != plans[0].st.ratio) oneRatio = false;
         if (plans[i].st.ratio < minRatio) minRatio = plans[i].st.ratio;
+        if (plans[i].st.ratio > maxRatio) maxRatio = plans[i].st.ratio;
         if (plans[i].outputs > maxOut) maxOut = plans[i].outputs;
         totalOut += plans[i].outputs;
     }
 
     ArtLaunchPlan lp;
-    plan_launch (lead, minRatio, oneRatio, maxOut, totalOut, true, lp);
+    plan_launch (lead, minRatio, maxRatio, oneRatio, maxOut, totalOut, true, lp);
     std::vector<ArtJob> jobs;
     jobs.reserve (count);
     int ctas = 0;
@@ -1090,18 +1097,19 @@ extern "C" int artDevRunBlocksInterleaved (ArtDev *dev, const ArtCallPlan *plans
     dev->lastStream = st;
     const int C = dev->C;
 
-    double minRatio = plans[0].st.ratio;
+    double minRatio = plans[0].st.ratio, maxRatio = plans[0].st.ratio;
     unsigned int maxOut = 0;
     unsigned long long totalOut = 0;
     long long totalIn = 0;
     for (int i = 0; i < count; ++i) {
         if (plans[i].st.ratio < minRatio) minRatio = plans[i].st.ratio;
+        if (plans[i].st.ratio > maxRatio) maxRatio = plans[i].st.ratio;
         if (plans[i].outputs > maxOut) maxOut = plans[i].outputs;
         totalOut += plans[i].outputs;
         totalIn += plans[i].consumed;
     }
     ArtLaunchPlan lp;
-    plan_launch (dev, minRatio, false, maxOut, totalOut, false, lp);
+    plan_launch (dev, minRatio, maxRatio, false, maxOut, totalOut, false, lp);
 
     std::vector<ArtJob> jobs;
     jobs.reserve (count + 1);

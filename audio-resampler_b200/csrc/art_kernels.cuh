@@ -59,6 +59,8 @@ struct ArtClass {
     int Wp;          // floats per smem plane
     int numJobs;
     int sort;        // 1: group a tile's outputs by filter row before convolving
+    int unity;       // 1: every ratio of the launch is so close to 1 that consecutive outputs share a filter-row pair for >= 8 outputs
+                     //    on average (asynchronous sample-rate conversion): the any-ratio kernel then register-blocks consecutive outputs
     float absSum;    // max over bank rows of sum |tap|: bounds sum |h| of any interpolated filter
 };
 

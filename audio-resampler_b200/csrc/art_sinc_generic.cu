@@ -225,6 +225,145 @@ __device__ __forceinline__ void art_run_tile_f32 (const ArtTileCtx &t, const Art
     }
 }
 
+/* Near-unity ratios (ASRC): runs of CONSECUTIVE outputs share one filter-row pair and their windows start at consecutive
+ * samples, so output r of a run is sum_k h[k] x[s + r + k]: a plain FIR over a sliding window that can be register-blocked.
+ * The tile is cut into mini-runs of up to four such outputs.  A warp takes eight of them: lane (q, g) works on mini-run g and
+ * the q-th quarter of the taps, keeps a four-sample window of channel vectors in registers and loads ONE new vector per tap
+ * for 4 outputs x CV channels x 2 rows of multiply-adds (the row-sorted form above loads one vector per output and tap and is
+ * bound by shared-memory bandwidth at twice the FMA time).  FFMA2 pairs run over adjacent channels -- the vector load delivers
+ * them as aligned register pairs and the coefficient is the scalar operand, so no instruction is spent on packing.  The staged
+ * window is skewed by one slot every eight so that the eight lanes of a quarter, whose windows start four samples apart, fall
+ * on different banks. */
+#define ART_SKEW(p) ((p) + ((p) >> 3))
+template <int CV> struct ArtPairs;
+template <> struct ArtPairs<2> { typedef unsigned long long type;
+    __device__ static unsigned long long get (const unsigned long long &x, int)   { return x; } };
+template <> struct ArtPairs<4> { typedef ulonglong2 type;
+    __device__ static unsigned long long get (const ulonglong2 &x, int p) { return p ? x.y : x.x; } };
+
+template <int CV>
+__device__ __forceinline__ void art_run_unity (const ArtTileCtx &t, const ArtJob &job, const float *__restrict__ bank,
+                                               int kk, int e0, int len, int lane)
+{
+    const int q = lane >> 3;
+    const int Tq = t.Tp >> 2;                                          // taps per quarter: a multiple of 8, rows are zero-padded to Tp
+    const float *__restrict__ rowA = bank + (size_t) kk * t.Tp + q * Tq;
+    const float *__restrict__ rowB = rowA + t.Tp;
+    const int p0 = (int) ((long long) t.srel[e0] - t.sFirst) + q * Tq; // window position of (output 0 of the mini-run, first tap of the quarter)
+    const float fOut = t.wgt[e0 + min (q, max (len, 1) - 1)];          // this lane finishes output q of its mini-run
+
+    if constexpr (CV >= 2) {
+        typedef typename ArtPairs<CV>::type PairT;
+        constexpr int NP = CV / 2;
+        for (int cg = 0; cg < t.nc; cg += CV) {
+            unsigned long long accA[4][NP], accB[4][NP];               // per output: channel pairs of the row A / row B sums
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int p = 0; p < NP; ++p) { accA[r][p] = 0ull; accB[r][p] = 0ull; }
+            const PairT *plane = reinterpret_cast<const PairT *> (t.xs) + (size_t) (cg / CV) * t.Wp;
+            PairT w0 = plane[ART_SKEW (p0)], w1 = plane[ART_SKEW (p0 + 1)], w2 = plane[ART_SKEW (p0 + 2)], w3;
+#define ART_UNITY_TAP(ca, cb, x0, x1, x2, x3)                                                   \
+            do {                                                                                \
+                const unsigned long long ca2 = art_pack2 (ca, ca), cb2 = art_pack2 (cb, cb);    \
+                _Pragma ("unroll")                                                              \
+                for (int p = 0; p < NP; ++p) {                                                  \
+                    art_ffma2 (accA[0][p], ArtPairs<CV>::get (x0, p), ca2);                     \
+                    art_ffma2 (accB[0][p], ArtPairs<CV>::get (x0, p), cb2);                     \
+                    art_ffma2 (accA[1][p], ArtPairs<CV>::get (x1, p), ca2);                     \
+                    art_ffma2 (accB[1][p], ArtPairs<CV>::get (x1, p), cb2);                     \
+                    art_ffma2 (accA[2][p], ArtPairs<CV>::get (x2, p), ca2);                     \
+                    art_ffma2 (accB[2][p], ArtPairs<CV>::get (x2, p), cb2);                     \
+                    art_ffma2 (accA[3][p], ArtPairs<CV>::get (x3, p), ca2);                     \
+                    art_ffma2 (accB[3][p], ArtPairs<CV>::get (x3, p), cb2);                     \
+                }                                                                               \
+            } while (0)
+            for (int k = 0; k < Tq; k += 4) {                          // the window rotates through the four registers: no moves
+                const float4 a4 = __ldg (reinterpret_cast<const float4 *> (rowA + k));
+                const float4 b4 = __ldg (reinterpret_cast<const float4 *> (rowB + k));
+                w3 = plane[ART_SKEW (p0 + k + 3)]; ART_UNITY_TAP (a4.x, b4.x, w0, w1, w2, w3);
+                w0 = plane[ART_SKEW (p0 + k + 4)]; ART_UNITY_TAP (a4.y, b4.y, w1, w2, w3, w0);
+                w1 = plane[ART_SKEW (p0 + k + 5)]; ART_UNITY_TAP (a4.z, b4.z, w2, w3, w0, w1);
+                w2 = plane[ART_SKEW (p0 + k + 6)]; ART_UNITY_TAP (a4.w, b4.w, w3, w0, w1, w2);
+            }
+#undef ART_UNITY_TAP
+            // sum the four tap quarters; the halving exchanges leave output q (all channels, both rows) in lane (q, g)
+            float val[4][2 * CV];                                      // [output][A ch0 .. A ch(CV-1), B ch0 ..]
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    art_unpack2 (accA[r][p], val[r][2 * p], val[r][2 * p + 1]);
+                    art_unpack2 (accB[r][p], val[r][CV + 2 * p], val[r][CV + 2 * p + 1]);
+                }
+            float half2[2][2 * CV], fin[2 * CV];
+            const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                for (int e = 0; e < 2 * CV; ++e) {
+                    const float send = up16 ? val[rr][e] : val[rr + 2][e], keep = up16 ? val[rr + 2][e] : val[rr][e];
+                    half2[rr][e] = keep + __shfl_xor_sync (0xffffffffu, send, 16);
+                }
+#pragma unroll
+            for (int e = 0; e < 2 * CV; ++e) {
+                const float send = up8 ? half2[0][e] : half2[1][e], keep = up8 ? half2[1][e] : half2[0][e];
+                fin[e] = keep + __shfl_xor_sync (0xffffffffu, send, 8);
+            }
+            if (q < len) {
+#pragma unroll
+                for (int v = 0; v < CV; ++v)
+                    if (cg + v < t.nc)
+                        *art_out_ptr (job, t.c0 + cg + v, (long long) t.n0 + e0 + q) = fmaf (fOut, fin[CV + v] - fin[v], fin[v]);
+            }
+        }
+    }
+    else {
+        // one channel: the pair is (row A, row B) of one output and the sample is the scalar operand
+        for (int cg = 0; cg < t.nc; ++cg) {
+            unsigned long long acc[4] = { 0ull, 0ull, 0ull, 0ull };
+            const float *plane = t.xs + (size_t) cg * t.Wp;
+            float w0 = plane[ART_SKEW (p0)], w1 = plane[ART_SKEW (p0 + 1)], w2 = plane[ART_SKEW (p0 + 2)], w3;
+#define ART_UNITY_TAP(ca, cb, x0, x1, x2, x3)                                                   \
+            do {                                                                                \
+                const unsigned long long c2 = art_pack2 (ca, cb);                               \
+                art_ffma2 (acc[0], c2, art_pack2 (x0, x0));                                     \
+                art_ffma2 (acc[1], c2, art_pack2 (x1, x1));                                     \
+                art_ffma2 (acc[2], c2, art_pack2 (x2, x2));                                     \
+                art_ffma2 (acc[3], c2, art_pack2 (x3, x3));                                     \
+            } while (0)
+            for (int k = 0; k < Tq; k += 4) {
+                const float4 a4 = __ldg (reinterpret_cast<const float4 *> (rowA + k));
+                const float4 b4 = __ldg (reinterpret_cast<const float4 *> (rowB + k));
+                w3 = plane[ART_SKEW (p0 + k + 3)]; ART_UNITY_TAP (a4.x, b4.x, w0, w1, w2, w3);
+                w0 = plane[ART_SKEW (p0 + k + 4)]; ART_UNITY_TAP (a4.y, b4.y, w1, w2, w3, w0);
+                w1 = plane[ART_SKEW (p0 + k + 5)]; ART_UNITY_TAP (a4.z, b4.z, w2, w3, w0, w1);
+                w2 = plane[ART_SKEW (p0 + k + 6)]; ART_UNITY_TAP (a4.w, b4.w, w3, w0, w1, w2);
+            }
+#undef ART_UNITY_TAP
+            float val[4][2];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) art_unpack2 (acc[r], val[r][0], val[r][1]);
+            float half2[2][2], fin[2];
+            const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float send = up16 ? val[rr][e] : val[rr + 2][e], keep = up16 ? val[rr + 2][e] : val[rr][e];
+                    half2[rr][e] = keep + __shfl_xor_sync (0xffffffffu, send, 16);
+                }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const float send = up8 ? half2[0][e] : half2[1][e], keep = up8 ? half2[1][e] : half2[0][e];
+                fin[e] = keep + __shfl_xor_sync (0xffffffffu, send, 8);
+            }
+            if (q < len)
+                *art_out_ptr (job, t.c0 + cg, (long long) t.n0 + e0 + q) = fmaf (fOut, fin[1] - fin[0], fin[0]);
+        }
+    }
+}
+
 template <bool INTERP, bool PRECISE, int CV, int SLOTS>
 __device__ __forceinline__ void art_run_any (const ArtTileCtx &t, const ArtJob &job, const float *__restrict__ bank,
                                              int kk, int e0, int len, int lane)
@@ -327,8 +466,10 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
     __syncthreads ();
 
     const long long sFirst = sh_first;
-    const int span = (int) (sh_last - sFirst) + k.Tp;            // samples of window the tile touches
-    if (span > k.Wp) {
+    const bool unity = INTERP && !PRECISE && k.unity;             // consecutive-output chunks instead of row-sorted runs (see art_run_unity)
+    // samples of window the tile touches (the unity form reads up to 3 + 32 positions past a chunk's last window: zero taps, but staged)
+    const int span = (int) (sh_last - sFirst) + k.Tp + (unity ? 40 : 0);
+    if ((unity ? ART_SKEW (span) + 1 : span) > k.Wp) {
         if (tid == 0)
             printf ("libresampler_b200: tile window %d exceeds plane %d (ratio %g)\n", span, k.Wp, job.ratio);
         __trap ();
@@ -342,14 +483,75 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
             const int total = span * k.Cg;
             for (int e = tid; e < total; e += ART_G_THREADS) {
                 const int j = e / k.Cg, cc = e - j * k.Cg;
-                xs[((cc / CV) * k.Wp + j) * CV + (cc % CV)] = cc < nc ? art_fetch (job, T, c0 + cc, sFirst + j) : 0.0f;
+                const int js = unity ? ART_SKEW (j) : j;
+                xs[((cc / CV) * k.Wp + js) * CV + (cc % CV)] = cc < nc ? art_fetch (job, T, c0 + cc, sFirst + j) : 0.0f;
             }
         }
         else {
             for (int cc = 0; cc < k.Cg; ++cc)
-                for (int j = tid; j < span; j += ART_G_THREADS)
-                    xs[((cc / CV) * k.Wp + j) * CV + (cc % CV)] = cc < nc ? art_fetch (job, T, c0 + cc, sFirst + j) : 0.0f;
+                for (int j = tid; j < span; j += ART_G_THREADS) {
+                    const int js = unity ? ART_SKEW (j) : j;
+                    xs[((cc / CV) * k.Wp + js) * CV + (cc % CV)] = cc < nc ? art_fetch (job, T, c0 + cc, sFirst + j) : 0.0f;
+                }
         }
+    }
+
+    /* ---- 2u. near-unity ratios: cut the tile into mini-runs of <= 4 consecutive outputs with one row pair and consecutive
+     *          windows, in natural order (no sort) -------------------------------------------------------------------------- */
+    if (unity) {
+        const int per = (cnt + ART_G_THREADS - 1) / ART_G_THREADS;
+        const int i0 = min (tid * per, cnt), i1 = min (i0 + per, cnt);
+        auto boundary = [&] (int i) -> bool { return i == 0 || key[i] != key[i - 1] || srel[i] != srel[i - 1] + 1; };
+        // the last boundary at or before every thread's range (block-wide running maximum)
+        int lastB = -1;
+        for (int i = i0; i < i1; ++i) if (boundary (i)) lastB = i;
+        int inc = lastB;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync (0xffffffffu, inc, o);
+            if (lane >= o) inc = max (inc, a);
+        }
+        if (lane == 31) sh_scan[warp] = inc;
+        __syncthreads ();
+        int carry = __shfl_up_sync (0xffffffffu, inc, 1);
+        if (lane == 0) carry = -1;
+        for (int w = 0; w < warp; ++w) carry = max (carry, sh_scan[w]);
+        // mini-run starts: every boundary and every 4th output after it
+        int nat = carry, mine = 0;
+        for (int i = i0; i < i1; ++i) {
+            if (boundary (i)) nat = i;
+            mine += ((i - nat) & 3) == 0;
+        }
+        int incC = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync (0xffffffffu, incC, o);
+            if (lane >= o) incC += a;
+        }
+        if (lane == 31) sh_scan2[warp] = incC;
+        __syncthreads ();
+        int at = incC - mine;
+        for (int w = 0; w < warp; ++w) at += sh_scan2[w];
+        nat = carry;
+        for (int i = i0; i < i1; ++i) {
+            if (boundary (i)) nat = i;
+            if (((i - nat) & 3) == 0) order[at++] = (unsigned short) i;
+        }
+        int totalMini = 0;
+        for (int w = 0; w < ART_G_WARPS; ++w) totalMini += sh_scan2[w];
+        __syncthreads ();
+
+        ArtTileCtx t;
+        t.xs = xs; t.srel = srel; t.wgt = wgt; t.order = order;
+        t.sFirst = sFirst; t.n0 = n0; t.c0 = c0; t.nc = nc; t.Wp = k.Wp; t.Tp = k.Tp; t.half = half;
+        for (int m0 = warp * 8; m0 < totalMini; m0 += ART_G_WARPS * 8) {
+            const int m = m0 + (lane & 7);                        // lane group g = lane & 7 takes mini-run m0 + g
+            const bool live = m < totalMini;
+            const int e0 = order[live ? m : totalMini - 1];
+            const int e1 = m + 1 < totalMini ? order[m + 1] : cnt;
+            art_run_unity<CV> (t, job, k.bank, key[e0], e0, live ? e1 - e0 : 0, lane);
+        }
+        return;
     }
 
     /* ---- 2. group by filter row ---------------------------------------------------------- */
@@ -478,6 +680,7 @@ void artPlanGenericGeometry (ArtClass &k, double minRatio, unsigned int maxOutpu
         for (int Cg = maxCg; Cg >= cv; Cg -= cv) {
             ArtClass t = k;
             t.NB = NB; t.Cg = Cg; t.Wp = plane_floats (NB, minRatio, k.Tp);
+            if (k.unity) t.Wp = ((t.Wp + 40) * 9 / 8 + 40) & ~31;        // skewed layout (one slot in eight) + the unity form's over-read
             if (t.Wp >= (1 << 26) || generic_smem (t) > budget)
                 continue;
             double perRow = (double) NB / (k.F + 1);
@@ -492,6 +695,7 @@ void artPlanGenericGeometry (ArtClass &k, double minRatio, unsigned int maxOutpu
     k.NB = bestNB;
     k.Cg = bestCg;
     k.Wp = plane_floats (bestNB, minRatio, k.Tp);
+    if (k.unity) k.Wp = ((k.Wp + 40) * 9 / 8 + 40) & ~31;
     g.CV = cv;
     g.smemBytes = generic_smem (k);
 }

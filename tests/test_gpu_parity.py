@@ -320,3 +320,19 @@ def test_endpoint_extrapolation(ch, preset, src, dst, advance):
         yg, ug, gg = g.process(x, 20000, ratio, flush_after=True, planar=planar)
         yo, uo, go = o.process(x, 20000, ratio, flush_after=True)
         assert (ug, gg) == (uo, go) and A.peak_error(yg, yo) <= TOL
+
+
+@pytest.mark.parametrize("ch,preset,ratio", [
+    (1, 2, 1.0), (2, 2, 1.00002), (3, 1, 0.9999), (8, 2, 1.0001), (5, 3, 0.99997), (2, 4, 1.00005), (4, 2, 1.0 - 3.8e-4), (2, 2, 1.0 + 4.5e-4),
+])
+def test_near_unity_ratios(ch, preset, ratio):
+    """asynchronous sample-rate conversion: ratios within a few hundred ppm of 1 take the register-blocked form of the any-ratio
+    kernel (runs of consecutive outputs that share a filter-row pair); the last two cases sit either side of its applicability
+    limit |1/r - 1| * filters <= 1/8.  Several calls, one of them flushing."""
+    filters, taps = A.PRESETS[preset]
+    g, o = _pair(ch, taps, filters, lowpass_ratio=0.0)
+    g.advance(taps / 2); o.advance(taps / 2)
+    rng = np.random.default_rng(int(ratio * 1e6) % 1000 + ch)
+    for b, n in enumerate([6000, 333, 9000]):
+        x = rng.uniform(-0.5, 0.5, (n, ch)).astype(np.float32)
+        _check_call(g, o, x, n + taps + 64, ratio, flush_after=(b == 2))

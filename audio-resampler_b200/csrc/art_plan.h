@@ -53,12 +53,16 @@ ART_HD double art_exact_bound (double x)
 {
     union { double d; unsigned long long u; } v;
     unsigned long long m;
-    int E, tz = 0;
+    int E, tz;
     v.d = x;
     E = (int) ((v.u >> 52) & 0x7ff);
     m = v.u & 0xfffffffffffffULL;
     if (E) m |= 1ULL << 52; else E = 1;                /* subnormal */
-    while (!(m & 1)) { m >>= 1; ++tz; }                 /* m != 0 because x != 0 */
+#ifdef __CUDA_ARCH__
+    tz = __ffsll ((long long) m) - 1;                   /* m != 0 because x != 0 */
+#else
+    tz = __builtin_ctzll (m);
+#endif
     v.u = (unsigned long long) (E - 1075 + tz + 53 + 1023) << 52;    /* 2^(53+e), e = E-1075+tz */
     return v.d;
 }
@@ -184,7 +188,7 @@ ART_HD ArtLoopPlan art_plan_loop (const ArtLoopState *s, int numIn, int numOut)
     /* largest N <= numOut with N == 0 or inputs_before(N-1) <= numIn (monotone in N).  The answer is
      * within a couple of units of (I + numIn - T/2 - P) * ratio, so bracket it from that estimate with
      * doubling steps and bisect only inside the bracket: ~4 predicate evaluations instead of ~log2(numOut). */
-#define ART_OK(N) ((N) == 0 || art_inputs_before (s, (N) - 1) <= numIn)
+#define ART_OK(N) ((N) == 0 || art_inputs_before_fast (s, (N) - 1) <= numIn)
     if (hi > 0 && ART_OK (hi))
         lo = hi;
     else if (hi > 0) {
@@ -215,7 +219,7 @@ ART_HD ArtLoopPlan art_plan_loop (const ArtLoopState *s, int numIn, int numOut)
     if (numOut <= 0)
         p.inputs = 0;
     else if (lo == (unsigned int) numOut)
-        p.inputs = (unsigned int) art_inputs_before (s, lo - 1);   /* output space ran out */
+        p.inputs = (unsigned int) art_inputs_before_fast (s, lo - 1);   /* output space ran out */
     else
         p.inputs = (unsigned int) numIn;                            /* input ran out        */
 

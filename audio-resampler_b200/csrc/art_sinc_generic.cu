@@ -479,7 +479,31 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
     {
         // xs[(group * Wp + j) * CV + v] = sample j of channel group*CV + v
         const bool interleavedSrc = (job.inPlanes == nullptr) && (job.inCS == 1);
-        if (interleavedSrc) {
+        typedef typename ArtVec<CV>::type VecT;
+        // whole channel vectors straight from an interleaved block: one LDG.64/128 and one STS.64/128 per CV samples
+        const bool vectorSrc = CV > 1 && interleavedSrc && nc == k.Cg && (job.inFS % CV) == 0 &&
+                               (reinterpret_cast<uintptr_t> (job.in + c0) % (sizeof (float) * CV)) == 0;
+        if (vectorSrc) {
+            const int Q = k.Cg / CV, total = span * Q;
+            const long long lo = -job.prevAvail, hi = job.inValid;
+            VecT *xv = reinterpret_cast<VecT *> (xs);
+            for (int e = tid; e < total; e += ART_G_THREADS) {
+                const int j = e / Q, cq = e - j * Q;
+                const int js = unity ? ART_SKEW (j) : j;
+                const long long idx = sFirst + j;
+                VecT v;
+                if (idx >= lo && idx < hi)
+                    v = __ldg (reinterpret_cast<const VecT *> (job.in + idx * job.inFS + c0 + cq * CV));
+                else {
+                    alignas (16) float tmp[CV];
+#pragma unroll
+                    for (int u = 0; u < CV; ++u) tmp[u] = art_fetch (job, T, c0 + cq * CV + u, idx);
+                    v = *reinterpret_cast<VecT *> (tmp);
+                }
+                xv[(size_t) cq * k.Wp + js] = v;
+            }
+        }
+        else if (interleavedSrc) {
             const int total = span * k.Cg;
             for (int e = tid; e < total; e += ART_G_THREADS) {
                 const int j = e / k.Cg, cc = e - j * k.Cg;
@@ -658,6 +682,13 @@ static int plane_floats (int NB, double ratio, int Tp)
     return (((int) span) + 31) & ~31;
 }
 
+/* plane pitch of the near-unity form: the skewed layout (one slot in eight), its over-read of 40 positions, and a pitch of
+ * 4 mod 8 vectors so that the two planes an 8-channel CTA stages side by side start on different banks */
+static int unity_plane (int Wp)
+{
+    return ((((Wp + 40) * 9 / 8 + 40) + 7) & ~7) + 4;
+}
+
 void artPlanGenericGeometry (ArtClass &k, double minRatio, unsigned int maxOutputs, int smCount, ArtLaunchGeom &g)
 {
     const size_t budget = 110 * 1024;        // two CTAs per SM inside the 227 KB carve-out
@@ -680,7 +711,7 @@ void artPlanGenericGeometry (ArtClass &k, double minRatio, unsigned int maxOutpu
         for (int Cg = maxCg; Cg >= cv; Cg -= cv) {
             ArtClass t = k;
             t.NB = NB; t.Cg = Cg; t.Wp = plane_floats (NB, minRatio, k.Tp);
-            if (k.unity) t.Wp = ((t.Wp + 40) * 9 / 8 + 40) & ~31;        // skewed layout (one slot in eight) + the unity form's over-read
+            if (k.unity) t.Wp = unity_plane (t.Wp);
             if (t.Wp >= (1 << 26) || generic_smem (t) > budget)
                 continue;
             double perRow = (double) NB / (k.F + 1);
@@ -695,7 +726,7 @@ void artPlanGenericGeometry (ArtClass &k, double minRatio, unsigned int maxOutpu
     k.NB = bestNB;
     k.Cg = bestCg;
     k.Wp = plane_floats (bestNB, minRatio, k.Tp);
-    if (k.unity) k.Wp = ((k.Wp + 40) * 9 / 8 + 40) & ~31;
+    if (k.unity) k.Wp = unity_plane (k.Wp);
     g.CV = cv;
     g.smemBytes = generic_smem (k);
 }

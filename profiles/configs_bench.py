@@ -85,13 +85,20 @@ def run_asrc(name, ch, preset, blocks, block_frames, steps=10):
         step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(st); made = 0
+    t0 = time.perf_counter(); e0.record(st); made = 0
     for _ in range(steps):
         made += step()
+    host = (time.perf_counter() - t0) * 1e3          # time the host spent planning and enqueueing (no waiting)
     e1.record(st); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    lib.resampleB200ProfileEnable(1)
+    for _ in range(steps):
+        step()
+    kms = C.c_double(); nk = lib.resampleB200ProfileCollect(C.byref(kms)); lib.resampleB200ProfileEnable(0)
     sps = made * ch / (ms * 1e-3)
     print(json.dumps({"config": name, "Gsamples_per_s": round(sps / 1e9, 2), "ms_per_step": round(ms / steps, 3),
+                      "host_ms_per_step": round(host / steps, 3), "kernel_ms_per_step": round(kms.value / steps, 3),
+                      "kernel_Gsamples_per_s": round(made * ch / (kms.value * 1e-3) / 1e9, 2) if kms.value else None,
                       "hbm_frac": round(sps * 8.0 / 6553e9, 4), "kernel": "generic (per-block ratio)"}), flush=True)
     lib.resampleFree(ctx)
 

@@ -634,6 +634,40 @@ static long long first_frame_read (const ArtJob &j, const ArtClass &k, unsigned 
     return (long long) floor (pos) - (k.Tref / 2 + k.lead) + 1 + (long long) w * 15LL * k.Tref - j.origin;
 }
 
+/* Job lists travel through a small ring of pinned buffers per GPU.  A pageable source larger than the runtime's staging
+ * threshold (64 KB: ~400 jobs) makes cudaMemcpyAsync wait until the stream has reached the copy, i.e. for the previous
+ * launch -- an ASRC sequence of 1024 blocks per launch then alternates host and GPU work instead of overlapping them. */
+struct ArtJobRing { char *host; size_t slotCap; cudaEvent_t done[8]; bool used[8]; unsigned int next; };
+static ArtJobRing g_jobRing[16];
+static std::mutex g_jobRingMutex;
+
+static void upload_jobs (void *d_dst, const void *src, size_t bytes, cudaStream_t stream)
+{
+    int device = 0;
+    ART_CUDA_CHECK (cudaGetDevice (&device));
+    std::lock_guard<std::mutex> lock (g_jobRingMutex);
+    ArtJobRing &ring = g_jobRing[device & 15];
+    if (bytes > ring.slotCap) {                                   // one pinned arena of eight slots, grown rarely
+        for (int i = 0; i < 8; ++i)
+            if (ring.used[i]) { ART_CUDA_CHECK (cudaEventSynchronize (ring.done[i])); ring.used[i] = false; }
+        if (ring.host) cudaFreeHost (ring.host);
+        ring.host = nullptr; ring.slotCap = 0;
+        const size_t cap = ((bytes * 2 < 65536 ? 65536 : bytes * 2) + 255) & ~(size_t) 255;
+        ART_CUDA_CHECK (cudaHostAlloc ((void **) &ring.host, cap * 8, cudaHostAllocDefault));
+        ring.slotCap = cap;
+    }
+    const unsigned int i = ring.next++ & 7u;
+    if (ring.used[i])
+        ART_CUDA_CHECK (cudaEventSynchronize (ring.done[i]));     // the copy issued eight launches ago
+    else if (!ring.done[i])
+        ART_CUDA_CHECK (cudaEventCreateWithFlags (&ring.done[i], cudaEventDisableTiming));
+    char *slot = ring.host + (size_t) i * ring.slotCap;
+    memcpy (slot, src, bytes);
+    ART_CUDA_CHECK (cudaMemcpyAsync (d_dst, slot, bytes, cudaMemcpyHostToDevice, stream));
+    ART_CUDA_CHECK (cudaEventRecord (ring.done[i], stream));
+    ring.used[i] = true;
+}
+
 static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cudaStream_t stream, ArtDev *owner = nullptr)
 {
     if (jobs.empty ())
@@ -743,8 +777,7 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
     ArtJob *d_jobs = nullptr;
     if (n > 1) {
         ART_CUDA_CHECK (cudaMallocAsync (&d_jobs, sizeof (ArtJob) * n, stream));
-        // pageable source: staged by the runtime before the call returns
-        ART_CUDA_CHECK (cudaMemcpyAsync (d_jobs, jobs.data (), sizeof (ArtJob) * n, cudaMemcpyHostToDevice, stream));
+        upload_jobs (d_jobs, jobs.data (), sizeof (ArtJob) * n, stream);
     }
     if (ctas > 0) {
         if (lp.periodic) {

@@ -151,13 +151,13 @@ __device__ __forceinline__ void u_commit (unsigned int bar)
 }
 
 /* optional role timing (ART_B200_UPROF=1): cycles spent waiting / working per role, summed over CTAs */
-__device__ unsigned long long g_uprof[16];
+__device__ unsigned long long g_uprof[24];
 __device__ unsigned long long g_utime[160][4];         // per CTA (last launch): globaltimer at entry, first MMA issue, last accFull commit, exit
 __device__ __forceinline__ unsigned long long u_gtime () { unsigned long long t; asm volatile ("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define UCLK() (prof ? clock64 () : 0ll)
 #define UPROF_ADD(slot, cyc) do { if (prof) pacc[slot] += (unsigned int) (cyc); } while (0)      /* role-local, flushed once per thread */
-#define UPROF_DECL()  unsigned int pacc[16] = { 0 }
-#define UPROF_FLUSH() do { if (prof) { _Pragma ("unroll") for (int i_ = 0; i_ < 16; ++i_) if (pacc[i_]) atomicAdd (&g_uprof[i_], (unsigned long long) pacc[i_]); } } while (0)
+#define UPROF_DECL()  unsigned int pacc[24] = { 0 }
+#define UPROF_FLUSH() do { if (prof) { _Pragma ("unroll") for (int i_ = 0; i_ < 24; ++i_) if (pacc[i_]) atomicAdd (&g_uprof[i_], (unsigned long long) pacc[i_]); } } while (0)
 
 __device__ __forceinline__ void u_tmem_ld8 (unsigned int addr, unsigned int (&r)[8])
 {
@@ -688,7 +688,9 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
         Src cur = source (blockIdx.x < totalTiles ? blockIdx.x : 0);
         if ((int) blockIdx.x < totalTiles) fetch (cur, 0, vn);
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++lt) {
+            long long q0t = UCLK ();
             const int e = quantum (lt);
+            if (ctid == 0) UPROF_ADD (17, UCLK () - q0t);
             const float invq = __int_as_float ((127 - e) << 23);
             const unsigned long long invq2 = art_pack2 (invq, invq), magic2 = art_pack2 (12582912.0f, 12582912.0f),
                                      neg2 = art_pack2 (-1.0f, -1.0f), k2048 = art_pack2 (2048.0f, 2048.0f);
@@ -697,6 +699,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             const bool more = tile + (int) gridDim.x < totalTiles;
             Src nxt = cur;
             for (int i = 0; i < KI; ++i) {
+                long long h0t = UCLK ();
 #pragma unroll
                 for (int uu = 0; uu < NV; ++uu) v[uu] = vn[uu];
                 // the next pair's loads (of the next tile after the last pair) fly while this pair is converted
@@ -707,6 +710,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                 if (i + 1 < KI) fetch (cur, i + 1, vn);
                 else if (more) fetch (nxt, 0, vn);
                 long long c0t = UCLK ();
+                if (ctid == 0) UPROF_ADD (18, c0t - h0t);
                 const unsigned int sl = (unsigned int) i % (unsigned int) NS, use = lt * rep + (unsigned int) i / (unsigned int) NS;
                 u_mbar_wait_relaxed (pEmptyA (sl), (use & 1) ^ 1);
                 long long cb = UCLK ();
@@ -869,7 +873,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             long long e3 = UCLK ();
             if ((long long) tile + 3LL * gridDim.x < totalTiles)
                 scanTile (tile + 3 * gridDim.x, lt + 3u);
-            if (tid == 12 * 32) { UPROF_ADD (8, e1 - e0); UPROF_ADD (9, e2 - e1); UPROF_ADD (6, e3 - e2); UPROF_ADD (10, 1); UPROF_ADD (2, UCLK () - e3); }
+            if (tid == 12 * 32) { UPROF_ADD (8, e1 - e0); UPROF_ADD (9, e2 - e1); UPROF_ADD (6, e3 - e2); UPROF_ADD (10, 1); UPROF_ADD (16, UCLK () - e3); }
         }
         UPROF_FLUSH ();
     }
@@ -1065,7 +1069,7 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
         if (const char *d = getenv ("ART_B200_UDBG")) roleProf |= atoi (d) << 4;
 #endif
         if (roleProf & 1) atexit ([] () {
-            unsigned long long h[16];
+            unsigned long long h[24];
             cudaDeviceSynchronize ();
             if (cudaMemcpyFromSymbol (h, g_uprof, sizeof h) != cudaSuccess) return;
             const double n = h[10] ? (double) h[10] : 1.0;
@@ -1082,10 +1086,10 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
                 if (nn) fprintf (stderr, "[art] umma timeline of the last launch (us from first CTA entry; avg / max over %d CTAs): entry %.1f | first MMA %.1f / %.1f | last MMA commit %.1f / %.1f | exit %.1f / %.1f (min %.1f)\n",
                                  nn, e0 / nn / 1e3, a1 / nn / 1e3, m1 / 1e3, a2 / nn / 1e3, m2 / 1e3, a3 / nn / 1e3, m3 / 1e3, lo3 / 1e3);
             }
-            fprintf (stderr, "[art] umma cycles per tile: producer wait-empty %.0f | mma wait-planes %.0f wait-acc+scan %.0f wait-h %.0f tile %.0f | "
-                     "convert wait-planes %.0f | epilogue wait %.0f drain %.0f | tiles %.0f | mma issue %.0f commit %.0f region %.0f | epilogue store %.0f | convert split %.0f fence %.0f arrive %.0f\n",
+            fprintf (stderr, "[art] umma cycles per tile: producer wait-empty %.0f | mma wait-planes %.0f wait-acc %.0f wait-h %.0f tile %.0f | "
+                     "convert wait-planes %.0f | epilogue wait %.0f drain %.0f | tiles %.0f | mma issue %.0f commit %.0f region %.0f | epilogue store %.0f scan %.0f | convert split %.0f fence %.0f arrive %.0f quantum-wait %.0f loads+head %.0f\n",
                      h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[8] / n, h[9] / n, n, h[11] / n, h[12] / n, h[13] / n,
-                     h[6] / n, h[7] / n, h[14] / n, h[15] / n);
+                     h[6] / n, h[16] / n, h[7] / n, h[14] / n, h[15] / n, h[17] / n, h[18] / n);
         });
     }
     if (u.cg == 4)      umma_launch_one<4> (k, uu, totalTiles, grid, single, d_jobs, roleProf, stream);

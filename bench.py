@@ -346,10 +346,15 @@ class DeviceBatch:
             done = lib.resampleProcessBlocksInterleavedDevice(self.ctxs[0], C.c_void_p(self.x[r, 0].data_ptr()), self.bf, self.br, w.asrc_blocks,
                                                               C.c_void_p(self.y[r, 0].data_ptr()), self.cap, self.bres, self.bpos, self.stream_ptr)
             assert done == w.asrc_blocks
-            return sum(x.output_generated for x in self.bres)
+            return int(self._generated(self.bres))
         lib.resampleBatchProcessInterleavedDevice(self.ctx_arr, w.streams, self.in_arr[r], self.nin, self.out_arr[r], self.nout,
                                                   self.ratios, self.res, self.stream_ptr)
-        return sum(x.output_generated for x in self.res)
+        return int(self._generated(self.res))
+
+    @staticmethod
+    def _generated(results):
+        # a numpy view of the ResampleResult array: a Python loop over 1024 ctypes structs costs more than the launch it follows
+        return np.frombuffer(results, dtype=np.uint32)[1::2].sum(dtype=np.int64)
 
     def close(self):
         for c in self.ctxs:
@@ -753,7 +758,7 @@ def measure_e2e(lib, pkg, torch, dist, world, dev, streams, frames, args):
 
     def batch():
         lib.resampleBatchProcessInterleaved(ctx_arr, n, in_arr, nin_arr, out_arr, nout_arr, ratio_arr, res_arr)
-        return sum(r.output_generated for r in res_arr)
+        return int(np.frombuffer(res_arr, dtype=np.uint32)[1::2].sum(dtype=np.int64))
 
     for _ in range(2):
         batch()

@@ -24,6 +24,11 @@ KEYS = [
     "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
     "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum", "sm__cycles_elapsed.avg", "sm__cycles_active.avg",
+    # tensor pipe (tcgen05 MMAs run on the hmma sub-pipe) and the tensor-memory path
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
+    "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
 ]
 STALLS = "smsp__average_warps_issue_stalled_"
 TAIL = "_per_issue_active.ratio"

@@ -94,6 +94,7 @@ struct ArtUmma {
     int rows;            // 16-byte row slots of a plane of the signal operand: cg * periods, padded
     int DH;              // filter quantum is 2^-DH
     int stages;          // depth of the filter stage ring
+    int depth;           // raw plane pairs the converters keep in flight (cp.async ring in shared memory): 2 .. 4
     int tableHalfs;      // fp16 elements per table: numK * 3 * 2 * Npad * 8
     unsigned short *H;   // [tables][G][numK][3 splits][2 k-planes][Npad][8]  fp16 bit patterns
     int *S0;             // [jobs][G]  region index of tap 0 of the group's first phase, period 0

@@ -139,6 +139,19 @@ __device__ __forceinline__ unsigned int u_lds32 (unsigned int addr) { unsigned i
 __device__ __forceinline__ uint2 u_lds64 (unsigned int addr) { uint2 v; asm volatile ("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory"); return v; }
 __device__ __forceinline__ void u_sts64 (unsigned int addr, uint2 v) { asm volatile ("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(addr), "r"(v.x), "r"(v.y) : "memory"); }
 
+/* raw-sample staging of the converters: per ring slot (= one pair of planes) [period group][tap][converter thread] x CGT floats */
+__host__ __device__ constexpr unsigned int u_staging_groups (int cgt) { return cgt == 1 ? 5u : (cgt == 2 ? 3u : 2u); }
+__host__ __device__ constexpr unsigned int u_staging_slot (int cgt) { return u_staging_groups (cgt) * 2u * ART_U_CONV * 4u * (unsigned int) cgt; }
+
+__device__ __forceinline__ void u_cp_async (unsigned int dst, const void *src, int bytes, bool live)
+{
+    // src-size 0 writes zeros: samples that must read as silence cost the same instruction as real ones
+    const unsigned int n = live ? (unsigned int) bytes : 0u;
+    if (bytes == 16)     asm volatile ("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(n) : "memory");
+    else if (bytes == 8) asm volatile ("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst), "l"(src), "r"(n) : "memory");
+    else                 asm volatile ("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(src), "r"(n) : "memory");
+}
+
 __device__ __forceinline__ bool u_elect ()
 {
     unsigned int pred;
@@ -390,7 +403,8 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
     asm volatile ("mov.u32 %0, %1;" : "=r"(xcBase) : "r"(u_smem (smem)));       // opaque: never rematerialised from the generic pointer
     const unsigned int stBase = xcBase + (unsigned int) digits * splitBytes;
     const unsigned int scratchBase = stBase + (unsigned int) u.stages * stageBytes;
-    const unsigned int ctl = scratchBase + 8u * ART_U_SCRATCH;
+    const unsigned int stagingBase = scratchBase + 8u * ART_U_SCRATCH;          // converters' ring of raw samples (cp.async), see below
+    const unsigned int ctl = stagingBase + (unsigned int) u.depth * u_staging_slot (CGT);
     const int units = u.stages / ART_U_GROUP;             // ring slots of ART_U_GROUP k-steps
 #define hFullA(s)   (ctl + 8u * (unsigned int) (s))
 #define hEmptyA(s)  (ctl + 64u + 8u * (unsigned int) (s))
@@ -584,16 +598,22 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
         UPROF_DECL ();
         /* a lane converts TWO neighbouring taps of a period, for all CGT channels of the tile (one conversion and one 32-bit
          * store per digit and channel for the two); a warp covers 4 periods x 16 taps, the 8 warps take every 8th group of 4 */
-        constexpr int UN = CGT == 1 ? 5 : (CGT == 2 ? 3 : 2);               // period groups per warp: periods <= 160 / 96 / 64
+        constexpr int UN = (int) u_staging_groups (CGT);                    // period groups per warp: periods <= 160 / 96 / 64
         constexpr int NV = 2 * UN * CGT;
         const int r0 = 4 * cw + (lane >> 3);                                // this lane's period in the warp's first group
         const int off0 = M * r0 + 2 * (lane & 7);                           // its first sample's offset inside the tile, plane pair 0
         unsigned int lt = 0;
-        float v[NV], vn[NV];                                                 // [(group * 2 + tap) * CGT + channel]
 
-        /* what a lane needs to fetch its samples of one tile.  Inside the caller's block a sample is base[idx * fs];
-         * tiles that touch the history or run past the end of the input take the same loads from a clamped address
-         * and zero what must read as silence, so that all loads of a plane pair are still issued back to back */
+        /* The samples reach the converters through a ring of `depth` raw pairs in shared memory filled by cp.async: a lane
+         * requests ITS samples of the pair `depth - 1` iterations ahead (no registers are tied up while they fly -- with loads
+         * into registers only one pair could be in flight, and the ~1400 cycles a pair's loads take were exposed ten times per
+         * tile) and reads them back itself, so the ring needs no synchronisation beyond cp.async.wait_group. */
+        const int depth = u.depth;
+        constexpr unsigned int planeStride = ART_U_CONV * 4u * CGT, slotBytes = u_staging_slot (CGT);
+        const unsigned int stg = stagingBase + (unsigned int) ctid * (4u * CGT);
+
+        /* what a lane needs to request its samples of one tile.  Inside the caller's block a sample is base[idx * fs];
+         * tiles that touch the history or run past the end of the input classify every sample (history / silence) */
         struct Src { const float *pc[CGT]; const float *h0, *dummy; long long fs; int loRel, hiRel; bool fast, vec; };
         auto source = [&] (int tile) -> Src {
             Src sc;
@@ -606,7 +626,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
 #pragma unroll
             for (int cc = 0; cc < CGT; ++cc)
                 sc.pc[cc] = (job.inPlanes ? job.inPlanes[w.c0 + cc] : job.in + (long long) (w.c0 + cc) * job.inCS) + R0 * sc.fs;
-            // all channels of a frame from one load: interleaved with the tile's channels adjacent and the vector aligned
+            // all channels of a frame from one copy: interleaved with the tile's channels adjacent and the vector aligned
             sc.vec = CGT > 1 && job.inPlanes == nullptr && job.inCS == 1 && (sc.fs % CGT) == 0 &&
                      (reinterpret_cast<unsigned long long> (job.in + w.c0) & (4u * CGT - 1u)) == 0;
             const float *hist = job.hist + (long long) w.c0 * T + T + job.prevAvail;     // hist[idx]: -T - prevAvail <= idx < -prevAvail (+ cc * T)
@@ -635,58 +655,63 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             return e;
         };
         auto rowOk = [&] (int uu) -> bool { return r0 + 32 * uu < periods; };
-        auto fetch = [&] (const Src &sc, int i, float (&dst)[NV]) {
+        // request this lane's samples of plane pair i of the tile `sc` describes into ring slot `slot`
+        auto request = [&] (const Src &sc, int i, unsigned int slot) {
+            const unsigned int sb = stg + slot * slotBytes;
+            if (dbg & 1) return;
             if (sc.fast) {
                 const long long at = (long long) (off0 + 16 * i) * sc.fs, rowStep = (long long) (32 * M) * sc.fs;
 #pragma unroll
                 for (int uu = 0; uu < UN; ++uu) {
-                    const bool ok = rowOk (uu) && !(dbg & 1);
+                    if (!rowOk (uu)) continue;
                     const long long o = at + uu * rowStep;
-                    if (CGT == 2 && sc.vec) {
-                        const float2 a = ok ? __ldg (reinterpret_cast<const float2 *> (sc.pc[0] + o)) : make_float2 (0.0f, 0.0f);
-                        const float2 b = ok ? __ldg (reinterpret_cast<const float2 *> (sc.pc[0] + o + sc.fs)) : make_float2 (0.0f, 0.0f);
-                        dst[(2 * uu) * CGT] = a.x; dst[(2 * uu) * CGT + (CGT > 1)] = a.y;
-                        dst[(2 * uu + 1) * CGT] = b.x; dst[(2 * uu + 1) * CGT + (CGT > 1)] = b.y;
-                    }
-                    else if (CGT == 4 && sc.vec) {
-                        const float4 a = ok ? __ldg (reinterpret_cast<const float4 *> (sc.pc[0] + o)) : make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
-                        const float4 b = ok ? __ldg (reinterpret_cast<const float4 *> (sc.pc[0] + o + sc.fs)) : make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
-                        dst[(2 * uu) * CGT] = a.x; dst[(2 * uu) * CGT + (CGT > 1)] = a.y; dst[(2 * uu) * CGT + 2 * (CGT > 2)] = a.z; dst[(2 * uu) * CGT + 3 * (CGT > 2)] = a.w;
-                        dst[(2 * uu + 1) * CGT] = b.x; dst[(2 * uu + 1) * CGT + (CGT > 1)] = b.y; dst[(2 * uu + 1) * CGT + 2 * (CGT > 2)] = b.z; dst[(2 * uu + 1) * CGT + 3 * (CGT > 2)] = b.w;
+                    if (CGT > 1 && sc.vec) {
+                        u_cp_async (sb + (unsigned int) (2 * uu) * planeStride, sc.pc[0] + o, 4 * CGT, true);
+                        u_cp_async (sb + (unsigned int) (2 * uu + 1) * planeStride, sc.pc[0] + o + sc.fs, 4 * CGT, true);
                     }
                     else {
 #pragma unroll
                         for (int cc = 0; cc < CGT; ++cc) {
-                            dst[(2 * uu) * CGT + cc] = ok ? __ldg (sc.pc[cc] + o) : 0.0f;
-                            dst[(2 * uu + 1) * CGT + cc] = ok ? __ldg (sc.pc[cc] + o + sc.fs) : 0.0f;
+                            u_cp_async (sb + (unsigned int) (2 * uu) * planeStride + 4u * cc, sc.pc[cc] + o, 4, true);
+                            u_cp_async (sb + (unsigned int) (2 * uu + 1) * planeStride + 4u * cc, sc.pc[cc] + o + sc.fs, 4, true);
                         }
                     }
                 }
             }
             else {
-                // boundary tiles: one plane-pair group at a time keeps the pointer set small
 #pragma unroll
                 for (int uu = 0; uu < UN; ++uu) {
-                    const float *ptr[2 * CGT];
-                    bool ok[2 * CGT];
+                    if (!rowOk (uu)) continue;
 #pragma unroll
                     for (int e = 0; e < 2 * CGT; ++e) {
                         const int tap = e / CGT, cc = e - tap * CGT;
                         const int rel = off0 + 16 * i + 32 * M * uu + tap;
                         const bool inBlock = rel >= sc.loRel && rel < sc.hiRel, inHist = rel < sc.loRel && rel >= sc.loRel - T;
-                        ok[e] = (inBlock || inHist) && rowOk (uu);
-                        ptr[e] = inBlock ? sc.pc[cc] + (long long) rel * sc.fs : (inHist ? sc.h0 + (long long) cc * T + rel : sc.dummy);
+                        const float *ptr = inBlock ? sc.pc[cc] + (long long) rel * sc.fs : (inHist ? sc.h0 + (long long) cc * T + rel : sc.dummy);
+                        u_cp_async (sb + (unsigned int) (2 * uu + tap) * planeStride + 4u * cc, ptr, 4, inBlock || inHist);
                     }
-#pragma unroll
-                    for (int e = 0; e < 2 * CGT; ++e) dst[2 * uu * CGT + e] = __ldg (ptr[e]);
-#pragma unroll
-                    for (int e = 0; e < 2 * CGT; ++e) dst[2 * uu * CGT + e] = ok[e] ? dst[2 * uu * CGT + e] : 0.0f;
                 }
             }
         };
+        // the request side runs `depth - 1` pairs ahead of the conversion, across tile boundaries
+        int rtile = blockIdx.x, ri = 0;
+        unsigned int rslot = 0;
+        Src rsrc = source (rtile < totalTiles ? rtile : 0);
+        auto requestNext = [&] () {
+            if (rtile < totalTiles) {
+                request (rsrc, ri, rslot);
+                if (++ri == KI) {
+                    ri = 0;
+                    rtile += gridDim.x;
+                    if (rtile < totalTiles) rsrc = source (rtile);
+                }
+            }
+            asm volatile ("cp.async.commit_group;" ::: "memory");           // one group per pair, empty or not: the wait below counts groups
+            if (++rslot == (unsigned int) depth) rslot = 0;
+        };
+        for (int d = 0; d + 1 < depth; ++d) requestNext ();
+        unsigned int cslot = 0;
 
-        Src cur = source (blockIdx.x < totalTiles ? blockIdx.x : 0);
-        if ((int) blockIdx.x < totalTiles) fetch (cur, 0, vn);
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++lt) {
             long long q0t = UCLK ();
             const int e = quantum (lt);
@@ -696,19 +721,33 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                                      neg2 = art_pack2 (-1.0f, -1.0f), k2048 = art_pack2 (2048.0f, 2048.0f);
             if (ctid == 0)
                 u_stsf (sScaleA (lt & 3), __int_as_float ((127 + e) << 23) * __int_as_float ((127 - u.DH) << 23));
-            const bool more = tile + (int) gridDim.x < totalTiles;
-            Src nxt = cur;
             for (int i = 0; i < KI; ++i) {
                 long long h0t = UCLK ();
+                requestNext ();
+                // all but the newest depth - 1 groups have landed: this pair's samples are in its slot
+                if (depth == 4)      asm volatile ("cp.async.wait_group 3;" ::: "memory");
+                else if (depth == 3) asm volatile ("cp.async.wait_group 2;" ::: "memory");
+                else                 asm volatile ("cp.async.wait_group 1;" ::: "memory");
+                const unsigned int sb = stg + cslot * slotBytes;
+                if (++cslot == (unsigned int) depth) cslot = 0;
+                float v[NV];                                                 // [(group * 2 + tap) * CGT + channel]
 #pragma unroll
-                for (int uu = 0; uu < NV; ++uu) v[uu] = vn[uu];
-                // the next pair's loads (of the next tile after the last pair) fly while this pair is converted
-                // (the next tile's job lookup is a chain of dependent global loads: done early, at the first pair, where
-                //  the converters have a whole tile of slack, not in front of the last pair the MMAs are waiting for).
-                // (Two pairs ahead was tried: the extra registers spill and the conversion slows down by more than the loads gain.)
-                if (i == 0 && more) nxt = source (tile + gridDim.x);
-                if (i + 1 < KI) fetch (cur, i + 1, vn);
-                else if (more) fetch (nxt, 0, vn);
+                for (int uu = 0; uu < UN; ++uu) {
+#pragma unroll
+                    for (int tap = 0; tap < 2; ++tap) {
+                        const unsigned int at = sb + (unsigned int) (2 * uu + tap) * planeStride;
+                        if (CGT == 1) v[2 * uu + tap] = rowOk (uu) ? u_ldsf (at) : 0.0f;
+                        else if (CGT == 2) {
+                            const uint2 w2 = rowOk (uu) ? u_lds64 (at) : make_uint2 (0u, 0u);
+                            v[(2 * uu + tap) * CGT] = __uint_as_float (w2.x); v[(2 * uu + tap) * CGT + (CGT > 1)] = __uint_as_float (w2.y);
+                        }
+                        else {
+                            const uint2 w2 = rowOk (uu) ? u_lds64 (at) : make_uint2 (0u, 0u), w3 = rowOk (uu) ? u_lds64 (at + 8u) : make_uint2 (0u, 0u);
+                            v[(2 * uu + tap) * CGT] = __uint_as_float (w2.x); v[(2 * uu + tap) * CGT + (CGT > 1)] = __uint_as_float (w2.y);
+                            v[(2 * uu + tap) * CGT + 2 * (CGT > 2)] = __uint_as_float (w3.x); v[(2 * uu + tap) * CGT + 3 * (CGT > 2)] = __uint_as_float (w3.y);
+                        }
+                    }
+                }
                 long long c0t = UCLK ();
                 if (ctid == 0) UPROF_ADD (18, c0t - h0t);
                 const unsigned int sl = (unsigned int) i % (unsigned int) NS, use = lt * rep + (unsigned int) i / (unsigned int) NS;
@@ -760,8 +799,8 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                 if (lane == 0) u_mbar_arrive (pFullA (sl));                          // one arrival per warp: 256 serialised arrivals cost ~500 cycles
                 if (ctid == 0) { UPROF_ADD (7, cc_ - cb); UPROF_ADD (14, cd - cc_); UPROF_ADD (15, UCLK () - cd); }
             }
-            cur = nxt;
         }
+        asm volatile ("cp.async.wait_all;" ::: "memory");
         UPROF_FLUSH ();
     }
     else {
@@ -894,7 +933,8 @@ int g_artTensorDigits = -1;        // signal digits of the tensor-core form: 3 (
 static size_t umma_smem (const ArtUmma &u)
 {
     const size_t xc = (size_t) u.digits * (2 * u.NS) * u.rows * 16;          // one split per signal digit
-    return xc + (size_t) u.stages * 3 * 2 * u.Npad * 16 + 8 * ART_U_SCRATCH + 384 + ART_U_MAXK * 8 + 64 + 4 * 32;
+    return xc + (size_t) u.stages * 3 * 2 * u.Npad * 16 + 8 * ART_U_SCRATCH + (size_t) u.depth * u_staging_slot (u.cg) +
+           384 + ART_U_MAXK * 8 + 64 + 4 * 32;
 }
 
 #define ART_U_SMEM_MAX (227 * 1024)
@@ -974,21 +1014,31 @@ bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsi
         else while ((rows & 7) == 0 || (rows & 7) == 4) ++rows;
         if (rows > 144) continue;
         u.rows = rows;
-        u.stages = ART_U_STAGES;
-        // operand A: all KI plane pairs of a row if they fit, else a ring of NS | KI slots -- pairs are used in order, each
-        // for all of its row shifts in a row, so a slot can take pair i + NS as soon as the MMAs of pair i are done.
-        // The filter ring shrinks to 4 k-steps before the operand gives up a slot.
+        // Shared memory is shared out between operand A (a ring of NS | KI plane-pair slots -- pairs are used in order, each
+        // for all of its row shifts in a row, so a slot can take pair i + NS as soon as the MMAs of pair i are done), the
+        // filter stage ring and the converters' raw-sample ring.  What the converters need most is loads in flight
+        // (min (depth - 1, NS) pairs), then a filter ring of 6 k-steps, then operand slots.
         u.NS = 0;
-        for (int ns = u.KI < ART_U_MAXKI ? u.KI : ART_U_MAXKI; ns >= 1 && !u.NS; --ns) {
-            if (u.KI % ns) continue;
-            u.NS = ns;
-            for (u.stages = ART_U_STAGES; u.stages > 2 * ART_U_GROUP && umma_smem (u) > ART_U_SMEM_MAX; u.stages -= ART_U_GROUP) { }
-            if (umma_smem (u) > ART_U_SMEM_MAX) u.NS = 0;
+        {
+            long best = -1;
+            int bNS = 0, bDepth = 0, bStages = 0;
+            for (int depth = 4; depth >= 2; --depth)
+                for (int ns = u.KI < ART_U_MAXKI ? u.KI : ART_U_MAXKI; ns >= 1; --ns) {
+                    if (u.KI % ns) continue;
+                    if (ns < 2 && u.KI > 1) continue;              // a ring slot of two k-steps may straddle two pairs: both must be resident
+                    u.NS = ns; u.depth = depth;
+                    for (u.stages = ART_U_STAGES; u.stages > 2 * ART_U_GROUP && umma_smem (u) > ART_U_SMEM_MAX; u.stages -= ART_U_GROUP) { }
+                    if (umma_smem (u) > ART_U_SMEM_MAX) continue;
+                    const int flying = depth - 1 < ns ? depth - 1 : ns;
+                    const long score = 1000L * flying + 100L * (u.stages < 6 ? u.stages : 6) + ns;
+                    if (score > best) { best = score; bNS = ns; bDepth = depth; bStages = u.stages; }
+                }
+            u.NS = bNS; u.depth = bDepth; u.stages = bStages;
         }
         if (!u.NS) continue;
         if (getenv ("ART_B200_TRACE"))
-            fprintf (stderr, "[art] umma L=%d M=%d G=%d Npad=%d KI=%d NS=%d numK=%d cg=%d rows=%d DH=%d digits=%d stages=%d smem=%zu\n",
-                     u.L, u.M, u.G, u.Npad, u.KI, u.NS, u.numK, u.cg, u.rows, u.DH, u.digits, u.stages, umma_smem (u));
+            fprintf (stderr, "[art] umma L=%d M=%d G=%d Npad=%d KI=%d NS=%d numK=%d cg=%d rows=%d DH=%d digits=%d stages=%d depth=%d smem=%zu\n",
+                     u.L, u.M, u.G, u.Npad, u.KI, u.NS, u.numK, u.cg, u.rows, u.DH, u.digits, u.stages, u.depth, umma_smem (u));
         return true;
     }
     return false;

@@ -382,7 +382,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
 {
     const int prof = profArg & 1;
 #ifdef ART_B200_ABLATE              /* measurement builds only: bits that SKIP work (wrong results by construction) */
-    const int dbg = profArg >> 4;
+    const int dbg = (profArg >> 4) & 255;
 #else
     constexpr int dbg = 0;
 #endif

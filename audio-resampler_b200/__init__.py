@@ -61,6 +61,27 @@ class Biquad(C.Structure):
                 ("order", C.c_int), ("index", C.c_int)]
 
 
+# the PATH_WIDTH=64 library (libresampler_b200_64.so): the same structures with double samples
+LIB64_PATH = HERE / "lib" / "libresampler_b200_64.so"
+
+
+class Resample64(C.Structure):
+    _fields_ = [(n, (C.POINTER(C.POINTER(C.c_double)) if n == "filters" else t)) for n, t in Resample._fields_]
+
+
+class BiquadCoefficients64(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("a0", "a1", "a2", "a3", "a4", "b1", "b2", "b3", "b4")]
+
+
+class Decimate64(C.Structure):
+    _fields_ = [(n, (C.POINTER(C.c_double) if n == "feedback" else t)) for n, t in Decimate._fields_]
+
+
+class Biquad64(C.Structure):
+    _fields_ = [("a", C.c_double * 5), ("b", C.c_double * 5), ("x", C.c_double * 4), ("y", C.c_double * 4),
+                ("order", C.c_int), ("index", C.c_int)]
+
+
 def build(verbose: bool = False) -> Path:
     """Compile csrc/ for sm_100a (nvcc cross-compiles without a GPU)."""
     r = subprocess.run(["make", "-C", str(HERE), "-j", str(os.cpu_count() or 4)], capture_output=True, text=True)
@@ -72,18 +93,31 @@ def build(verbose: bool = False) -> Path:
 
 
 _lib = None
+_lib64 = None
 
 
 def load() -> C.CDLL:
     """dlopen the library and attach the prototypes of include/*.h.  Raises when the
     library is missing: there is no Python or CPU fallback for any of it."""
     global _lib
-    if _lib is not None:
-        return _lib
-    if not LIB_PATH.exists():
-        raise RuntimeError(f"{LIB_PATH} not built; run __graft_entry__.build()")
-    lib = C.CDLL(str(LIB_PATH), mode=os.RTLD_LOCAL)
-    ctx, f32p = C.POINTER(Resample), C.POINTER(C.c_float)
+    if _lib is None:
+        _lib = _open(LIB_PATH, C.c_float, Resample, Biquad, BiquadCoefficients, Decimate)
+    return _lib
+
+
+def load64() -> C.CDLL:
+    """the PATH_WIDTH=64 build of the same sources: every sample pointer is a double pointer"""
+    global _lib64
+    if _lib64 is None:
+        _lib64 = _open(LIB64_PATH, C.c_double, Resample64, Biquad64, BiquadCoefficients64, Decimate64)
+    return _lib64
+
+
+def _open(path, sample, Resample, Biquad, BiquadCoefficients, Decimate) -> C.CDLL:
+    if not path.exists():
+        raise RuntimeError(f"{path} not built; run __graft_entry__.build()")
+    lib = C.CDLL(str(path), mode=os.RTLD_LOCAL)
+    ctx, f32p = C.POINTER(Resample), C.POINTER(sample)
     f32pp, vp, dbl, i32 = C.POINTER(f32p), C.c_void_p, C.c_double, C.c_int
     proto = {
         # include/resampler.h
@@ -107,7 +141,7 @@ def load() -> C.CDLL:
         "biquad_lowpass": (None, [C.POINTER(BiquadCoefficients), dbl]),
         "biquad_highpass": (None, [C.POINTER(BiquadCoefficients), dbl]),
         "biquad_apply_buffer": (None, [C.POINTER(Biquad), f32p, i32, i32]),
-        "biquad_apply_sample": (C.c_float, [C.POINTER(Biquad), C.c_float]),
+        "biquad_apply_sample": (sample, [C.POINTER(Biquad), sample]),
         # include/resampler_b200.h (device pointers travel as integers)
         "resampleB200SetDevice": (i32, [i32]),
         "resampleB200GetDeviceCount": (i32, []),
@@ -147,7 +181,6 @@ def load() -> C.CDLL:
     for name, (res, args) in proto.items():
         fn = getattr(lib, name)          # AttributeError here = the library does not export what include/*.h declares
         fn.restype, fn.argtypes = res, args
-    _lib = lib
     return lib
 
 

@@ -101,7 +101,7 @@ static void stage_to_ring (const ArtBiquadStage *s, Biquad *f, int advanced)
     }
 }
 
-static void run_cascade (Biquad *const *stages, int numStages, int numChannels, float *buffer, int numFrames, int stride, int onDevice, void *stream)
+static void run_cascade (Biquad *const *stages, int numStages, int numChannels, artsample_t *buffer, int numFrames, int stride, int onDevice, void *stream)
 {
     ArtBiquadStage *flat;
     int s, c;
@@ -127,12 +127,12 @@ void biquad_apply_buffer (Biquad *f, artsample_t *buffer, int num_samples, int s
     run_cascade (one, 1, 1, buffer, num_samples, stride, 0, NULL);
 }
 
-void biquad_apply_cascade_interleaved (Biquad *const *stages, int numStages, int numChannels, float *buffer, int numFrames)
+void biquad_apply_cascade_interleaved (Biquad *const *stages, int numStages, int numChannels, artsample_t *buffer, int numFrames)
 {
     run_cascade (stages, numStages, numChannels, buffer, numFrames, numChannels, 0, NULL);
 }
 
-void biquad_apply_cascade_interleaved_device (Biquad *const *stages, int numStages, int numChannels, float *d_buffer, int numFrames, void *stream)
+void biquad_apply_cascade_interleaved_device (Biquad *const *stages, int numStages, int numChannels, artsample_t *d_buffer, int numFrames, void *stream)
 {
     run_cascade (stages, numStages, numChannels, d_buffer, numFrames, numChannels, 1, stream);
 }

@@ -87,10 +87,17 @@ __device__ __forceinline__ R Cascade<R, S, ORD, HIST>::step (R in)
                 acc = __fsub_rn (__fadd_rn (acc, __fmul_rn (xh[s][d - 1], a[s][d])), __fmul_rn (b[s][d], yh[s][d - 1]));
         }
         else {
+#if ART_WIDE            /* the wide build's output pass runs here: the reference's operation order, nothing contracted */
+            acc = __dmul_rn (in, a[s][0]);
+#pragma unroll
+            for (int d = 1; d <= ORD; ++d)
+                acc = __dsub_rn (__dadd_rn (acc, __dmul_rn (xh[s][d - 1], a[s][d])), __dmul_rn (b[s][d], yh[s][d - 1]));
+#else
             acc = in * a[s][0];
 #pragma unroll
             for (int d = 1; d <= ORD; ++d)
                 acc = acc + xh[s][d - 1] * a[s][d] - b[s][d] * yh[s][d - 1];
+#endif
         }
 #pragma unroll
         for (int d = HIST - 1; d > 0; --d) { xh[s][d] = xh[s][d - 1]; yh[s][d] = yh[s][d - 1]; }
@@ -102,7 +109,7 @@ __device__ __forceinline__ R Cascade<R, S, ORD, HIST>::step (R in)
 }
 
 template <int S, int ORD>
-__global__ void bq_zero_state_kernel (BqGeom g, const ArtBiquadStage *st, const float *buf, double *ZS)
+__global__ void bq_zero_state_kernel (BqGeom g, const ArtBiquadStage *st, const artsample_t *buf, double *ZS)
 {
     constexpr int NST = 2 * S * ORD;
     const long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x;     // channel fastest
@@ -113,7 +120,7 @@ __global__ void bq_zero_state_kernel (BqGeom g, const ArtBiquadStage *st, const 
     f.zero ();
     const long long f0 = (long long) k * g.chunk;
     const int len = k == g.numChunks - 1 ? g.lastLen : g.chunk;
-    const float *p = buf + f0 * g.stride + c;
+    const artsample_t *p = buf + f0 * g.stride + c;
     for (int i = 0; i < len; ++i)
         f.step ((double) __ldg (p + (long long) i * g.stride));
     f.storeState (ZS + ((long long) c * g.numChunks + k) * NST);
@@ -179,13 +186,13 @@ __global__ void bq_propagate_kernel (BqGeom g, const ArtBiquadStage *st, const d
 }
 
 template <int S, int ORD>
-__global__ void bq_output_kernel (BqGeom g, const ArtBiquadStage *st, ArtBiquadStage *stOut, float *buf, const double *Zstart)
+__global__ void bq_output_kernel (BqGeom g, const ArtBiquadStage *st, ArtBiquadStage *stOut, artsample_t *buf, const double *Zstart)
 {
     constexpr int NST = 2 * S * ORD;
     const long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x;     // channel fastest
     const int k = (int) (e / g.channels), c = (int) (e - (long long) k * g.channels);
     if (k >= g.numChunks) return;
-    Cascade<float, S, ORD, 4> f;
+    Cascade<artsample_t, S, ORD, 4> f;
     f.loadCoeffs (st, g.channels, c);
     f.zero ();
     if (k == 0) {
@@ -200,13 +207,13 @@ __global__ void bq_output_kernel (BqGeom g, const ArtBiquadStage *st, ArtBiquadS
 #pragma unroll
         for (int s = 0; s < S; ++s)
 #pragma unroll
-            for (int d = 0; d < ORD; ++d) { f.xh[s][d] = (float) z[(s * 2) * ORD + d]; f.yh[s][d] = (float) z[(s * 2 + 1) * ORD + d]; }
+            for (int d = 0; d < ORD; ++d) { f.xh[s][d] = (artsample_t) z[(s * 2) * ORD + d]; f.yh[s][d] = (artsample_t) z[(s * 2 + 1) * ORD + d]; }
     }
     const long long f0 = (long long) k * g.chunk;
     const int len = k == g.numChunks - 1 ? g.lastLen : g.chunk;
-    float *p = buf + f0 * g.stride + c;
+    artsample_t *p = buf + f0 * g.stride + c;
     for (int i = 0; i < len; ++i) {
-        float *q = p + (long long) i * g.stride;
+        artsample_t *q = p + (long long) i * g.stride;
         *q = f.step (*q);
     }
     if (k == g.numChunks - 1) {
@@ -223,7 +230,7 @@ __global__ void bq_output_kernel (BqGeom g, const ArtBiquadStage *st, ArtBiquadS
 }
 
 template <int S, int ORD>
-void run_cascade (const BqGeom &g, const ArtBiquadStage *d_st, ArtBiquadStage *d_stOut, float *d_buf, cudaStream_t stream)
+void run_cascade (const BqGeom &g, const ArtBiquadStage *d_st, ArtBiquadStage *d_stOut, artsample_t *d_buf, cudaStream_t stream)
 {
     constexpr int NST = 2 * S * ORD;
     static_assert (NST <= 32, "state must fit one warp");
@@ -249,7 +256,7 @@ void run_cascade (const BqGeom &g, const ArtBiquadStage *d_st, ArtBiquadStage *d
 }
 
 template <int S>
-void run_cascade_order (int order, const BqGeom &g, const ArtBiquadStage *d_st, ArtBiquadStage *d_stOut, float *d_buf, cudaStream_t stream)
+void run_cascade_order (int order, const BqGeom &g, const ArtBiquadStage *d_st, ArtBiquadStage *d_stOut, artsample_t *d_buf, cudaStream_t stream)
 {
     if (order <= 2) run_cascade<S, 2> (g, d_st, d_stOut, d_buf, stream);
     else            run_cascade<S, 4> (g, d_st, d_stOut, d_buf, stream);
@@ -257,7 +264,7 @@ void run_cascade_order (int order, const BqGeom &g, const ArtBiquadStage *d_st, 
 
 }   // namespace
 
-extern "C" int artBiquadRun (ArtBiquadStage *stages, int numStages, int channels, float *buffer,
+extern "C" int artBiquadRun (ArtBiquadStage *stages, int numStages, int channels, artsample_t *buffer,
                              long long frames, int stride, int onDevice, void *streamPtr)
 {
     ART_GUARD_BEGIN
@@ -270,10 +277,10 @@ extern "C" int artBiquadRun (ArtBiquadStage *stages, int numStages, int channels
     cudaStream_t stream = (cudaStream_t) streamPtr;
     const size_t span = (size_t) (frames - 1) * stride + channels;
 
-    float *d_buf = buffer;
+    artsample_t *d_buf = buffer;
     if (!onDevice) {
-        ART_CUDA_CHECK (cudaMallocAsync (&d_buf, span * sizeof (float), stream));
-        ART_CUDA_CHECK (cudaMemcpyAsync (d_buf, buffer, span * sizeof (float), cudaMemcpyHostToDevice, stream));
+        ART_CUDA_CHECK (cudaMallocAsync (&d_buf, span * sizeof (artsample_t), stream));
+        ART_CUDA_CHECK (cudaMemcpyAsync (d_buf, buffer, span * sizeof (artsample_t), cudaMemcpyHostToDevice, stream));
     }
     ArtBiquadStage *d_st = nullptr, *d_stOut = nullptr;
     const size_t stBytes = sizeof (ArtBiquadStage) * (size_t) numStages * channels;
@@ -310,7 +317,7 @@ extern "C" int artBiquadRun (ArtBiquadStage *stages, int numStages, int channels
     std::vector<ArtBiquadStage> back ((size_t) numStages * channels);
     ART_CUDA_CHECK (cudaMemcpyAsync (back.data (), d_stOut, stBytes, cudaMemcpyDeviceToHost, stream));
     if (!onDevice)
-        ART_CUDA_CHECK (cudaMemcpyAsync (buffer, d_buf, span * sizeof (float), cudaMemcpyDeviceToHost, stream));
+        ART_CUDA_CHECK (cudaMemcpyAsync (buffer, d_buf, span * sizeof (artsample_t), cudaMemcpyDeviceToHost, stream));
     ART_CUDA_CHECK (cudaStreamSynchronize (stream));
     for (size_t i = 0; i < back.size (); ++i)
         for (int d = 0; d < 4; ++d) { stages[i].x[d] = back[i].x[d]; stages[i].y[d] = back[i].y[d]; }

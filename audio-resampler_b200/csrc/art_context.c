@@ -23,7 +23,7 @@
  * the lowpass ratio, under a 4-term Blackman-Harris or Hann window, normalised to unity DC
  * gain and rounded to float with the rounding error carried centre-outwards.
  * Follows init_filter, reference resampler.c:1090-1133 (window constants :1093-1096). */
-static void design_row (float *row, double *work, int taps, double fraction, double lowpass, int blackmanHarris)
+static void design_row (artsample_t *row, double *work, int taps, double fraction, double lowpass, int blackmanHarris)
 {
     const int half = taps / 2;
     double sum = 0.0, scale, carry = 0.0;
@@ -49,25 +49,25 @@ static void design_row (float *row, double *work, int taps, double fraction, dou
         for (pass = 0; pass < 2; ++pass) {
             t = pass ? half - 1 - k : half + k;
             work[t] *= scale;
-            row[t] = (float) (work[t] - carry);
+            row[t] = (artsample_t) (work[t] - carry);
             carry += row[t] - work[t];
         }
     }
 }
 
-static float **design_bank (int taps, int filters, double lowpass, int flags)
+static artsample_t **design_bank (int taps, int filters, double lowpass, int flags)
 {
-    float **rows = calloc ((size_t) filters + 1, sizeof *rows);
+    artsample_t **rows = calloc ((size_t) filters + 1, sizeof *rows);
     double *work = malloc (sizeof (double) * taps);
     int r, t;
 
     for (r = 0; r <= filters; ++r)
-        rows[r] = calloc (taps, sizeof (float));
+        rows[r] = calloc (taps, sizeof (artsample_t));
     for (r = 0; r < filters; ++r)                                   /* resampler.c:149-155 */
         design_row (rows[r], work, taps, (double) r / filters, lowpass, flags & BLACKMAN_HARRIS);
     for (t = 0; t < taps; ++t)                                      /* resampler.c:156-159 */
         rows[filters][(t + 1) % taps] = rows[0][t];
-    rows[0][taps - 1] = 0.0f;                                       /* resampler.c:167-168 */
+    rows[0][taps - 1] = 0;                                       /* resampler.c:167-168 */
     rows[filters][0] = 0.0f;
     free (work);
     return rows;
@@ -124,7 +124,7 @@ Resample *resampleInit (int numChannels, int numTaps, int numFilters, double low
     cxt->inputIndex = numTaps;
 
     mode = device_mode (flags);
-    cxt->device = artDevCreate (numChannels, numTaps, 0, numFilters, mode, (const float *const *) cxt->filters);
+    cxt->device = artDevCreate (numChannels, numTaps, 0, numFilters, mode, (const artsample_t *const *) cxt->filters);
     if (!cxt->device) {
         resampleFree (cxt);
         return NULL;
@@ -212,7 +212,7 @@ int resampleB200AttachPrefilter (Resample *cxt, const Biquad *sections, int numS
 {
     enum { MAXLEN = 1024 };
     double *g, *tmp, total = 0.0, tail;
-    float **rows;
+    artsample_t **rows;
     ArtDev *fresh;
     int s, n, d, r, m, k, len, lead, T, Tk, mode = ART_MODE_LOWPASS;        /* never the pass-through shortcut (resampler.c:1141-1142) */
 
@@ -271,17 +271,17 @@ int resampleB200AttachPrefilter (Resample *cxt, const Biquad *sections, int numS
 
     rows = calloc ((size_t) cxt->numFilters + 1, sizeof *rows);
     for (r = 0; r <= cxt->numFilters; ++r) {
-        const float *row = cxt->filters[r];
-        rows[r] = calloc (Tk, sizeof (float));
+        const artsample_t *row = cxt->filters[r];
+        rows[r] = calloc (Tk, sizeof (artsample_t));
         for (m = -lead + 1; m < T; ++m) {
             double acc = 0.0;
             for (k = m < 0 ? -m : 0; k < len && m + k < T; ++k)
                 acc += g[k] * (double) row[m + k];
-            rows[r][m + lead] = (float) acc;
+            rows[r][m + lead] = (artsample_t) acc;
         }
     }
     mode |= device_mode (cxt->flags);
-    fresh = artDevCreate (cxt->numChannels, Tk, lead, cxt->numFilters, mode, (const float *const *) rows);
+    fresh = artDevCreate (cxt->numChannels, Tk, lead, cxt->numFilters, mode, (const artsample_t *const *) rows);
     for (r = 0; r <= cxt->numFilters; ++r) free (rows[r]);
     free (rows);
     if (!fresh) {
@@ -352,10 +352,10 @@ enum { IO_HOST_INTERLEAVED, IO_HOST_PLANAR, IO_DEVICE_INTERLEAVED, IO_DEVICE_PLA
 static int run_call (Resample *cxt, int io, const ArtCallPlan *call, const void *in, void *out, void *stream)
 {
     switch (io) {
-        case IO_HOST_INTERLEAVED:   return artDevRunHostInterleaved (cxt->device, call, (const float *) in, (float *) out);
-        case IO_HOST_PLANAR:        return artDevRunHostPlanar (cxt->device, call, (const float *const *) in, (float *const *) out);
-        case IO_DEVICE_INTERLEAVED: return artDevRunDeviceInterleaved (cxt->device, call, (const float *) in, (float *) out, stream);
-        default:                    return artDevRunDevicePlanar (cxt->device, call, (const float *const *) in, (float *const *) out, stream);
+        case IO_HOST_INTERLEAVED:   return artDevRunHostInterleaved (cxt->device, call, (const artsample_t *) in, (artsample_t *) out);
+        case IO_HOST_PLANAR:        return artDevRunHostPlanar (cxt->device, call, (const artsample_t *const *) in, (artsample_t *const *) out);
+        case IO_DEVICE_INTERLEAVED: return artDevRunDeviceInterleaved (cxt->device, call, (const artsample_t *) in, (artsample_t *) out, stream);
+        default:                    return artDevRunDevicePlanar (cxt->device, call, (const artsample_t *const *) in, (artsample_t *const *) out, stream);
     }
 }
 
@@ -376,13 +376,13 @@ static int run_call_with_endpoints (Resample *cxt, int io, ArtCallPlan *call, co
     const int onDevice = io == IO_DEVICE_INTERLEAVED || io == IO_DEVICE_PLANAR;
     const int planar = io == IO_HOST_PLANAR || io == IO_DEVICE_PLANAR;
     void *st = onDevice ? stream : NULL;
-    float *hist = NULL, *tail = NULL;           /* [C][T] history at call entry; [C][half] predicted flush block (planar) */
-    const float **tailPlanes = NULL;
-    float *tailInterleaved = NULL;
+    artsample_t *hist = NULL, *tail = NULL;           /* [C][T] history at call entry; [C][half] predicted flush block (planar) */
+    const artsample_t **tailPlanes = NULL;
+    artsample_t *tailInterleaved = NULL;
     int c, i;
 
     if (flushing || ((cxt->flags & EXTRAPOLATE_PREFILL) && call->outputs)) {
-        hist = malloc (sizeof (float) * (size_t) C * T);
+        hist = malloc (sizeof (artsample_t) * (size_t) C * T);
         if (artDevGetHistoryOn (cxt->device, hist, st)) {
             free (hist);
             return -1;
@@ -390,12 +390,12 @@ static int run_call_with_endpoints (Resample *cxt, int io, ArtCallPlan *call, co
     }
 
     if (flushing) {                             /* postfillAllChannels, resampler.c:663-685 */
-        float *work = malloc (sizeof (float) * (size_t) T);
-        tail = malloc (sizeof (float) * (size_t) C * half);
+        artsample_t *work = malloc (sizeof (artsample_t) * (size_t) T);
+        tail = malloc (sizeof (artsample_t) * (size_t) C * half);
         for (c = 0; c < C; ++c) {
-            memcpy (work, hist + (size_t) c * T + half, sizeof (float) * half);
+            memcpy (work, hist + (size_t) c * T + half, sizeof (artsample_t) * half);
             artExtendForward (work, half, half);
-            memcpy (tail + (size_t) c * half, work + half, sizeof (float) * half);
+            memcpy (tail + (size_t) c * half, work + half, sizeof (artsample_t) * half);
         }
         free (work);
         call->inValid = call->pre;              /* the region's first T/2 frames now hold data */
@@ -407,17 +407,17 @@ static int run_call_with_endpoints (Resample *cxt, int io, ArtCallPlan *call, co
         const long long have = n0 + call->pre + u0;                     /* inputIndex - numTaps at that moment */
         cxt->flags &= ~EXTRAPOLATE_PREFILL;
         if (have >= 8 && have < T && n0 >= 0 && u0 <= call->inValid - (flushing ? call->pre : 0) + 0LL) {
-            float *line = malloc (sizeof (float) * (size_t) T);         /* the ring's first T slots: [have, T) predicted, then ... */
-            float *first = u0 ? malloc (sizeof (float) * (size_t) u0 * C) : NULL;   /* the call's first u0 input frames */
+            artsample_t *line = malloc (sizeof (artsample_t) * (size_t) T);         /* the ring's first T slots: [have, T) predicted, then ... */
+            artsample_t *first = u0 ? malloc (sizeof (artsample_t) * (size_t) u0 * C) : NULL;   /* the call's first u0 input frames */
             if (u0) {
-                if (!onDevice && !planar) memcpy (first, in, sizeof (float) * (size_t) u0 * C);
+                if (!onDevice && !planar) memcpy (first, in, sizeof (artsample_t) * (size_t) u0 * C);
                 else if (!onDevice)
-                    for (c = 0; c < C; ++c) for (i = 0; i < u0; ++i) first[(size_t) i * C + c] = ((const float *const *) in)[c][i];
-                else if (!planar) failed |= artDevFetch (cxt->device, (const float *) in, (size_t) u0 * C, first, st);
+                    for (c = 0; c < C; ++c) for (i = 0; i < u0; ++i) first[(size_t) i * C + c] = ((const artsample_t *const *) in)[c][i];
+                else if (!planar) failed |= artDevFetch (cxt->device, (const artsample_t *) in, (size_t) u0 * C, first, st);
                 else {
-                    float *plane = malloc (sizeof (float) * (size_t) u0);
+                    artsample_t *plane = malloc (sizeof (artsample_t) * (size_t) u0);
                     for (c = 0; c < C; ++c) {
-                        failed |= artDevFetch (cxt->device, ((const float *const *) in)[c], (size_t) u0, plane, st);
+                        failed |= artDevFetch (cxt->device, ((const artsample_t *const *) in)[c], (size_t) u0, plane, st);
                         for (i = 0; i < u0; ++i) first[(size_t) i * C + c] = plane[i];
                     }
                     free (plane);
@@ -425,7 +425,7 @@ static int run_call_with_endpoints (Resample *cxt, int io, ArtCallPlan *call, co
             }
             for (c = 0; c < C; ++c) {
                 /* newest `have` samples, oldest first, at the end of `line`: earlier calls, the flush block, this call */
-                float *seq = line + T - have;
+                artsample_t *seq = line + T - have;
                 long long at = 0;
                 for (i = 0; i < n0; ++i) seq[at++] = hist[(size_t) c * T + T - n0 + i];
                 for (i = 0; i < call->pre; ++i) seq[at++] = tail ? tail[(size_t) c * half + i] : 0.0f;
@@ -451,13 +451,13 @@ static int run_call_with_endpoints (Resample *cxt, int io, ArtCallPlan *call, co
             failed = run_call (cxt, io, call, tailPlanes, out, stream);
         }
         else {
-            tailInterleaved = malloc (sizeof (float) * (size_t) C * half);
+            tailInterleaved = malloc (sizeof (artsample_t) * (size_t) C * half);
             for (c = 0; c < C; ++c) for (i = 0; i < half; ++i) tailInterleaved[(size_t) i * C + c] = tail[(size_t) c * half + i];
             failed = run_call (cxt, io, call, tailInterleaved, out, stream);
         }
     }
     else if (planar) {
-        const float *d_tail = artDevStage (cxt->device, tail, (size_t) C * half, st);
+        const artsample_t *d_tail = artDevStage (cxt->device, tail, (size_t) C * half, st);
         if (!d_tail)
             failed = -1;
         else {
@@ -467,8 +467,8 @@ static int run_call_with_endpoints (Resample *cxt, int io, ArtCallPlan *call, co
         }
     }
     else {
-        const float *d_tail;
-        tailInterleaved = malloc (sizeof (float) * (size_t) C * half);
+        const artsample_t *d_tail;
+        tailInterleaved = malloc (sizeof (artsample_t) * (size_t) C * half);
         for (c = 0; c < C; ++c) for (i = 0; i < half; ++i) tailInterleaved[(size_t) i * C + c] = tail[(size_t) c * half + i];
         d_tail = artDevStage (cxt->device, tailInterleaved, (size_t) C * half, st);
         failed = d_tail ? run_call (cxt, io, call, d_tail, out, stream) : -1;
@@ -488,13 +488,13 @@ static int run_flush_prefiltered (Resample *cxt, int io, const ArtCallPlan *call
 {
     const int T = cxt->numTaps, lead = cxt->prefilterLead, Tk = T + lead, C = cxt->numChannels;
     const int onDevice = io == IO_DEVICE_INTERLEAVED || io == IO_DEVICE_PLANAR;
-    float *raw = malloc (sizeof (float) * (size_t) C * Tk), *filtered = malloc (sizeof (float) * (size_t) C * T);
+    artsample_t *raw = malloc (sizeof (artsample_t) * (size_t) C * Tk), *filtered = malloc (sizeof (artsample_t) * (size_t) C * T);
     ArtDev *fused = cxt->device;
     int c, i, k, failed;
 
     failed = artDevGetHistoryOn (fused, raw, onDevice ? stream : NULL);
     if (!failed && !cxt->plainDevice) {
-        cxt->plainDevice = artDevCreate (C, T, 0, cxt->numFilters, device_mode (cxt->flags), (const float *const *) cxt->filters);
+        cxt->plainDevice = artDevCreate (C, T, 0, cxt->numFilters, device_mode (cxt->flags), (const artsample_t *const *) cxt->filters);
         failed = cxt->plainDevice == NULL;
     }
     if (!failed) {
@@ -503,7 +503,7 @@ static int run_flush_prefiltered (Resample *cxt, int io, const ArtCallPlan *call
                 double acc = 0.0;
                 for (k = 0; k < lead; ++k)
                     acc += cxt->prefilterTaps[k] * (double) raw[(size_t) c * Tk + lead + i - k];
-                filtered[(size_t) c * T + i] = (float) acc;
+                filtered[(size_t) c * T + i] = (artsample_t) acc;
             }
         failed = artDevSetHistory (cxt->plainDevice, filtered);
     }
@@ -549,12 +549,12 @@ ResampleResult resampleProcess (Resample *cxt, const artsample_t *const *input, 
     return process_one (cxt, IO_HOST_PLANAR, input, numInputFrames, (void *) output, numOutputFrames, ratio, NULL);
 }
 
-ResampleResult resampleProcessInterleavedDevice (Resample *cxt, const float *d_input, int numInputFrames, float *d_output, int numOutputFrames, double ratio, void *stream)
+ResampleResult resampleProcessInterleavedDevice (Resample *cxt, const artsample_t *d_input, int numInputFrames, artsample_t *d_output, int numOutputFrames, double ratio, void *stream)
 {
     return process_one (cxt, IO_DEVICE_INTERLEAVED, d_input, numInputFrames, d_output, numOutputFrames, ratio, stream);
 }
 
-ResampleResult resampleProcessDevice (Resample *cxt, const float *const *d_input, int numInputFrames, float *const *d_output, int numOutputFrames, double ratio, void *stream)
+ResampleResult resampleProcessDevice (Resample *cxt, const artsample_t *const *d_input, int numInputFrames, artsample_t *const *d_output, int numOutputFrames, double ratio, void *stream)
 {
     return process_one (cxt, IO_DEVICE_PLANAR, d_input, numInputFrames, (void *) d_output, numOutputFrames, ratio, stream);
 }
@@ -603,14 +603,14 @@ static int needs_endpoint_work (const Resample *cxt, int numInputFrames)
 
 
 void resampleBatchProcessInterleavedDevice (Resample *const *cxts, int numContexts,
-                                            const float *const *d_inputs, const int *numInputFrames,
-                                            float *const *d_outputs, const int *numOutputFrames,
+                                            const artsample_t *const *d_inputs, const int *numInputFrames,
+                                            artsample_t *const *d_outputs, const int *numOutputFrames,
                                             const double *ratios, ResampleResult *results, void *stream)
 {
     ArtCallPlan *calls;
     ArtDev **devs;
-    const float **din;
-    float **dout;
+    const artsample_t **din;
+    artsample_t **dout;
     ArtSaved *saved;
     int *owner;
     int i, n = 0, live = 0;
@@ -655,14 +655,14 @@ void resampleBatchProcessInterleavedDevice (Resample *const *cxts, int numContex
 }
 
 void resampleBatchProcessInterleaved (Resample *const *cxts, int numContexts,
-                                      const float *const *inputs, const int *numInputFrames,
-                                      float *const *outputs, const int *numOutputFrames,
+                                      const artsample_t *const *inputs, const int *numInputFrames,
+                                      artsample_t *const *outputs, const int *numOutputFrames,
                                       const double *ratios, ResampleResult *results)
 {
     ArtCallPlan *calls;
     ArtDev **devs;
-    const float **hin;
-    float **hout;
+    const artsample_t **hin;
+    artsample_t **hout;
     ArtSaved *saved;
     int *owner;
     int i, n = 0;
@@ -705,9 +705,9 @@ void resampleBatchProcessInterleaved (Resample *const *cxts, int numContexts,
     free (owner);
 }
 
-int resampleProcessBlocksInterleavedDevice (Resample *cxt, const float *d_input, const int *blockFrames,
+int resampleProcessBlocksInterleavedDevice (Resample *cxt, const artsample_t *d_input, const int *blockFrames,
                                             const double *ratios, int numBlocks,
-                                            float *d_output, int outputCapacityFrames,
+                                            artsample_t *d_output, int outputCapacityFrames,
                                             ResampleResult *results, double *positions, void *stream)
 {
     ArtCallPlan *calls;

@@ -105,14 +105,14 @@ static int run_batch (Decimate *const *cxts, int n, const void *const *in, int p
             l->context = i;
             l->frames = frames[i] > 0 ? frames[i] : 0;
             l->bits = d->outputBits; l->bytes = d->outputBytes; l->pad = d->outputBytes - used;
-            l->scaler = (float) ((1 << d->outputBits) / 2.0 * d->outputGain);
+            l->scaler = (artsample_t) ((1 << d->outputBits) / 2.0 * d->outputGain);
             l->dither = (d->flags & DITHER_ENABLED) ? 1 : 0;
             l->ditherType = d->dither_type;
             l->shaping = (d->flags & SHAPING_ENABLED) ? 1 : 0;
             l->rng = d->tpdf_generators ? d->tpdf_generators[c] : 0;
             l->feedback = d->feedback[c];
-            if (planarIn)  { l->in = ((const float *const *) in[i])[c]; l->inStride = 1; }
-            else           { l->in = (const float *) in[i] + c; l->inStride = d->numChannels; }
+            if (planarIn)  { l->in = ((const artsample_t *const *) in[i])[c]; l->inStride = 1; }
+            else           { l->in = (const artsample_t *) in[i] + c; l->inStride = d->numChannels; }
             if (planarOut) { l->out = ((unsigned char *const *) out[i])[c]; l->outStride = d->outputBytes; }
             else           { l->out = (unsigned char *) out[i] + (size_t) c * d->outputBytes; l->outStride = d->numChannels * d->outputBytes; }
             if (d->noise_shapers) {

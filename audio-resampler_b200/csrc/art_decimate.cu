@@ -20,21 +20,21 @@ namespace {
 __device__ __forceinline__ unsigned int lcg15 (unsigned int x) { return ((x << 4) - x) ^ 1u; }
 
 /* tpdf_dither, decimator.c:361-373: -1 <= n < 1; type -1 / 0 / +1 = negative / no / positive intersample correlation */
-__device__ __forceinline__ float tpdf (unsigned int &gen, int type)
+__device__ __forceinline__ artsample_t tpdf (unsigned int &gen, int type)
 {
     unsigned int r = lcg15 (lcg15 (gen));
     const unsigned int first = type ? (gen ^ (unsigned int) (type >> 31)) : ~r;
     r = lcg15 (lcg15 (lcg15 (r)));
     gen = r;
-    return (float) (((double) ((first >> 1) + (r >> 1)) / 2147483648.0) - 1.0);
+    return (artsample_t) (((double) ((first >> 1) + (r >> 1)) / 2147483648.0) - 1.0);
 }
 
 /* quantise one sample (decimator.c:176-198); returns the container's low `used` bytes in an int */
-__device__ __forceinline__ int quantise (const ArtDecLane &L, float x, float dith, float feedback, float &code, int &clipped)
+__device__ __forceinline__ int quantise (const ArtDecLane &L, artsample_t x, artsample_t dith, artsample_t feedback, artsample_t &code, int &clipped)
 {
     const int top = (1 << (L.bits - 1)) - 1, bottom = ~top;
-    code = __fsub_rn (__fmul_rn (x, L.scaler), feedback);
-    int v = (int) floor ((double) __fadd_rn (code, dith) + 0.5);
+    code = art_sub (art_mul (x, L.scaler), feedback);
+    int v = (int) floor ((double) art_add (code, dith) + 0.5);
     clipped = 0;
     return v > top ? (clipped = 1, top) : (v < bottom ? (clipped = 1, bottom) : v);
 }
@@ -55,31 +55,31 @@ art_decimate_serial_kernel (ArtDecLane *__restrict__ lanes, int numLanes)
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= numLanes) return;
     ArtDecLane L = lanes[id];
-    float xs[4] = { L.x[0], L.x[1], L.x[2], L.x[3] }, ys[4] = { L.y[0], L.y[1], L.y[2], L.y[3] };
-    float feedback = L.feedback;
+    artsample_t xs[4] = { L.x[0], L.x[1], L.x[2], L.x[3] }, ys[4] = { L.y[0], L.y[1], L.y[2], L.y[3] };
+    artsample_t feedback = L.feedback;
     unsigned int rng = L.rng;
     int clips = 0;
-    const float *in = L.in;
+    const artsample_t *in = L.in;
     unsigned char *out = L.out;
     for (int i0 = 0; i0 < L.frames; i0 += 8) {
-        float xin[8];
+        artsample_t xin[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) xin[r] = i0 + r < L.frames ? __ldg (in + (size_t) (i0 + r) * L.inStride) : 0.0f;
+        for (int r = 0; r < 8; ++r) xin[r] = i0 + r < L.frames ? __ldg (in + (size_t) (i0 + r) * L.inStride) : (artsample_t) 0;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
             if (i0 + r >= L.frames) break;
-            const float dith = L.dither ? tpdf (rng, L.ditherType) : 0.0f;
-            float code;
+            const artsample_t dith = L.dither ? tpdf (rng, L.ditherType) : (artsample_t) 0;
+            artsample_t code;
             int clipped;
             /* the reference quantises first and clips afterwards; the shaper sees the UNCLIPPED value (decimator.c:183-195) */
             const int top = (1 << (L.bits - 1)) - 1, bottom = ~top;
-            code = __fsub_rn (__fmul_rn (xin[r], L.scaler), feedback);
-            int v = (int) floor ((double) __fadd_rn (code, dith) + 0.5);
+            code = art_sub (art_mul (xin[r], L.scaler), feedback);
+            int v = (int) floor ((double) art_add (code, dith) + 0.5);
             if (L.shaping) {                                  /* biquad_apply_sample, biquad.c:78-102 */
-                const float e = __fsub_rn ((float) v, code);
-                float sum = __fmul_rn (e, L.a[0]);
+                const artsample_t e = art_sub ((artsample_t) v, code);
+                artsample_t sum = art_mul (e, L.a[0]);
                 for (int d = L.order; d >= 1; --d)
-                    sum = __fadd_rn (sum, __fsub_rn (__fmul_rn (xs[d - 1], L.a[d]), __fmul_rn (L.b[d], ys[d - 1])));
+                    sum = art_add (sum, art_sub (art_mul (xs[d - 1], L.a[d]), art_mul (L.b[d], ys[d - 1])));
                 xs[3] = xs[2]; xs[2] = xs[1]; xs[1] = xs[0]; xs[0] = e;
                 ys[3] = ys[2]; ys[2] = ys[1]; ys[1] = ys[0]; ys[0] = sum;
                 feedback = sum;
@@ -104,9 +104,9 @@ art_decimate_parallel_kernel (ArtDecLane *__restrict__ lanes, int numLanes, int 
     const ArtDecLane &L = lanes[lane];
     int clips = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.frames; i += gridDim.x * blockDim.x) {
-        float code;
+        artsample_t code;
         int clipped;
-        const int v = quantise (L, __ldg (L.in + (size_t) i * L.inStride), 0.0f, L.feedback, code, clipped);
+        const int v = quantise (L, __ldg (L.in + (size_t) i * L.inStride), (artsample_t) 0, L.feedback, code, clipped);
         clips += clipped;
         put_sample (L, L.out + (size_t) i * L.outStride, v);
     }
@@ -116,7 +116,7 @@ art_decimate_parallel_kernel (ArtDecLane *__restrict__ lanes, int numLanes, int 
 
 /* floatIntegersLE, decimator.c:416-450 */
 __global__ void __launch_bounds__ (256)
-art_float_integers_kernel (const unsigned char *__restrict__ in, float gain, int bits, int bytes, int stride, float *__restrict__ out, int count)
+art_float_integers_kernel (const unsigned char *__restrict__ in, artsample_t gain, int bits, int bytes, int stride, artsample_t *__restrict__ out, int count)
 {
     const int used = (bits + 7) / 8;
     for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long) gridDim.x * blockDim.x) {
@@ -125,7 +125,7 @@ art_float_integers_kernel (const unsigned char *__restrict__ in, float gain, int
         if (bits <= 8) v = (int) p[0] - 128;
         else if (bits <= 16) v = (short) (p[0] | (p[1] << 8));
         else v = p[0] | (p[1] << 8) | ((int) (signed char) p[2] << 16);
-        out[i] = __fmul_rn ((float) v, gain);
+        out[i] = art_mul ((artsample_t) v, gain);
     }
 }
 
@@ -165,7 +165,7 @@ extern "C" int artDecimateRun (ArtDecLane *lanes, int numLanes, int numContexts,
                 while (e < numLanes && lanes[e].context == L.context) ++e;
             Piece p;
             p.hostIn = L.in; p.hostOut = L.out;
-            p.inBytes = (size_t) L.frames * L.inStride * sizeof (float);
+            p.inBytes = (size_t) L.frames * L.inStride * sizeof (artsample_t);
             p.outBytes = (size_t) L.frames * L.outStride;
             p.inAt = at; at += (p.inBytes + 255) & ~(size_t) 255;
             p.outAt = at; at += (p.outBytes + 255) & ~(size_t) 255;
@@ -179,7 +179,7 @@ extern "C" int artDecimateRun (ArtDecLane *lanes, int numLanes, int numContexts,
                 ART_CUDA_CHECK (cudaMemcpyAsync (scratch + p.inAt, p.hostIn, p.inBytes, cudaMemcpyHostToDevice, stream));
         for (int i = 0; i < numLanes; ++i) {
             const Piece &p = pieces[pieceOf[i]];
-            dl[i].in = reinterpret_cast<const float *> (scratch + p.inAt) + (lanes[i].in - reinterpret_cast<const float *> (p.hostIn));
+            dl[i].in = reinterpret_cast<const artsample_t *> (scratch + p.inAt) + (lanes[i].in - reinterpret_cast<const artsample_t *> (p.hostIn));
             dl[i].out = scratch + p.outAt + (lanes[i].out - reinterpret_cast<unsigned char *> (p.hostOut));
         }
     }
@@ -210,24 +210,24 @@ extern "C" int artDecimateRun (ArtDecLane *lanes, int numLanes, int numContexts,
     ART_GUARD_END (-1)
 }
 
-extern "C" int artFloatIntegersRun (const unsigned char *input, double gain, int bits, int bytes, int stride, float *output, int count,
+extern "C" int artFloatIntegersRun (const unsigned char *input, double gain, int bits, int bytes, int stride, artsample_t *output, int count,
                                     int onDevice, void *streamPtr)
 {
     ART_GUARD_BEGIN
     if (count <= 0 || bits > 24) return 0;              // (the reference does nothing above 24 bits either)
     cudaStream_t stream = (cudaStream_t) streamPtr;
-    const float g = (float) (bits <= 8 ? gain / 128.0 : (bits <= 16 ? gain / 32768.0 : gain / 8388608.0));
+    const artsample_t g = (artsample_t) (bits <= 8 ? gain / 128.0 : (bits <= 16 ? gain / 32768.0 : gain / 8388608.0));
     const size_t inBytes = (size_t) count * stride * bytes;     // the last sample's trailing channels are never read, but belong to the block
     const unsigned char *d_in = input;
-    float *d_out = output;
+    artsample_t *d_out = output;
     unsigned char *scratch = nullptr;
     if (!onDevice) {
         const size_t inRound = (inBytes + 255) & ~(size_t) 255;
-        ART_CUDA_CHECK (cudaMallocAsync (&scratch, inRound + (size_t) count * sizeof (float), stream));
+        ART_CUDA_CHECK (cudaMallocAsync (&scratch, inRound + (size_t) count * sizeof (artsample_t), stream));
         // only (count - 1) * stride * bytes + bytes bytes are guaranteed to exist behind `input`
         ART_CUDA_CHECK (cudaMemcpyAsync (scratch, input, (size_t) (count - 1) * stride * bytes + bytes, cudaMemcpyHostToDevice, stream));
         d_in = scratch;
-        d_out = reinterpret_cast<float *> (scratch + inRound);
+        d_out = reinterpret_cast<artsample_t *> (scratch + inRound);
     }
     int blocks = (count + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
@@ -235,7 +235,7 @@ extern "C" int artFloatIntegersRun (const unsigned char *input, double gain, int
     ART_CUDA_CHECK (cudaGetLastError ());
     ++g_artLaunches;
     if (!onDevice) {
-        ART_CUDA_CHECK (cudaMemcpyAsync (output, d_out, (size_t) count * sizeof (float), cudaMemcpyDeviceToHost, stream));
+        ART_CUDA_CHECK (cudaMemcpyAsync (output, d_out, (size_t) count * sizeof (artsample_t), cudaMemcpyDeviceToHost, stream));
         ART_CUDA_CHECK (cudaStreamSynchronize (stream));
         ART_CUDA_CHECK (cudaFreeAsync (scratch, stream));
     }

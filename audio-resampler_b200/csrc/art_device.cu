@@ -125,22 +125,22 @@ struct ArtBank {
     int device, T, Tp, F, refs;
     float absSum;
     unsigned long long hash;
-    float *d_rows;
-    std::vector<float> packed;
+    artsample_t *d_rows;
+    std::vector<artsample_t> packed;
 };
 
 static std::mutex g_bankMutex;
 static std::vector<ArtBank *> g_banks;
 
-static ArtBank *bank_acquire (int device, int T, int F, const float *const *rows)
+static ArtBank *bank_acquire (int device, int T, int F, const artsample_t *const *rows)
 {
     const int Tp = (T + 31) & ~31;
-    std::vector<float> packed ((size_t) (F + 2) * Tp, 0.0f);
+    std::vector<artsample_t> packed ((size_t) (F + 2) * Tp, (artsample_t) 0);
     unsigned long long h = 1469598103934665603ULL;
     for (int r = 0; r <= F; ++r) {
-        memcpy (&packed[(size_t) r * Tp], rows[r], sizeof (float) * T);
+        memcpy (&packed[(size_t) r * Tp], rows[r], sizeof (artsample_t) * T);
         const unsigned char *b = reinterpret_cast<const unsigned char *> (rows[r]);
-        for (size_t i = 0; i < sizeof (float) * T; ++i) { h ^= b[i]; h *= 1099511628211ULL; }
+        for (size_t i = 0; i < sizeof (artsample_t) * T; ++i) { h ^= b[i]; h *= 1099511628211ULL; }
     }
     std::lock_guard<std::mutex> lock (g_bankMutex);
     for (ArtBank *b : g_banks)
@@ -157,8 +157,8 @@ static ArtBank *bank_acquire (int device, int T, int F, const float *const *rows
         for (int t = 0; t < T; ++t) s += fabs ((double) b->packed[(size_t) r * Tp + t]);
         if (s > b->absSum) b->absSum = (float) s;
     }
-    if (cudaMalloc (&b->d_rows, b->packed.size () * sizeof (float)) != cudaSuccess ||
-        cudaMemcpy (b->d_rows, b->packed.data (), b->packed.size () * sizeof (float), cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (cudaMalloc (&b->d_rows, b->packed.size () * sizeof (artsample_t)) != cudaSuccess ||
+        cudaMemcpy (b->d_rows, b->packed.data (), b->packed.size () * sizeof (artsample_t), cudaMemcpyHostToDevice) != cudaSuccess) {
         fprintf (stderr, "libresampler_b200: cannot place the filter bank on the GPU: %s\n",
                  cudaGetErrorString (cudaGetLastError ()));
         delete b;
@@ -186,11 +186,11 @@ struct ArtDev {
     ArtBank *bank;
     cudaStream_t stream;
     cudaStream_t lastStream;        // where the most recent device-pointer call was enqueued (reset has to wait for it)
-    float *hist[2];
+    artsample_t *hist[2];
     int cur;
-    float *d_in, *d_out;
+    artsample_t *d_in, *d_out;
     size_t inCap, outCap;           // floats
-    float *d_stage;                 // flush block of the endpoint extrapolation (device-pointer calls)
+    artsample_t *d_stage;                 // flush block of the endpoint extrapolation (device-pointer calls)
     size_t stageCap;
     ArtClass klass;
     // host-pointer path: copies in, kernels and copies out run on three streams so that PCIe traffic in
@@ -260,7 +260,7 @@ static void use_device (const ArtDev *dev)
         ART_CUDA_CHECK (cudaSetDevice (dev->device));
 }
 
-extern "C" ArtDev *artDevCreate (int channels, int taps, int lead, int filters, int mode, const float *const *rows)
+extern "C" ArtDev *artDevCreate (int channels, int taps, int lead, int filters, int mode, const artsample_t *const *rows)
 {
     ART_GUARD_BEGIN
     int device = 0, count = 0;
@@ -301,7 +301,7 @@ extern "C" ArtDev *artDevCreate (int channels, int taps, int lead, int filters, 
     dev->bank = bank_acquire (device, taps, filters, rows);
     if (!dev->bank) { delete dev; return nullptr; }
     ART_CUDA_CHECK (cudaStreamCreateWithFlags (&dev->stream, cudaStreamNonBlocking));
-    const size_t histBytes = sizeof (float) * (size_t) (channels > 0 ? channels : 1) * taps;
+    const size_t histBytes = sizeof (artsample_t) * (size_t) (channels > 0 ? channels : 1) * taps;
     for (int i = 0; i < 2; ++i) {
         ART_CUDA_CHECK (cudaMalloc (&dev->hist[i], histBytes));
         ART_CUDA_CHECK (cudaMemset (dev->hist[i], 0, histBytes));
@@ -356,7 +356,7 @@ extern "C" int artDevReset (ArtDev *dev)
     if (dev->lastStream && dev->lastStream != dev->stream && cudaStreamSynchronize (dev->lastStream) != cudaSuccess)
         (void) cudaGetLastError ();
     dev->lastStream = nullptr;
-    ART_CUDA_CHECK (cudaMemsetAsync (dev->hist[dev->cur], 0, sizeof (float) * (size_t) dev->C * dev->T, dev->stream));
+    ART_CUDA_CHECK (cudaMemsetAsync (dev->hist[dev->cur], 0, sizeof (artsample_t) * (size_t) dev->C * dev->T, dev->stream));
     ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
     return 0;
     ART_GUARD_END (-1)
@@ -387,52 +387,52 @@ extern "C" int artDevSynchronize (ArtDev *dev)
     ART_GUARD_END (-1)
 }
 
-extern "C" int artDevGetHistory (ArtDev *dev, float *hostPlanar)
+extern "C" int artDevGetHistory (ArtDev *dev, artsample_t *hostPlanar)
 {
     ART_GUARD_BEGIN
     use_device (dev);
     ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
-    ART_CUDA_CHECK (cudaMemcpy (hostPlanar, dev->hist[dev->cur], sizeof (float) * (size_t) dev->C * dev->T, cudaMemcpyDeviceToHost));
+    ART_CUDA_CHECK (cudaMemcpy (hostPlanar, dev->hist[dev->cur], sizeof (artsample_t) * (size_t) dev->C * dev->T, cudaMemcpyDeviceToHost));
     return 0;
     ART_GUARD_END (-1)
 }
 
 /* ---- endpoint extrapolation support (art_context.c): small synchronous transfers at a stream's start and end ---- */
-extern "C" int artDevGetHistoryOn (ArtDev *dev, float *hostPlanar, void *stream)
+extern "C" int artDevGetHistoryOn (ArtDev *dev, artsample_t *hostPlanar, void *stream)
 {
     ART_GUARD_BEGIN
     use_device (dev);
     cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
-    ART_CUDA_CHECK (cudaMemcpyAsync (hostPlanar, dev->hist[dev->cur], sizeof (float) * (size_t) dev->C * dev->T, cudaMemcpyDeviceToHost, st));
+    ART_CUDA_CHECK (cudaMemcpyAsync (hostPlanar, dev->hist[dev->cur], sizeof (artsample_t) * (size_t) dev->C * dev->T, cudaMemcpyDeviceToHost, st));
     ART_CUDA_CHECK (cudaStreamSynchronize (st));
     return 0;
     ART_GUARD_END (-1)
 }
 
-extern "C" int artDevPatchHistory (ArtDev *dev, int channel, int first, int count, const float *values, void *stream)
+extern "C" int artDevPatchHistory (ArtDev *dev, int channel, int first, int count, const artsample_t *values, void *stream)
 {
     ART_GUARD_BEGIN
     use_device (dev);
     cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
     // pageable source: staged by the runtime before the call returns
-    ART_CUDA_CHECK (cudaMemcpyAsync (dev->hist[dev->cur] + (size_t) channel * dev->T + first, values, sizeof (float) * (size_t) count,
+    ART_CUDA_CHECK (cudaMemcpyAsync (dev->hist[dev->cur] + (size_t) channel * dev->T + first, values, sizeof (artsample_t) * (size_t) count,
                                      cudaMemcpyHostToDevice, st));
     return 0;
     ART_GUARD_END (-1)
 }
 
-extern "C" int artDevFetch (ArtDev *dev, const float *d_src, size_t floats, float *host, void *stream)
+extern "C" int artDevFetch (ArtDev *dev, const artsample_t *d_src, size_t floats, artsample_t *host, void *stream)
 {
     ART_GUARD_BEGIN
     use_device (dev);
     cudaStream_t st = stream ? (cudaStream_t) stream : dev->stream;
-    ART_CUDA_CHECK (cudaMemcpyAsync (host, d_src, sizeof (float) * floats, cudaMemcpyDeviceToHost, st));
+    ART_CUDA_CHECK (cudaMemcpyAsync (host, d_src, sizeof (artsample_t) * floats, cudaMemcpyDeviceToHost, st));
     ART_CUDA_CHECK (cudaStreamSynchronize (st));
     return 0;
     ART_GUARD_END (-1)
 }
 
-extern "C" float *artDevStage (ArtDev *dev, const float *host, size_t floats, void *stream)
+extern "C" artsample_t *artDevStage (ArtDev *dev, const artsample_t *host, size_t floats, void *stream)
 {
     ART_GUARD_BEGIN
     use_device (dev);
@@ -441,19 +441,19 @@ extern "C" float *artDevStage (ArtDev *dev, const float *host, size_t floats, vo
         ART_CUDA_CHECK (cudaStreamSynchronize (st));
         cudaFree (dev->d_stage);
         dev->stageCap = floats + 1024;
-        ART_CUDA_CHECK (cudaMalloc (&dev->d_stage, dev->stageCap * sizeof (float)));
+        ART_CUDA_CHECK (cudaMalloc (&dev->d_stage, dev->stageCap * sizeof (artsample_t)));
     }
-    ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_stage, host, sizeof (float) * floats, cudaMemcpyHostToDevice, st));
+    ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_stage, host, sizeof (artsample_t) * floats, cudaMemcpyHostToDevice, st));
     return dev->d_stage;
     ART_GUARD_END (nullptr)
 }
 
-extern "C" int artDevSetHistory (ArtDev *dev, const float *hostPlanar)
+extern "C" int artDevSetHistory (ArtDev *dev, const artsample_t *hostPlanar)
 {
     ART_GUARD_BEGIN
     use_device (dev);
     ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
-    ART_CUDA_CHECK (cudaMemcpy (dev->hist[dev->cur], hostPlanar, sizeof (float) * (size_t) dev->C * dev->T, cudaMemcpyHostToDevice));
+    ART_CUDA_CHECK (cudaMemcpy (dev->hist[dev->cur], hostPlanar, sizeof (artsample_t) * (size_t) dev->C * dev->T, cudaMemcpyHostToDevice));
     return 0;
     ART_GUARD_END (-1)
 }
@@ -532,7 +532,7 @@ static void plan_launch (ArtDev *lead, double minRatio, double maxRatio, bool on
     // one sample per output, the filter-row pair changes every 1 / (|1/r - 1| * F) outputs, and runs of consecutive outputs share it
     {
         const double dLo = fabs (1.0 / minRatio - 1.0), dHi = fabs (1.0 / maxRatio - 1.0), d = dLo > dHi ? dLo : dHi;
-        lp.k.unity = (lp.k.mode & ART_MODE_INTERP) && !(lp.k.mode & ART_MODE_PRECISE) && d * lp.k.F <= 0.125 && !getenv ("ART_B200_NOUNITY");
+        lp.k.unity = !ART_WIDE && (lp.k.mode & ART_MODE_INTERP) && !(lp.k.mode & ART_MODE_PRECISE) && d * lp.k.F <= 0.125 && !getenv ("ART_B200_NOUNITY");
     }
     artPlanGenericGeometry (lp.k, minRatio, total32, lead->smCount, lp.g);
 }
@@ -574,12 +574,12 @@ static int append_job (const ArtLaunchPlan &lp, const ArtJob &base, std::vector<
  * carry one useful sample (and 8 tiles would fetch the same sector), and the epilogue would store 4 bytes per sector.
  * Such launches go through planar scratch in HBM instead: one coalesced transposition in, one out (+16 bytes of
  * traffic per sample on a path that sits far below the HBM roofline). */
-struct ArtXpose { const float *src; float *dst; long long frames, pitch; };
+struct ArtXpose { const artsample_t *src; artsample_t *dst; long long frames, pitch; };
 
 __global__ void __launch_bounds__ (256)
 art_deinterleave_kernel (const ArtXpose *__restrict__ g, int C, int groups)            // dst[c * pitch + f] = src[f * C + c]
 {
-    __shared__ float t[32][33];
+    __shared__ artsample_t t[32][33];
     for (int z = blockIdx.z; z < groups; z += gridDim.z) {
         const ArtXpose x = g[z];
         const long long f0 = (long long) blockIdx.x * 32;
@@ -603,7 +603,7 @@ art_deinterleave_kernel (const ArtXpose *__restrict__ g, int C, int groups)     
 __global__ void __launch_bounds__ (256)
 art_interleave_kernel (const ArtXpose *__restrict__ g, int C, int groups)              // dst[f * C + c] = src[c * pitch + f]
 {
-    __shared__ float t[32][33];
+    __shared__ artsample_t t[32][33];
     for (int z = blockIdx.z; z < groups; z += gridDim.z) {
         const ArtXpose x = g[z];
         const long long f0 = (long long) blockIdx.x * 32;
@@ -677,7 +677,7 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
 
     // tensor-core kernel on interleaved blocks of many channels: planar scratch (see above).  Segments of one call sit
     // next to each other in `jobs` and share their pointers: one scratch pair per call.
-    float *scratch = nullptr;
+    artsample_t *scratch = nullptr;
     ArtXpose *d_xpose = nullptr;
     std::vector<ArtXpose> xin, xout;
     long long maxInFrames = 0, maxOutFrames = 0;
@@ -715,8 +715,8 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
                 if (inFirst > inFrames) inFirst = inFrames;
                 const long long inPitch = (inFrames + 31) & ~31LL, outPitch = (outFrames + 31) & ~31LL;
                 // src/dst are offset so that scratch index f still means frame f of the call
-                xin.push_back ({ jobs[i].in + inFirst * C, reinterpret_cast<float *> (inFirst), inFrames - inFirst, inPitch });
-                xout.push_back ({ reinterpret_cast<const float *> (outFirst), jobs[i].out + outFirst * C, outFrames - outFirst, outPitch });
+                xin.push_back ({ jobs[i].in + inFirst * C, reinterpret_cast<artsample_t *> (inFirst), inFrames - inFirst, inPitch });
+                xout.push_back ({ reinterpret_cast<const artsample_t *> (outFirst), jobs[i].out + outFirst * C, outFrames - outFirst, outPitch });
                 inAt.push_back (floats); floats += (size_t) C * inPitch;
                 outAt.push_back (floats); floats += (size_t) C * outPitch;
                 if (inFrames - inFirst > maxInFrames) maxInFrames = inFrames - inFirst;
@@ -724,7 +724,7 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
                 for (int q = i; q < e; ++q) groupOf[q] = (int) xin.size () - 1;
                 i = e;
             }
-            ART_CUDA_CHECK (cudaMallocAsync (&scratch, floats * sizeof (float), stream));
+            ART_CUDA_CHECK (cudaMallocAsync (&scratch, floats * sizeof (artsample_t), stream));
             for (int q = 0; q < n; ++q) {
                 ArtJob &j = jobs[q];
                 const int gi = groupOf[q];
@@ -856,13 +856,13 @@ static void reserve (ArtDev *dev, size_t inFloats, size_t outFloats)
         ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
         cudaFree (dev->d_in);
         dev->inCap = inFloats + inFloats / 4 + 1024;
-        ART_CUDA_CHECK (cudaMalloc (&dev->d_in, dev->inCap * sizeof (float)));
+        ART_CUDA_CHECK (cudaMalloc (&dev->d_in, dev->inCap * sizeof (artsample_t)));
     }
     if (outFloats > dev->outCap) {
         ART_CUDA_CHECK (cudaStreamSynchronize (dev->stream));
         cudaFree (dev->d_out);
         dev->outCap = outFloats + outFloats / 4 + 1024;
-        ART_CUDA_CHECK (cudaMalloc (&dev->d_out, dev->outCap * sizeof (float)));
+        ART_CUDA_CHECK (cudaMalloc (&dev->d_out, dev->outCap * sizeof (artsample_t)));
     }
 }
 
@@ -872,7 +872,7 @@ static void reserve (ArtDev *dev, size_t inFloats, size_t outFloats)
  * needs the input frames up to art_inputs_before(last output of c), so its upload, its kernels and its
  * download form a three-stage pipeline across pieces.  The samples are the same as for one big launch:
  * every output is evaluated from (P, I, n) alone. */
-extern "C" int artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, const float *in, float *out)
+extern "C" int artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, const artsample_t *in, artsample_t *out)
 {
     ART_GUARD_BEGIN
     use_device (dev);
@@ -890,15 +890,15 @@ extern "C" int artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, c
 
     if (pieces == 1) {
         if (inFloats)
-            ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_in, in, inFloats * sizeof (float), cudaMemcpyHostToDevice, dev->stream));
+            ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_in, in, inFloats * sizeof (artsample_t), cudaMemcpyHostToDevice, dev->stream));
         ArtJob job;
         fill_job (dev, *plan, job);
         job.in = dev->d_in;  job.inFS = C;  job.inCS = 1;
         job.out = dev->d_out; job.outFS = C; job.outCS = 1;
         run_single (dev, *plan, job, dev->stream);
         if (outFloats)
-            ART_CUDA_CHECK (cudaMemcpyAsync (out, dev->d_out, outFloats * sizeof (float), cudaMemcpyDeviceToHost, dev->stream));
-        wait_for (dev, dev->stream, (inFloats + outFloats) * sizeof (float));
+            ART_CUDA_CHECK (cudaMemcpyAsync (out, dev->d_out, outFloats * sizeof (artsample_t), cudaMemcpyDeviceToHost, dev->stream));
+        wait_for (dev, dev->stream, (inFloats + outFloats) * sizeof (artsample_t));
         return 0;
     }
 
@@ -913,7 +913,7 @@ extern "C" int artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, c
         if (need > plan->inValid) need = plan->inValid;
         if (need < uploaded) need = uploaded;
         if (need > uploaded)
-            ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_in + uploaded * C, in + uploaded * C, (size_t) (need - uploaded) * C * sizeof (float),
+            ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_in + uploaded * C, in + uploaded * C, (size_t) (need - uploaded) * C * sizeof (artsample_t),
                                              cudaMemcpyHostToDevice, dev->sIn));
         uploaded = need;
         ART_CUDA_CHECK (cudaEventRecord (dev->events[2 * c], dev->sIn));
@@ -934,12 +934,12 @@ extern "C" int artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, c
         ART_CUDA_CHECK (cudaEventRecord (dev->events[2 * c + 1], dev->stream));
         ART_CUDA_CHECK (cudaStreamWaitEvent (dev->sOut, dev->events[2 * c + 1], 0));
         if (n1 > n0)
-            ART_CUDA_CHECK (cudaMemcpyAsync (out + (size_t) n0 * C, dev->d_out + (size_t) n0 * C, (size_t) (n1 - n0) * C * sizeof (float),
+            ART_CUDA_CHECK (cudaMemcpyAsync (out + (size_t) n0 * C, dev->d_out + (size_t) n0 * C, (size_t) (n1 - n0) * C * sizeof (artsample_t),
                                              cudaMemcpyDeviceToHost, dev->sOut));
     }
     finish_job (dev, *plan);
     // the last download was enqueued after everything else of this call (sOut waits for the last kernel)
-    wait_for (dev, dev->sOut, (inFloats + outFloats) * sizeof (float));
+    wait_for (dev, dev->sOut, (inFloats + outFloats) * sizeof (artsample_t));
     return 0;
     ART_GUARD_END (-1)
 }
@@ -948,10 +948,10 @@ extern "C" int artDevRunHostInterleaved (ArtDev *dev, const ArtCallPlan *plan, c
  * group's uploads, one launch for the group, its downloads (group size 1 measured best on B200: 64 us
  * per 2 MB stereo stream against a PCIe floor of 42 us). */
 extern "C" int artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
-                                           const float *const *d_in, float *const *d_out, void *stream);
+                                           const artsample_t *const *d_in, artsample_t *const *d_out, void *stream);
 
 extern "C" int artDevRunHostBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
-                                               const float *const *in, float *const *out)
+                                               const artsample_t *const *in, artsample_t *const *out)
 {
     ART_GUARD_BEGIN
     if (count <= 0) return 0;
@@ -961,8 +961,8 @@ extern "C" int artDevRunHostBatchInterleaved (ArtDev *const *devs, const ArtCall
     const int groups = (count + group - 1) / group;
     host_pipe_init (lead, 2 * (size_t) groups);
     const size_t C = lead->C;
-    std::vector<const float *> dIn (count);
-    std::vector<float *> dOut (count);
+    std::vector<const artsample_t *> dIn (count);
+    std::vector<artsample_t *> dOut (count);
     for (int g = 0; g < groups; ++g) {
         const int i0 = g * group, i1 = i0 + group < count ? i0 + group : count;
         for (int i = i0; i < i1; ++i) {
@@ -975,7 +975,7 @@ extern "C" int artDevRunHostBatchInterleaved (ArtDev *const *devs, const ArtCall
             dIn[i] = dev->d_in;
             dOut[i] = dev->d_out;
             if (inFloats)
-                ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_in, in[i], inFloats * sizeof (float), cudaMemcpyHostToDevice, lead->sIn));
+                ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_in, in[i], inFloats * sizeof (artsample_t), cudaMemcpyHostToDevice, lead->sIn));
         }
         ART_CUDA_CHECK (cudaEventRecord (lead->events[2 * g], lead->sIn));
         ART_CUDA_CHECK (cudaStreamWaitEvent (lead->stream, lead->events[2 * g], 0));
@@ -986,7 +986,7 @@ extern "C" int artDevRunHostBatchInterleaved (ArtDev *const *devs, const ArtCall
         for (int i = i0; i < i1; ++i) {
             const size_t outFloats = (size_t) plans[i].outputs * C;
             if (outFloats)
-                ART_CUDA_CHECK (cudaMemcpyAsync (out[i], devs[i]->d_out, outFloats * sizeof (float), cudaMemcpyDeviceToHost, lead->sOut));
+                ART_CUDA_CHECK (cudaMemcpyAsync (out[i], devs[i]->d_out, outFloats * sizeof (artsample_t), cudaMemcpyDeviceToHost, lead->sOut));
         }
     }
     // sOut's last download waits for the last launch, which waits for the last upload
@@ -996,7 +996,7 @@ extern "C" int artDevRunHostBatchInterleaved (ArtDev *const *devs, const ArtCall
     ART_GUARD_END (-1)
 }
 
-extern "C" int artDevRunHostPlanar (ArtDev *dev, const ArtCallPlan *plan, const float *const *in, float *const *out)
+extern "C" int artDevRunHostPlanar (ArtDev *dev, const ArtCallPlan *plan, const artsample_t *const *in, artsample_t *const *out)
 {
     ART_GUARD_BEGIN
     use_device (dev);
@@ -1004,22 +1004,22 @@ extern "C" int artDevRunHostPlanar (ArtDev *dev, const ArtCallPlan *plan, const 
     const size_t nin = plan->inValid, nout = plan->outputs;
     reserve (dev, nin * C, nout * C);
     for (size_t c = 0; c < C && nin; ++c)
-        ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_in + c * nin, in[c], nin * sizeof (float), cudaMemcpyHostToDevice, dev->stream));
+        ART_CUDA_CHECK (cudaMemcpyAsync (dev->d_in + c * nin, in[c], nin * sizeof (artsample_t), cudaMemcpyHostToDevice, dev->stream));
     ArtJob job;
     fill_job (dev, *plan, job);
     job.in = dev->d_in;  job.inFS = 1;  job.inCS = (long long) nin;
     job.out = dev->d_out; job.outFS = 1; job.outCS = (long long) nout;
     run_single (dev, *plan, job, dev->stream);
     for (size_t c = 0; c < C && nout; ++c)
-        ART_CUDA_CHECK (cudaMemcpyAsync (out[c], dev->d_out + c * nout, nout * sizeof (float), cudaMemcpyDeviceToHost, dev->stream));
-    wait_for (dev, dev->stream, (nin + nout) * C * sizeof (float));
+        ART_CUDA_CHECK (cudaMemcpyAsync (out[c], dev->d_out + c * nout, nout * sizeof (artsample_t), cudaMemcpyDeviceToHost, dev->stream));
+    wait_for (dev, dev->stream, (nin + nout) * C * sizeof (artsample_t));
     return 0;
     ART_GUARD_END (-1)
 }
 
 /* ---- device-memory entry points ------------------------------------------------------------------------ */
 
-extern "C" int artDevRunDeviceInterleaved (ArtDev *dev, const ArtCallPlan *plan, const float *d_in, float *d_out, void *stream)
+extern "C" int artDevRunDeviceInterleaved (ArtDev *dev, const ArtCallPlan *plan, const artsample_t *d_in, artsample_t *d_out, void *stream)
 {
     ART_GUARD_BEGIN
     use_device (dev);
@@ -1034,7 +1034,7 @@ extern "C" int artDevRunDeviceInterleaved (ArtDev *dev, const ArtCallPlan *plan,
     ART_GUARD_END (-1)
 }
 
-extern "C" int artDevRunDevicePlanar (ArtDev *dev, const ArtCallPlan *plan, const float *const *d_in, float *const *d_out, void *stream)
+extern "C" int artDevRunDevicePlanar (ArtDev *dev, const ArtCallPlan *plan, const artsample_t *const *d_in, artsample_t *const *d_out, void *stream)
 {
     ART_GUARD_BEGIN
     use_device (dev);
@@ -1062,8 +1062,8 @@ extern "C" int artDevRunDevicePlanar (ArtDev *dev, const ArtCallPlan *plan, cons
         ART_CUDA_CHECK (cudaMallocAsync (&table, sizeof (void *) * 2 * C, st));
         // pageable source: staged by the runtime before the call returns
         ART_CUDA_CHECK (cudaMemcpyAsync (table, h.data (), sizeof (void *) * 2 * C, cudaMemcpyHostToDevice, st));
-        if (d_in && !uniformIn) job.inPlanes = reinterpret_cast<const float *const *> (table);
-        if (!uniformOut) job.outPlanes = reinterpret_cast<float *const *> (table) + C;
+        if (d_in && !uniformIn) job.inPlanes = reinterpret_cast<const artsample_t *const *> (table);
+        if (!uniformOut) job.outPlanes = reinterpret_cast<artsample_t *const *> (table) + C;
     }
     run_single (dev, *plan, job, st);
     if (table)
@@ -1075,7 +1075,7 @@ extern "C" int artDevRunDevicePlanar (ArtDev *dev, const ArtCallPlan *plan, cons
 /* ---- many contexts, one launch ----------------------------------------------------------------------------- */
 
 extern "C" int artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPlan *plans, int count,
-                                           const float *const *d_in, float *const *d_out, void *stream)
+                                           const artsample_t *const *d_in, artsample_t *const *d_out, void *stream)
 {
     ART_GUARD_BEGIN
     if (count <= 0) return 0;
@@ -1121,7 +1121,7 @@ extern "C" int artDevRunBatchInterleaved (ArtDev *const *devs, const ArtCallPlan
 
 extern "C" int artDevRunBlocksInterleaved (ArtDev *dev, const ArtCallPlan *plans, int count,
                                             const long long *inOffset, const long long *outOffset,
-                                            const float *d_in, float *d_out, void *stream)
+                                            const artsample_t *d_in, artsample_t *d_out, void *stream)
 {
     ART_GUARD_BEGIN
     if (count <= 0) return 0;

@@ -14,13 +14,13 @@
 enum { ORDER = 4, ROUND_LIMIT = 100000 };          /* NCOEFFS, MAXLOOPS: extrapolator.h:26-32 */
 
 typedef struct {
-    const float *x;        /* the known samples                       */
+    const artsample_t *x;  /* the known samples                       */
     int evals;             /* samples that have ORDER predecessors     */
     float c[ORDER];        /* c[0] weighs the newest predecessor       */
 } Fit;
 
 /* the prediction filter applied to the ORDER samples starting at w: sum_j c[ORDER-1-j] * w[j] */
-static double predict (const float *c, const float *w)
+static double predict (const float *c, const artsample_t *w)
 {
     double acc = 0.0;
     int j;
@@ -84,7 +84,7 @@ static void fit (Fit *f)
 
     memset (f->c, 0, sizeof f->c);
     for (k = 0; k < f->evals; ++k) {                /* extrapolator.c:101-107 */
-        const float s = f->x[k + ORDER], p = f->x[k + ORDER - 1];
+        const artsample_t s = f->x[k + ORDER], p = f->x[k + ORDER - 1];
         diff_energy += (s - p) * (s - p);
         energy += s * s;
     }
@@ -143,21 +143,21 @@ static void fit (Fit *f)
     }
 }
 
-void artExtendForward (float *x, int known, int more)
+void artExtendForward (artsample_t *x, int known, int more)
 {
     Fit f;
     int i;
-    memset (x + known, 0, sizeof (float) * (size_t) more);       /* extrapolator.c:29 */
+    memset (x + known, 0, sizeof (artsample_t) * (size_t) more);       /* extrapolator.c:29 */
     f.x = x;
     f.evals = known - ORDER;
     fit (&f);
     for (i = 0; i < more; ++i)                                     /* :32-40 */
-        x[known + i] = (float) -predict (f.c, x + known - ORDER + i);
+        x[known + i] = (artsample_t) -predict (f.c, x + known - ORDER + i);
 }
 
-void artExtendBackward (float *end, int known, int more)
+void artExtendBackward (artsample_t *end, int known, int more)
 {
-    float *mirror = calloc ((size_t) known + (size_t) more, sizeof (float));
+    artsample_t *mirror = calloc ((size_t) known + (size_t) more, sizeof (artsample_t));
     int i;
     for (i = 0; i < known; ++i)
         mirror[i] = end[-1 - i];

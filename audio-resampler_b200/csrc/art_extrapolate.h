@@ -8,15 +8,16 @@
  */
 #ifndef ART_EXTRAPOLATE_H
 #define ART_EXTRAPOLATE_H
+#include "art_sample.h"
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
 /* x[0 .. known) are given; writes x[known .. known + more) */
-void artExtendForward (float *x, int known, int more);
+void artExtendForward (artsample_t *x, int known, int more);
 /* end[-1] (newest) ... end[-known] are given; writes end[-known-1] ... end[-known-more] */
-void artExtendBackward (float *end, int known, int more);
+void artExtendBackward (artsample_t *end, int known, int more);
 
 #ifdef __cplusplus
 }

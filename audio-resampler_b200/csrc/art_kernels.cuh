@@ -26,6 +26,7 @@
 #include <exception>
 #include <atomic>
 #include "art_plan.h"
+#include "art_sample.h"
 
 struct ArtJob {
     double        P, ratio;          // loop-entry outputOffset, effective ratio
@@ -37,19 +38,19 @@ struct ArtJob {
     long long     consumed;          // region frames that enter the history (history kernel)
     int           tile0;             // first tile / CTA of this job inside the launch
     unsigned int  nStart;            // call-relative index of this job's first output (segments of one call)
-    const float  *hist;              // [C][T] history at call entry
-    float        *histOut;           // [C][T] history after the call (may be null)
-    const float  *in;                // base of region frame 0, channel 0
-    float        *out;
+    const artsample_t *hist;         // [C][T] history at call entry
+    artsample_t  *histOut;           // [C][T] history after the call (may be null)
+    const artsample_t *in;           // base of region frame 0, channel 0
+    artsample_t  *out;
     long long     inFS, inCS, outFS, outCS;      // frame / channel strides in floats
-    const float *const *inPlanes;    // optional per-channel pointer tables (device memory)
-    float *const       *outPlanes;
+    const artsample_t *const *inPlanes;    // optional per-channel pointer tables (device memory)
+    artsample_t *const *outPlanes;
     int           table;             // periodic kernel: which phase table this job reads
     int           repJob;            // periodic kernel: entry t holds the job whose state defines table t
 };
 
 struct ArtClass {
-    const float *bank;
+    const artsample_t *bank;
     int T, Tp, F, C, mode;   // T = taps of a bank row = depth of the history (Tref + lead)
     int Tref;        // numTaps of the reference context: what the control loop's position arithmetic (art_plan.h) runs on
     int lead;        // taps in front of the reference's window: a folded-in pre-filter (art_context.c) extends every filter into the
@@ -144,19 +145,28 @@ __device__ __forceinline__ void art_ffma2 (unsigned long long &acc, unsigned lon
     asm ("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
 }
 
-__device__ __forceinline__ float art_fetch (const ArtJob &j, int T, int c, long long idx)
+/* sample arithmetic in the reference's operation order, never contracted into FMAs (the byte / state parity of the integer and
+ * biquad stages depends on it), for either sample width */
+__device__ __forceinline__ float  art_mul (float a, float b)   { return __fmul_rn (a, b); }
+__device__ __forceinline__ float  art_add (float a, float b)   { return __fadd_rn (a, b); }
+__device__ __forceinline__ float  art_sub (float a, float b)   { return __fsub_rn (a, b); }
+__device__ __forceinline__ double art_mul (double a, double b) { return __dmul_rn (a, b); }
+__device__ __forceinline__ double art_add (double a, double b) { return __dadd_rn (a, b); }
+__device__ __forceinline__ double art_sub (double a, double b) { return __dsub_rn (a, b); }
+
+__device__ __forceinline__ artsample_t art_fetch (const ArtJob &j, int T, int c, long long idx)
 {
     if (idx >= j.inValid)
-        return 0.0f;
+        return 0;
     if (idx >= -j.prevAvail) {
-        const float *p = j.inPlanes ? j.inPlanes[c] + idx * j.inFS : j.in + idx * j.inFS + c * j.inCS;
+        const artsample_t *p = j.inPlanes ? j.inPlanes[c] + idx * j.inFS : j.in + idx * j.inFS + c * j.inCS;
         return __ldg (p);
     }
     const long long h = T + idx + j.prevAvail;
-    return h >= 0 ? j.hist[(long long) c * T + h] : 0.0f;
+    return h >= 0 ? j.hist[(long long) c * T + h] : (artsample_t) 0;
 }
 
-__device__ __forceinline__ float *art_out_ptr (const ArtJob &j, int c, long long frame)
+__device__ __forceinline__ artsample_t *art_out_ptr (const ArtJob &j, int c, long long frame)
 {
     return j.outPlanes ? j.outPlanes[c] + frame * j.outFS : j.out + frame * j.outFS + c * j.outCS;
 }

@@ -55,14 +55,21 @@ __device__ __forceinline__ int art_find_job (const ArtJob *jobs, int numJobs, in
 }
 
 template <int CV> struct ArtVec;
+#if ART_WIDE        /* double samples: one LDS.64 / LDS.128 brings one or two channels */
+typedef double artweight_t;
+template <> struct ArtVec<1> { typedef double  type; __device__ static double get (const double  &x, int)   { return x; } };
+template <> struct ArtVec<2> { typedef double2 type; __device__ static double get (const double2 &x, int v) { return v ? x.y : x.x; } };
+#else
+typedef float artweight_t;
 template <> struct ArtVec<1> { typedef float  type; __device__ static float get (const float  &x, int)   { return x; } };
 template <> struct ArtVec<2> { typedef float2 type; __device__ static float get (const float2 &x, int v) { return v ? x.y : x.x; } };
 template <> struct ArtVec<4> { typedef float4 type; __device__ static float get (const float4 &x, int v) { return v == 0 ? x.x : v == 1 ? x.y : v == 2 ? x.z : x.w; } };
+#endif
 
 struct ArtTileCtx {
-    const float *xs;                 // staged window, [group][Wp][CV]
+    const artsample_t *xs;           // staged window, [group][Wp][CV]
     const int *srel;                 // region index of the first tap, per tile-local output
-    const float *wgt;                // interpolation weight, per tile-local output
+    const artweight_t *wgt;          // interpolation weight, per tile-local output
     const unsigned short *order;     // tile-local output indices grouped by filter row
     long long sFirst;                // region index staged at xs[.][0]
     unsigned int n0;                 // first output frame of the tile
@@ -72,16 +79,16 @@ struct ArtTileCtx {
 
 /* SLOTS outputs that share the row pair `kk`, all channel groups of the CTA. */
 template <bool INTERP, typename AccT, int CV, int SLOTS>
-__device__ __forceinline__ void art_run_tile (const ArtTileCtx &t, const ArtJob &job, const float *__restrict__ bank,
+__device__ __forceinline__ void art_run_tile (const ArtTileCtx &t, const ArtJob &job, const artsample_t *__restrict__ bank,
                                               int kk, int e0, int len, int lane)
 {
     typedef typename ArtVec<CV>::type VecT;
-    const float *__restrict__ rowA = bank + (size_t) kk * t.Tp + lane;
-    const float *__restrict__ rowB = rowA + t.Tp;
+    const artsample_t *__restrict__ rowA = bank + (size_t) kk * t.Tp + lane;
+    const artsample_t *__restrict__ rowB = rowA + t.Tp;
     const int NI = t.Tp >> 5;
 
     int off[SLOTS];
-    float f[SLOTS];
+    artweight_t f[SLOTS];
 #pragma unroll
     for (int j = 0; j < SLOTS; ++j) {
         const int i = t.order[e0 + min (j, len - 1)];            // idle slots shadow the last real entry
@@ -129,10 +136,11 @@ __device__ __forceinline__ void art_run_tile (const ArtTileCtx &t, const ArtJob 
         constexpr int LPV = 32 / (SLOTS * CV);                   // lanes holding the same value
         const int q = lane / LPV, j = q / CV, v = q - j * CV;
         if ((lane % LPV) == 0 && j < len && cg + v < t.nc)
-            *art_out_ptr (job, t.c0 + cg + v, (long long) t.n0 + t.order[e0 + j]) = (float) total;
+            *art_out_ptr (job, t.c0 + cg + v, (long long) t.n0 + t.order[e0 + j]) = (artsample_t) total;
     }
 }
 
+#if !ART_WIDE       /* the packed-FP32 forms belong to the float path */
 /* float32 version of art_run_tile built on packed FFMA2.  Interpolated: one accumulator pair per
  * (output, channel) holds (row A sum, row B sum), the coefficient pair (A[k], B[k]) is packed once per
  * tap and the sample is a scalar operand -- half the FMA issue slots of the scalar form.  Not
@@ -364,13 +372,23 @@ __device__ __forceinline__ void art_run_unity (const ArtTileCtx &t, const ArtJob
     }
 }
 
+#endif
+
 template <bool INTERP, bool PRECISE, int CV, int SLOTS>
-__device__ __forceinline__ void art_run_any (const ArtTileCtx &t, const ArtJob &job, const float *__restrict__ bank,
+__device__ __forceinline__ void art_run_any (const ArtTileCtx &t, const ArtJob &job, const artsample_t *__restrict__ bank,
                                              int kk, int e0, int len, int lane)
 {
+#if ART_WIDE
+    art_run_tile<INTERP, double, CV, SLOTS> (t, job, bank, kk, e0, len, lane);
+#else
     if (PRECISE) art_run_tile<INTERP, double, CV, SLOTS> (t, job, bank, kk, e0, len, lane);
     else         art_run_tile_f32<INTERP, CV, SLOTS> (t, job, bank, kk, e0, len, lane);
+#endif
 }
+
+#ifndef ART_SKEW
+#define ART_SKEW(p) (p)
+#endif
 
 template <bool INTERP, bool PRECISE, int CV>
 __global__ void __launch_bounds__ (ART_G_THREADS, 2)
@@ -381,10 +399,10 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
     const int nkeysPad = (nkeys + 2 + 3) & ~3;
     const int maxRuns = k.NB / ART_RUN + nkeys + 8;
 
-    float *xs = reinterpret_cast<float *> (smem_raw);                   // [Cg/CV][Wp][CV]
-    int *srel = reinterpret_cast<int *> (xs + (size_t) k.Cg * k.Wp);    // [NB] region index of the first tap
-    float *wgt = reinterpret_cast<float *> (srel + k.NB);               // [NB] interpolation weight
-    int *binEnd = reinterpret_cast<int *> (wgt + k.NB);                 // [nkeysPad] counts -> starts -> ends
+    artsample_t *xs = reinterpret_cast<artsample_t *> (smem_raw);       // [Cg/CV][Wp][CV]
+    artweight_t *wgt = reinterpret_cast<artweight_t *> (xs + (size_t) k.Cg * k.Wp);   // [NB] interpolation weight
+    int *srel = reinterpret_cast<int *> (wgt + k.NB);                   // [NB] region index of the first tap
+    int *binEnd = srel + k.NB;                                          // [nkeysPad] counts -> starts -> ends
     int *chunk0 = binEnd + nkeysPad;                                    // [nkeysPad] first run index per key
     unsigned int *runTab = reinterpret_cast<unsigned int *> (chunk0 + nkeysPad);      // [maxRuns] key<<20 | start<<4 | len-1
     unsigned short *key = reinterpret_cast<unsigned short *> (runTab + maxRuns);      // [NB]
@@ -440,14 +458,14 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
         // region index of the first tap: ring index (whole - half + 1), un-compacted, minus origin
         const long long s = (long long) whole - half + 1 + (long long) w * D - job.origin;
         int kk;
-        float f = 0.0f;
+        artweight_t f = 0;
         if (INTERP) {
             double ph = fr * F;                                   // resampler.c:1149-1152
             int row = (int) floor (ph);
             ph -= row;
             if (row >= F) { row = F - 1; ph = 1.0; }             // fr*F rounded up to F: same point on the bank
             kk = row;
-            f = (float) ph;
+            f = (artweight_t) ph;
         }
         else {
             int row = (int) floor (fr * F + 0.5);                 // resampler.c:1137
@@ -466,7 +484,7 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
     __syncthreads ();
 
     const long long sFirst = sh_first;
-    const bool unity = INTERP && !PRECISE && k.unity;             // consecutive-output chunks instead of row-sorted runs (see art_run_unity)
+    const bool unity = !ART_WIDE && INTERP && !PRECISE && k.unity;    // consecutive-output chunks instead of row-sorted runs (see art_run_unity)
     // samples of window the tile touches (the unity form reads up to 3 + 32 positions past a chunk's last window: zero taps, but staged)
     const int span = (int) (sh_last - sFirst) + k.Tp + (unity ? 40 : 0);
     if ((unity ? ART_SKEW (span) + 1 : span) > k.Wp) {
@@ -482,7 +500,7 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
         typedef typename ArtVec<CV>::type VecT;
         // whole channel vectors straight from an interleaved block: one LDG.64/128 and one STS.64/128 per CV samples
         const bool vectorSrc = CV > 1 && interleavedSrc && nc == k.Cg && (job.inFS % CV) == 0 &&
-                               (reinterpret_cast<uintptr_t> (job.in + c0) % (sizeof (float) * CV)) == 0;
+                               (reinterpret_cast<uintptr_t> (job.in + c0) % (sizeof (artsample_t) * CV)) == 0;
         if (vectorSrc) {
             const int Q = k.Cg / CV, total = span * Q;
             const long long lo = -job.prevAvail, hi = job.inValid;
@@ -495,7 +513,7 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
                 if (idx >= lo && idx < hi)
                     v = __ldg (reinterpret_cast<const VecT *> (job.in + idx * job.inFS + c0 + cq * CV));
                 else {
-                    alignas (16) float tmp[CV];
+                    alignas (16) artsample_t tmp[CV];
 #pragma unroll
                     for (int u = 0; u < CV; ++u) tmp[u] = art_fetch (job, T, c0 + cq * CV + u, idx);
                     v = *reinterpret_cast<VecT *> (tmp);
@@ -508,20 +526,21 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
             for (int e = tid; e < total; e += ART_G_THREADS) {
                 const int j = e / k.Cg, cc = e - j * k.Cg;
                 const int js = unity ? ART_SKEW (j) : j;
-                xs[((cc / CV) * k.Wp + js) * CV + (cc % CV)] = cc < nc ? art_fetch (job, T, c0 + cc, sFirst + j) : 0.0f;
+                xs[((cc / CV) * k.Wp + js) * CV + (cc % CV)] = cc < nc ? art_fetch (job, T, c0 + cc, sFirst + j) : (artsample_t) 0;
             }
         }
         else {
             for (int cc = 0; cc < k.Cg; ++cc)
                 for (int j = tid; j < span; j += ART_G_THREADS) {
                     const int js = unity ? ART_SKEW (j) : j;
-                    xs[((cc / CV) * k.Wp + js) * CV + (cc % CV)] = cc < nc ? art_fetch (job, T, c0 + cc, sFirst + j) : 0.0f;
+                    xs[((cc / CV) * k.Wp + js) * CV + (cc % CV)] = cc < nc ? art_fetch (job, T, c0 + cc, sFirst + j) : (artsample_t) 0;
                 }
         }
     }
 
     /* ---- 2u. near-unity ratios: cut the tile into mini-runs of <= 4 consecutive outputs with one row pair and consecutive
      *          windows, in natural order (no sort) -------------------------------------------------------------------------- */
+#if !ART_WIDE
     if (unity) {
         const int per = (cnt + ART_G_THREADS - 1) / ART_G_THREADS;
         const int i0 = min (tid * per, cnt), i1 = min (i0 + per, cnt);
@@ -577,6 +596,7 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
         }
         return;
     }
+#endif
 
     /* ---- 2. group by filter row ---------------------------------------------------------- */
     int totalRuns;
@@ -671,7 +691,7 @@ static size_t generic_smem (const ArtClass &k)
     const int nkeys = NUM_KEYS (k.F);
     const int nkeysPad = (nkeys + 2 + 3) & ~3;
     const int maxRuns = k.NB / ART_RUN + nkeys + 8;
-    return (size_t) k.Cg * k.Wp * 4 + (size_t) k.NB * (4 + 4 + 2 + 2) + (size_t) nkeysPad * 8 + (size_t) maxRuns * 4 + 16;
+    return (size_t) k.Cg * k.Wp * sizeof (artsample_t) + (size_t) k.NB * (sizeof (artweight_t) + 4 + 2 + 2) + (size_t) nkeysPad * 8 + (size_t) maxRuns * 4 + 16;
 }
 
 static int plane_floats (int NB, double ratio, int Tp)
@@ -694,7 +714,7 @@ void artPlanGenericGeometry (ArtClass &k, double minRatio, unsigned int maxOutpu
     const size_t budget = 110 * 1024;        // two CTAs per SM inside the 227 KB carve-out
     const int C = k.C;
     int cv = C >= 4 ? 4 : (C >= 2 ? 2 : 1);
-    if (k.mode & ART_MODE_PRECISE) cv = C >= 2 ? 2 : 1;
+    if ((k.mode & ART_MODE_PRECISE) || ART_WIDE) cv = C >= 2 ? 2 : 1;
     const int maxCg = ((C < 8 ? C : 8) + cv - 1) / cv * cv;
 
     // small calls: shorter tiles so that the grid still covers the GPU
@@ -764,9 +784,15 @@ void artLaunchGeneric (const ArtClass &k, const ArtLaunchGeom &g, const ArtJob &
         else if (interp)              launch_one<true, true, CVV> (k, g, single, d_jobs, stream);  \
         else                          launch_one<false, true, CVV> (k, g, single, d_jobs, stream); \
     } while (0)
+#if ART_WIDE        /* double samples, double accumulation: the "precise" instances are the only ones */
+    if (g.CV == 2) { if (interp) launch_one<true, true, 2> (k, g, single, d_jobs, stream); else launch_one<false, true, 2> (k, g, single, d_jobs, stream); }
+    else           { if (interp) launch_one<true, true, 1> (k, g, single, d_jobs, stream); else launch_one<false, true, 1> (k, g, single, d_jobs, stream); }
+    (void) precise;
+#else
     if (g.CV == 4) ART_DISPATCH (4);
     else if (g.CV == 2) ART_DISPATCH (2);
     else ART_DISPATCH (1);
+#endif
 #undef ART_DISPATCH
 }
 

@@ -37,6 +37,8 @@
 #include "art_kernels.cuh"
 #include "art_device.h"
 
+#if !ART_WIDE       /* a float-path optimisation: the wide (PATH_WIDTH=64) build keeps to the any-ratio kernel */
+
 #define ART_P_THREADS 256
 #define ART_P_WARPS   (ART_P_THREADS / 32)
 #define ART_P_ROWS_MAX 4
@@ -624,3 +626,13 @@ void artLaunchPeriodic (const ArtClass &k, const ArtPeriodic &p, int CV, int tot
     else ART_LP (1);
 #undef ART_LP
 }
+
+#else   /* ART_WIDE */
+
+bool artRational (double, int, int *, int *) { return false; }
+bool artPlanPeriodic (const ArtClass &, double, unsigned int, unsigned long long, int, ArtPeriodic &, int &) { return false; }
+unsigned int artPeriodicSegmentOutputs (const ArtPeriodic &, double) { return 0; }
+int artPeriodicCtas (const ArtPeriodic &, unsigned int) { return 0; }
+void artLaunchPeriodic (const ArtClass &, const ArtPeriodic &, int, int, int, int, const ArtJob &, const ArtJob *, cudaStream_t) { }
+
+#endif

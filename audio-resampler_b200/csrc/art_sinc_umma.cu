@@ -48,6 +48,8 @@
 #include "art_kernels.cuh"
 #include "art_device.h"
 
+#if !ART_WIDE       /* a float-path optimisation: the wide (PATH_WIDTH=64) build keeps to the any-ratio kernel */
+
 #define ART_U_THREADS 640           /* warpgroup 0: producer + 2 MMA warps (+1 idle); 1-2: converters; 3-4: epilogue */
 #define ART_U_EPI     256           /* epilogue threads */
 #define ART_U_CONV    256           /* converter threads */
@@ -1147,3 +1149,14 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
     else                umma_launch_one<1> (k, uu, totalTiles, grid, single, d_jobs, roleProf, stream);
     g_artLaunches += 2;
 }
+
+#else   /* ART_WIDE */
+
+int g_artTensorDigits = -1;
+bool artPlanUmma (const ArtClass &, double, unsigned int, unsigned long long, int, ArtUmma &) { return false; }
+int artUmmaTiles (const ArtUmma &, int, unsigned int) { return 0; }
+size_t artUmmaTableBytes (const ArtUmma &, int, int, int) { return 0; }
+void artUmmaCarve (ArtUmma &, void *, int, int) { }
+void artLaunchUmma (const ArtClass &, const ArtUmma &, int, int, int, int, const ArtJob &, const ArtJob *, cudaStream_t) { }
+
+#endif

@@ -19,7 +19,11 @@
 #include <math.h>
 
 #ifndef ART_B200_RESAMPLER_H
+#if defined(PATH_WIDTH) && (PATH_WIDTH==64)     /* reference biquad.h:21-25 */
+typedef double artsample_t;
+#else
 typedef float artsample_t;
+#endif
 #endif
 
 typedef struct {

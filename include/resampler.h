@@ -8,8 +8,10 @@
  * it is CUDA (sm_100a); there is no CPU fallback: without a usable Blackwell GPU the init
  * functions print the CUDA error and return NULL.
  *
- * Only the 32-bit float data path is provided (the reference's PATH_WIDTH=64 build is out
- * of scope).
+ * Like the reference, the header serves two builds: compiled with -DPATH_WIDTH=64 every sample
+ * (buffers, filter bank, biquad and decimator state) is a double and the caller links
+ * libresampler_b200_64.so (what the reference's art64 / artest64 targets do with its own
+ * sources, Makefile:12-19); otherwise samples are floats and the library is libresampler_b200.so.
  */
 #ifndef ART_B200_RESAMPLER_H
 #define ART_B200_RESAMPLER_H
@@ -20,7 +22,11 @@
 #include <stdio.h>
 #include <math.h>
 
-typedef float artsample_t;                      /* reference resampler.h:22-26 (32-bit path) */
+#if defined(PATH_WIDTH) && (PATH_WIDTH==64)     /* reference resampler.h:22-26 */
+typedef double artsample_t;
+#else
+typedef float artsample_t;
+#endif
 
 /* reference resampler.h:28-38 */
 #define SUBSAMPLE_INTERPOLATE   0x1

@@ -62,25 +62,25 @@ unsigned long long resampleB200ProfileCollect (double *totalMs);
 
 /* device-pointer twins of resampleProcessInterleaved (resampler.c:550) / resampleProcess (:433).
  * A flush is numInputFrames == -1, as in the reference. */
-ResampleResult resampleProcessInterleavedDevice (Resample *cxt, const float *d_input, int numInputFrames,
-                                                 float *d_output, int numOutputFrames, double ratio, void *stream);
-ResampleResult resampleProcessDevice (Resample *cxt, const float *const *d_input, int numInputFrames,
-                                      float *const *d_output, int numOutputFrames, double ratio, void *stream);
+ResampleResult resampleProcessInterleavedDevice (Resample *cxt, const artsample_t *d_input, int numInputFrames,
+                                                 artsample_t *d_output, int numOutputFrames, double ratio, void *stream);
+ResampleResult resampleProcessDevice (Resample *cxt, const artsample_t *const *d_input, int numInputFrames,
+                                      artsample_t *const *d_output, int numOutputFrames, double ratio, void *stream);
 
 /* Many independent contexts of identical configuration (same channels/taps/filters/lowpass/flags,
  * same GPU) in ONE launch -- what workers.c's per-channel threads and a caller's per-stream loop
  * become on a GPU.  Element i of every array belongs to cxts[i].  results may be NULL. */
 void resampleBatchProcessInterleavedDevice (Resample *const *cxts, int numContexts,
-                                            const float *const *d_inputs, const int *numInputFrames,
-                                            float *const *d_outputs, const int *numOutputFrames,
+                                            const artsample_t *const *d_inputs, const int *numInputFrames,
+                                            artsample_t *const *d_outputs, const int *numOutputFrames,
                                             const double *ratios, ResampleResult *results, void *stream);
 
 /* The same for HOST buffers: uploads, kernels and downloads of successive contexts are pipelined on
  * three streams (PCIe in both directions overlaps the convolution); returns when all outputs are in
  * host memory.  Pinned host buffers are needed for the copies to be asynchronous. */
 void resampleBatchProcessInterleaved (Resample *const *cxts, int numContexts,
-                                      const float *const *inputs, const int *numInputFrames,
-                                      float *const *outputs, const int *numOutputFrames,
+                                      const artsample_t *const *inputs, const int *numInputFrames,
+                                      artsample_t *const *outputs, const int *numOutputFrames,
                                       const double *ratios, ResampleResult *results);
 
 /* ASRC: numBlocks consecutive blocks of ONE stream, block b holding blockFrames[b] input frames
@@ -89,9 +89,9 @@ void resampleBatchProcessInterleaved (Resample *const *cxts, int numContexts,
  * are contiguous in d_input; outputs are packed contiguously into d_output.  Stops early -- and
  * returns the number of blocks completed -- when a block cannot consume all of its input within
  * outputCapacityFrames. */
-int resampleProcessBlocksInterleavedDevice (Resample *cxt, const float *d_input, const int *blockFrames,
+int resampleProcessBlocksInterleavedDevice (Resample *cxt, const artsample_t *d_input, const int *blockFrames,
                                             const double *ratios, int numBlocks,
-                                            float *d_output, int outputCapacityFrames,
+                                            artsample_t *d_output, int outputCapacityFrames,
                                             ResampleResult *results, double *positions, void *stream);
 
 /* Fused pre-filter.  art.c runs a cascade of biquad lowpass sections over the input block in front of a downsampling resampler
@@ -112,9 +112,9 @@ int resampleB200AttachPrefilter (Resample *cxt, const Biquad *sections, int numS
  * numChannels Biquads over one interleaved buffer, in ONE pass over memory.  stages[s] points at
  * the caller's array of numChannels Biquad structs for stage s (e.g. lowpass1, lowpass2). */
 void biquad_apply_cascade_interleaved (Biquad *const *stages, int numStages, int numChannels,
-                                       float *buffer, int numFrames);
+                                       artsample_t *buffer, int numFrames);
 void biquad_apply_cascade_interleaved_device (Biquad *const *stages, int numStages, int numChannels,
-                                              float *d_buffer, int numFrames, void *stream);
+                                              artsample_t *d_buffer, int numFrames, void *stream);
 
 #ifdef __cplusplus
 }

@@ -25,7 +25,7 @@
 
 /* One windowed-sinc row centred `fraction` of a sample past tap taps/2-1.
  * Restates init_filter, resampler.c:1090-1133. */
-static void build_row (const OracleResampler *r, float *row, double *scratch, double fraction)
+static void build_row (const OracleResampler *r, osample_t *row, double *scratch, double fraction)
 {
     static const double bh[4] = { 0.35875, 0.48829, 0.14128, 0.01168 };   /* resampler.c:1093-1096 */
     const int taps = r->taps, half = taps / 2;
@@ -59,7 +59,7 @@ static void build_row (const OracleResampler *r, float *row, double *scratch, do
         for (int j = 0; j < 2; ++j) {
             int t = order[j];
             scratch[t] *= gain;
-            row[t] = (float) (scratch[t] - carried);
+            row[t] = (osample_t) (scratch[t] - carried);
             carried += row[t] - scratch[t];
         }
     }
@@ -87,8 +87,8 @@ OracleResampler *oracle_init (int channels, int taps, int phases, double lowpass
     r->flags = flags;
     r->lowpass_ratio = lowpass_ratio;
     r->ring_len = 16 * taps;                                                /* :139 */
-    r->bank = calloc ((size_t) (phases + 1) * taps, sizeof (float));
-    r->ring = calloc ((size_t) (channels > 0 ? channels : 1) * r->ring_len, sizeof (float));
+    r->bank = calloc ((size_t) (phases + 1) * taps, sizeof (osample_t));
+    r->ring = calloc ((size_t) (channels > 0 ? channels : 1) * r->ring_len, sizeof (osample_t));
 
     double *scratch = malloc (sizeof (double) * taps);
     for (int p = 0; p < phases; ++p)                                        /* :149-155 */
@@ -96,7 +96,7 @@ OracleResampler *oracle_init (int channels, int taps, int phases, double lowpass
     free (scratch);
 
     /* the extra row is row 0 delayed by one tap (:156-159) ... */
-    float *last = r->bank + (size_t) phases * taps;
+    osample_t *last = r->bank + (size_t) phases * taps;
     for (int t = 0; t < taps; ++t)
         last[(t + 1) % taps] = r->bank[t];
     /* ... and the two window outliers are cleared (:167-168) */
@@ -159,7 +159,7 @@ void oracle_free (OracleResampler *r)
 /* resampleReset, resampler.c:383-397 */
 void oracle_reset (OracleResampler *r)
 {
-    memset (r->ring, 0, sizeof (float) * (size_t) r->channels * r->ring_len);
+    memset (r->ring, 0, sizeof (osample_t) * (size_t) r->channels * r->ring_len);
     r->read_pos = r->taps / 2;
     r->write_index = r->taps;
     r->flags &= ~ORC_FLUSHED;
@@ -182,7 +182,7 @@ double oracle_position (const OracleResampler *r)
     return r->read_pos + (r->taps / 2.0) - r->write_index;
 }
 
-const float *oracle_bank_row (const OracleResampler *r, int row)
+const osample_t *oracle_bank_row (const OracleResampler *r, int row)
 {
     return r->bank + (size_t) row * r->taps;
 }
@@ -191,16 +191,16 @@ const float *oracle_bank_row (const OracleResampler *r, int row)
 
 /* apply_filter "version 2", resampler.c:1033-1044: float accumulator, pairs
  * taken from both ends towards the middle. */
-static double dot_outside_in (const float *coef, const float *x, int taps)
+static double dot_outside_in (const osample_t *coef, const osample_t *x, int taps)
 {
-    float acc = 0.0f;
+    osample_t acc = 0.0f;
     for (int lo = 0, hi = taps - 1; lo < hi; ++lo, --hi)
         acc += (coef[lo] * x[lo]) + (coef[hi] * x[hi]);
     return acc;
 }
 
 /* apply_filter_precise, resampler.c:1049-1057 */
-static double dot_double (const float *coef, const float *x, int taps)
+static double dot_double (const osample_t *coef, const osample_t *x, int taps)
 {
     double acc = 0.0;
     for (int t = 0; t < taps; ++t)
@@ -211,9 +211,9 @@ static double dot_double (const float *coef, const float *x, int taps)
 /* subsample_interpolate / subsample_no_interpolate and their _precise twins,
  * resampler.c:1135-1181.  `line` is one channel's ring, `where` the read
  * position in ring coordinates. */
-static double sample_at (const OracleResampler *r, const float *line, double where)
+static double sample_at (const OracleResampler *r, const osample_t *line, double where)
 {
-    double (*dot) (const float *, const float *, int) =
+    double (*dot) (const osample_t *, const osample_t *, int) =
         (r->flags & ORC_EXTENDED_MATH) ? dot_double : dot_outside_in;      /* :191-196 */
     const int taps = r->taps;
     const double whole = floor (where);
@@ -222,13 +222,13 @@ static double sample_at (const OracleResampler *r, const float *line, double whe
         double frac = (where - whole) * r->phases;                          /* :1149-1150 */
         int row = (int) floor (frac);
         frac -= row;                                                        /* :1152 */
-        const float *x = line + (int) whole - taps / 2 + 1;                 /* :1153 */
+        const osample_t *x = line + (int) whole - taps / 2 + 1;                 /* :1153 */
         return dot (r->bank + (size_t) row * taps, x, taps) * (1.0 - frac) +
                dot (r->bank + (size_t) (row + 1) * taps, x, taps) * frac;   /* :1155-1156 */
     }
 
     int row = (int) floor ((where - whole) * r->phases + 0.5);              /* :1137 */
-    const float *centre = line + (int) whole;
+    const osample_t *centre = line + (int) whole;
     if (!(r->flags & ORC_LOWPASS) && row % r->phases == 0)                  /* :1141-1142 */
         return centre[row / r->phases];
     return dot (r->bank + (size_t) row * taps, centre - taps / 2 + 1, taps);   /* :1144 */
@@ -245,7 +245,7 @@ static double sample_at (const OracleResampler *r, const float *line, double whe
 #define ORC_LPC_ORDER 4
 #define ORC_LPC_MAX_ROUNDS 100000
 
-static double predictor_output (const float *coef, const float *window)        /* sum_c coef[N-1-c] * window[c] */
+static double predictor_output (const float *coef, const osample_t *window)        /* sum_c coef[N-1-c] * window[c] */
 {
     double acc = 0.0;
     for (int c = 0; c < ORC_LPC_ORDER; ++c)
@@ -285,7 +285,7 @@ static void from_reflection (const double *refl, double *lpc)                   
     }
 }
 
-static void fit_predictor (const float *x, int count, float *coef)              /* extrapolator.c:93-240 */
+static void fit_predictor (const osample_t *x, int count, float *coef)              /* extrapolator.c:93-240 */
 {
     const int evals = count - ORC_LPC_ORDER;
     double signal_energy = 0.0, delta_energy = 0.0, best, step = 3.0 / 16.0;
@@ -294,7 +294,7 @@ static void fit_predictor (const float *x, int count, float *coef)              
 
     memset (coef, 0, sizeof (float) * ORC_LPC_ORDER);
     for (int i = 0; i < evals; ++i) {                                            /* :101-107 */
-        const float now = x[i + ORC_LPC_ORDER], before = x[i + ORC_LPC_ORDER - 1];
+        const osample_t now = x[i + ORC_LPC_ORDER], before = x[i + ORC_LPC_ORDER - 1];
         delta_energy += (now - before) * (now - before);
         signal_energy += now * now;
     }
@@ -353,20 +353,20 @@ static void fit_predictor (const float *x, int count, float *coef)              
 }
 
 /* extrapolate_forward, extrapolator.c:22-43: x[0..known) are given, x[known..known+more) are written */
-void oracle_extend_forward (float *x, int known, int more)
+void oracle_extend_forward (osample_t *x, int known, int more)
 {
     float coef[ORC_LPC_ORDER];
-    memset (x + known, 0, sizeof (float) * more);
+    memset (x + known, 0, sizeof (osample_t) * more);
     fit_predictor (x, known, coef);
     for (int i = 0; i < more; ++i)
-        x[known + i] = (float) -predictor_output (coef, x + known - ORC_LPC_ORDER + i);
+        x[known + i] = (osample_t) -predictor_output (coef, x + known - ORC_LPC_ORDER + i);
 }
 
 /* extrapolate_reverse, extrapolator.c:49-65: end[-1], end[-2] ... end[-known] are given (newest first when read
  * backwards), end[-known-1] ... end[-known-more] are written */
-void oracle_extend_backward (float *end, int known, int more)
+void oracle_extend_backward (osample_t *end, int known, int more)
 {
-    float *flip = calloc ((size_t) known + more, sizeof (float));
+    osample_t *flip = calloc ((size_t) known + more, sizeof (osample_t));
     for (int i = 0; i < known; ++i) flip[i] = end[-1 - i];
     oracle_extend_forward (flip, known, more);
     for (int i = known; i < known + more; ++i) end[-1 - i] = flip[i];
@@ -379,8 +379,8 @@ static void compact_ring (OracleResampler *r)
 {
     const int drop = r->ring_len - r->taps;
     for (int c = 0; c < r->channels; ++c) {
-        float *line = r->ring + (size_t) c * r->ring_len;
-        memmove (line, line + drop, sizeof (float) * r->taps);
+        osample_t *line = r->ring + (size_t) c * r->ring_len;
+        memmove (line, line + drop, sizeof (osample_t) * r->taps);
     }
     r->read_pos -= drop;
     r->write_index -= drop;
@@ -393,8 +393,8 @@ static void append_silence (OracleResampler *r)
     if (r->ring_len - r->write_index < half)
         compact_ring (r);
     for (int c = 0; c < r->channels; ++c) {
-        float *line = r->ring + (size_t) c * r->ring_len;
-        memset (line + r->write_index, 0, sizeof (float) * (r->ring_len - r->write_index));
+        osample_t *line = r->ring + (size_t) c * r->ring_len;
+        memset (line + r->write_index, 0, sizeof (osample_t) * (r->ring_len - r->write_index));
         if (r->flags & ORC_EXTRAPOLATE)                                     /* :677-680 */
             oracle_extend_forward (line + r->write_index - half, half, half);
     }
@@ -405,8 +405,8 @@ static void append_silence (OracleResampler *r)
 /* The control loop shared by resampleProcess (resampler.c:433-541) and
  * resampleProcessInterleaved (:550-658).  in_base[c]/out_base[c] point at
  * frame 0 of channel c; consecutive frames are *_stride floats apart. */
-static OracleResult run (OracleResampler *r, const float *const *in_base, int in_stride, int n_in,
-                         float *const *out_base, int out_stride, int n_out, double ratio)
+static OracleResult run (OracleResampler *r, const osample_t *const *in_base, int in_stride, int n_in,
+                         osample_t *const *out_base, int out_stride, int n_out, double ratio)
 {
     OracleResult res = { 0, 0 };
     const int half = r->taps / 2;
@@ -439,7 +439,7 @@ static OracleResult run (OracleResampler *r, const float *const *in_base, int in
             }
             for (int c = 0; c < r->channels; ++c)
                 out_base[c][(size_t) res.output_generated * out_stride] =
-                    (float) sample_at (r, r->ring + (size_t) c * r->ring_len, r->read_pos + step);
+                    (osample_t) sample_at (r, r->ring + (size_t) c * r->ring_len, r->read_pos + step);
             step = ++res.output_generated / ratio;                          /* :526 */
             n_out--;
         }
@@ -453,23 +453,23 @@ static OracleResult run (OracleResampler *r, const float *const *in_base, int in
     return res;
 }
 
-OracleResult oracle_process_interleaved (OracleResampler *r, const float *in, int n_in,
-                                         float *out, int n_out, double ratio)
+OracleResult oracle_process_interleaved (OracleResampler *r, const osample_t *in, int n_in,
+                                         osample_t *out, int n_out, double ratio)
 {
     const int C = r->channels;
-    const float **ib = malloc (sizeof *ib * (C > 0 ? C : 1));
-    float **ob = malloc (sizeof *ob * (C > 0 ? C : 1));
+    const osample_t **ib = malloc (sizeof *ib * (C > 0 ? C : 1));
+    osample_t **ob = malloc (sizeof *ob * (C > 0 ? C : 1));
     for (int c = 0; c < C; ++c) { ib[c] = in ? in + c : NULL; ob[c] = out + c; }
     OracleResult res = run (r, ib, C, n_in, ob, C, n_out, ratio);
     free (ib); free (ob);
     return res;
 }
 
-OracleResult oracle_process_planar (OracleResampler *r, const float *const *in, int n_in,
-                                    float *const *out, int n_out, double ratio)
+OracleResult oracle_process_planar (OracleResampler *r, const osample_t *const *in, int n_in,
+                                    osample_t *const *out, int n_out, double ratio)
 {
     const int C = r->channels;
-    const float **ib = malloc (sizeof *ib * (C > 0 ? C : 1));
+    const osample_t **ib = malloc (sizeof *ib * (C > 0 ? C : 1));
     for (int c = 0; c < C; ++c) ib[c] = in ? in[c] : NULL;
     OracleResult res = run (r, ib, 1, n_in, out, 1, n_out, ratio);
     free (ib);
@@ -477,8 +477,8 @@ OracleResult oracle_process_planar (OracleResampler *r, const float *const *in, 
 }
 
 /* resampleProcessAndFlushInterleaved, resampler.c:741-758 */
-OracleResult oracle_process_flush_interleaved (OracleResampler *r, const float *in, int n_in,
-                                               float *out, int n_out, double ratio)
+OracleResult oracle_process_flush_interleaved (OracleResampler *r, const osample_t *in, int n_in,
+                                               osample_t *out, int n_out, double ratio)
 {
     OracleResult res = oracle_process_interleaved (r, in, n_in, out, n_out, ratio);
     if ((n_in -= res.input_used) != 0 || (n_out -= res.output_generated) == 0)
@@ -490,13 +490,13 @@ OracleResult oracle_process_flush_interleaved (OracleResampler *r, const float *
 }
 
 /* resampleProcessAndFlush, resampler.c:712-739 */
-OracleResult oracle_process_flush_planar (OracleResampler *r, const float *const *in, int n_in,
-                                          float *const *out, int n_out, double ratio)
+OracleResult oracle_process_flush_planar (OracleResampler *r, const osample_t *const *in, int n_in,
+                                          osample_t *const *out, int n_out, double ratio)
 {
     OracleResult res = oracle_process_planar (r, in, n_in, out, n_out, ratio);
     if ((n_in -= res.input_used) != 0 || (n_out -= res.output_generated) == 0)
         return res;
-    float **shifted = malloc (sizeof *shifted * r->channels);
+    osample_t **shifted = malloc (sizeof *shifted * r->channels);
     for (int c = 0; c < r->channels; ++c) shifted[c] = out[c] + res.output_generated;
     OracleResult tail = oracle_process_planar (r, NULL, -1, shifted, n_out, ratio);
     free (shifted);
@@ -573,8 +573,8 @@ void oracle_biquad_highpass (OracleBiquadCoeffs *c, double f) { biquad_common (c
 /* biquad_init, biquad.c:51-74 */
 void oracle_biquad_init (OracleBiquad *q, const OracleBiquadCoeffs *c, double gain)
 {
-    const float fwd[5] = { c->a0, c->a1, c->a2, c->a3, c->a4 };
-    const float bwd[5] = { 0.0f, c->b1, c->b2, c->b3, c->b4 };
+    const osample_t fwd[5] = { c->a0, c->a1, c->a2, c->a3, c->a4 };
+    const osample_t bwd[5] = { 0.0f, c->b1, c->b2, c->b3, c->b4 };
     memset (q, 0, sizeof *q);
     for (int i = 0; i < 5; ++i) {
         q->a[i] = fwd[i] * gain;
@@ -589,11 +589,11 @@ void oracle_biquad_init (OracleBiquad *q, const OracleBiquadCoeffs *c, double ga
 /* biquad_apply_buffer, biquad.c:106-163: direct form I in float, the newest
  * history entry sits at cursor & 3.  The sum is formed left to right exactly
  * as the reference's expression is written. */
-void oracle_biquad_run (OracleBiquad *q, float *buf, int count, int stride)
+void oracle_biquad_run (OracleBiquad *q, osample_t *buf, int count, int stride)
 {
     int cur = q->cursor;
     while (count--) {
-        float acc = *buf * q->a[0];
+        osample_t acc = *buf * q->a[0];
         for (int d = 1; d <= q->order; ++d) {
             int slot = (cur - (d - 1)) & 3;
             acc = acc + (q->xh[slot] * q->a[d]) - (q->b[d] * q->yh[slot]);
@@ -609,7 +609,7 @@ void oracle_biquad_run (OracleBiquad *q, float *buf, int count, int stride)
 /* ------------------------------------------------------------------ noise */
 
 /* fill_buffer_with_noise, artest.c:744-754 */
-void oracle_noise (unsigned long long *state, float *dst, int count)
+void oracle_noise (unsigned long long *state, osample_t *dst, int count)
 {
     unsigned long long s = *state;
     while (count--) {
@@ -626,9 +626,9 @@ void oracle_noise (unsigned long long *state, float *dst, int count)
  * interleaved entry points; channel state lives in one struct per channel. */
 
 /* biquad_apply_sample, biquad.c:78-102 */
-static float shaper_step (OracleBiquad *q, float in)
+static osample_t shaper_step (OracleBiquad *q, osample_t in)
 {
-    float acc = in * q->a[0];
+    osample_t acc = in * q->a[0];
     int cur = q->cursor & 3;
     for (int d = q->order; d >= 1; --d) {
         int slot = (cur - (d - 1)) & 3;
@@ -709,15 +709,15 @@ static double tpdf (unsigned int *gen, int type)
 }
 
 /* one channel: decimator.c:170-199 (= :243-272, :301-333) */
-static int decimate_channel (OracleDecimator *d, int c, const float *in, int in_stride, int frames, unsigned char *out, int out_stride_bytes)
+static int decimate_channel (OracleDecimator *d, int c, const osample_t *in, int in_stride, int frames, unsigned char *out, int out_stride_bytes)
 {
-    const float scaler = (1 << d->bits) / 2.0 * d->gain;
+    const osample_t scaler = (1 << d->bits) / 2.0 * d->gain;
     const int pad = d->bytes - ((d->bits + 7) / 8);
     const int bias = (d->bits <= 8) * 128, top = (1 << (d->bits - 1)) - 1, bottom = ~top, shl = (24 - d->bits) % 8;
     int clips = 0;
     for (int i = 0; i < frames; ++i, in += in_stride, out += out_stride_bytes) {
-        const float dith = (d->flags & 0x7) ? tpdf (&d->lane[c].rng, d->dither) : 0.0;
-        const float code = (*in * scaler) - d->lane[c].feedback;
+        const osample_t dith = (d->flags & 0x7) ? tpdf (&d->lane[c].rng, d->dither) : 0.0;
+        const osample_t code = (*in * scaler) - d->lane[c].feedback;
         int v = floor (code + dith + 0.5);
         unsigned char *o = out;
         if (d->flags & 0xf00)
@@ -732,7 +732,7 @@ static int decimate_channel (OracleDecimator *d, int c, const float *in, int in_
     return clips;
 }
 
-int oracle_decimate_interleaved (OracleDecimator *d, const float *in, int frames, unsigned char *out)
+int oracle_decimate_interleaved (OracleDecimator *d, const osample_t *in, int frames, unsigned char *out)
 {
     int clips = 0;
     for (int c = 0; c < d->channels; ++c)
@@ -740,7 +740,7 @@ int oracle_decimate_interleaved (OracleDecimator *d, const float *in, int frames
     return clips;
 }
 
-int oracle_decimate_planar (OracleDecimator *d, const float *const *in, int frames, unsigned char *const *out)
+int oracle_decimate_planar (OracleDecimator *d, const osample_t *const *in, int frames, unsigned char *const *out)
 {
     int clips = 0;
     for (int c = 0; c < d->channels; ++c)
@@ -749,10 +749,10 @@ int oracle_decimate_planar (OracleDecimator *d, const float *const *in, int fram
 }
 
 /* floatIntegersLE, decimator.c:416-450 */
-void oracle_float_integers (const unsigned char *in, double gain, int bits, int bytes, int stride, float *out, int count)
+void oracle_float_integers (const unsigned char *in, double gain, int bits, int bytes, int stride, osample_t *out, int count)
 {
     const int used = (bits + 7) / 8;
-    const float g = bits <= 8 ? gain / 128.0 : (bits <= 16 ? gain / 32768.0 : gain / 8388608.0);
+    const osample_t g = bits <= 8 ? gain / 128.0 : (bits <= 16 ? gain / 32768.0 : gain / 8388608.0);
     in += bytes - used;
     for (int i = 0; i < count; ++i, in += (size_t) stride * bytes) {
         int v;

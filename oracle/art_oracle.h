@@ -17,6 +17,14 @@
 #ifndef ART_ORACLE_H
 #define ART_ORACLE_H
 
+/* the sample type, as in the reference (resampler.h:22-26): liboracle.so is the float path, liboracle64.so (-DPATH_WIDTH=64) the
+ * path on which samples, taps and filter state are doubles */
+#if defined(PATH_WIDTH) && (PATH_WIDTH==64)
+typedef double osample_t;
+#else
+typedef float osample_t;
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -44,8 +52,8 @@ typedef struct OracleResampler {
     int     write_index;       /* "inputIndex"                                   */
     double  read_pos;          /* "outputOffset"                                 */
     double  fixed_ratio, lowpass_ratio;
-    float  *bank;              /* (phases + 1) rows of taps floats, contiguous   */
-    float  *ring;              /* channels rows of ring_len floats, contiguous   */
+    osample_t  *bank;              /* (phases + 1) rows of taps floats, contiguous   */
+    osample_t  *ring;              /* channels rows of ring_len floats, contiguous   */
 } OracleResampler;
 
 OracleResampler *oracle_init (int channels, int taps, int phases, double lowpass_ratio, int flags);
@@ -55,41 +63,41 @@ void   oracle_free (OracleResampler *r);
 void   oracle_reset (OracleResampler *r);
 void   oracle_advance (OracleResampler *r, double delta);
 double oracle_position (const OracleResampler *r);
-const float *oracle_bank_row (const OracleResampler *r, int row);
+const osample_t *oracle_bank_row (const OracleResampler *r, int row);
 
 /* One strided core serves the planar and the interleaved entry points of the
  * reference: sample (frame f, channel c) lives at base_c[f * frame_stride],
  * with base_c = in[c] (planar, frame_stride 1) or in + c (interleaved,
  * frame_stride = channels).  n_in < 0 requests a flush. */
-OracleResult oracle_process_interleaved (OracleResampler *r, const float *in, int n_in,
-                                         float *out, int n_out, double ratio);
-OracleResult oracle_process_planar (OracleResampler *r, const float *const *in, int n_in,
-                                    float *const *out, int n_out, double ratio);
-OracleResult oracle_process_flush_interleaved (OracleResampler *r, const float *in, int n_in,
-                                               float *out, int n_out, double ratio);
-OracleResult oracle_process_flush_planar (OracleResampler *r, const float *const *in, int n_in,
-                                          float *const *out, int n_out, double ratio);
+OracleResult oracle_process_interleaved (OracleResampler *r, const osample_t *in, int n_in,
+                                         osample_t *out, int n_out, double ratio);
+OracleResult oracle_process_planar (OracleResampler *r, const osample_t *const *in, int n_in,
+                                    osample_t *const *out, int n_out, double ratio);
+OracleResult oracle_process_flush_interleaved (OracleResampler *r, const osample_t *in, int n_in,
+                                               osample_t *out, int n_out, double ratio);
+OracleResult oracle_process_flush_planar (OracleResampler *r, const osample_t *const *in, int n_in,
+                                          osample_t *const *out, int n_out, double ratio);
 unsigned int oracle_required_input (const OracleResampler *r, int n_out, double ratio);
 unsigned int oracle_expected_output (const OracleResampler *r, int n_in, double ratio);
 
 /* biquad.h:27-35 */
-typedef struct { float a0, a1, a2, a3, a4, b1, b2, b3, b4; } OracleBiquadCoeffs;
+typedef struct { osample_t a0, a1, a2, a3, a4, b1, b2, b3, b4; } OracleBiquadCoeffs;
 typedef struct {
-    float a[5], b[5];
-    float xh[4], yh[4];
+    osample_t a[5], b[5];
+    osample_t xh[4], yh[4];
     int   order, cursor;
 } OracleBiquad;
 
 void oracle_biquad_lowpass (OracleBiquadCoeffs *c, double frequency);
 void oracle_biquad_highpass (OracleBiquadCoeffs *c, double frequency);
 void oracle_biquad_init (OracleBiquad *q, const OracleBiquadCoeffs *c, double gain);
-void oracle_biquad_run (OracleBiquad *q, float *buf, int count, int stride);
+void oracle_biquad_run (OracleBiquad *q, osample_t *buf, int count, int stride);
 
 /* decimator.c: float -> integer with TPDF dither and noise shaping (decimateInit :29-100, decimateProcess*LE :112-291),
  * and its lossless inverse floatIntegersLE (:416-450).  Flag values are decimator.h:29-41. */
 typedef struct {
     unsigned int rng;           /* "tpdf_generators[ch]" */
-    float        feedback;      /* "feedback[ch]"        */
+    osample_t        feedback;      /* "feedback[ch]"        */
     OracleBiquad shaper;        /* "noise_shapers[ch]"   */
 } OracleDecimatorLane;
 
@@ -101,16 +109,16 @@ typedef struct {
 
 OracleDecimator *oracle_decimate_init (int channels, int bits, int bytes, double gain, int rate, int flags);
 void oracle_decimate_free (OracleDecimator *d);
-int  oracle_decimate_interleaved (OracleDecimator *d, const float *in, int frames, unsigned char *out);
-int  oracle_decimate_planar (OracleDecimator *d, const float *const *in, int frames, unsigned char *const *out);
-void oracle_float_integers (const unsigned char *in, double gain, int bits, int bytes, int stride, float *out, int count);
+int  oracle_decimate_interleaved (OracleDecimator *d, const osample_t *in, int frames, unsigned char *out);
+int  oracle_decimate_planar (OracleDecimator *d, const osample_t *const *in, int frames, unsigned char *const *out);
+void oracle_float_integers (const unsigned char *in, double gain, int bits, int bytes, int stride, osample_t *out, int count);
 
 /* artest.c:744-754 -- the reference's synthetic noise generator (state passed explicitly). */
-void oracle_noise (unsigned long long *state, float *dst, int count);
+void oracle_noise (unsigned long long *state, osample_t *dst, int count);
 
 /* extrapolator.c:22-65, exported for the tests */
-void oracle_extend_forward (float *x, int known, int more);
-void oracle_extend_backward (float *end, int known, int more);
+void oracle_extend_forward (osample_t *x, int known, int more);
+void oracle_extend_backward (osample_t *end, int known, int more);
 
 #ifdef __cplusplus
 }

@@ -41,21 +41,30 @@ class Result(C.Structure):
 
 f32p = C.POINTER(C.c_float)
 f32pp = C.POINTER(f32p)
+f64p = C.POINTER(C.c_double)
+f64pp = C.POINTER(f64p)
 
 
 def _ptr(a: np.ndarray):
-    return a.ctypes.data_as(f32p)
+    return a.ctypes.data_as(f64p if a.dtype == np.float64 else f32p)
+
+
+def _sample(lib):
+    """numpy dtype and ctypes pointer type of a library's samples: float32, or float64 for the PATH_WIDTH=64 builds"""
+    return (np.float64, f64p) if getattr(lib, "_wide", False) else (np.float32, f32p)
 
 
 def _build_oracle():
     subprocess.run(["make", "-s", "-C", str(ORACLE_DIR)], check=True, capture_output=True)
 
 
-def load_oracle() -> C.CDLL:
-    so = ORACLE_DIR / "liboracle.so"
+def load_oracle(wide: bool = False) -> C.CDLL:
+    so = ORACLE_DIR / ("liboracle64.so" if wide else "liboracle.so")
     if not so.exists() or so.stat().st_mtime < (ORACLE_DIR / "art_oracle.c").stat().st_mtime:
         _build_oracle()
-    lib = C.CDLL(str(so))
+    lib = C.CDLL(str(so), mode=os.RTLD_LOCAL)
+    lib._wide = wide
+    f32p, f32pp = (f64p, f64pp) if wide else (globals()["f32p"], globals()["f32pp"])
     vp = C.c_void_p
     lib.oracle_init.restype = vp
     lib.oracle_init.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
@@ -102,10 +111,28 @@ class Biquad(C.Structure):
                 ("order", C.c_int), ("index", C.c_int)]
 
 
-def bind_reference_api(lib: C.CDLL) -> C.CDLL:
+class RefResample64(C.Structure):
+    _fields_ = [(n, (f64pp if n in ("buffers", "filters") else t)) for n, t in RefResample._fields_]
+
+
+class BiquadCoefficients64(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("a0", "a1", "a2", "a3", "a4", "b1", "b2", "b3", "b4")]
+
+
+class Biquad64(C.Structure):
+    _fields_ = [("a", C.c_double * 5), ("b", C.c_double * 5), ("x", C.c_double * 4), ("y", C.c_double * 4),
+                ("order", C.c_int), ("index", C.c_int)]
+
+
+def bind_reference_api(lib: C.CDLL, wide: bool = False) -> C.CDLL:
     """Attach the prototypes of resampler.h:64-78 and biquad.h:41-47 (shared by the
-    reference build and by the product, which exports the same symbols)."""
-    ctx = C.POINTER(RefResample)
+    reference build and by the product, which exports the same symbols).  wide: the PATH_WIDTH=64 builds."""
+    lib._wide = wide
+    f32p, f32pp = (f64p, f64pp) if wide else (globals()["f32p"], globals()["f32pp"])
+    Biquad, BiquadCoefficients = (Biquad64, BiquadCoefficients64) if wide else (globals()["Biquad"], globals()["BiquadCoefficients"])
+    sample_c = C.c_double if wide else C.c_float
+    ctx = C.POINTER(RefResample64 if wide else RefResample)
+    lib._ctx_type = ctx
     lib.resampleInit.restype = ctx
     lib.resampleInit.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]
     lib.resampleFixedRatioInit.restype = ctx
@@ -144,17 +171,17 @@ def bind_reference_api(lib: C.CDLL) -> C.CDLL:
     lib.biquad_highpass.restype = None
     lib.biquad_apply_buffer.argtypes = [C.POINTER(Biquad), f32p, C.c_int, C.c_int]
     lib.biquad_apply_buffer.restype = None
-    lib.biquad_apply_sample.argtypes = [C.POINTER(Biquad), C.c_float]
-    lib.biquad_apply_sample.restype = C.c_float
+    lib.biquad_apply_sample.argtypes = [C.POINTER(Biquad), sample_c]
+    lib.biquad_apply_sample.restype = sample_c
     return lib
 
 
-def reference_path() -> Path:
-    return ORACLE_DIR / "_ref" / "libartref.so"
+def reference_path(wide: bool = False) -> Path:
+    return ORACLE_DIR / "_ref" / ("libartref64.so" if wide else "libartref.so")
 
 
-def load_reference() -> C.CDLL | None:
-    so = reference_path()
+def load_reference(wide: bool = False) -> C.CDLL | None:
+    so = reference_path(wide)
     if not so.exists():
         try:
             _build_oracle()
@@ -163,20 +190,22 @@ def load_reference() -> C.CDLL | None:
     if not so.exists():
         return None
     # RTLD_LOCAL: the product exports the same symbol names
-    return bind_reference_api(C.CDLL(str(so), mode=os.RTLD_LOCAL))
+    return bind_reference_api(C.CDLL(str(so), mode=os.RTLD_LOCAL), wide)
 
 
-def product_path() -> Path:
-    return PKG_DIR / "lib" / "libresampler_b200.so"
+def product_path(wide: bool = False) -> Path:
+    return PKG_DIR / "lib" / ("libresampler_b200_64.so" if wide else "libresampler_b200.so")
 
 
-def load_product() -> C.CDLL:
-    so = product_path()
+def load_product(wide: bool = False) -> C.CDLL:
+    so = product_path(wide)
     if not so.exists():
         raise RuntimeError(f"{so} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
-    lib = bind_reference_api(C.CDLL(str(so), mode=os.RTLD_LOCAL))
+    lib = bind_reference_api(C.CDLL(str(so), mode=os.RTLD_LOCAL), wide)
     # the extension entry points the tests use (include/resampler_b200.h)
-    ctx = C.POINTER(RefResample)
+    ctx = lib._ctx_type
+    f32p = f64p if wide else globals()["f32p"]
+    Biquad = Biquad64 if wide else globals()["Biquad"]
     lib.resampleB200SetTensorPath.restype = None
     lib.resampleB200SetTensorPath.argtypes = [C.c_int]
     lib.resampleB200AttachPrefilter.restype = C.c_int
@@ -385,18 +414,19 @@ class _ApiStream:
     def process(self, x: np.ndarray | None, n_out: int, ratio: float, *, flush_after=False, planar=False):
         """x: (frames, channels) float32, or None for an explicit flush call (numInputFrames = -1)."""
         ch = self.channels
+        dt, f32p = _sample(self.lib)
         if x is None:
             n_in = -1
         else:
-            x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, ch)
+            x = np.ascontiguousarray(x, dtype=dt).reshape(-1, ch)
             n_in = x.shape[0]
         if not planar:
-            out = np.zeros((max(n_out, 1), ch), np.float32)
+            out = np.zeros((max(n_out, 1), ch), dt)
             fn = self.lib.resampleProcessAndFlushInterleaved if flush_after else self.lib.resampleProcessInterleaved
             res = fn(self.ctx, _ptr(x) if x is not None else None, n_in, _ptr(out), n_out, ratio)
             return out[:res.output_generated].copy(), res.input_used, res.output_generated
         planes_in = np.ascontiguousarray(x.T) if x is not None else None
-        planes_out = np.zeros((ch, max(n_out, 1)), np.float32)
+        planes_out = np.zeros((ch, max(n_out, 1)), dt)
         in_arr = (f32p * ch)(*[_ptr(planes_in[c]) for c in range(ch)]) if x is not None else None
         out_arr = (f32p * ch)(*[_ptr(planes_out[c]) for c in range(ch)])
         fn = self.lib.resampleProcessAndFlush if flush_after else self.lib.resampleProcess
@@ -450,18 +480,19 @@ class _OracleStream:
 
     def process(self, x, n_out, ratio, *, flush_after=False, planar=False):
         ch = self.channels
+        dt, f32p = _sample(self.lib)
         if x is None:
             n_in = -1
         else:
-            x = np.ascontiguousarray(x, dtype=np.float32).reshape(-1, ch)
+            x = np.ascontiguousarray(x, dtype=dt).reshape(-1, ch)
             n_in = x.shape[0]
         if not planar:
-            out = np.zeros((max(n_out, 1), ch), np.float32)
+            out = np.zeros((max(n_out, 1), ch), dt)
             fn = self.lib.oracle_process_flush_interleaved if flush_after else self.lib.oracle_process_interleaved
             res = fn(self.ctx, _ptr(x) if x is not None else None, n_in, _ptr(out), n_out, ratio)
             return out[:res.output_generated].copy(), res.input_used, res.output_generated
         planes_in = np.ascontiguousarray(x.T) if x is not None else None
-        planes_out = np.zeros((ch, max(n_out, 1)), np.float32)
+        planes_out = np.zeros((ch, max(n_out, 1)), dt)
         in_arr = (f32p * ch)(*[_ptr(planes_in[c]) for c in range(ch)]) if x is not None else None
         out_arr = (f32p * ch)(*[_ptr(planes_out[c]) for c in range(ch)])
         fn = self.lib.oracle_process_flush_planar if flush_after else self.lib.oracle_process_planar
@@ -516,6 +547,30 @@ def oracle_compact_ring(o):
 def oracle_stream(*a, **k): return _OracleStream(oracle(), *a, **k)
 def reference_stream(*a, **k): return _ApiStream(reference(), *a, **k)
 def product_stream(*a, **k): return _ApiStream(product(), *a, **k)
+
+
+# the PATH_WIDTH=64 builds (double samples) of the three libraries
+def oracle64():
+    if "oracle64" not in _cache:
+        _cache["oracle64"] = load_oracle(True)
+    return _cache["oracle64"]
+
+
+def reference64():
+    if "reference64" not in _cache:
+        _cache["reference64"] = load_reference(True)
+    return _cache["reference64"]
+
+
+def product64():
+    if "product64" not in _cache:
+        _cache["product64"] = load_product(True)
+    return _cache["product64"]
+
+
+def oracle_stream64(*a, **k): return _OracleStream(oracle64(), *a, **k)
+def reference_stream64(*a, **k): return _ApiStream(reference64(), *a, **k)
+def product_stream64(*a, **k): return _ApiStream(product64(), *a, **k)
 
 
 def artest_noise(count: int, state: int = 0x3141592653589793):

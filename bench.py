@@ -630,6 +630,10 @@ def measure_configs(lib, pkg, torch, dist, world, rank, dev, stream, peak, args)
         (f"cfg3 with the pre-filter as separate biquad_apply_cascade_interleaved_device calls (the reference's call pattern)",
          Workload("cfg3sep", ch3, 4, 96000, 44100, 1, 1 << 19, lowpass_hz=20000, biquad=True), 4),
         (f"cfg3 without the biquad pre-filter", Workload("cfg3nb", ch3, 4, 96000, 44100, 1, 1 << 19, lowpass_hz=20000), 6),
+        (f"cfg3 via resampleFixedRatioInit (art.c:827: 147 filters, no interpolation, automatic lowpass)",
+         Workload("cfg3f", ch3, 4, 96000, 44100, 1, 1 << 19, fixed=True), 3),
+        (f"cfg3 via resampleFixedRatioInit, tensor-core kernel by opt-in (resampleB200SetTensorPath(3))",
+         Workload("cfg3ft", ch3, 4, 96000, 44100, 1, 1 << 19, fixed=True, tensor_mode=3), 6),
         (f"cfg4 {n4} of 1024 stereo contexts per GPU, preset -3 48->44.1k lowpass 20 kHz, 2^15-frame blocks",
          Workload("cfg4s", 2, 3, 48000, 44100, n4, 1 << 15, lowpass_hz=20000), 6),
         (f"cfg4 {n4} of 1024 stereo contexts per GPU, 2^18-frame blocks",
@@ -700,7 +704,7 @@ def measure_e2e(lib, pkg, torch, dist, world, dev, streams, frames, args):
 
     # -- reference-facing API: long-lived host threads, each owning every T-th stream --------------------------------
     ctxs = fresh()
-    T = max(1, min(args.e2e_threads, n))
+    T = max(1, min(args.e2e_threads or min(16, max(4, host_cores() // max(world, 1))), n))
     start, done = threading.Barrier(T + 1), threading.Barrier(T + 1)
     made_by = [0] * T
     rounds = {"n": 0}
@@ -795,7 +799,7 @@ def main():
                     help="input frames per stream per block (= per launch): 23.8 s of audio; 74 streams x 112 tiles = 56 tiles per SM")
     ap.add_argument("--launches-per-step", type=int, default=56, help="blocks every stream advances by in one step (~0.9 ms each)")
     ap.add_argument("--e2e-streams", type=int, default=64)
-    ap.add_argument("--e2e-threads", type=int, default=8)
+    ap.add_argument("--e2e-threads", type=int, default=0, help="host threads per rank in the end-to-end leg; 0 = the CPUs this rank may use, between 4 and 16")
     ap.add_argument("--e2e-frames", type=int, default=1 << 18, help="input frames per host call in the end-to-end leg")
     ap.add_argument("--e2e-steps", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")

@@ -8,7 +8,7 @@ ncu --set full --clock-control none --import-source on -k regex:art_sinc_umma_ke
     python bench.py --steps 1 --warmup 1 --launches-per-step 4 --no-configs --no-cpu --no-e2e > gpurun_out/ncu_umma.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:art_sinc_generic -s 3 -c 1 -o gpurun_out/r02_generic_final \
     python profiles/asrc_one.py > gpurun_out/ncu_generic.log 2>&1
-ncu --set full --clock-control none -k regex:biquad -s 8 -c 8 -o gpurun_out/r02_biquad \
+ncu --set full --clock-control none -k regex:bq_ -s 8 -c 8 -o gpurun_out/r02_biquad \
     python profiles/biquad_one.py > gpurun_out/ncu_biquad.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches.csv \
     python bench.py --steps 2 --warmup 1 --launches-per-step 8 --no-configs --no-cpu --no-e2e > gpurun_out/bench_under_ncu.log 2>&1

@@ -121,8 +121,15 @@ __global__ void bq_zero_state_kernel (BqGeom g, const ArtBiquadStage *st, const 
     const long long f0 = (long long) k * g.chunk;
     const int len = k == g.numChunks - 1 ? g.lastLen : g.chunk;
     const artsample_t *p = buf + f0 * g.stride + c;
-    for (int i = 0; i < len; ++i)
-        f.step ((double) __ldg (p + (long long) i * g.stride));
+    // the recurrence is one dependent chain per thread: fetch 16 samples at a time so that a load's latency is paid once
+    // per batch, not once per step (the un-batched loop ran at 0.7 TB/s)
+    for (int i0 = 0; i0 < len; i0 += 16) {
+        artsample_t v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = i0 + r < len ? __ldg (p + (long long) (i0 + r) * g.stride) : (artsample_t) 0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) if (i0 + r < len) f.step ((double) v[r]);
+    }
     f.storeState (ZS + ((long long) c * g.numChunks + k) * NST);
 }
 
@@ -152,36 +159,84 @@ __global__ void bq_transition_kernel (BqGeom g, const ArtBiquadStage *st, double
     }
 }
 
-/* one warp per channel; lane r owns component r of the state */
+/* One block per channel.  The start state of chunk k+1 is M z_k + zs_k (M: the chunk's transition, zs_k: its zero-state
+ * response) -- a serial chain over the chunks, which a single warp walked in 0.35 us per chunk (the longest of the four
+ * kernels).  Two levels instead: warp w takes a group of G consecutive chunks; (1) every warp runs its group from a zero start
+ * state, (2) warp 0 chains the groups with M^G, (3) every warp re-runs its group from its true start and writes the chunk start
+ * states.  Serial depth G + groups + G instead of numChunks.  Lane r owns component r of the state. */
 template <int S, int ORD>
-__global__ void bq_propagate_kernel (BqGeom g, const ArtBiquadStage *st, const double *ZS, const double *M, double *Zstart)
+__global__ void __launch_bounds__ (512)
+bq_propagate_kernel (BqGeom g, const ArtBiquadStage *st, const double *ZS, const double *M, double *Zstart)
 {
     constexpr int NST = 2 * S * ORD;
-    const int c = blockIdx.x * (blockDim.x / 32) + (threadIdx.x / 32), lane = threadIdx.x & 31;
-    if (c >= g.channels) return;
+    __shared__ double shM[NST * NST], shP[NST * NST], shY[16][NST], shZ[16][NST];
+    const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
     const int r = lane < NST ? lane : NST - 1;
-    // start state of the whole call: the caller's Biquad structs
-    double z;
-    {
-        const int s = r / (2 * ORD), rem = r - s * 2 * ORD;
-        const ArtBiquadStage &q = st[s * g.channels + c];
-        z = rem < ORD ? (double) q.x[rem] : (double) q.y[rem - ORD];
+    const int G = (g.numChunks + warps - 1) / warps;                        // chunks per group
+    const int groups = (g.numChunks + G - 1) / G;
+    const double *Mc = M + (long long) c * 2 * NST * NST;                   // [0]: a full chunk's transition
+    for (int i = threadIdx.x; i < NST * NST; i += blockDim.x) shM[i] = Mc[i];
+    double row[NST];
+#pragma unroll
+    for (int j = 0; j < NST; ++j) row[j] = Mc[r * NST + j];
+    __syncthreads ();
+    const int k0 = warp * G, k1 = min (k0 + G, g.numChunks);
+    const double *zs = ZS + (long long) c * g.numChunks * NST;
+    auto advance = [&] (double z, int k) -> double {                        // M z + zs_k, component r
+        double acc = zs[(long long) k * NST + r];
+#pragma unroll
+        for (int j = 0; j < NST; ++j) acc += row[j] * __shfl_sync (0xffffffffu, z, j);
+        return acc;
+    };
+    if (warp < groups) {
+        double z = 0.0;
+        for (int k = k0; k < k1; ++k) z = advance (z, k);
+        if (lane < NST) shY[warp][lane] = z;
     }
-    const double *Mc = M + (long long) c * 2 * NST * NST;
-    double rowFull[NST], rowLast[NST];
+    __syncthreads ();
+    if (warp == 0) {
+        // row r of M^G by G - 1 multiplications with M (G <= a few dozen, NST <= 32); the power lives in shared memory
+        if (lane < NST)
 #pragma unroll
-    for (int j = 0; j < NST; ++j) { rowFull[j] = Mc[r * NST + j]; rowLast[j] = Mc[(NST + r) * NST + j]; }
-    for (int k = 0; k < g.numChunks; ++k) {
-        const long long at = ((long long) c * g.numChunks + k) * NST;
-        if (lane < NST) Zstart[at + r] = z;
-        double acc = ZS[at + r];
-        const bool last = k == g.numChunks - 1;
+            for (int j = 0; j < NST; ++j) shP[lane * NST + j] = row[j];
+        __syncwarp ();
+        for (int t = 1; t < G; ++t) {
+            double nx[NST];
 #pragma unroll
-        for (int j = 0; j < NST; ++j) {
-            const double zj = __shfl_sync (0xffffffffu, z, j);
-            acc += (last ? rowLast[j] : rowFull[j]) * zj;
+            for (int j = 0; j < NST; ++j) {
+                double a = 0.0;
+#pragma unroll
+                for (int i = 0; i < NST; ++i) a += shP[r * NST + i] * shM[i * NST + j];
+                nx[j] = a;
+            }
+            __syncwarp ();
+            if (lane < NST)
+#pragma unroll
+                for (int j = 0; j < NST; ++j) shP[lane * NST + j] = nx[j];
+            __syncwarp ();
         }
-        z = acc;
+        // start state of the whole call: the caller's Biquad structs
+        double z;
+        {
+            const int s = r / (2 * ORD), rem = r - s * 2 * ORD;
+            const ArtBiquadStage &q = st[s * g.channels + c];
+            z = rem < ORD ? (double) q.x[rem] : (double) q.y[rem - ORD];
+        }
+        for (int w = 0; w < groups; ++w) {
+            if (lane < NST) shZ[w][lane] = z;
+            double acc = shY[w][r];
+#pragma unroll
+            for (int j = 0; j < NST; ++j) acc += shP[r * NST + j] * __shfl_sync (0xffffffffu, z, j);
+            z = acc;
+        }
+    }
+    __syncthreads ();
+    if (warp < groups) {
+        double z = shZ[warp][r];
+        for (int k = k0; k < k1; ++k) {
+            if (lane < NST) Zstart[((long long) c * g.numChunks + k) * NST + r] = z;
+            z = advance (z, k);
+        }
     }
 }
 
@@ -212,9 +267,14 @@ __global__ void bq_output_kernel (BqGeom g, const ArtBiquadStage *st, ArtBiquadS
     const long long f0 = (long long) k * g.chunk;
     const int len = k == g.numChunks - 1 ? g.lastLen : g.chunk;
     artsample_t *p = buf + f0 * g.stride + c;
-    for (int i = 0; i < len; ++i) {
-        artsample_t *q = p + (long long) i * g.stride;
-        *q = f.step (*q);
+    for (int i0 = 0; i0 < len; i0 += 16) {
+        artsample_t v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = i0 + r < len ? p[(long long) (i0 + r) * g.stride] : (artsample_t) 0;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) if (i0 + r < len) v[r] = f.step (v[r]);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) if (i0 + r < len) p[(long long) (i0 + r) * g.stride] = v[r];
     }
     if (k == g.numChunks - 1) {
         // leave the state the reference would leave: the four newest inputs/outputs of every
@@ -245,7 +305,7 @@ void run_cascade (const BqGeom &g, const ArtBiquadStage *d_st, ArtBiquadStage *d
     const unsigned int gridCK = (unsigned int) ((work + tx - 1) / tx);
     bq_zero_state_kernel<S, ORD><<<gridCK, tx, 0, stream>>> (g, d_st, d_buf, ZS);
     bq_transition_kernel<S, ORD><<<(g.channels * NST + 63) / 64, 64, 0, stream>>> (g, d_st, M);
-    bq_propagate_kernel<S, ORD><<<(g.channels + 3) / 4, 128, 0, stream>>> (g, d_st, ZS, M, Zstart);
+    bq_propagate_kernel<S, ORD><<<g.channels, g.numChunks >= 128 ? 512 : 128, 0, stream>>> (g, d_st, ZS, M, Zstart);
     bq_output_kernel<S, ORD><<<gridCK, tx, 0, stream>>> (g, d_st, d_stOut, d_buf, Zstart);
     ART_CUDA_CHECK (cudaGetLastError ());
     g_artLaunches += 4;

@@ -382,11 +382,11 @@ __global__ void __launch_bounds__ (ART_U_THREADS, 1)
 art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const __grid_constant__ ArtJob single,
                       const ArtJob *__restrict__ jobs, int totalTiles, int profArg)
 {
+#ifdef ART_B200_ABLATE              /* measurement builds only: role counters (ART_B200_UPROF) and bits that SKIP work (wrong results by construction) */
     const int prof = profArg & 1;
-#ifdef ART_B200_ABLATE              /* measurement builds only: bits that SKIP work (wrong results by construction) */
     const int dbg = (profArg >> 4) & 255;
 #else
-    constexpr int dbg = 0;
+    constexpr int prof = 0, dbg = 0;
 #endif
     extern __shared__ __align__ (1024) unsigned char smem[];
 
@@ -656,17 +656,21 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             if (m > 0.0f) { (void) frexpf (m, &e); e -= ART_U_DX; e = e < -114 ? -114 : (e > 116 ? 116 : e); }      // m < 2^(e + 11): every finite float fits
             return e;
         };
-        auto rowOk = [&] (int uu) -> bool { return r0 + 32 * uu < periods; };
+        unsigned int okMask = 0;
+#pragma unroll
+        for (int uu = 0; uu < UN; ++uu) okMask |= (r0 + 32 * uu < periods ? 1u : 0u) << uu;
+        auto rowOk = [&] (int uu) -> bool { return (okMask >> uu) & 1u; };
         // request this lane's samples of plane pair i of the tile `sc` describes into ring slot `slot`
         auto request = [&] (const Src &sc, int i, unsigned int slot) {
             const unsigned int sb = stg + slot * slotBytes;
             if (dbg & 1) return;
             if (sc.fast) {
-                const long long at = (long long) (off0 + 16 * i) * sc.fs, rowStep = (long long) (32 * M) * sc.fs;
+                // tile-relative element offsets fit 32 bits (a tile spans ~10^4 frames)
+                const int fs = (int) sc.fs, at = (off0 + 16 * i) * fs, rowStep = 32 * M * fs;
 #pragma unroll
                 for (int uu = 0; uu < UN; ++uu) {
                     if (!rowOk (uu)) continue;
-                    const long long o = at + uu * rowStep;
+                    const int o = at + uu * rowStep;
                     if (CGT > 1 && sc.vec) {
                         u_cp_async (sb + (unsigned int) (2 * uu) * planeStride, sc.pc[0] + o, 4 * CGT, true);
                         u_cp_async (sb + (unsigned int) (2 * uu + 1) * planeStride, sc.pc[0] + o + sc.fs, 4 * CGT, true);
@@ -713,6 +717,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
         };
         for (int d = 0; d + 1 < depth; ++d) requestNext ();
         unsigned int cslot = 0;
+        unsigned int useBase = 0;                                           // uses of operand slot 0 before this tile
 
         for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++lt) {
             long long q0t = UCLK ();
@@ -723,6 +728,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                                      neg2 = art_pack2 (-1.0f, -1.0f), k2048 = art_pack2 (2048.0f, 2048.0f);
             if (ctid == 0)
                 u_stsf (sScaleA (lt & 3), __int_as_float ((127 + e) << 23) * __int_as_float ((127 - u.DH) << 23));
+            unsigned int sl = 0, use = useBase;                           // operand slot of pair i = i % NS, and how often it was used before
             for (int i = 0; i < KI; ++i) {
                 long long h0t = UCLK ();
                 requestNext ();
@@ -752,7 +758,6 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                 }
                 long long c0t = UCLK ();
                 if (ctid == 0) UPROF_ADD (18, c0t - h0t);
-                const unsigned int sl = (unsigned int) i % (unsigned int) NS, use = lt * rep + (unsigned int) i / (unsigned int) NS;
                 u_mbar_wait_relaxed (pEmptyA (sl), (use & 1) ^ 1);
                 long long cb = UCLK ();
                 if (ctid == 0) UPROF_ADD (5, cb - c0t);
@@ -800,7 +805,9 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                 __syncwarp ();
                 if (lane == 0) u_mbar_arrive (pFullA (sl));                          // one arrival per warp: 256 serialised arrivals cost ~500 cycles
                 if (ctid == 0) { UPROF_ADD (7, cc_ - cb); UPROF_ADD (14, cd - cc_); UPROF_ADD (15, UCLK () - cd); }
+                if (++sl == (unsigned int) NS) { sl = 0; ++use; }
             }
+            useBase += rep;
         }
         asm volatile ("cp.async.wait_all;" ::: "memory");
         UPROF_FLUSH ();
@@ -1116,8 +1123,9 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
     const int grid = totalTiles < smCount ? totalTiles : smCount;
     static int roleProf = -1;
     if (roleProf < 0) {
-        roleProf = getenv ("ART_B200_UPROF") ? 1 : 0;
+        roleProf = 0;
 #ifdef ART_B200_ABLATE
+        roleProf = getenv ("ART_B200_UPROF") ? 1 : 0;
         if (const char *d = getenv ("ART_B200_UDBG")) roleProf |= atoi (d) << 4;
 #endif
         if (roleProf & 1) atexit ([] () {

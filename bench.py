@@ -557,10 +557,11 @@ def run_gpu_arm(args):
         prof = ROOT / "profiles" / cand
         if prof.exists():
             try:
-                roofline["traffic"] = json.loads(prof.read_text()).get("dram_bytes_per_launch")
-                roofline["traffic_source"] = (f"profiles/{prof.name} (ncu --set full of this kernel on 64 streams x 2^18 frames, scaled by "
-                                              "the launch's algorithmic bytes)")
-                roofline["traffic"] = roofline["traffic"] * (per_launch_samples * bpos) / (64 * 285344 * 2 * bpos)
+                digest = json.loads(prof.read_text())
+                captured = float(digest.get("launch_output_samples", 64 * 285344 * 2))      # geometry of the captured launch
+                roofline["traffic"] = digest.get("dram_bytes_per_launch") * per_launch_samples / captured
+                roofline["traffic_source"] = (f"profiles/{prof.name} (ncu --set full of this kernel on a launch of {captured / 1e6:.1f} M output "
+                                              "samples, scaled to this launch by its algorithmic bytes)")
                 break
             except Exception:
                 pass

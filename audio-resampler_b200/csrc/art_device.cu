@@ -800,7 +800,12 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
                 ART_CUDA_CHECK (cudaMallocAsync (&tables, bytes, stream));
             if (lp.umma) {
                 artUmmaCarve (lp.um, tables, numTables, n);
-                artLaunchUmma (lp.k, lp.um, ctas, n, numTables, lp.smCount, jobs[0], d_jobs, stream);
+                // whole-frame copies in the converters need every job's block interleaved with the tile's channels adjacent and aligned
+                bool vecIn = lp.um.cg > 1;
+                for (const ArtJob &j : jobs)
+                    vecIn = vecIn && j.inPlanes == nullptr && j.inCS == 1 && (j.inFS % lp.um.cg) == 0 &&
+                            (reinterpret_cast<uintptr_t> (j.in) % (sizeof (float) * lp.um.cg)) == 0;
+                artLaunchUmma (lp.k, lp.um, ctas, n, numTables, lp.smCount, jobs[0], d_jobs, vecIn, stream);
             }
             else {
                 lp.per.Hblk = reinterpret_cast<float *> (tables);

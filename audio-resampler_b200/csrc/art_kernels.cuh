@@ -193,7 +193,7 @@ int  artUmmaTiles (const ArtUmma &u, int channels, unsigned int outputs);
 size_t artUmmaTableBytes (const ArtUmma &u, int numTables, int numJobs, int totalTiles);
 void artUmmaCarve (ArtUmma &u, void *tables, int numTables, int numJobs);
 void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int numJobs, int numTables, int smCount,
-                    const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream);
+                    const ArtJob &single, const ArtJob *d_jobs, bool vecIn, cudaStream_t stream);
 
 extern std::atomic<unsigned long long> g_artLaunches;
 extern int g_artTensorMode;

@@ -377,7 +377,7 @@ art_umma_prep_kernel (const ArtClass k, const ArtUmma u, const __grid_constant__
  * fastest: physical row CGT * r + cc of the signal operand is period r of channel c0 + cc, and the row shift a of a k-step is
  * +16 * CGT * a bytes on the descriptor.  The converters then read all CGT channels of a frame with ONE vector load (an
  * interleaved stereo block wastes no half sectors), and the epilogue's stores cover whole frames. */
-template <int CGT>
+template <int CGT, bool VEC>
 __global__ void __launch_bounds__ (ART_U_THREADS, 1)
 art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const __grid_constant__ ArtJob single,
                       const ArtJob *__restrict__ jobs, int totalTiles, int profArg)
@@ -671,7 +671,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                 for (int uu = 0; uu < UN; ++uu) {
                     if (!rowOk (uu)) continue;
                     const int o = at + uu * rowStep;
-                    if (CGT > 1 && sc.vec) {
+                    if (VEC) {                                              // (host-checked for every job of the launch)
                         u_cp_async (sb + (unsigned int) (2 * uu) * planeStride, sc.pc[0] + o, 4 * CGT, true);
                         u_cp_async (sb + (unsigned int) (2 * uu + 1) * planeStride, sc.pc[0] + o + sc.fs, 4 * CGT, true);
                     }
@@ -1078,11 +1078,11 @@ void artUmmaCarve (ArtUmma &u, void *tables, int numTables, int numJobs)
     u.tileJob = reinterpret_cast<int *> (p);
 }
 
-template <int CGT>
+template <int CGT, bool VEC>
 static void umma_launch_one (const ArtClass &k, const ArtUmma &u, int totalTiles, int grid, const ArtJob &single, const ArtJob *d_jobs,
                              int roleProf, cudaStream_t stream)
 {
-    static bool configured[16] = { false };
+    static bool configured[16] = { false };                 // per instantiation and device
     int device = 0;
     ART_CUDA_CHECK (cudaGetDevice (&device));
     if (!configured[device & 15]) {
@@ -1090,21 +1090,21 @@ static void umma_launch_one (const ArtClass &k, const ArtUmma &u, int totalTiles
         // the pool that comes from is threads x registers-per-thread as compiled, so check that it suffices -- a warpgroup
         // asking for registers that never become free would spin forever
         cudaFuncAttributes fa;
-        ART_CUDA_CHECK (cudaFuncGetAttributes (&fa, art_sinc_umma_kernel<CGT>));
+        ART_CUDA_CHECK (cudaFuncGetAttributes (&fa, art_sinc_umma_kernel<CGT, VEC>));
         if (128 * (fa.numRegs - 56) + 256 * (fa.numRegs - 88) < 256 * (120 - fa.numRegs) || fa.numRegs < 88 || fa.numRegs > 120)
             artRaise ("art_sinc_umma_kernel was compiled with %d registers per thread: its register re-allocation plan does not hold", fa.numRegs);
-        ART_CUDA_CHECK (cudaFuncSetAttribute (art_sinc_umma_kernel<CGT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ART_U_SMEM_MAX));
+        ART_CUDA_CHECK (cudaFuncSetAttribute (art_sinc_umma_kernel<CGT, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, ART_U_SMEM_MAX));
         configured[device & 15] = true;
     }
     void *prof;
     artProfileBegin (stream, &prof);
-    art_sinc_umma_kernel<CGT><<<grid, ART_U_THREADS, umma_smem (u), stream>>> (k, u, single, d_jobs, totalTiles, roleProf);
+    art_sinc_umma_kernel<CGT, VEC><<<grid, ART_U_THREADS, umma_smem (u), stream>>> (k, u, single, d_jobs, totalTiles, roleProf);
     artProfileEnd (stream, prof);
     ART_CUDA_CHECK (cudaGetLastError ());
 }
 
 void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int numJobs, int numTables, int smCount,
-                    const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream)
+                    const ArtJob &single, const ArtJob *d_jobs, bool vecIn, cudaStream_t stream)
 {
     if (totalTiles <= 0) return;
     int histBlocks = (k.C * k.T + 127) / 128;
@@ -1152,9 +1152,13 @@ void artLaunchUmma (const ArtClass &k, const ArtUmma &u, int totalTiles, int num
                      h[6] / n, h[16] / n, h[7] / n, h[14] / n, h[15] / n, h[17] / n, h[18] / n);
         });
     }
-    if (u.cg == 4)      umma_launch_one<4> (k, uu, totalTiles, grid, single, d_jobs, roleProf, stream);
-    else if (u.cg == 2) umma_launch_one<2> (k, uu, totalTiles, grid, single, d_jobs, roleProf, stream);
-    else                umma_launch_one<1> (k, uu, totalTiles, grid, single, d_jobs, roleProf, stream);
+    // vecIn: every job reads an interleaved block whose frames hold the tile's channels adjacent and aligned, so the converters
+    // copy whole frames (one 8- or 16-byte cp.async per tap); a compile-time property of the kernel, not a per-lane branch
+    if (u.cg == 4)      { if (vecIn) umma_launch_one<4, true> (k, uu, totalTiles, grid, single, d_jobs, roleProf, stream);
+                          else       umma_launch_one<4, false> (k, uu, totalTiles, grid, single, d_jobs, roleProf, stream); }
+    else if (u.cg == 2) { if (vecIn) umma_launch_one<2, true> (k, uu, totalTiles, grid, single, d_jobs, roleProf, stream);
+                          else       umma_launch_one<2, false> (k, uu, totalTiles, grid, single, d_jobs, roleProf, stream); }
+    else                umma_launch_one<1, false> (k, uu, totalTiles, grid, single, d_jobs, roleProf, stream);
     g_artLaunches += 2;
 }
 
@@ -1165,6 +1169,6 @@ bool artPlanUmma (const ArtClass &, double, unsigned int, unsigned long long, in
 int artUmmaTiles (const ArtUmma &, int, unsigned int) { return 0; }
 size_t artUmmaTableBytes (const ArtUmma &, int, int, int) { return 0; }
 void artUmmaCarve (ArtUmma &, void *, int, int) { }
-void artLaunchUmma (const ArtClass &, const ArtUmma &, int, int, int, int, const ArtJob &, const ArtJob *, cudaStream_t) { }
+void artLaunchUmma (const ArtClass &, const ArtUmma &, int, int, int, int, const ArtJob &, const ArtJob *, bool, cudaStream_t) { }
 
 #endif

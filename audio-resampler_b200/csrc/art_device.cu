@@ -682,7 +682,7 @@ static void dispatch (ArtLaunchPlan &lp, std::vector<ArtJob> &jobs, int ctas, cu
     std::vector<ArtXpose> xin, xout;
     long long maxInFrames = 0, maxOutFrames = 0;
     const int C = lp.k.C;
-    if (lp.umma && ctas > 0 && C >= 8) {
+    if (lp.umma && ctas > 0 && C >= 8 && lp.um.cg < 4) {            // (four channels per tile read 16-byte slices of the frames directly)
         bool ok = true;
         for (const ArtJob &j : jobs)
             ok &= j.inPlanes == nullptr && j.outPlanes == nullptr && j.inCS == 1 && j.inFS == C && j.outCS == 1 && j.outFS == C && j.prevAvail == 0;

@@ -227,6 +227,24 @@ __device__ __forceinline__ float u_scan_tile (const ArtJob &job, int CGT, int c0
         const long long fs = job.inFS;
         if (!job.inPlanes && job.inCS == 1 && fs == CGT)                    // the frames hold exactly the tile's channels
             span (job.in + c0 + a * fs, (b - a) * fs);
+        else if (!job.inPlanes && job.inCS == 1 && CGT > 1 && (fs % CGT) == 0 &&
+                 (reinterpret_cast<unsigned long long> (job.in + c0) & (4u * CGT - 1u)) == 0) {
+            // an interleaved block of more channels than the tile takes: one vector per frame, eight frames in flight per lane
+            const float *base = job.in + c0 + a * fs;
+            const long long n = b - a;
+            for (long long i0 = wi * 32 + lane; i0 < n; i0 += 8LL * stride) {
+                float4 v[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const long long i = i0 + (long long) r * stride;
+                    if (i >= n) v[r] = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+                    else if (CGT == 4) v[r] = __ldg (reinterpret_cast<const float4 *> (base + i * fs));
+                    else { const float2 t = __ldg (reinterpret_cast<const float2 *> (base + i * fs)); v[r] = make_float4 (t.x, t.y, 0.0f, 0.0f); }
+                }
+#pragma unroll
+                for (int r = 0; r < 8; ++r) { U_TAKE (v[r].x); U_TAKE (v[r].y); U_TAKE (v[r].z); U_TAKE (v[r].w); }
+            }
+        }
         else
             for (int cc = 0; cc < CGT; ++cc) {
                 const float *base = (job.inPlanes ? job.inPlanes[c0 + cc] : job.in + (long long) (c0 + cc) * job.inCS) + a * fs;
@@ -766,7 +784,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                                          (unsigned int) (CGT * r0) * 16u;
 #pragma unroll
                 for (int uu = 0; uu < UN; ++uu) {
-                    if (rowOk (uu)) {
+                    if (rowOk (uu) && !(dbg & 128)) {
 #pragma unroll
                         for (int cc = 0; cc < CGT; ++cc) {
                             // both taps at once in packed fp32 (fma.rn.f32x2): u = x / q;  X = rint (u) by the 1.5 * 2^23 trick (|u| <= 2^11);
@@ -800,7 +818,8 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                     }
                 }
                 long long cc_ = UCLK ();
-                asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> tensor-core reads
+                if (!(dbg & 64))
+                    asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core reads
                 long long cd = UCLK ();
                 __syncwarp ();
                 if (lane == 0) u_mbar_arrive (pFullA (sl));                          // one arrival per warp: 256 serialised arrivals cost ~500 cycles
@@ -1010,9 +1029,10 @@ bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsi
     u.tableHalfs = u.numK * 3 * 2 * u.Npad * 8;
 
     // channels per tile: the 128 MMA rows are 128 / cg periods x cg channels (channel fastest), so that the converters read
-    // whole frames of an interleaved block and the epilogue stores whole frames; more channels go through planar scratch
-    // (art_device.cu) one channel per tile.  Fewer when the row shifts no longer fit the operand.
-    for (int cg = (k.C == 4 ? 4 : ((k.C == 2 || k.C == 6) ? 2 : 1)); cg >= 1; cg >>= 1) {
+    // whole frames (or 16-byte slices of the frames of a many-channel block) and the epilogue stores them; channel counts
+    // that are not a multiple of 4 go through planar scratch from 8 channels on (art_device.cu).  Fewer channels per tile when
+    // the row shifts no longer fit the operand.
+    for (int cg = (k.C % 4 == 0 ? 4 : (k.C % 2 == 0 ? 2 : 1)); cg >= 1; cg >>= 1) {
         u.cg = cg;
         u.periods = ART_U_ROWS / cg + aMax;
         // rows: cg * periods, padded so that the 16-byte row slots a warp of converters writes into the two planes of a pair
@@ -1021,7 +1041,7 @@ bool artPlanUmma (const ArtClass &k, double ratio, unsigned int maxOutputs, unsi
         if (cg == 1) while ((rows & 1) || (rows & 7) < 2 || (rows & 7) > 6) ++rows;
         else if (cg == 2) while (!(rows & 1)) ++rows;
         else while ((rows & 7) == 0 || (rows & 7) == 4) ++rows;
-        if (rows > 144) continue;
+        if (rows > 152) continue;
         u.rows = rows;
         // Shared memory is shared out between operand A (a ring of NS | KI plane-pair slots -- pairs are used in order, each
         // for all of its row shifts in a row, so a slot can take pair i + NS as soon as the MMAs of pair i are done), the

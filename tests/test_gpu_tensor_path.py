@@ -49,6 +49,8 @@ def _check_call(g, o, x, cap, ratio, tol=TOL, **kw):
     (4, 3, 96000, 48000, 0),            # 1/2: 160 periods per row, M = 320
     (2, 3, 44100, 96000, 0),            # 320/147: two phase groups of 160
     (1, 2, 8000, 44100, 0),             # 441/80: three phase groups of 147
+    (12, 2, 44100, 48000, 0),           # many channels, a multiple of 4: tiles of four channels read 16-byte slices of the interleaved frames
+    (10, 2, 96000, 44100, 0),           # many channels, not a multiple of 4: through planar scratch (art_device.cu)
 ])
 def test_configs_on_the_tensor_path(forced_tensor_path, ch, preset, src, dst, lowpass_hz):
     lib = forced_tensor_path

@@ -260,7 +260,7 @@ def run_reference_arm(args):
     samples, secs, calls = 0, 0.0, 0
     kind = "reference"
     for _ in range(args.steps):
-        s, dt, kind, calls = cpu_run(w, cores, seconds=1.2)
+        s, dt, kind, calls = cpu_run(w, cores, seconds=2.5)       # long enough that the slowest thread's tail at the closing barrier is ~1 %
         samples += s; secs += dt
     value = samples / secs / 1e6
     line = {

@@ -390,8 +390,11 @@ __device__ __forceinline__ void art_run_any (const ArtTileCtx &t, const ArtJob &
 #define ART_SKEW(p) (p)
 #endif
 
-template <bool INTERP, bool PRECISE, int CV>
-__global__ void __launch_bounds__ (ART_G_THREADS, 2)
+/* UNITY: the near-unity form (art_run_unity) as a kernel of its own: it needs ~85 registers where the row-sorted form takes
+ * 128, so -- for one or two channels per vector; four need the registers -- three CTAs fit an SM instead of two and the serial
+ * phases of a tile (positions, staging, the mini-run scan) of one CTA overlap the multiply-adds of the others */
+template <bool INTERP, bool PRECISE, int CV, bool UNITY>
+__global__ void __launch_bounds__ (ART_G_THREADS, (UNITY && CV <= 2) ? 3 : 2)
 art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single, const ArtJob *__restrict__ jobs)
 {
     extern __shared__ __align__ (16) unsigned char smem_raw[];
@@ -484,7 +487,7 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
     __syncthreads ();
 
     const long long sFirst = sh_first;
-    const bool unity = !ART_WIDE && INTERP && !PRECISE && k.unity;    // consecutive-output chunks instead of row-sorted runs (see art_run_unity)
+    constexpr bool unity = !ART_WIDE && INTERP && !PRECISE && UNITY;  // consecutive-output chunks instead of row-sorted runs (see art_run_unity)
     // samples of window the tile touches (the unity form reads up to 3 + 32 positions past a chunk's last window: zero taps, but staged)
     const int span = (int) (sh_last - sFirst) + k.Tp + (unity ? 40 : 0);
     if ((unity ? ART_SKEW (span) + 1 : span) > k.Wp) {
@@ -541,7 +544,7 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
     /* ---- 2u. near-unity ratios: cut the tile into mini-runs of <= 4 consecutive outputs with one row pair and consecutive
      *          windows, in natural order (no sort) -------------------------------------------------------------------------- */
 #if !ART_WIDE
-    if (unity) {
+    if constexpr (unity) {
         const int per = (cnt + ART_G_THREADS - 1) / ART_G_THREADS;
         const int i0 = min (tid * per, cnt), i1 = min (i0 + per, cnt);
         auto boundary = [&] (int i) -> bool { return i == 0 || key[i] != key[i - 1] || srel[i] != srel[i - 1] + 1; };
@@ -711,7 +714,7 @@ static int unity_plane (int Wp)
 
 void artPlanGenericGeometry (ArtClass &k, double minRatio, unsigned int maxOutputs, int smCount, ArtLaunchGeom &g)
 {
-    const size_t budget = 110 * 1024;        // two CTAs per SM inside the 227 KB carve-out
+    const size_t budget = (k.unity && k.C < 4 ? 74 : 110) * 1024;     // two CTAs per SM inside the 227 KB carve-out (three of the near-unity kernel at CV <= 2)
     const int C = k.C;
     int cv = C >= 4 ? 4 : (C >= 2 ? 2 : 1);
     if ((k.mode & ART_MODE_PRECISE) || ART_WIDE) cv = C >= 2 ? 2 : 1;
@@ -751,10 +754,10 @@ void artPlanGenericGeometry (ArtClass &k, double minRatio, unsigned int maxOutpu
     g.smemBytes = generic_smem (k);
 }
 
-template <bool INTERP, bool PRECISE, int CV>
+template <bool INTERP, bool PRECISE, int CV, bool UNITY = false>
 static void launch_one (const ArtClass &k, const ArtLaunchGeom &g, const ArtJob &single, const ArtJob *d_jobs, cudaStream_t stream)
 {
-    auto kern = art_sinc_generic_kernel<INTERP, PRECISE, CV>;
+    auto kern = art_sinc_generic_kernel<INTERP, PRECISE, CV, UNITY>;
     static size_t configured[16] = { 0 };      // per device: the opt-in is per (function, context)
     int device = 0;
     ART_CUDA_CHECK (cudaGetDevice (&device));
@@ -779,7 +782,8 @@ void artLaunchGeneric (const ArtClass &k, const ArtLaunchGeom &g, const ArtJob &
     const bool interp = k.mode & ART_MODE_INTERP, precise = k.mode & ART_MODE_PRECISE;
 #define ART_DISPATCH(CVV)                                                                 \
     do {                                                                                  \
-        if (interp && !precise)       launch_one<true, false, CVV> (k, g, single, d_jobs, stream); \
+        if (interp && !precise && k.unity) launch_one<true, false, CVV, true> (k, g, single, d_jobs, stream); \
+        else if (interp && !precise)  launch_one<true, false, CVV> (k, g, single, d_jobs, stream); \
         else if (!interp && !precise) launch_one<false, false, CVV> (k, g, single, d_jobs, stream); \
         else if (interp)              launch_one<true, true, CVV> (k, g, single, d_jobs, stream);  \
         else                          launch_one<false, true, CVV> (k, g, single, d_jobs, stream); \

@@ -171,6 +171,27 @@ __device__ __forceinline__ artsample_t *art_out_ptr (const ArtJob &j, int c, lon
     return j.outPlanes ? j.outPlanes[c] + frame * j.outFS : j.out + frame * j.outFS + c * j.outCS;
 }
 
+/* The job a tile / CTA belongs to: the last job whose first tile is <= tile (jobs[0].tile0 == 0).  Called by whole warps with a
+ * warp-uniform `tile`: every lane probes one candidate (a 33-ary search), so a launch of a thousand jobs -- an ASRC sequence of
+ * 1024 blocks, BASELINE config 4's contexts -- costs two dependent loads per CTA instead of ten. */
+__device__ __forceinline__ int art_find_job_warp (const ArtJob *jobs, int numJobs, int tile)
+{
+    const int lane = threadIdx.x & 31;
+    int lo = 0, hi = numJobs - 1;
+    while (lo < hi) {
+        const int step = (hi - lo + 31) / 32;
+        int idx = lo + (lane + 1) * step;
+        if (idx > hi) idx = hi;
+        const bool ok = jobs[idx].tile0 <= tile;                 // monotone in the lane index
+        const int c = __popc (__ballot_sync (0xffffffffu, ok));
+        if (c == 32) { lo = hi; break; }
+        const int firstFalse = min (lo + (c + 1) * step, hi);
+        if (c) lo = min (lo + c * step, hi);
+        hi = firstFalse - 1;
+    }
+    return lo;
+}
+
 /* launchers (host side, C++ linkage, defined next to their kernels) */
 struct ArtLaunchGeom { int totalTiles; size_t smemBytes; int CV; };
 

@@ -44,16 +44,6 @@
 #define KEY_PASS1(F) ((F) + 2)      /* ... of the one after it (row index == F)                  */
 #define NUM_KEYS(F)  ((F) + 3)
 
-__device__ __forceinline__ int art_find_job (const ArtJob *jobs, int numJobs, int tile)
-{
-    int lo = 0, hi = numJobs - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (jobs[mid].tile0 <= tile) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
-
 template <int CV> struct ArtVec;
 #if ART_WIDE        /* double samples: one LDS.64 / LDS.128 brings one or two channels */
 typedef double artweight_t;
@@ -424,7 +414,7 @@ art_sinc_generic_kernel (const ArtClass k, const __grid_constant__ ArtJob single
     // channel group varies fastest across the grid, so the CTAs reading the same frames run together (L2)
     const int groups = (k.C + k.Cg - 1) / k.Cg;
     const int tileIdx = blockIdx.x / groups, cgroup = blockIdx.x - tileIdx * groups;
-    const ArtJob &job = jobs ? jobs[k.numJobs > 1 ? art_find_job (jobs, k.numJobs, tileIdx) : 0] : single;
+    const ArtJob &job = jobs ? jobs[k.numJobs > 1 ? art_find_job_warp (jobs, k.numJobs, tileIdx) : 0] : single;
     const unsigned int t0 = (unsigned int) (tileIdx - job.tile0) * (unsigned int) k.NB;
     if (t0 >= job.outputs)
         return;

@@ -48,16 +48,6 @@ template <> struct ArtPVec<1> { typedef float  type; __device__ static float get
 template <> struct ArtPVec<2> { typedef float2 type; __device__ static float get (const float2 &x, int v) { return v ? x.y : x.x; } };
 template <> struct ArtPVec<4> { typedef float4 type; __device__ static float get (const float4 &x, int v) { return v == 0 ? x.x : v == 1 ? x.y : v == 2 ? x.z : x.w; } };
 
-__device__ __forceinline__ int art_find_job_p (const ArtJob *jobs, int numJobs, int cta)
-{
-    int lo = 0, hi = numJobs - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (jobs[mid].tile0 <= cta) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
-
 /* ---- TMA bulk copy + mbarrier (sm_90+/sm_100: cp.async.bulk -> SASS UBLKCP) ---------------------- */
 __device__ __forceinline__ unsigned int art_smem_u32 (const void *p)
 {
@@ -223,7 +213,7 @@ art_sinc_periodic_kernel (const ArtClass k, const ArtPeriodic p, const __grid_co
     // block run together, so each 128-byte line comes from DRAM once and from L2 for the other groups
     const int groups = (k.C + CV - 1) / CV;
     const int cta = blockIdx.x / groups, cgroup = blockIdx.x - cta * groups;
-    const int seg = jobs ? (k.numJobs > 1 ? art_find_job_p (jobs, k.numJobs, cta) : 0) : 0;
+    const int seg = jobs ? (k.numJobs > 1 ? art_find_job_warp (jobs, k.numJobs, cta) : 0) : 0;
     const ArtJob &job = jobs ? jobs[seg] : single;
     const int L = p.L, M = p.M, T = k.T;
     const int Q = (int) ((job.outputs + L - 1) / L);             // periods in this segment

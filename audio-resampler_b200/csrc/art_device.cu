@@ -13,6 +13,7 @@
 #include <cstdarg>
 #include <time.h>
 #include <mutex>
+#include <sched.h>
 #include <vector>
 #include "art_kernels.cuh"
 #include "art_device.h"
@@ -217,39 +218,44 @@ static void host_pipe_init (ArtDev *dev, size_t events)
     }
 }
 
-/* Wait for a host call's last transfer.  cudaStreamSynchronize spins a core (the runtime's default schedule); that is the
- * lowest latency for a 50-us call, but a process that keeps several large calls in flight from several threads -- and eight
- * such processes on one host -- would burn every core on polling.  Calls that move more than ~1 MB sleep on an event
- * created with cudaEventBlockingSync instead: the wake-up costs a few microseconds against >= 50 us of transfer. */
-static int g_waitMode = -1;         // ART_B200_WAIT: 0 spin (cudaStreamSynchronize), 1 sleep on a blocking-sync event, 2 (default) poll briefly, then sleep
+/* Wait for a host call's last transfer.  cudaStreamSynchronize spins inside the driver (the runtime's default schedule): the
+ * lowest latency, and what keeps PCIe busy when a process has several calls in flight from several threads -- a sleeping wait
+ * costs a wake-up per call (one GPU, 16 threads, 2 MB calls: 9.1 Gsamples/s end to end against 11.3-11.4 spinning; polling
+ * cudaEventQuery from every thread is no better, 8.5: the queries contend with the other threads' submissions).  Spinning needs a
+ * core per waiting thread, so the default (mode 2) spins while the process has no more waiting threads than CPUs it may run on
+ * and sleeps on a blocking-sync event otherwise; eight ranks x 4 threads on a 32-CPU host measured the same under either
+ * (17.6 / 17.7 Gsamples/s, profiles/r02_e2e_scale_n8.txt: the host's memory system is the limit there). */
+static int g_waitMode = -1;         // ART_B200_WAIT: "spin" 0, "block" 1 (sleep on a blocking-sync event), default 2 (spin while there are cores for it)
+static std::atomic<int> g_waiters { 0 };
+static int g_cpus = 0;
 
 static void wait_for (ArtDev *dev, cudaStream_t stream, size_t bytesMoved)
 {
     if (g_waitMode < 0) {
         const char *e = getenv ("ART_B200_WAIT");
+        cpu_set_t set;
+        g_cpus = sched_getaffinity (0, sizeof set, &set) == 0 ? CPU_COUNT (&set) : 1;
         g_waitMode = !e ? 2 : (!strcmp (e, "spin") ? 0 : (!strcmp (e, "block") ? 1 : 2));
     }
-    if (bytesMoved < (1u << 20) || g_waitMode == 0) {
+    bool spin = bytesMoved < (1u << 20) || g_waitMode == 0;
+    if (!spin && g_waitMode == 2) {
+        const int now = ++g_waiters;
+        spin = now <= g_cpus;
+        if (spin) {
+            const cudaError_t e_ = cudaStreamSynchronize (stream);
+            --g_waiters;
+            ART_CUDA_CHECK (e_);
+            return;
+        }
+        --g_waiters;
+    }
+    if (spin) {
         ART_CUDA_CHECK (cudaStreamSynchronize (stream));
         return;
     }
     if (!dev->doneEvent)
         ART_CUDA_CHECK (cudaEventCreateWithFlags (&dev->doneEvent, cudaEventBlockingSync | cudaEventDisableTiming));
     ART_CUDA_CHECK (cudaEventRecord (dev->doneEvent, stream));
-    if (g_waitMode == 2) {
-        // a lone call finishes within ~100 us: polling catches it without a sleep/wake-up; calls queued behind the transfers of
-        // other threads or other processes (measured at 8 GPUs: ~3 ms per 2 MB call, the host's memory system is the limit,
-        // profiles/r02_e2e_scale_n8.txt) fall through to the sleeping wait instead of burning a core each
-        timespec t0, t;
-        clock_gettime (CLOCK_MONOTONIC, &t0);
-        for (;;) {
-            const cudaError_t q = cudaEventQuery (dev->doneEvent);
-            if (q == cudaSuccess) return;
-            if (q != cudaErrorNotReady) ART_CUDA_CHECK (q);
-            clock_gettime (CLOCK_MONOTONIC, &t);
-            if ((t.tv_sec - t0.tv_sec) * 1000000000LL + (t.tv_nsec - t0.tv_nsec) > 500000LL) break;
-        }
-    }
     ART_CUDA_CHECK (cudaEventSynchronize (dev->doneEvent));
 }
 

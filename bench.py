@@ -783,7 +783,7 @@ def measure_e2e(lib, pkg, torch, dist, world, dev, streams, frames, args):
     return {"value": value, "unit": "Msamples/s",
             "h2d_bytes_per_step": int(n * frames * ch * 4), "d2h_bytes_per_step": int(per_step_out * ch * 4),
             "api": "resampleProcessInterleaved (host pointers, pinned), "
-                   f"{n} streams x {frames} frames per step, {T} host threads per rank (blocking-sync waits), {steps} steps in {dt:.2f} s",
+                   f"{n} streams x {frames} frames per step, {T} host threads per rank (the library waits spinning while the process has a CPU per waiting thread, ART_B200_WAIT), {steps} steps in {dt:.2f} s",
             "batched_value": batched,
             "batched_api": "resampleBatchProcessInterleaved (host pointers, pinned), one call per step, one host thread per rank"}
 

@@ -54,6 +54,10 @@ unsigned long long resampleB200TensorLaunches (void);
  *                       taps, ~15 % faster.
  * The environment variable ART_B200_DIGITS sets the initial value. */
 void resampleB200SetTensorDigits (int digits);
+/* Non-finite input (NaN, Inf): the reference's outputs are non-finite exactly where a filter window holds such a sample.  The
+ * kernels here evaluate zero-padded windows (0 x NaN is NaN), so they return non-finite values for those outputs and for up to one
+ * period of outputs (the ratio's numerator, 160 at 44.1k->48k) on either side; every other output is unaffected (a non-finite
+ * sample is left out of a tile's block scaling).  tests/test_gpu_tensor_path.py pins this. */
 /* measurement aid: when enabled, every convolution kernel launch is bracketed by CUDA events on its
  * own stream; Collect waits for them, returns how many launches were timed and their summed
  * duration in milliseconds, and clears the list */

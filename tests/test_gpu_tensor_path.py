@@ -261,3 +261,36 @@ def test_error_relative_to_the_local_peak(forced_tensor_path, step_db, digits):
         assert row["tensor"]["local_relative"] <= TOL                    # ... and so has the tensor-core form by default
     else:
         assert row["tensor"]["local_abs_over_tile_peak"] <= 2.0 ** -22   # the documented guarantee of the 2-digit mode
+
+
+def test_non_finite_samples_poison_their_neighbourhood_only():
+    """A NaN or Inf input sample makes the reference's outputs non-finite exactly where a window holds it (every tap multiplies it,
+    resampler.c:1033-1044).  The kernels pad: the FFMA form's windows to a multiple of 32 taps, the tensor-core form's to the band
+    of a tile row -- zero taps, but 0 x NaN is NaN -- so they poison a superset: at most one tile row (L outputs) more on either
+    side.  Everything else must be finite and within tolerance: a non-finite sample must not upset a tile's block scaling."""
+    lib = A.product()
+    filters, taps = A.PRESETS[3]
+    ratio = 48000 / 44100
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-0.5, 0.5, (40000, 2)).astype(np.float32)
+    x[12345, 0] = np.nan
+    x[30000, 1] = np.inf
+    o = A.oracle_stream(2, taps, filters, 0.0); o.advance(taps / 2)
+    yo, uo, mo = o.process(x, 50000, ratio)
+    bad_o = ~np.isfinite(yo)
+    assert bad_o.any()
+    try:
+        for mode in (0, 2):
+            lib.resampleB200SetTensorPath(mode)
+            g = A.product_stream(2, taps, filters, 0.0); g.advance(taps / 2)
+            y, u, m = g.process(x, 50000, ratio)
+            assert (u, m) == (uo, mo)
+            bad = ~np.isfinite(y)
+            assert not (bad_o & ~bad).any(), "an output the reference poisons came out finite"
+            extra = np.argwhere(bad & ~bad_o)[:, 0]
+            lo_, hi_ = np.argwhere(bad_o)[:, 0].min(), np.argwhere(bad_o)[:, 0].max()
+            assert extra.size == 0 or (extra.min() >= lo_ - 160 and extra.max() <= hi_ + 160)
+            ok = ~bad
+            assert np.max(np.abs(y[ok] - yo[ok])) <= TOL * np.max(np.abs(yo[ok]))
+    finally:
+        lib.resampleB200SetTensorPath(1)

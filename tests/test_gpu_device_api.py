@@ -220,13 +220,15 @@ def test_single_context_device_calls(lib, mode, ratio):
         assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
 
 
-def test_host_call_of_many_channels_in_pipelined_pieces(lib):
-    """a host interleaved call large enough to be cut into pipelined pieces (>= 2^21 output samples), 8 channels, tensor form:
-    pieces after the first start at an output offset and go through planar scratch -- against the FFMA form of the same
-    call and, on its first and last stretch, against the oracle"""
-    ch, taps, filters = 8, 156, 320
+@pytest.mark.parametrize("ch", [8, 10])
+def test_host_call_of_many_channels_in_pipelined_pieces(lib, ch):
+    """a host interleaved call large enough to be cut into pipelined pieces (>= 2^21 output samples), many channels, tensor
+    form: pieces after the first start at an output offset; 8 channels run as tiles of four channels straight from the interleaved
+    block, 10 channels go through planar scratch (which must transpose only what each piece owns) -- against the FFMA form of
+    the same call and, on its first stretch, against the oracle"""
+    taps, filters = 156, 320
     ratio = 48000 / 44100
-    n = 300_000                                              # -> 326 k frames x 8 channels = 2.6 M output samples: 2 pieces
+    n = 300_000                                              # -> 326 k frames x 8 (10) channels = 2.6 M (3.3 M) output samples: 2-3 pieces
     rng = np.random.default_rng(308)
     x = rng.uniform(-0.5, 0.5, (n, ch)).astype(np.float32)
     cap = int(n * ratio) + 1000

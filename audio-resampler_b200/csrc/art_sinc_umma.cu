@@ -656,6 +656,17 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             sc.hiRel = hiR < -(1 << 30) ? -(1 << 30) : (hiR > (1 << 30) ? (1 << 30) : (int) hiR);
             sc.h0 = hist + R0;
             sc.dummy = hist + lo - 1;                                         // any readable address: the newest history sample
+            if (!sc.fast) {
+                // a tile that touches the history or the end of the input (every tile of a short block): the classification is
+                // only needed by the warps whose rows actually reach outside the block -- decided once per tile and warp
+                bool plain = true;
+#pragma unroll
+                for (int uu = 0; uu < UN; ++uu) {
+                    const int rel = off0 + 32 * M * uu;                       // this lane's first sample of pair 0; its last: + 16 * KI - 1
+                    plain = plain && (r0 + 32 * uu >= periods || (rel >= sc.loRel && rel + 16 * KI <= sc.hiRel));
+                }
+                sc.fast = __all_sync (0xffffffffu, plain);
+            }
             return sc;
         };
         /* the tile's block maximum -> its power-of-two quantum.  The epilogue warps scan every tile three tiles ahead of its

@@ -411,6 +411,18 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (prof && tid == 0 && blockIdx.x < 160) g_utime[blockIdx.x][0] = u_gtime ();
     const int L = u.L, M = u.M, Npad = u.Npad, KI = u.KI, NS = u.NS, numK = u.numK, C = k.C, T = k.T;
+    /* This CTA's i-th tile (-1: no more).  Channel groups of one frame range are neighbours in the launch and want to run at the
+     * same time on different SMs (they share sectors and DRAM pages: BASELINE config 3 loses a third otherwise), which is what
+     * round-robin (blockIdx + i * grid) gives.  When a tile holds all channels there is nothing to share, and round-robin has a
+     * trap: it hands a CTA the same KIND of tile every time whenever the tiles per job divide the grid -- with BASELINE config 4's
+     * four tiles per 2^15-frame block on 148 = 4 x 37 CTAs a quarter of the SMs got nothing but the tiles that start at the
+     * history and ran 50 % longer than the rest.  Those launches give every CTA a contiguous range of tiles instead. */
+    // tile i of this CTA = tStart + i * tStep, i < tCount
+    const bool contiguous = C == CGT;
+    const int tileLo = (int) (((long long) totalTiles * blockIdx.x) / gridDim.x), tileHi = (int) (((long long) totalTiles * (blockIdx.x + 1)) / gridDim.x);
+    const int tStart = contiguous ? tileLo : (int) blockIdx.x;
+    const int tStep = contiguous ? 1 : (int) gridDim.x;
+    const int tCount = contiguous ? tileHi - tileLo : (totalTiles - (int) blockIdx.x + (int) gridDim.x - 1) / (int) gridDim.x;
     const int CG = C / CGT;                                 // channel groups: tiles per (period block, phase group)
     constexpr int PR = ART_U_ROWS / CGT;                    // periods per tile
     const int digits = u.digits;                            // signal digits: 2, or 3 (one more MMA per k-step)
@@ -497,7 +509,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
         if (lane == 0) {
             UPROF_DECL ();
             unsigned int us = 0, ph = 0;
-            for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
+            for (int it = 0, tile = tStart; it < tCount; ++it, tile += tStep) {
                 const ArtJob &job = jobOf (tile);
                 const int grp = ((tile - job.tile0) / CG) % u.G;
                 const unsigned short *tab = u.H + ((size_t) job.table * u.G + grp) * u.tableHalfs;
@@ -534,7 +546,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
         const unsigned int bLo0 = ((stBase >> 4) & 0x3fffu) | ((((unsigned int) Npad * 16u >> 4) & 0x3fffu) << 16);
         const unsigned int aSplitU = splitBytes >> 4;
         unsigned int us = 0, ph = 0, lt = 0;
-        for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++lt) {
+        for (int tile = tStart; (int) lt < tCount; ++lt, tile += tStep) {
             long long t1 = UCLK ();
             u_mbar_wait (accEmptyA, (lt & 1) ^ 1);                            // the epilogue has drained the accumulators
             long long t2 = UCLK ();
@@ -598,7 +610,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
         asm volatile ("setmaxnreg.dec.sync.aligned.u32 56;");
         if (lane == 0) {
             unsigned int us = 0, ph = 0;
-            for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x) {
+            for (int it = 0, tile = tStart; it < tCount; ++it, tile += tStep) {
                 for (int ks0 = 0; ks0 < numK; ks0 += ART_U_GROUP) {
                     const int cnt = numK - ks0 < ART_U_GROUP ? numK - ks0 : ART_U_GROUP;
                     u_mbar_wait (hEmptyA (us), ph);
@@ -729,16 +741,16 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             }
         };
         // the request side runs `depth - 1` pairs ahead of the conversion, across tile boundaries
-        int rtile = blockIdx.x, ri = 0;
+        int rit = 0, rtile = tStart, ri = 0;                                 // rit < tCount: a tile is left to request
         unsigned int rslot = 0;
-        Src rsrc = source (rtile < totalTiles ? rtile : 0);
+        Src rsrc = source (tCount > 0 ? rtile : 0);
         auto requestNext = [&] () {
-            if (rtile < totalTiles) {
+            if (rit < tCount) {
                 request (rsrc, ri, rslot);
                 if (++ri == KI) {
                     ri = 0;
-                    rtile += gridDim.x;
-                    if (rtile < totalTiles) rsrc = source (rtile);
+                    ++rit; rtile += tStep;
+                    if (rit < tCount) rsrc = source (rtile);
                 }
             }
             asm volatile ("cp.async.commit_group;" ::: "memory");           // one group per pair, empty or not: the wait below counts groups
@@ -748,7 +760,7 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
         unsigned int cslot = 0;
         unsigned int useBase = 0;                                           // uses of operand slot 0 before this tile
 
-        for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++lt) {
+        for (int tile = tStart; (int) lt < tCount; ++lt, tile += tStep) {
             long long q0t = UCLK ();
             const int e = quantum (lt);
             if (ctid == 0) UPROF_ADD (17, UCLK () - q0t);
@@ -869,14 +881,14 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
             __syncwarp ();
         };
         for (int ahead = 0; ahead < 3; ++ahead)
-            if ((long long) blockIdx.x + (long long) ahead * gridDim.x < totalTiles)
-                scanTile (blockIdx.x + ahead * gridDim.x, (unsigned int) ahead);
+            if (ahead < tCount)
+                scanTile (tStart + ahead * tStep, (unsigned int) ahead);
         // store mapping after the transposition: a lane owns channel lane % CGT and phase (lane / CGT) % 8 of period lane / (8 * CGT):
         // one store instruction covers 4 / CGT periods x 8 phases x CGT channels, i.e. whole frames, 32 bytes or more per period
         const int scc = lane % CGT, sjj = (lane / CGT) & 7, spp = lane / (8 * CGT);
         constexpr int PPI = 4 / CGT;
         unsigned int lt = 0;
-        for (int tile = blockIdx.x; tile < totalTiles; tile += gridDim.x, ++lt) {
+        for (int tile = tStart; (int) lt < tCount; ++lt, tile += tStep) {
             const ArtJob &job = jobOf (tile);
             const Where w = whereIs (job, tile);
             const int grp = w.grp;
@@ -949,8 +961,8 @@ art_sinc_umma_kernel (const ArtClass k, const __grid_constant__ ArtUmma u, const
                 }
             }
             long long e3 = UCLK ();
-            if ((long long) tile + 3LL * gridDim.x < totalTiles)
-                scanTile (tile + 3 * gridDim.x, lt + 3u);
+            if ((int) lt + 3 < tCount)
+                scanTile (tile + 3 * tStep, lt + 3u);
             if (tid == 12 * 32) { UPROF_ADD (8, e1 - e0); UPROF_ADD (9, e2 - e1); UPROF_ADD (6, e3 - e2); UPROF_ADD (10, 1); UPROF_ADD (16, UCLK () - e3); }
         }
         UPROF_FLUSH ();

@@ -309,10 +309,21 @@ __device__ __forceinline__ void art_run_unity (const ArtTileCtx &t, const ArtJob
                 fin[e] = keep + __shfl_xor_sync (0xffffffffu, send, 8);
             }
             if (q < len) {
+                float o[CV];
 #pragma unroll
-                for (int v = 0; v < CV; ++v)
-                    if (cg + v < t.nc)
-                        *art_out_ptr (job, t.c0 + cg + v, (long long) t.n0 + e0 + q) = fmaf (fOut, fin[CV + v] - fin[v], fin[v]);
+                for (int v = 0; v < CV; ++v) o[v] = fmaf (fOut, fin[CV + v] - fin[v], fin[v]);
+                // the CV channels of a frame of an interleaved block: one vector store
+                float *dst = art_out_ptr (job, t.c0 + cg, (long long) t.n0 + e0 + q);
+                if (!job.outPlanes && job.outCS == 1 && cg + CV <= t.nc && (reinterpret_cast<uintptr_t> (dst) % (sizeof (float) * CV)) == 0) {
+                    if constexpr (CV == 4) *reinterpret_cast<float4 *> (dst) = make_float4 (o[0], o[1], o[2], o[3]);
+                    else                   *reinterpret_cast<float2 *> (dst) = make_float2 (o[0], o[1]);
+                }
+                else {
+#pragma unroll
+                    for (int v = 0; v < CV; ++v)
+                        if (cg + v < t.nc)
+                            *art_out_ptr (job, t.c0 + cg + v, (long long) t.n0 + e0 + q) = o[v];
+                }
             }
         }
     }

@@ -574,6 +574,7 @@ def run_gpu_arm(args):
     configs = None
     if not args.no_configs:
         configs = measure_configs(lib, pkg, torch, dist, world, rank, dev, work_stream, peak, args)
+        configs.append(measure_wide(pkg, torch, dist, world, rank, dev, work_stream, peak, args))
 
     line = {
         "metric": METRIC, "value": value, "unit": "Msamples/s",
@@ -672,6 +673,82 @@ def measure_configs(lib, pkg, torch, dist, world, rank, dev, stream, peak, args)
             row["cpu"] = (f"{kind}, RESAMPLE_MULTITHREADED, one 64-channel context" if mt else f"{kind}, {cores} contexts on {cores} threads") + f", {dt:.1f} s"
         out.append(row)
     return out
+
+
+def measure_wide(pkg, torch, dist, world, rank, dev, stream, peak, args):
+    """One row for the PATH_WIDTH=64 library (libresampler_b200_64.so: double samples): the metric's
+    configuration, device-resident, and -- on one GPU -- the reference's own PATH_WIDTH=64 build on the host beside it."""
+    lib64 = pkg.load64()
+    ch, (filters, taps), ratio = 2, PRESETS[3], 48000 / 44100
+    n, frames = 64, 1 << 16
+    lib64.resampleB200SetDevice(dev.index or 0)
+    ctxs = [lib64.resampleInit(ch, taps, filters, 0.0, FLAGS) for _ in range(n)]
+    assert all(ctxs), "resampleInit (PATH_WIDTH=64) failed"
+    for c in ctxs:
+        lib64.resampleAdvancePosition(c, taps / 2)
+    x = torch.rand((n, frames, ch), device=dev, dtype=torch.float64) - 0.5
+    cap = int(frames * ratio) + taps + 16
+    y = torch.empty((n, cap, ch), device=dev, dtype=torch.float64)
+    ca = (C.POINTER(pkg.Resample64) * n)(*ctxs)
+    ia = (C.c_void_p * n)(*[x[i].data_ptr() for i in range(n)]); oa = (C.c_void_p * n)(*[y[i].data_ptr() for i in range(n)])
+    ni, no = (C.c_int * n)(*([frames] * n)), (C.c_int * n)(*([cap] * n))
+    ra = (C.c_double * n)(*([ratio] * n)); res = (pkg.ResampleResult * n)()
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def step():
+        lib64.resampleBatchProcessInterleavedDevice(ca, n, ia, ni, oa, no, ra, res, sp)
+        return int(np.frombuffer(res, dtype=np.uint32)[1::2].sum(dtype=np.int64))
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream); made = 0
+    launches = 5
+    for _ in range(launches):
+        made += step()
+    e1.record(stream); torch.cuda.synchronize()
+    ms_max, tot = reduce_over_ranks(dist if world > 1 else None, dev, e0.elapsed_time(e1), float(made))
+    gs = tot * ch / (ms_max * 1e-3) / 1e9
+    row = {"config": "PATH_WIDTH=64 library (double samples): stereo preset -3 44.1->48k, 64 streams x 2^16 frames", "Gsamples_per_s": gs,
+           "ms_per_launch": ms_max / launches, "kernel": "generic (double multiply-adds)", "hbm_frac": gs * 8.0 * (1.0 + 1.0 / ratio) / peak,
+           "filters": filters, "interpolated": True}
+    for c in ctxs:
+        lib64.resampleFree(c)
+    del x, y
+    torch.cuda.empty_cache()
+    if world == 1 and rank == 0 and not args.no_cpu:
+        import artlibs as A
+        if A.reference64() is not None:
+            cores = host_cores()
+            block = 16384
+            xin = np.random.default_rng(5).uniform(-0.5, 0.5, (block, ch))
+            streams = [A.reference_stream64(ch, taps, filters, 0.0, FLAGS) for _ in range(cores)]
+            for s in streams:
+                s.advance(taps / 2)
+            made_by = [0] * cores
+            calls = 40
+            go = threading.Barrier(cores + 1)
+
+            def work(t):
+                s = streams[t]
+                out = np.empty((int(block * ratio) + taps + 16, ch))
+                fn, xp, op = s.lib.resampleProcessInterleaved, xin.ctypes.data_as(A.f64p), out.ctypes.data_as(A.f64p)
+                fn(s.ctx, xp, block, op, out.shape[0], ratio)
+                go.wait()
+                tot_ = 0
+                for _ in range(calls):
+                    tot_ += fn(s.ctx, xp, block, op, out.shape[0], ratio).output_generated
+                made_by[t] = tot_
+                go.wait()
+            pool = [threading.Thread(target=work, args=(t,), daemon=True) for t in range(cores)]
+            for th in pool:
+                th.start()
+            go.wait(); t0 = time.perf_counter(); go.wait(); dt = time.perf_counter() - t0
+            for th in pool:
+                th.join()
+            row["cpu_Msamples_per_s"] = sum(made_by) * ch / dt / 1e6
+            row["cpu"] = f"reference built with -DPATH_WIDTH=64, {cores} contexts on {cores} threads, {dt:.1f} s"
+    return row
 
 
 def measure_e2e(lib, pkg, torch, dist, world, dev, streams, frames, args):

@@ -260,7 +260,14 @@ __device__ __forceinline__ void art_run_unity (const ArtTileCtx &t, const ArtJob
 #pragma unroll
                 for (int p = 0; p < NP; ++p) { accA[r][p] = 0ull; accB[r][p] = 0ull; }
             const PairT *plane = reinterpret_cast<const PairT *> (t.xs) + (size_t) (cg / CV) * t.Wp;
-            PairT w0 = plane[ART_SKEW (p0)], w1 = plane[ART_SKEW (p0 + 1)], w2 = plane[ART_SKEW (p0 + 2)], w3;
+            /* skewed position of p0 + 8 * kb + d = skew (p0) + 9 * kb + d + ((p0 % 8 + d) / 8): the lane-dependent part is a constant
+             * per d, so the window walks with ONE add per load (base + offset) instead of re-deriving the skew for every tap */
+            const PairT *wbase = plane + ART_SKEW (p0);
+            const int r8 = p0 & 7;
+            int woff[11];
+#pragma unroll
+            for (int d = 0; d < 11; ++d) woff[d] = d + ((r8 + d) >> 3);
+            PairT w0 = wbase[woff[0]], w1 = wbase[woff[1]], w2 = wbase[woff[2]], w3;
 #define ART_UNITY_TAP(ca, cb, x0, x1, x2, x3)                                                   \
             do {                                                                                \
                 const unsigned long long ca2 = art_pack2 (ca, ca), cb2 = art_pack2 (cb, cb);    \
@@ -276,13 +283,19 @@ __device__ __forceinline__ void art_run_unity (const ArtTileCtx &t, const ArtJob
                     art_ffma2 (accB[3][p], ArtPairs<CV>::get (x3, p), cb2);                     \
                 }                                                                               \
             } while (0)
-            for (int k = 0; k < Tq; k += 4) {                          // the window rotates through the four registers: no moves
+            for (int k = 0; k < Tq; k += 8, wbase += 9) {              // the window rotates through the four registers: no moves
                 const float4 a4 = __ldg (reinterpret_cast<const float4 *> (rowA + k));
                 const float4 b4 = __ldg (reinterpret_cast<const float4 *> (rowB + k));
-                w3 = plane[ART_SKEW (p0 + k + 3)]; ART_UNITY_TAP (a4.x, b4.x, w0, w1, w2, w3);
-                w0 = plane[ART_SKEW (p0 + k + 4)]; ART_UNITY_TAP (a4.y, b4.y, w1, w2, w3, w0);
-                w1 = plane[ART_SKEW (p0 + k + 5)]; ART_UNITY_TAP (a4.z, b4.z, w2, w3, w0, w1);
-                w2 = plane[ART_SKEW (p0 + k + 6)]; ART_UNITY_TAP (a4.w, b4.w, w3, w0, w1, w2);
+                const float4 a8 = __ldg (reinterpret_cast<const float4 *> (rowA + k + 4));
+                const float4 b8 = __ldg (reinterpret_cast<const float4 *> (rowB + k + 4));
+                w3 = wbase[woff[3]];  ART_UNITY_TAP (a4.x, b4.x, w0, w1, w2, w3);
+                w0 = wbase[woff[4]];  ART_UNITY_TAP (a4.y, b4.y, w1, w2, w3, w0);
+                w1 = wbase[woff[5]];  ART_UNITY_TAP (a4.z, b4.z, w2, w3, w0, w1);
+                w2 = wbase[woff[6]];  ART_UNITY_TAP (a4.w, b4.w, w3, w0, w1, w2);
+                w3 = wbase[woff[7]];  ART_UNITY_TAP (a8.x, b8.x, w0, w1, w2, w3);
+                w0 = wbase[woff[8]];  ART_UNITY_TAP (a8.y, b8.y, w1, w2, w3, w0);
+                w1 = wbase[woff[9]];  ART_UNITY_TAP (a8.z, b8.z, w2, w3, w0, w1);
+                w2 = wbase[woff[10]]; ART_UNITY_TAP (a8.w, b8.w, w3, w0, w1, w2);
             }
 #undef ART_UNITY_TAP
             // sum the four tap quarters; the halving exchanges leave output q (all channels, both rows) in lane (q, g)

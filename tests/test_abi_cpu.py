@@ -70,3 +70,44 @@ def test_biquad_design_runs_on_host():
     q = pkg.Biquad()
     lib.biquad_init(C.byref(q), C.byref(co), 1.0)
     assert q.order == 2 and q.index == 0
+
+
+@pytest.mark.parametrize("width", [32, 64])
+def test_c_caller_compiles_and_links_against_the_headers(tmp_path, width):
+    """A plain C caller, compiled against include/*.h exactly as a caller of the reference would be (-DPATH_WIDTH=64 selects the
+    double-sample build, reference resampler.h:22-26), links against the matching library and sees the reference's struct layout."""
+    import subprocess
+    src = tmp_path / "caller.c"
+    src.write_text(r'''
+#include <stddef.h>
+#include <stdio.h>
+#include "resampler.h"
+#include "biquad.h"
+#include "decimator.h"
+#include "resampler_b200.h"
+int main (void)
+{
+    Resample *r;
+    BiquadCoefficients c;
+    printf ("%d %d %d %d %d\n", (int) sizeof (artsample_t), (int) offsetof (Resample, outputOffset), (int) offsetof (Resample, filters),
+            (int) sizeof (Biquad), (int) sizeof (ResampleResult));
+    biquad_lowpass (&c, 0.2);                       /* host-side design: works without a GPU */
+    printf ("%d\n", c.a0 > 0 && c.a1 > c.a0);
+    r = resampleInit (2, 48, 48, 0.0, SUBSAMPLE_INTERPOLATE | BLACKMAN_HARRIS);      /* NULL + message when no CUDA device is usable */
+    printf ("%d\n", r != NULL);
+    resampleFree (r);
+    return 0;
+}
+''')
+    lib = "resampler_b200_64" if width == 64 else "resampler_b200"
+    libdir = ROOT / "audio-resampler_b200" / "lib"
+    exe = tmp_path / "caller"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(src), f"-L{libdir}", f"-l{lib}", f"-Wl,-rpath,{libdir}", "-lm", "-o", str(exe)]
+    if width == 64:
+        cmd.insert(1, "-DPATH_WIDTH=64")
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.split("\n")
+    assert lines[0].split() == [str(width // 8), "32", "72", "80" if width == 32 else "152", "8"]
+    assert lines[1].strip() == "1"
